@@ -1,0 +1,260 @@
+/*
+ * rl8_b200 — C-ABI of the B200-native PPO rollout-and-update engine.
+ *
+ * The upstream reference (theOGognf/rl8) is pure Python on stock PyTorch and has no FFI
+ * of its own; its plug-in points are Python protocols.  This header is
+ * the boundary those Python classes bind underneath: every entry point below replaces
+ * the body of one reference function (cited as path:line relative to the upstream
+ * repository root) and is what a ctypes / cffi stub in the reference would call
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 (RL8_OK) or a negative rl8_status; nothing throws;
+ *   - no function allocates, frees or synchronises; all tensor pointers are DEVICE
+ *     pointers owned by the caller (torch tensors on the host side);
+ *   - the last argument is the cudaStream_t to launch on (the caller's current stream);
+ *   - `N` = number of environments, `T` = horizon, `D` = observation width,
+ *     `P` = policy-head width (number of discrete actions, or 2 = {mean, log_std raw}),
+ *     `H` = hidden width (256 in the reference's default models);
+ *   - rollout storage is HORIZON-MAJOR: a field is `[T+1][N]` floats (obs `[T+1][D][N]`),
+ *     so one time step is one contiguous, coalesced slab.  The reference's env-major
+ *     `[N, T+1, ...]` tensors are strided views of the same memory.
+ *   - flattened transition index (the reference's `buffer.reshape(-1)` row,
+ *     src/rl8/algorithms/_feedforward.py:473-481) is `row = n*T + t`.
+ */
+#ifndef RL8_B200_H
+#define RL8_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rl8_stream_t; /* cudaStream_t */
+
+typedef enum {
+  RL8_OK = 0,
+  RL8_ERR_ARG = -1,         /* bad argument (null pointer, unsupported size) */
+  RL8_ERR_CUDA = -2,        /* a CUDA launch failed; see rl8_last_error() */
+  RL8_ERR_UNSUPPORTED = -3, /* combination outside the fused path */
+  RL8_ERR_WORKSPACE = -4    /* caller workspace too small */
+} rl8_status;
+
+typedef enum {
+  RL8_ENV_DISCRETE_DUMMY = 0,   /* src/rl8/env.py:233-259 */
+  RL8_ENV_CONTINUOUS_DUMMY = 1, /* src/rl8/env.py:206-230 */
+  RL8_ENV_CARTPOLE = 2,         /* examples/cartpole/env.py */
+  RL8_ENV_MOUNTAIN_CAR = 3,     /* examples/mountain_car/env.py */
+  RL8_ENV_PENDULUM = 4          /* examples/pendulum/env.py */
+} rl8_env_kind;
+
+typedef enum {
+  RL8_DIST_CATEGORICAL = 0,    /* src/rl8/distributions.py:125-132 */
+  RL8_DIST_NORMAL = 1,         /* src/rl8/distributions.py:135-144 */
+  RL8_DIST_SQUASHED_NORMAL = 2 /* src/rl8/distributions.py:147-170 */
+} rl8_dist_kind;
+
+typedef enum {
+  RL8_PREC_FP32 = 0, /* CUDA-core fp32 GEMMs (parity mode; reference `enable_amp=False`) */
+  RL8_PREC_BF16 = 1  /* tcgen05 bf16 GEMMs, fp32 accumulate (reference `enable_amp=True`) */
+} rl8_precision;
+
+/* Environment constants, already rounded the way the reference rounds them (Python
+ * double arithmetic between scalars, then one cast to f32 per tensor op).  Index map:
+ *   dummy        p[0]=bounds
+ *   cartpole     p[0]=force_mag p[1]=gravity p[2]=length p[3]=pole_mass
+ *                p[4]=pole_mass_length p[5]=total_mass p[6]=tau p[7]=(4.0/3.0)
+ *                p[8]=1.0 if kinematics_integrator != "euler" else 0.0
+ *   mountain_car p[0]=force_mag p[1]=goal_position p[2]=goal_velocity p[3]=gravity
+ *                p[4]=max_position p[5]=max_speed p[6]=min_position
+ *   pendulum     p[0]=dt p[1]=3g/(2l) p[2]=3/(m l^2) p[3]=max_speed p[4]=max_torque
+ *                p[5]=pi p[6]=2*pi
+ */
+typedef struct {
+  float p[16];
+} rl8_env_cfg;
+
+/* Default feedforward model (src/rl8/models/_feedforward.py:234-383): two independent
+ * MLPs D->H->H->P (policy) and D->H->H->1 (value), ReLU after the first two layers.
+ * All pointers address one flat fp32 parameter (or gradient) buffer. */
+typedef struct {
+  int32_t D, H, P;
+  const float *pi_w1, *pi_b1, *pi_w2, *pi_b2, *pi_w3, *pi_b3; /* [H,D] [H] [H,H] [H] [P,H] [P] */
+  const float *vf_w1, *vf_b1, *vf_w2, *vf_b2, *vf_w3, *vf_b3; /* ... [1,H] [1] */
+} rl8_model;
+
+/* PPO hyper-parameters of one update (src/rl8/nn/functional.py:259-363). */
+typedef struct {
+  float clip_param;
+  float dual_clip_param; /* <= 0: disabled (the reference tests truthiness, :335) */
+  float entropy_coeff;
+  float vf_clip_param;
+  float vf_coeff;
+  float loss_scale; /* 1 / grad_accumulation_steps (src/rl8/algorithms/_feedforward.py:545) */
+} rl8_ppo_hparams;
+
+/* ---- library ------------------------------------------------------------------- */
+
+/* ABI version of this header; bumped on any signature change. */
+int rl8_abi_version(void);
+/* Text of the last CUDA error seen by this library on the calling thread ("" if none). */
+const char* rl8_last_error(void);
+
+/* ---- environments: Env.reset / Env.step (src/rl8/env.py:100-128) ------------------ */
+
+/* state[S][N] <- reset distribution applied to `noise[S][N]` (standard normal for
+ * cartpole / mountain_car, U[0,1) for dummy / pendulum), and the initial observation.
+ * obs element (n, d) is written at obs[n*obs_stride_n + d*obs_stride_d].
+ * Replaces DummyEnv.reset (src/rl8/env.py:197-203), CartPole.reset
+ * (examples/cartpole/env.py:128-136), MountainCar.reset (examples/mountain_car/env.py:92-102),
+ * Pendulum.reset (examples/pendulum/env.py:94-106). */
+int rl8_env_reset(int env_kind, const rl8_env_cfg* cfg, const float* noise, float* state,
+                  float* obs, int64_t obs_stride_n, int64_t obs_stride_d, int64_t N,
+                  rl8_stream_t stream);
+
+/* obs <- observation of the current state[S][N] (the tail of every reference reset/step,
+ * e.g. examples/cartpole/env.py:133-136); used after installing a state by hand. */
+int rl8_env_observe(int env_kind, const float* state, float* obs, int64_t obs_stride_n,
+                    int64_t obs_stride_d, int64_t N, rl8_stream_t stream);
+
+/* One transition of every environment.  `action` is int64[N] for discrete envs and
+ * f32[N] for continuous ones.  Replaces DiscreteDummyEnv.step (src/rl8/env.py:253-259),
+ * ContinuousDummyEnv.step (:224-230), examples/cartpole/env.py:12-64,
+ * examples/mountain_car/env.py:12-38, examples/pendulum/env.py:12-39. */
+int rl8_env_step(int env_kind, const rl8_env_cfg* cfg, float* state, const void* action,
+                 float* obs, int64_t obs_stride_n, int64_t obs_stride_d, float* reward,
+                 int64_t N, rl8_stream_t stream);
+
+/* ---- action distributions (src/rl8/distributions.py:98-170) ------------------------ */
+
+/* features[B][P] (logits, or {mean, log_std} with log_std already tanh'ed) + injected
+ * noise (Exp(1) [B][P] for categorical, N(0,1) [B] otherwise; ignored when
+ * `deterministic`) -> action (int64[B] or f32[B]) and logp[B] (may be NULL). */
+int rl8_dist_sample(int dist_kind, const float* features, int32_t P, const float* noise,
+                    int deterministic, void* action, float* logp, int64_t B,
+                    rl8_stream_t stream);
+
+/* logp[B] and entropy[B] (either may be NULL) of given actions.  Entropy of the squashed
+ * normal is undefined in the reference (:153-157) -> RL8_ERR_UNSUPPORTED. */
+int rl8_dist_logp_entropy(int dist_kind, const float* features, int32_t P, const void* action,
+                          float* logp, float* entropy, int64_t B, rl8_stream_t stream);
+
+/* ---- GAE (src/rl8/nn/functional.py:50-123) ----------------------------------------- */
+
+/* rewards/values/advantages/returns hold (T+1) x N elements addressed as
+ * ptr[n*stride_n + t*stride_t].  rewards are divided by (reward_scale + 1e-8) IN PLACE,
+ * advantages/returns are written for all T+1 slots (A_T = 0, ret_T = V_T).  When
+ * `normalize` is set, the first T slots of the advantages are standardised with the
+ * unbiased std over N*T elements; `moments` (3 doubles: sum, sum of squares, count) is
+ * scratch, zeroed by the caller, and may be all-reduced across ranks between the two
+ * calls.  `returns` and `moments` may be NULL.  gamma / gae_lambda / reward_scale are the
+ * reference's Python doubles: `gamma*gae_lambda` and `reward_scale + 1e-8` are formed in
+ * double and rounded to f32 once, as torch does for scalar operands.
+ * Layout decides the kernel: stride_n == 1 (horizon-major) -> one env per lane, sequential
+ * in t, 128-bit coalesced; stride_t == 1 (env-major, the reference layout) -> one env row
+ * per warp, warp-level reverse scan over the horizon; anything else -> strided sequential. */
+int rl8_gae_scan(float* rewards, const float* values, float* advantages, float* returns,
+                 int64_t N, int32_t T, int64_t stride_n, int64_t stride_t, double gamma,
+                 double gae_lambda, double reward_scale, double* moments, rl8_stream_t stream);
+int rl8_gae_normalize(float* advantages, int64_t N, int32_t T, int64_t stride_n, int64_t stride_t,
+                      const double* moments, rl8_stream_t stream);
+
+/* ---- collect statistics (src/rl8/algorithms/_feedforward.py:410-436) ----------------- */
+
+/* From horizon-major rewards[T+1][N] and reversed discounted returns rdr[T+1][N] (may be
+ * NULL) accumulate into acc[16] doubles (caller sets acc[0..5] = 0, acc[6] = acc[8] = +inf,
+ * acc[7] = acc[9] = -inf; sums all-reduce with SUM, extrema with MIN / MAX:
+ *   0 sum r, 1 sum r^2, 2 sum R, 3 sum R^2, 4 sum rdr, 5 sum rdr^2 (slots 1..T),
+ *   6 min r, 7 max r, 8 min R, 9 max R) where R = per-env sum of rewards over t < T. */
+int rl8_collect_stats(const float* rewards, const float* rdr, int64_t N, int32_t T, double* acc,
+                      rl8_stream_t stream);
+
+/* ---- policy / value networks ------------------------------------------------------- */
+
+/* Bytes of workspace rl8_mlp_forward needs for `rows` rows. */
+int64_t rl8_mlp_forward_workspace(int32_t H, int64_t rows);
+
+/* out[rows][P_out] = MLP(obs) for one of the two networks of `model` (which = 0 policy,
+ * 1 value).  obs element (r, d) is read at obs[r*obs_stride_r + d*obs_stride_d].
+ * Replaces DefaultDiscreteModel.forward / value_function and the continuous twin
+ * (src/rl8/models/_feedforward.py:292-310, 365-383).  For the continuous policy head the
+ * second output is tanh'ed (log_std, :299) when `apply_tanh_log_std` is set. */
+int rl8_mlp_forward(const rl8_model* model, int which, const float* obs, int64_t obs_stride_r,
+                    int64_t obs_stride_d, int64_t rows, float* out, int apply_tanh_log_std,
+                    int precision, void* workspace, int64_t workspace_bytes, rl8_stream_t stream);
+
+/* ---- collect(): the T-step rollout (src/rl8/algorithms/_feedforward.py:359-408) ------- */
+
+typedef struct {
+  int32_t env_kind, dist_kind, T, deterministic;
+  int64_t N;
+  float gamma;
+  int32_t normalize_rewards; /* maintain rdr (src/rl8/algorithms/_feedforward.py:378-383) */
+  rl8_env_cfg env_cfg;
+  float* env_state;    /* [S][N], advanced in place */
+  float* obs;          /* [T+1][D][N]; slab 0 holds the initial observation */
+  void* actions;       /* [T+1][N] int64 (discrete) or f32 (continuous) */
+  float* logp;         /* [T+1][N] */
+  float* values;       /* [T+1][N]; all T+1 slabs are written (bootstrap value included) */
+  float* rewards;      /* [T+1][N] */
+  float* rdr;          /* [T+1][N] or NULL; slab 0 is an input */
+  const float* noise;  /* [T][N][P] Exp(1) (categorical) or [T][N] N(0,1); NULL if deterministic */
+} rl8_rollout;
+
+int64_t rl8_collect_workspace(const rl8_model* model, int64_t N, int32_t T, int precision);
+int rl8_collect(const rl8_model* model, const rl8_rollout* ro, int precision, void* workspace,
+                int64_t workspace_bytes, rl8_stream_t stream);
+
+/* ---- step(): one PPO minibatch (src/rl8/algorithms/_feedforward.py:512-585) ------------ */
+
+typedef struct {
+  int32_t dist_kind, T;
+  int64_t N;
+  const float* obs;        /* [T+1][D][N] */
+  const void* actions;     /* [T+1][N] */
+  const float* logp;       /* [T+1][N] */
+  const float* advantages; /* [T+1][N] */
+  const float* returns;    /* [T+1][N] */
+} rl8_batch;
+
+int64_t rl8_ppo_workspace(const rl8_model* model, int64_t max_rows, int precision);
+
+/* Forward + PPO losses + backward for the `M` transitions whose flattened indices
+ * (row = n*T + t) are rows[0..M) (int64 device array), or row_begin..row_begin+M when
+ * `rows` is NULL.  Gradients of `loss_scale * total / world` are ACCUMULATED into
+ * `grads` (same flat layout as the parameters; the caller zeroes them at an optimizer
+ * step boundary); `mean_denominator` is the global minibatch size the means divide by
+ * (M on one GPU, M * world_size when ranks all-reduce gradients).  `loss_sums` receives
+ * 5 doubles: sum entropy, sum policy surrogate, sum vf loss, sum kl, count -- raw sums
+ * over the M rows, so ranks can all-reduce them. */
+int rl8_ppo_minibatch(const rl8_model* model, const rl8_model* grads, const rl8_batch* batch,
+                      const int64_t* rows, int64_t row_begin, int64_t M, double mean_denominator,
+                      const rl8_ppo_hparams* hp, double* loss_sums, int precision,
+                      void* workspace, int64_t workspace_bytes, rl8_stream_t stream);
+
+/* ppo_losses (src/rl8/nn/functional.py:259-363) on given network outputs: features[B][P]
+ * (logits | {mean, log_std}), values[B], and the stored batch columns (all [B], unit
+ * stride).  loss_sums as above; d_features[B][P] / d_values[B] (either may be NULL) receive
+ * d(loss_scale * total)/d(output) with means over `mean_denominator` -- for the continuous
+ * head the second column is the gradient w.r.t. the PRE-tanh log_std output. */
+int rl8_ppo_losses(int dist_kind, const float* features, int32_t P, const float* values,
+                   const void* actions, const float* logp_old, const float* advantages,
+                   const float* returns, int64_t B, double mean_denominator,
+                   const rl8_ppo_hparams* hp, double* loss_sums, float* d_features,
+                   float* d_values, rl8_stream_t stream);
+
+/* ---- optimizer: clip_grad_norm_ + Adam (src/rl8/algorithms/_feedforward.py:586-593) ----- */
+
+/* norm_out[0] = global L2 norm of grads (device float).  Then
+ *   g *= min(1, max_norm / (norm + 1e-6));  Adam(lr, betas, eps) with torch's default
+ *   (non-amsgrad, no weight decay) update order.  `step` is the 1-based update count.
+ * Scalars are the reference's Python doubles; bias corrections are formed in double. */
+int rl8_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                  double max_norm, double lr, double beta1, double beta2, double eps,
+                  int64_t step, float* norm_out, rl8_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RL8_B200_H */

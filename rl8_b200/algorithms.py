@@ -1,0 +1,620 @@
+"""Feedforward PPO: ``AlgorithmConfig(...).build(env_cls)``, ``collect()``, ``step()``.
+
+Drop-in for src/rl8/algorithms/_feedforward.py (``AlgorithmConfig`` 29-179, ``Algorithm``
+182-697) with the hot path on sm_100a kernels:
+
+* ``collect()`` -> one ``rl8_collect`` call (T fused policy-forward / sample / env-step /
+  buffer-write steps + a batched value pass) and one ``rl8_collect_stats`` reduction; ONE
+  device->host readback per call (the reference does nine).
+* ``step()`` -> ``rl8_gae_scan`` / ``rl8_gae_normalize``, then per minibatch
+  ``rl8_ppo_minibatch`` (forward + clipped losses + hand-derived backward) and
+  ``rl8_clip_adam``; loss statistics stay on the device until the end of the call.
+
+Multi-GPU: environments shard across ranks -- every rank builds its own ``Algorithm`` with
+its share of ``num_envs`` -- and, when ``torch.distributed`` is initialised, gradients are
+summed with one NCCL all-reduce per optimizer step and the global statistics (advantage
+moments, reward scale, loss sums) with one small all-reduce per phase.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+import time
+from dataclasses import asdict, dataclass
+from typing import Any, Literal
+
+import torch
+import torch.distributed as dist
+import torch.optim as optim
+
+from . import _lib
+from .buffer import RolloutBuffer
+from .data import AlgorithmHparams, AlgorithmState, CollectStats, DataKeys, Device, MemoryStats, StepStats
+from .distributions import Distribution
+from .env import Env, KernelEnv
+from .models import Model
+from .policies import Policy
+from .schedulers import EntropyScheduler, LRScheduler, ScheduleKind
+from .specs import Categorical, Composite, Unbounded
+
+
+@dataclass
+class AlgorithmConfig:
+    """Configuration of a feedforward PPO algorithm (same fields and defaults as the
+    reference, src/rl8/algorithms/_feedforward.py:33-173)."""
+
+    model: None | Model = None
+    model_cls: None | type[Model] = None
+    model_config: None | dict[str, Any] = None
+    distribution_cls: None | type[Distribution] = None
+    #: Transitions per env per ``collect`` (buffer is ``[num_envs, horizon + 1]``).
+    horizon: int = 32
+    #: ``collect`` calls between env resets (negative: reset once, ever).
+    horizons_per_env_reset: int = 1
+    #: Parallel environments ON THIS RANK.
+    num_envs: int = 8192
+    optimizer_cls: type[optim.Optimizer] = optim.Adam
+    optimizer_config: None | dict[str, Any] = None
+    accumulate_grads: bool = False
+    #: Mixed precision: ``False`` -> fp32 CUDA-core GEMMs (bit-comparable with the
+    #: reference's fp32 path), ``True`` -> bf16 tcgen05 GEMMs with fp32 accumulation.
+    enable_amp: bool = False
+    lr_schedule: None | list[tuple[int, float]] = None
+    lr_schedule_kind: ScheduleKind = "step"
+    entropy_coeff: float = 0.0
+    entropy_coeff_schedule: None | list[tuple[int, float]] = None
+    entropy_coeff_schedule_kind: ScheduleKind = "step"
+    gae_lambda: float = 0.95
+    gamma: float = 0.95
+    #: ``None``: the whole buffer is one batch.
+    sgd_minibatch_size: None | int = None
+    num_sgd_iters: int = 4
+    shuffle_minibatches: bool = True
+    clip_param: float = 0.2
+    vf_clip_param: float = 5.0
+    dual_clip_param: None | float = None
+    vf_coeff: float = 1.0
+    target_kl_div: None | float = None
+    max_grad_norm: float = 5.0
+    normalize_advantages: bool = True
+    normalize_rewards: bool = True
+    device: Device | Literal["auto"] = "auto"
+
+    def build(self, env_cls: Any) -> "Algorithm":
+        """Build and validate an :class:`Algorithm`."""
+        algo = Algorithm(env_cls, config=self)
+        algo.validate()
+        return algo
+
+
+class _NoopGradScaler:
+    """bf16 needs no loss scaling; kept so ``algo.grad_scaler`` exists like the reference's."""
+
+    def __init__(self, enabled: bool) -> None:
+        self._enabled = enabled
+
+    def is_enabled(self) -> bool:
+        return self._enabled
+
+    def get_scale(self) -> float:
+        return 1.0
+
+
+def memory_stats() -> MemoryStats:
+    free, total = torch.cuda.mem_get_info()
+    return {"memory/free": free, "memory/total": total, "memory/percent": 100 * (total - free) / total}
+
+
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class _RunningMean:
+    def __init__(self) -> None:
+        self.avg, self.n = 0.0, 0
+
+    def update(self, v: float) -> None:
+        self.avg = (v + self.n * self.avg) / (self.n + 1)
+        self.n += 1
+
+
+class Algorithm:
+    """PPO over a tensor-batched environment with the rollout and the update on CUDA kernels."""
+
+    def __init__(self, env_cls: Any, /, config: None | AlgorithmConfig = None) -> None:
+        config = config or AlgorithmConfig()
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "rl8_b200 needs a CUDA device (B200, sm_100a): there is no CPU path."
+            )
+        device = "cuda" if config.device == "auto" else str(config.device)
+        if torch.device(device).type != "cuda":
+            raise RuntimeError(f"device={device!r}: rl8_b200 runs on CUDA only.")
+        if device == "cuda":
+            device = f"cuda:{torch.cuda.current_device()}"
+        self._lib = _lib.load()
+        max_num_envs = getattr(env_cls, "max_num_envs", config.num_envs)
+        num_envs = min(config.num_envs, max_num_envs)
+        horizon = min(config.horizon, getattr(env_cls, "max_horizon", 1_000_000))
+        self.env: Env = env_cls(num_envs, horizon, device=device)
+        for name in ("observation_spec", "action_spec"):
+            spec = getattr(self.env, name)
+            if not isinstance(spec, (Unbounded, Categorical)):
+                raise TypeError(f"`{name}` must be an Unbounded or Categorical spec")
+        self.policy = Policy(
+            self.env.observation_spec,
+            self.env.action_spec,
+            model=config.model,
+            model_cls=config.model_cls,
+            model_config=config.model_config,
+            distribution_cls=config.distribution_cls,
+            device=device,
+        )
+        self.policy.precision = _lib.PREC_BF16 if config.enable_amp else _lib.PREC_FP32
+        self.buffer_spec = Composite(
+            {
+                DataKeys.OBS: self.env.observation_spec,
+                DataKeys.REWARDS: Unbounded(1, device=device),
+                DataKeys.ACTIONS: self.env.action_spec,
+                DataKeys.LOGP: Unbounded(1, device=device),
+                DataKeys.VALUES: Unbounded(1, device=device),
+                DataKeys.ADVANTAGES: Unbounded(1, device=device),
+                DataKeys.RETURNS: Unbounded(1, device=device),
+            }
+        )
+        if config.normalize_rewards:
+            self.buffer_spec.set(DataKeys.REVERSED_DISCOUNTED_RETURNS, Unbounded(1, device=device))
+        self.buffer = RolloutBuffer(self.buffer_spec, num_envs, horizon, device)
+        if config.optimizer_cls is not optim.Adam:
+            raise NotImplementedError(
+                "the fused update implements Adam (the reference default); other optimizer"
+                " classes are outside the fused hot path"
+            )
+        optimizer_config = dict(config.optimizer_config or {"lr": 1e-3})
+        unsupported = {k: v for k, v in optimizer_config.items()
+                       if k not in ("lr", "betas", "eps") and v}
+        if unsupported:
+            raise NotImplementedError(f"fused Adam does not implement {sorted(unsupported)}")
+        # A real torch optimizer object holds the param groups (lr schedules mutate them);
+        # the update itself runs in rl8_clip_adam on the flat buffers below.
+        self.optimizer = optim.Adam(self.policy.model.parameters(), **optimizer_config)
+        flat = self.policy.model.flat_params
+        self._grads = torch.zeros_like(flat)
+        self._exp_avg = torch.zeros_like(flat)
+        self._exp_avg_sq = torch.zeros_like(flat)
+        self._grad_norm = torch.zeros(1, device=device)
+        self._opt_steps = 0
+        self.lr_scheduler = LRScheduler(
+            self.optimizer, schedule=config.lr_schedule, kind=config.lr_schedule_kind
+        )
+        self.entropy_scheduler = EntropyScheduler(
+            config.entropy_coeff,
+            schedule=config.entropy_coeff_schedule,
+            kind=config.entropy_coeff_schedule_kind,
+        )
+        sgd_minibatch_size = config.sgd_minibatch_size or num_envs * horizon
+        self.hparams = AlgorithmHparams(
+            accumulate_grads=config.accumulate_grads,
+            clip_param=config.clip_param,
+            device=device,
+            dual_clip_param=config.dual_clip_param,
+            enable_amp=config.enable_amp,
+            gae_lambda=config.gae_lambda,
+            gamma=config.gamma,
+            horizon=horizon,
+            horizons_per_env_reset=config.horizons_per_env_reset,
+            max_grad_norm=config.max_grad_norm,
+            normalize_advantages=config.normalize_advantages,
+            normalize_rewards=config.normalize_rewards,
+            num_envs=num_envs,
+            num_sgd_iters=config.num_sgd_iters,
+            sgd_minibatch_size=sgd_minibatch_size,
+            shuffle_minibatches=config.shuffle_minibatches,
+            target_kl_div=config.target_kl_div,
+            vf_clip_param=config.vf_clip_param,
+            vf_coeff=config.vf_coeff,
+        ).validate()
+        self.state = AlgorithmState()
+        self.grad_scaler = _NoopGradScaler(config.enable_amp)
+        self.device = torch.device(device)
+        self._fused_env = isinstance(self.env, KernelEnv)
+        self._ws: dict[str, torch.Tensor] = {}
+        self._stats_acc = torch.zeros(16, dtype=torch.float64, device=device)
+        init = [0.0] * 16
+        init[6] = init[8] = math.inf
+        init[7] = init[9] = -math.inf
+        self._stats_init = torch.tensor(init, dtype=torch.float64, device=device)
+        self._moments = torch.zeros(3, dtype=torch.float64, device=device)
+        max_updates = self.hparams.num_sgd_iters * self.hparams.num_minibatches
+        self._loss_sums = torch.zeros(max_updates, 5, dtype=torch.float64, device=device)
+        #: test / debugging hook: called with the named (unclipped) gradients of every update
+        self._on_grads: Any = None
+        #: number of kernels of this library launched by the last collect() / step()
+        self.last_launches = {"collect": 0, "step": 0}
+
+    # ------------------------------------------------------------------------------------
+    @property
+    def horizons_per_env_reset(self) -> int:
+        return self.hparams.horizons_per_env_reset
+
+    def memory_stats(self) -> MemoryStats:
+        return memory_stats()
+
+    @property
+    def params(self) -> dict[str, Any]:
+        return {
+            "env_cls": type(self.env).__name__,
+            "model_cls": type(self.policy.model).__name__,
+            "distribution_cls": self.policy.distribution_cls.__name__,
+            "optimizer_cls": type(self.optimizer).__name__,
+            "entropy_coeff": self.entropy_scheduler.coeff,
+            **asdict(self.hparams),
+        }
+
+    def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------
+    # collect
+    # ------------------------------------------------------------------------------------
+    def collect(
+        self, *, env_config: None | dict[str, Any] = None, deterministic: bool = False
+    ) -> CollectStats:
+        """Roll the policy out for ``horizon`` steps into the buffer
+        (src/rl8/algorithms/_feedforward.py:301-441)."""
+        start = time.perf_counter_ns()
+        hp, buf = self.hparams, self.buffer
+        N, T = hp.num_envs, hp.horizon
+        obs_hm = buf.hm[DataKeys.OBS]
+        rdr_hm = buf.hm.get(DataKeys.REVERSED_DISCOUNTED_RETURNS)
+        env_was_reset = False
+        carry = (self.state.horizons and hp.horizons_per_env_reset < 0) or (
+            self.state.horizons % hp.horizons_per_env_reset
+        )
+        if carry:
+            obs_hm[0].copy_(obs_hm[T])
+            if rdr_hm is not None:
+                rdr_hm[0].copy_(rdr_hm[T])
+        else:
+            obs0 = self.env.reset(config=env_config)
+            obs_hm[0].copy_(obs0.reshape(N, -1).T)
+            env_was_reset = True
+            if rdr_hm is not None:
+                rdr_hm[0].zero_()
+
+        P = self.policy.model.head_width
+        dist_cls = self.policy.distribution_cls
+        noise = None
+        if not deterministic:
+            noise = dist_cls.draw_noise(T, N, P, self.device).contiguous()
+            assert noise.dtype == torch.float32 and noise.is_cuda
+        if self._fused_env:
+            self._collect_fused(noise, deterministic)
+        else:
+            self._collect_generic(noise, deterministic)
+
+        # statistics + reward scale: one reduction kernel, one readback
+        acc = self._stats_acc
+        acc.copy_(self._stats_init)
+        rc = self._lib.rl8_collect_stats(
+            _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(rdr_hm), N, T, _lib.ptr(acc), _lib.stream()
+        )
+        _lib.check(rc, "rl8_collect_stats")
+        self.last_launches["collect"] += 1
+        world = _world()
+        if world > 1:
+            dist.all_reduce(acc[:6])
+            mins = torch.stack((acc[6], -acc[7], acc[8], -acc[9]))
+            dist.all_reduce(mins, op=dist.ReduceOp.MIN)
+            acc[6], acc[7], acc[8], acc[9] = mins[0], -mins[1], mins[2], -mins[3]
+        a = acc.tolist()  # the one device->host sync of collect()
+        n_r, n_R = float(N * T * world), float(N * world)
+
+        def mean_std(s: float, s2: float, n: float) -> tuple[float, float]:
+            mean = s / n
+            var = (s2 - s * mean) / (n - 1) if n > 1 else float("nan")
+            return mean, math.sqrt(max(var, 0.0)) if var == var else var
+
+        r_mean, r_std = mean_std(a[0], a[1], n_r)
+        R_mean, R_std = mean_std(a[2], a[3], n_R)
+        stats: CollectStats = {
+            "returns/min": a[8],
+            "returns/max": a[9],
+            "returns/mean": R_mean,
+            "returns/std": R_std,
+            "rewards/min": a[6],
+            "rewards/max": a[7],
+            "rewards/mean": r_mean,
+            "rewards/std": r_std,
+        }
+        self.state.horizons += 1
+        self.state.buffered = True
+        if hp.normalize_rewards:
+            # float(torch.std(rdr[:, 1:])) -- an f32 value in the reference
+            self.state.reward_scale = float(torch.tensor(mean_std(a[4], a[5], n_r)[1], dtype=torch.float32))
+        else:
+            self.state.reward_scale = 1.0
+        stats["env/resets"] = hp.num_envs * int(env_was_reset)
+        stats["env/steps"] = hp.num_envs * hp.horizon
+        stats["profiling/collect_ms"] = (time.perf_counter_ns() - start) / 1e6
+        return stats
+
+    def _rollout_struct(self, noise: None | torch.Tensor, deterministic: bool) -> _lib.Rollout:
+        hp, buf, env = self.hparams, self.buffer, self.env
+        assert isinstance(env, KernelEnv)
+        ro = _lib.Rollout()
+        ro.env_kind = env.rl8_kind
+        ro.dist_kind = self.policy.distribution_cls.rl8_kind
+        ro.T, ro.N = hp.horizon, hp.num_envs
+        ro.deterministic = int(deterministic)
+        ro.gamma = hp.gamma
+        ro.normalize_rewards = int(hp.normalize_rewards)
+        ro.env_cfg = env.rl8_cfg()
+        ro.env_state = env.state.data_ptr()
+        ro.obs = buf.hm[DataKeys.OBS].data_ptr()
+        ro.actions = buf.hm[DataKeys.ACTIONS].data_ptr()
+        ro.logp = buf.hm[DataKeys.LOGP].data_ptr()
+        ro.values = buf.hm[DataKeys.VALUES].data_ptr()
+        ro.rewards = buf.hm[DataKeys.REWARDS].data_ptr()
+        rdr = buf.hm.get(DataKeys.REVERSED_DISCOUNTED_RETURNS)
+        ro.rdr = rdr.data_ptr() if rdr is not None else None
+        ro.noise = noise.data_ptr() if noise is not None else None
+        return ro
+
+    def _collect_fused(self, noise: None | torch.Tensor, deterministic: bool) -> None:
+        hp = self.hparams
+        model = self.policy.model
+        m = model.struct_for(model.flat_params)
+        nbytes = int(self._lib.rl8_collect_workspace(m, hp.num_envs, hp.horizon, self.policy.precision))
+        if nbytes < 0:
+            _lib.check(nbytes, "rl8_collect_workspace")
+        ws = self._workspace("collect", nbytes)
+        ro = self._rollout_struct(noise, deterministic)
+        rc = self._lib.rl8_collect(m, ro, self.policy.precision, _lib.ptr(ws), ws.numel(), _lib.stream())
+        _lib.check(rc, "rl8_collect")
+        T = hp.horizon
+        self.last_launches["collect"] = (4 * T + 3 * (T + 1)) if self.policy.precision == _lib.PREC_FP32 else 2
+
+    def _collect_generic(self, noise: None | torch.Tensor, deterministic: bool) -> None:
+        """Rollout with a user-defined (Python / torch) environment: the policy forward,
+        sampling and log-probabilities still run on this library's kernels; ``env.step`` is
+        the user's code (the reference's Env plug-in point)."""
+        hp, buf = self.hparams, self.buffer
+        N, T = hp.num_envs, hp.horizon
+        obs_hm, act_hm = buf.hm[DataKeys.OBS], buf.hm[DataKeys.ACTIONS]
+        rdr_hm = buf.hm.get(DataKeys.REVERSED_DISCOUNTED_RETURNS)
+        P = self.policy.model.head_width
+        kind = self.policy.distribution_cls.rl8_kind
+        launches = 0
+        for t in range(T):
+            head = self.policy.forward_net(0, obs_hm[t].T)
+            nz = None if noise is None else noise[t]
+            rc = self._lib.rl8_dist_sample(
+                kind, _lib.ptr(head), P, _lib.ptr(nz), int(deterministic), _lib.ptr(act_hm[t]),
+                _lib.ptr(buf.hm[DataKeys.LOGP][t]), N, _lib.stream(),
+            )
+            _lib.check(rc, "rl8_dist_sample")
+            out = self.env.step(act_hm[t].view(N, 1))
+            rewards = out[DataKeys.REWARDS].reshape(N)
+            if rdr_hm is not None:
+                torch.add(rewards, rdr_hm[t], alpha=hp.gamma, out=rdr_hm[t + 1])
+            buf.hm[DataKeys.REWARDS][t].copy_(rewards)
+            obs_hm[t + 1].copy_(out[DataKeys.OBS].reshape(N, -1).T)
+            launches += 4
+        for t in range(T + 1):
+            self.policy.forward_net(1, obs_hm[t].T, out=buf.hm[DataKeys.VALUES][t].view(N, 1))
+            launches += 3
+        self.last_launches["collect"] = launches
+
+    # ------------------------------------------------------------------------------------
+    # step
+    # ------------------------------------------------------------------------------------
+    def step(self) -> StepStats:
+        """GAE, then ``num_sgd_iters`` PPO epochs over the buffer
+        (src/rl8/algorithms/_feedforward.py:443-615)."""
+        if not self.state.buffered:
+            raise RuntimeError(
+                f"{type(self).__name__} is not buffered. Call `collect` once prior to `step`."
+            )
+        start = time.perf_counter_ns()
+        hp, buf, lib = self.hparams, self.buffer, self._lib
+        N, T = hp.num_envs, hp.horizon
+        world = _world()
+        st = _lib.stream()
+        launches = 0
+
+        # -- GAE ---------------------------------------------------------------------------
+        self._moments.zero_()
+        rc = lib.rl8_gae_scan(
+            _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(buf.hm[DataKeys.VALUES]),
+            _lib.ptr(buf.hm[DataKeys.ADVANTAGES]), _lib.ptr(buf.hm[DataKeys.RETURNS]),
+            N, T, 1, N, hp.gamma, hp.gae_lambda, self.state.reward_scale,
+            _lib.ptr(self._moments), st,
+        )
+        _lib.check(rc, "rl8_gae_scan")
+        launches += 1
+        if hp.normalize_advantages:
+            if world > 1:
+                dist.all_reduce(self._moments)
+            rc = lib.rl8_gae_normalize(
+                _lib.ptr(buf.hm[DataKeys.ADVANTAGES]), N, T, 1, N, _lib.ptr(self._moments), st
+            )
+            _lib.check(rc, "rl8_gae_normalize")
+            launches += 1
+
+        # -- PPO epochs ---------------------------------------------------------------------
+        model = self.policy.model
+        m = model.struct_for(model.flat_params)
+        g = model.struct_for(self._grads)
+        prec = self.policy.precision
+        M = hp.sgd_minibatch_size
+        nbytes = int(lib.rl8_ppo_workspace(m, M, prec))
+        if nbytes < 0:
+            _lib.check(nbytes, "rl8_ppo_workspace")
+        ws = self._workspace("ppo", nbytes)
+        batch = _lib.Batch()
+        batch.dist_kind = self.policy.distribution_cls.rl8_kind
+        batch.T, batch.N = T, N
+        batch.obs = buf.hm[DataKeys.OBS].data_ptr()
+        batch.actions = buf.hm[DataKeys.ACTIONS].data_ptr()
+        batch.logp = buf.hm[DataKeys.LOGP].data_ptr()
+        batch.advantages = buf.hm[DataKeys.ADVANTAGES].data_ptr()
+        batch.returns = buf.hm[DataKeys.RETURNS].data_ptr()
+
+        accum = hp.num_minibatches if hp.accumulate_grads else 1
+        entropy_coeff = self.entropy_scheduler.coeff
+        if entropy_coeff != 0 and batch.dist_kind == _lib.DIST_SQUASHED_NORMAL:
+            self.policy.distribution_cls({}, model).entropy()  # raises like the reference
+        ppo = _lib.PpoHparams(
+            hp.clip_param, hp.dual_clip_param or 0.0, entropy_coeff, hp.vf_clip_param,
+            hp.vf_coeff, 1.0 / accum,
+        )
+        pg = self.optimizer.param_groups[0]
+        sums = self._loss_sums
+        sums.zero_()
+        self._grads.zero_()
+        k = 0  # minibatches processed
+        applied: list[bool] = []  # step boundary flags per minibatch
+        stop_early = False
+        mb_launches = 34 if prec == _lib.PREC_FP32 else 4
+        for _ in range(hp.num_sgd_iters):
+            perm = torch.randperm(N * T, device=self.device) if hp.shuffle_minibatches else None
+            for i in range(hp.num_minibatches):
+                step_this_batch = (i + 1) % accum == 0
+                rows = None if perm is None else perm[i * M : (i + 1) * M]
+                rc = lib.rl8_ppo_minibatch(
+                    m, g, batch, _lib.ptr(rows), i * M, M, float(M * world), ppo,
+                    ctypes.c_void_p(sums.data_ptr() + 40 * k), prec, _lib.ptr(ws), ws.numel(), st,
+                )
+                _lib.check(rc, "rl8_ppo_minibatch")
+                launches += mb_launches * max(1, -(-M // 65536))
+                applied.append(step_this_batch)
+                k += 1
+                if hp.target_kl_div is not None:
+                    # Early stopping needs this minibatch's KL on the host (the reference
+                    # syncs on every minibatch regardless); the triggering minibatch is not
+                    # applied (:576-585).
+                    row = sums[k - 1].clone()
+                    if world > 1:
+                        dist.all_reduce(row)
+                    kl = float(row[3] / row[4])
+                    if kl > 1.5 * hp.target_kl_div:
+                        stop_early = True
+                        self._grads.zero_()
+                        break
+                if step_this_batch:
+                    if world > 1:
+                        dist.all_reduce(self._grads)  # grads already carry 1 / (M * world)
+                    if self._on_grads is not None:
+                        self._on_grads(model.named_flat_views(self._grads))
+                    self._opt_steps += 1
+                    betas = pg.get("betas", (0.9, 0.999))
+                    rc = lib.rl8_clip_adam(
+                        _lib.ptr(model.flat_params), _lib.ptr(self._grads), _lib.ptr(self._exp_avg),
+                        _lib.ptr(self._exp_avg_sq), self._grads.numel(), hp.max_grad_norm,
+                        pg["lr"], betas[0], betas[1], pg.get("eps", 1e-8), self._opt_steps,
+                        _lib.ptr(self._grad_norm), st,
+                    )
+                    _lib.check(rc, "rl8_clip_adam")
+                    launches += 2
+                    self._grads.zero_()
+            if stop_early:
+                break
+
+        # -- statistics: one readback ----------------------------------------------------------
+        used = sums[:k]
+        if world > 1 and k:
+            used = used.clone()
+            dist.all_reduce(used)
+        rows_host = used.tolist()
+        keys = ("losses/entropy", "losses/policy", "losses/vf", "losses/total", "monitors/kl_div")
+        means = {key: _RunningMean() for key in keys}
+        coeff_e, coeff_v = _RunningMean(), _RunningMean()
+        run = dict.fromkeys(keys, 0.0)
+        for (s_ent, s_pol, s_vf, s_kl, cnt), reduce in zip(rows_host, applied):
+            ent, pol, vf, kl = s_ent / cnt, s_pol / cnt, s_vf / cnt, s_kl / cnt
+            total = hp.vf_coeff * vf - pol - (entropy_coeff * ent if entropy_coeff != 0 else 0.0)
+            run["losses/entropy"] += ent / accum
+            run["losses/policy"] += pol / accum
+            run["losses/vf"] += vf / accum
+            run["losses/total"] += total / accum
+            run["monitors/kl_div"] += kl / accum
+            coeff_e.update(entropy_coeff)
+            coeff_v.update(hp.vf_coeff)
+            if reduce:
+                for key in keys:
+                    means[key].update(run[key])
+                    run[key] = 0.0
+
+        self.lr_scheduler.step(hp.num_envs * self.state.horizons)
+        self.entropy_scheduler.step(hp.num_envs * self.state.horizons)
+
+        # Fresh (zeroed) buffer that only keeps the final observation (:603-610).
+        final_obs = buf.hm[DataKeys.OBS][T].clone()
+        buf.zero_()
+        buf.hm[DataKeys.OBS][T].copy_(final_obs)
+        self.state.buffered = False
+        self.last_launches["step"] = launches
+
+        stats: StepStats = {
+            "coefficients/entropy": coeff_e.avg,
+            "coefficients/vf": coeff_v.avg,
+            **{key: means[key].avg for key in keys},  # type: ignore[typeddict-item]
+        }
+        torch.cuda.current_stream().synchronize()
+        stats["profiling/step_ms"] = (time.perf_counter_ns() - start) / 1e6
+        return stats
+
+    # ------------------------------------------------------------------------------------
+    def validate(self) -> None:
+        """Shape checks on one reset / sample / step (src/rl8/algorithms/_feedforward.py:617-697)."""
+        N = self.hparams.num_envs
+        obs = self.env.reset()
+        self.env.observation_spec.assert_is_in(obs)
+        try:
+            self.buffer[DataKeys.OBS][:, 0, ...] = obs
+        except RuntimeError as e:
+            raise AssertionError(
+                f"The observation from {type(self.env).__name__}.reset doesn't match the"
+                " observation spec shape."
+            ) from e
+        sample = self.policy.sample(
+            {DataKeys.OBS: self.buffer[DataKeys.OBS][:, :1]},
+            kind="last",
+            return_actions=True,
+            return_logp=True,
+            return_values=True,
+        )
+        actions = sample[DataKeys.ACTIONS]
+        assert actions.ndim >= 2, "Actions must be at least 2D and have shape ``[N, ...]``."
+        self.env.action_spec.assert_is_in(actions)
+        try:
+            self.buffer[DataKeys.ACTIONS][:, 0, ...] = actions
+        except RuntimeError as e:
+            raise AssertionError(
+                "The action sampled from the policy doesn't match the action spec."
+            ) from e
+        assert sample[DataKeys.LOGP].shape == torch.Size([N, 1]), (
+            "Action log probabilities must be 2D and have shape ``[N, 1]``."
+        )
+        assert sample[DataKeys.VALUES].shape == torch.Size([N, 1]), (
+            "Expected value estimates must be 2D and have shape ``[N, 1]``."
+        )
+        out = self.env.step(actions)
+        obs = out[DataKeys.OBS]
+        self.env.observation_spec.assert_is_in(obs)
+        try:
+            self.buffer[DataKeys.OBS][:, 1, ...] = obs
+        except RuntimeError as e:
+            raise AssertionError(
+                f"The observation from {type(self.env).__name__}.step doesn't match the"
+                " observation spec shape."
+            ) from e
+        assert out[DataKeys.REWARDS].shape == torch.Size([N, 1]), (
+            "Rewards must be 2D and have shape ``[N, 1]``."
+        )
