@@ -1,0 +1,462 @@
+"""Benchmark of the PPO hot path: env transitions / s for ``collect()`` + ``step()``.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): CartPole, ``num_envs=65536`` PER GPU, ``horizon=32``,
+Categorical policy, default ``AlgorithmConfig`` update (4 SGD epochs, full batch).  A "step"
+is one ``collect()`` + one ``step()``.  ``value`` is timed with CUDA events around K steps
+(max over ranks); ``e2e`` repeats it through ``Trainer.step()`` with the sampling noise
+supplied from pinned host memory every step (H2D inside the timed region) and the stats read
+back (D2H).  Working set per step (buffer 112 MB + activations) exceeds nothing by itself,
+so an L2 flush (write of a 256 MB buffer) runs between timed iterations.
+
+``--impl reference`` times the CPU restatement of the reference's own algorithm
+(``oracle/ppo_oracle.py``, bit-exact with the upstream code on the build container, plain
+torch on all host cores) on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env transitions/sec (collect+PPO step)"
+UNIT = "transitions/s"
+
+
+def parse() -> argparse.Namespace:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--horizon", type=int, default=32)
+    ap.add_argument("--sgd-iters", type=int, default=4)
+    ap.add_argument("--minibatch", type=int, default=0, help="0 = whole buffer (reference default)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    return ap.parse_args()
+
+
+def workload_config(a: argparse.Namespace, world: int) -> dict:
+    return {
+        "workload": "CartPole feedforward PPO (BASELINE.json configs[1])",
+        "env": "CartPole",
+        "num_envs_per_gpu": a.num_envs_per_gpu,
+        "num_envs_total": a.num_envs_per_gpu * world,
+        "horizon": a.horizon,
+        "distribution": "Categorical",
+        "num_sgd_iters": a.sgd_iters,
+        "sgd_minibatch_size": a.minibatch or a.num_envs_per_gpu * a.horizon,
+        "parallelism": f"env-sharded dp{world}",
+        "l2": "flushed between timed iterations (256 MB write)",
+    }
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference)
+# ---------------------------------------------------------------------------------------
+
+
+def cpu_step_fn(N: int, T: int, sgd_iters: int, minibatch: int):
+    import torch
+
+    from oracle import ppo_oracle as O
+
+    torch.manual_seed(0)
+    params = O.init_params(5, "discrete", 3)
+    env = O.OracleEnv("cartpole", N)
+    buf = O.new_buffer(N, T, 5, "discrete")
+    dist = O.Dist("categorical")
+    opt: dict = {}
+
+    def step() -> None:
+        noise_fn = lambda t: torch.empty(N, 1, 3).exponential_(1)  # noqa: E731
+        stats = O.collect(params, env, buf, dist, None, noise_fn=noise_fn)
+        O.step(params, buf, dist, opt, reward_scale=stats["reward_scale"], num_sgd_iters=sgd_iters,
+               sgd_minibatch_size=minibatch or None, shuffle=bool(minibatch))
+
+    return step
+
+
+def cpu_probe(a: argparse.Namespace, budget_s: float, iters: int) -> tuple[int, float]:
+    """Pick the largest power-of-two num_envs (<= the workload's) whose `iters` steps fit the
+    budget; returns (num_envs, seconds per transition estimate)."""
+    N0 = 1024
+    fn = cpu_step_fn(N0, a.horizon, a.sgd_iters, 0)
+    fn()
+    t0 = time.perf_counter()
+    fn()
+    per_tr = (time.perf_counter() - t0) / (N0 * a.horizon)
+    N = a.num_envs_per_gpu
+    while N > 1024 and per_tr * N * a.horizon * iters > budget_s:
+        N //= 2
+    return N, per_tr
+
+
+def run_reference(a: argparse.Namespace) -> None:
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N, _ = cpu_probe(a, 150.0, a.steps + a.warmup)
+    fn = cpu_step_fn(N, a.horizon, a.sgd_iters, 0)
+    for _ in range(a.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = N * a.horizon * a.steps / dt
+    sample = f"CartPole num_envs={N} (of {a.num_envs_per_gpu}), horizon={a.horizon}, {a.steps} collect+step"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": a.gpus,
+        "steps": a.steps,
+        "warmup": a.warmup,
+        "ms_per_step": 1e3 * dt / a.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(a, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference (oracle/ppo_oracle.py, torch fp32 eager on all host"
+                " cores); the upstream package itself cannot be installed (tensordict/torchrl/mlflow"
+                " absent, no network)",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5,
+                ).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self) -> "ClockSampler":
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc) -> None:  # noqa: ANN002
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks() -> dict:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        p["source"] = "measured (MEASURED_PEAKS.json)"
+        return p
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+                "source": "fallback (B200_PROFILING.md)"}
+
+
+def run_ours(a: argparse.Namespace) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from rl8_b200 import AlgorithmConfig, Trainer, _lib
+    from rl8_b200.distributions import Categorical
+    from rl8_b200.env import CartPole
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    N, T = a.num_envs_per_gpu, a.horizon
+    lib = _lib.load()
+
+    def make(dist_cls=None, precision=a.precision):  # noqa: ANN001, ANN202
+        amp = precision in ("auto", "bf16")
+        try:
+            return AlgorithmConfig(
+                num_envs=N, horizon=T, num_sgd_iters=a.sgd_iters, sgd_minibatch_size=a.minibatch or None,
+                enable_amp=amp, distribution_cls=dist_cls,
+            ).build(CartPole), ("bf16" if amp else "f32")
+        except NotImplementedError:
+            if precision != "auto":
+                raise
+            return AlgorithmConfig(
+                num_envs=N, horizon=T, num_sgd_iters=a.sgd_iters, sgd_minibatch_size=a.minibatch or None,
+                enable_amp=False, distribution_cls=dist_cls,
+            ).build(CartPole), "f32"
+
+    torch.manual_seed(rank)
+    algo, dtype = make()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps: int, warmup: int) -> tuple[float, int]:  # noqa: ANN001
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        total_ms, launches = 0.0, 0
+        for _ in range(steps):
+            flush.zero_()  # L2 flush, outside the timed bracket
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            launches += step_fn()
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    def core_step() -> int:
+        algo.collect()
+        algo.step()
+        return algo.last_launches["collect"] + algo.last_launches["step"]
+
+    with ClockSampler(local) as clocks:
+        ms, launches = timed(core_step, a.steps, a.warmup)
+    value = N * T * world * a.steps / (ms / 1e3)
+
+    # ---- e2e: Trainer.step() with host-supplied noise (pinned, H2D every step) + stats D2H --------
+    host_noise = torch.empty(T, N, 3).exponential_(1).pin_memory()
+    dev_noise = torch.empty(T, N, 3, device=dev)
+
+    class HostNoise(Categorical):
+        @classmethod
+        def draw_noise(cls, steps, num, width, device):  # noqa: ANN001, ANN206
+            dev_noise.copy_(host_noise, non_blocking=True)
+            return dev_noise
+
+    algo2, _ = make(HostNoise, "bf16" if dtype == "bf16" else "fp32")
+    trainer = Trainer(algo2)
+
+    def e2e_step() -> int:
+        stats = trainer.step()
+        assert stats["losses/total"] == stats["losses/total"]
+        return algo2.last_launches["collect"] + algo2.last_launches["step"]
+
+    ms2, _ = timed(e2e_step, max(2, a.steps // 2), 2)
+    e2e_value = N * T * world * max(2, a.steps // 2) / (ms2 / 1e3)
+    h2d = host_noise.numel() * 4
+    d2h = 16 * 8 + algo2._loss_sums.numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines of the stream kernels + the update (rank 0) -----------------------------------
+    peaks = measured_peaks()
+    roofs = stream_rooflines(lib, _lib, dev, peaks)
+    upd = update_roofline(algo, _lib, peaks, dtype, flush)
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": a.steps,
+        "warmup": a.warmup,
+        "ms_per_step": ms / a.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": dtype,
+        "data": "synthetic",
+        "config": workload_config(a, world),
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": upd,
+        "stream_rooflines": roofs,
+        "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
+    }
+    if not a.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(a)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a: argparse.Namespace) -> dict:
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, _ = cpu_probe(a, a.cpu_budget_s, 2)
+    fn = cpu_step_fn(n, a.horizon, a.sgd_iters, 0)
+    fn()
+    t0 = time.perf_counter()
+    fn()
+    dt = time.perf_counter() - t0
+    return {
+        "value": n * a.horizon / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "sample": f"CartPole num_envs={n} (of {a.num_envs_per_gpu}), horizon={a.horizon}, 1 warm-up + 1 timed"
+                  " collect+step of oracle/ppo_oracle.py (torch fp32 eager)",
+    }
+
+
+def _time_kernel(fn, flush, iters: int = 10) -> float:  # noqa: ANN001
+    """Average ms of `fn` with an L2 flush before every timed launch."""
+    import torch
+
+    for _ in range(3):
+        fn()
+    total = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    return total / iters
+
+
+def stream_rooflines(lib, L, dev, peaks: dict) -> list[dict]:  # noqa: ANN001
+    """Achieved GB/s of the HBM-bound kernels (algorithmic bytes of SURVEY.md §8d / DESIGN.md)
+    at sizes well beyond L2: GAE at N=2^20, T=32 and the CartPole env step at N=2^24."""
+    import torch
+
+    from rl8_b200.env import CartPole
+
+    out = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hbm = float(peaks["hbm_gbs"])
+    # GAE scan (horizon-major): 8 B read + 12 B written per transition, + 12 B per env
+    N, T = 1 << 20, 32
+    r = torch.randn(T + 1, N, device=dev)
+    v = torch.randn(T + 1, N, device=dev)
+    adv, ret = torch.empty_like(r), torch.empty_like(r)
+    mom = torch.zeros(3, dtype=torch.float64, device=dev)
+    st = L.stream()
+    ms = _time_kernel(lambda: lib.rl8_gae_scan(L.ptr(r), L.ptr(v), L.ptr(adv), L.ptr(ret), N, T, 1, N,
+                                               0.95, 0.95, 1.0, L.ptr(mom), st), flush)
+    alg = 20.0 * N * T + 20.0 * N
+    out.append({"kernel": "gae_scan_hm_kernel", "bound": "hbm", "bytes": alg, "ms": ms,
+                "achieved": alg / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / hbm,
+                "shape": f"N={N} T={T}"})
+    ms = _time_kernel(lambda: lib.rl8_gae_normalize(L.ptr(adv), N, T, 1, N, L.ptr(mom), st), flush)
+    alg = 8.0 * N * T
+    out.append({"kernel": "gae_normalize_kernel", "bound": "hbm", "bytes": alg, "ms": ms,
+                "achieved": alg / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / hbm,
+                "shape": f"N={N} T={T}"})
+    del r, v, adv, ret
+    # CartPole env step: 64 B per env-step (16 R state + 8 R action + 16 W state + 20 W obs + 4 W reward)
+    N = 1 << 24
+    env = CartPole(N, 32, device=dev)
+    env.reset()
+    act = torch.randint(0, 3, (N,), device=dev)
+    cfg = env.rl8_cfg()
+    ms = _time_kernel(lambda: lib.rl8_env_step(env.rl8_kind, cfg, L.ptr(env.state), L.ptr(act), L.ptr(env._obs),
+                                               1, N, L.ptr(env._reward), N, st), flush)
+    alg = 64.0 * N
+    out.append({"kernel": "env_step_kernel<cartpole>", "bound": "hbm", "bytes": alg, "ms": ms,
+                "achieved": alg / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / hbm,
+                "shape": f"N={N}"})
+    return out
+
+
+def update_roofline(algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa: ANN001
+    """The update (forward + loss + backward over one minibatch) dominates a step: its GEMM
+    FLOPs are 3 x the forward's 2*2*H*H MACs per row (two networks)."""
+    import ctypes
+
+    import torch
+
+    hp = algo.hparams
+    N, T = hp.num_envs, hp.horizon
+    algo.collect()
+    model = algo.policy.model
+    m, g = model.struct_for(model.flat_params), model.struct_for(algo._grads)
+    M = hp.sgd_minibatch_size
+    ws = algo._workspace("ppo", int(algo._lib.rl8_ppo_workspace(m, M, algo.policy.precision)))
+    batch = L.Batch()
+    batch.dist_kind, batch.T, batch.N = 0, T, N
+    for k in ("obs", "actions", "logp", "advantages", "returns"):
+        setattr(batch, k, algo.buffer.hm[k].data_ptr())
+    ppo = L.PpoHparams(0.2, 0.0, 0.0, 5.0, 1.0, 1.0)
+    sums = torch.zeros(5, dtype=torch.float64, device=algo.device)
+
+    def fn() -> None:
+        rc = algo._lib.rl8_ppo_minibatch(m, g, batch, None, 0, M, float(M), ppo, L.ptr(sums),
+                                         algo.policy.precision, L.ptr(ws), ws.numel(), L.stream())
+        assert rc == 0, rc
+
+    ms = _time_kernel(fn, flush, iters=5)
+    H, D, P = 256, 5, 3
+    flops = M * 3.0 * 2.0 * (2 * H * H + 2 * D * H + (P + 1) * H)
+    peak = float(peaks["bf16_tflops_sustained"])
+    return {
+        "kernel": "rl8_ppo_minibatch (forward + losses + backward, one minibatch)",
+        "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
+        "frac": flops / ms / 1e9 / peak, "traffic": None, "ms": ms, "rows": M, "dtype": dtype,
+        "peak_source": peaks["source"] + " bf16 sustained",
+    }
+
+
+def main() -> None:
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()
