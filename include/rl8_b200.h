@@ -254,6 +254,15 @@ int rl8_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   double max_norm, double lr, double beta1, double beta2, double eps,
                   int64_t step, float* norm_out, rl8_stream_t stream);
 
+/* ---- test hook ------------------------------------------------------------------------ */
+
+/* D[128][N] = A[128][K] * B[N][K]^T through ONE tcgen05 GEMM (bf16 operands, fp32 accumulate)
+ * with each operand staged K-major or MN-major in the shared-memory operand format every
+ * tensor-core kernel of this library uses; pins the descriptor encodings in the parity
+ * tests.  N % 8 == 0, N <= 256; K % 16 == 0, K <= 256. */
+int rl8_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                    int a_mn_major, int b_mn_major, rl8_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ namespace rl8 {
 //   mode 0: obs[r*stride_r + d*stride_d]
 //   mode 1: flattened transition g = rows ? rows[r] : row_begin + r  (row = n*T + t) inside
 //           the horizon-major buffer obs[T+1][D][N]:  obs[(t*D + d)*N + n]
+//   mode 2: slab-major rows r = t*N + n of the same buffer (all T+1 slabs, value pass)
 struct RowMap {
   const float* obs;
   int mode;
@@ -20,6 +21,10 @@ struct RowMap {
   int64_t N;
   __host__ __device__ __forceinline__ int64_t offset(int64_t r) const {
     if (mode == 0) return r * stride_r;
+    if (mode == 2) {
+      int64_t t2 = r / N;
+      return t2 * (int64_t)D * N + (r - t2 * N);
+    }
     int64_t g = rows ? rows[r] : row_begin + r;
     int64_t n = g / T, t = g - n * T;
     return t * (int64_t)D * N + n;

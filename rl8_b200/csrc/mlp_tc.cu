@@ -1,22 +1,519 @@
-// Tensor-core (tcgen05, bf16 operands, fp32 accumulate in TMEM) path.  Placeholder entry
-// points until the kernels land: they fail loudly, there is no fallback.
+// Tensor-core path (RL8_PREC_BF16): tcgen05.mma with bf16 operands staged in shared memory
+// in the chunked format of tc.cuh, fp32 accumulators in TMEM, epilogues on CUDA cores.
+//
+//   tc_forward_kernel   one network over any number of rows (value pass of collect(),
+//                       rl8_mlp_forward): persistent CTAs, 128-row tiles, W2 resident in smem
+//                       (one 128 KB bulk-async copy per CTA), TMEM double-buffered so the
+//                       epilogue of tile i overlaps the MMAs of tile i+1.
+//   tc_rollout_kernel   the whole T-step rollout of a 128-env tile inside one persistent CTA:
+//                       layer 1 on CUDA cores -> 256x256 layer on tcgen05 -> head dot products,
+//                       sampling, log-prob, env transition (state in registers) and the
+//                       horizon-major buffer writes in the epilogue.  No grid-wide sync: envs
+//                       are independent.
+//   tc_selftest_kernel  one 128xNxK GEMM with either operand major, used by the parity tests to
+//                       pin the descriptor encodings.
+//
+// The first layer (K = D <= 8) and the heads (N = P <= 4) are not GEMM-shaped: they stay on
+// CUDA cores in fp32.  Only the 256x256 contraction runs in bf16.
+#include "dist.cuh"
 #include "mlp_fp32.cuh"
+#include "tc.cuh"
 
 namespace rl8 {
 
-int64_t collect_tc_workspace(const rl8_model*, int64_t, int32_t) { return RL8_ERR_UNSUPPORTED; }
-int collect_tc(const rl8_model*, const rl8_rollout*, void*, int64_t, cudaStream_t) {
-  return RL8_ERR_UNSUPPORTED;
+using namespace tc;
+
+constexpr int H = 256;         // hidden width
+constexpr int TILE = 128;      // rows (envs / transitions) per CTA tile == UMMA M
+constexpr int kW2Bytes = H * H * 2;
+constexpr int kTileBytes = TILE * H * 2;
+constexpr int kMaxPT = 4;      // widest head on the tensor-core path
+
+struct NetParams {
+  const uint8_t* w2_img;  // bf16, chunked [j = 256 rows][i = 256 cols]
+  const float *w1, *b1, *b2, *w3, *b3;
+  int D, P;
+};
+
+// Shared-memory plan of the forward / rollout kernels (dynamic smem, 128-byte aligned).
+struct Smem {
+  uint8_t w2[kW2Bytes];        // 131072
+  uint8_t a_tile[kTileBytes];  //  65536  H1 tile: K-major A operand
+  float w1t[8][H];             //   8192  w1t[d][i]
+  float b1[H], b2[H];          //   2048
+  float w3[kMaxPT][H];         //   4096
+  float obs[8][TILE];          //   4096  obs[d][r]
+  float part[2][TILE][kMaxPT]; //   4096  head partial sums per column half
+  uint64_t bar_w, bar_mma[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Smem) <= 227 * 1024, "smem plan exceeds the 227 KB CTA limit");
+
+// ---- weight packing: fp32 [256][256] row-major -> bf16 chunked image ------------------------
+__global__ void __launch_bounds__(256) pack_w2_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img) {
+  // one thread per 16-byte chunk: row j, column group c (8 consecutive i)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 256*32
+  if (idx >= H * (H / 8)) return;
+  const int j = idx % H, c = idx / H;
+  float v[8];
+  const float4 lo = *reinterpret_cast<const float4*>(w2 + j * H + c * 8);
+  const float4 hi = *reinterpret_cast<const float4*>(w2 + j * H + c * 8 + 4);
+  v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
+  store_chunk(img, chunk_offset<H>(j, c), v);
 }
+
+int launch_pack_w2(const float* w2, uint8_t* img, cudaStream_t st) {
+  pack_w2_kernel<<<H * (H / 8) / 256, 256, 0, st>>>(w2, img);
+  return check_launch("pack_w2");
+}
+
+// ---- shared device pieces ------------------------------------------------------------------------
+__device__ __forceinline__ void cta_setup(Smem& s, const NetParams& np, uint32_t tmem_cols) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&s.bar_w, 1);
+    mbar_init(&s.bar_mma[0], 1);
+    mbar_init(&s.bar_mma[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, tmem_cols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&s.bar_w, kW2Bytes);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      bulk_g2s(s.w2 + i * (kW2Bytes / 8), np.w2_img + i * (kW2Bytes / 8), kW2Bytes / 8, &s.bar_w);
+  }
+  for (int i = tid; i < 8 * H; i += blockDim.x) {
+    const int d = i / H, c = i - d * H;
+    s.w1t[d][c] = d < np.D ? np.w1[c * np.D + d] : 0.0f;
+  }
+  for (int i = tid; i < H; i += blockDim.x) s.b1[i] = np.b1[i], s.b2[i] = np.b2[i];
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  __syncthreads();
+  mbar_wait(&s.bar_w, 0);
+}
+
+// H1 = relu(b1 + obs @ w1^T) for the 128 rows staged in s.obs -> bf16 chunks in s.a_tile.
+// Thread -> row (tid & 127), 16 of the 32 column groups.
+__device__ __forceinline__ void layer1_to_tile(Smem& s, int D) {
+  const int r = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  float o[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) o[d] = s.obs[d][r];
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const int c = half + 2 * k, i0 = c * 8;
+    float acc[8];
+    const float4 ba = *reinterpret_cast<const float4*>(&s.b1[i0]);
+    const float4 bb = *reinterpret_cast<const float4*>(&s.b1[i0 + 4]);
+    acc[0] = ba.x, acc[1] = ba.y, acc[2] = ba.z, acc[3] = ba.w;
+    acc[4] = bb.x, acc[5] = bb.y, acc[6] = bb.z, acc[7] = bb.w;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      if (d < D) {
+        const float4 wa = *reinterpret_cast<const float4*>(&s.w1t[d][i0]);
+        const float4 wb = *reinterpret_cast<const float4*>(&s.w1t[d][i0 + 4]);
+        acc[0] = fmaf(o[d], wa.x, acc[0]), acc[1] = fmaf(o[d], wa.y, acc[1]);
+        acc[2] = fmaf(o[d], wa.z, acc[2]), acc[3] = fmaf(o[d], wa.w, acc[3]);
+        acc[4] = fmaf(o[d], wb.x, acc[4]), acc[5] = fmaf(o[d], wb.y, acc[5]);
+        acc[6] = fmaf(o[d], wb.z, acc[6]), acc[7] = fmaf(o[d], wb.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.0f);
+    store_chunk(s.a_tile, chunk_offset<TILE>(r, c), acc);
+  }
+}
+
+// Head partial sums of one accumulator: thread -> row 32*(warp%4)+lane, column half warp/4.
+// dot[p] = sum_{j in half} relu(z[r][j] + b2[j]) * w3[p][j]  -> s.part[half][r][p]
+template <int P>
+__device__ __forceinline__ void head_partials(Smem& s, uint32_t acc_tmem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane;
+  float dot[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) dot[p] = 0.0f;
+#pragma unroll 1
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const int col0 = half * 128 + c4 * 32;
+    float v[32];
+    tmem_ld32(acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float h2 = fmaxf(v[j] + s.b2[col0 + j], 0.0f);
+#pragma unroll
+      for (int p = 0; p < P; ++p) dot[p] = fmaf(h2, s.w3[p][col0 + j], dot[p]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) s.part[half][r][p] = dot[p];
+}
+
+// ---- forward kernel ---------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256, 1)
+tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ out, int tanh_col1) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  cta_setup(s, np, 512);
+  const uint32_t tmem = s.tmem_base;
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (rows + TILE - 1) / TILE;
+  const int64_t ds = map.dstride();
+  const float b3[kMaxPT] = {np.b3[0], P > 1 ? np.b3[1] : 0.f, P > 2 ? np.b3[2] : 0.f, P > 3 ? np.b3[3] : 0.f};
+
+  auto epilogue = [&](int64_t tile, int buf) {
+    head_partials<P>(s, tmem + (uint32_t)(buf * H));
+    fence_before_sync();
+    __syncthreads();
+    if (tid < TILE) {
+      const int64_t row = tile * TILE + tid;
+      if (row < rows) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          float v = s.part[0][tid][p] + s.part[1][tid][p] + b3[p];
+          if (tanh_col1 && p == 1) v = tanhf(v);
+          out[row * P + p] = v;
+        }
+      }
+    }
+  };
+
+  int it = 0;
+  int64_t prev_tile = -1;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    // stage observations (r fastest: coalesced for the SoA buffer)
+    for (int i = tid; i < 8 * TILE; i += blockDim.x) {
+      const int d = i / TILE, r = i - d * TILE;
+      const int64_t row = tile * TILE + r;
+      s.obs[d][r] = (d < np.D && row < rows) ? map.obs[map.offset(row) + d * ds] : 0.0f;
+    }
+    __syncthreads();
+    layer1_to_tile(s, np.D);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + (uint32_t)(buf * H), smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H,
+                 false, TILE, H, H, false);
+      mma_commit(&s.bar_mma[buf]);
+    }
+    if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1);  // overlaps the MMAs just issued
+    mbar_wait(&s.bar_mma[buf], (uint32_t)((it >> 1) & 1));
+    fence_after_sync();
+    prev_tile = tile;
+  }
+  if (prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1);
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+// ---- rollout kernel -----------------------------------------------------------------------------------
+struct RolloutArgs {
+  rl8_env_cfg cfg;
+  int dist_kind, deterministic, T;
+  int64_t N;
+  float gamma;
+  float* state;        // [S][N]
+  float* obs;          // [T+1][D][N]
+  void* actions;       // [T+1][N]
+  float* logp;         // [T+1][N]
+  float* rewards;      // [T+1][N]
+  float* rdr;          // [T+1][N] or null
+  const float* noise;  // [T][N][P] | [T][N]
+};
+
+template <int KIND, int P>
+__global__ void __launch_bounds__(256, 1) tc_rollout_kernel(NetParams np, RolloutArgs a) {
+  using Tr = EnvTraits<KIND>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  cta_setup(s, np, 256);
+  const uint32_t tmem = s.tmem_base;
+  const int tid = threadIdx.x;
+  const int64_t N = a.N;
+  const int64_t ntiles = (N + TILE - 1) / TILE;
+  float b3[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) b3[p] = np.b3[p];
+  uint32_t phase = 0;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t n = tile * TILE + tid;  // env of this thread (threads 0..127)
+    const bool owner = tid < TILE && n < N;
+    float st[Tr::S], rdr_prev = 0.0f;
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < Tr::S; ++i) st[i] = a.state[(int64_t)i * N + n];
+      if (a.rdr) rdr_prev = a.rdr[n];
+    }
+    if (tid < TILE) {
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        s.obs[d][tid] = (d < Tr::D && n < N) ? a.obs[(int64_t)d * N + n] : 0.0f;
+    }
+    __syncthreads();
+
+    for (int t = 0; t < a.T; ++t) {
+      layer1_to_tile(s, Tr::D);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        issue_gemm(tmem, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H, false);
+        mma_commit(&s.bar_mma[0]);
+      }
+      mbar_wait(&s.bar_mma[0], phase);
+      phase ^= 1;
+      fence_after_sync();
+      head_partials<P>(s, tmem);
+      fence_before_sync();
+      __syncthreads();
+      if (owner) {
+        float o[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) o[p] = s.part[0][tid][p] + s.part[1][tid][p] + b3[p];
+        float act, lp;
+        if constexpr (Tr::discrete) {
+          float norm[P], probs[P];
+          categorical_norm<P>(o, norm, probs);
+          int ai;
+          if (a.deterministic) {
+            ai = categorical_mode<P>(probs);
+          } else {
+            float q[P];
+            const float* nz = a.noise + ((int64_t)t * N + n) * P;
+#pragma unroll
+            for (int k = 0; k < P; ++k) q[k] = nz[k];
+            ai = categorical_sample<P>(probs, q);
+          }
+          lp = norm[0];
+#pragma unroll
+          for (int k = 1; k < P; ++k) lp = (ai == k) ? norm[k] : lp;
+          act = (float)ai;
+          ((long long*)a.actions)[(int64_t)t * N + n] = ai;
+        } else {
+          const float mean = o[0], scale = expf(tanhf(o[1]));
+          float x = a.deterministic ? mean : add(mul(a.noise[(int64_t)t * N + n], scale), mean);
+          if (a.dist_kind == RL8_DIST_SQUASHED_NORMAL) {
+            x = tanhf(x);
+            lp = squashed_logp(mean, scale, x, nullptr);
+          } else {
+            lp = normal_logp(mean, scale, x);
+          }
+          act = x;
+          ((float*)a.actions)[(int64_t)t * N + n] = x;
+        }
+        a.logp[(int64_t)t * N + n] = lp;
+        float ob[Tr::D], r;
+        env_step<KIND>(a.cfg, st, act, ob, r);
+        a.rewards[(int64_t)t * N + n] = r;
+        if (a.rdr) {
+          rdr_prev = add(mul(a.gamma, rdr_prev), r);
+          a.rdr[(int64_t)(t + 1) * N + n] = rdr_prev;
+        }
+#pragma unroll
+        for (int d = 0; d < Tr::D; ++d) {
+          a.obs[((int64_t)(t + 1) * Tr::D + d) * N + n] = ob[d];
+          s.obs[d][tid] = ob[d];
+        }
+      }
+      __syncthreads();
+    }
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < Tr::S; ++i) a.state[(int64_t)i * N + n] = st[i];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 256);
+}
+
+// ---- descriptor self-test --------------------------------------------------------------------------------
+// D[128][N] = A[128][K] * B[N][K]^T with A, B given row-major in fp32; each operand is staged
+// either K-major (tile rows = M/N index) or MN-major (tile rows = K index).
+__global__ void __launch_bounds__(256, 1)
+tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                   int N, int K, int a_mn, int b_mn) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* a_tile = smem_raw;                  // up to 64 KB
+  uint8_t* b_tile = smem_raw + 65536;          // up to 128 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 65536 + 131072);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(tmem_ptr, 256);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_ptr;
+  const int a_rows = a_mn ? K : 128, b_rows = b_mn ? K : N;
+  for (int i = tid; i < 128 * K; i += blockDim.x) {
+    const int m = i / K, k = i - m * K;
+    const int row = a_mn ? k : m, col = a_mn ? m : k;
+    const uint32_t off = row * 16 + (col / 8) * (a_rows * 16) + (col % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(a_tile + off) = __float2bfloat16(A[i]);
+  }
+  for (int i = tid; i < N * K; i += blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    const int row = b_mn ? k : n, col = b_mn ? n : k;
+    const uint32_t off = row * 16 + (col / 8) * (b_rows * 16) + (col % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(b_tile + off) = __float2bfloat16(B[i]);
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    fence_after_sync();
+    issue_gemm(tmem, smem_u32(a_tile), a_rows, a_mn != 0, smem_u32(b_tile), b_rows, b_mn != 0, 128, N,
+               K, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  fence_after_sync();
+  if (tid < 128) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      for (int j = 0; j < 8; ++j) D[r * N + c0 + j] = v[j];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 256);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+static int set_smem(const void* fn, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_last_error("cudaFuncSetAttribute", e);
+    return RL8_ERR_CUDA;
+  }
+  return RL8_OK;
+}
+
+static NetParams net_params(const rl8_model* m, int which, const uint8_t* img) {
+  NetParams np;
+  np.w2_img = img;
+  np.w1 = which ? m->vf_w1 : m->pi_w1;
+  np.b1 = which ? m->vf_b1 : m->pi_b1;
+  np.b2 = which ? m->vf_b2 : m->pi_b2;
+  np.w3 = which ? m->vf_w3 : m->pi_w3;
+  np.b3 = which ? m->vf_b3 : m->pi_b3;
+  np.D = m->D;
+  np.P = which ? 1 : m->P;
+  return np;
+}
+
+static int launch_forward(const NetParams& np, const RowMap& map, int64_t rows, float* out,
+                          int tanh_col1, cudaStream_t st) {
+  const int64_t ntiles = ceil_div(rows, TILE);
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  int rc;
+#define RL8_FWD(PV)                                                                       \
+  case PV:                                                                                \
+    if ((rc = set_smem((const void*)tc_forward_kernel<PV>, sizeof(Smem)))) return rc;      \
+    tc_forward_kernel<PV><<<grid, 256, sizeof(Smem), st>>>(np, map, rows, out, tanh_col1);  \
+    break;
+  switch (np.P) {
+    RL8_FWD(1) RL8_FWD(2) RL8_FWD(3) RL8_FWD(4)
+    default: return RL8_ERR_UNSUPPORTED;
+  }
+#undef RL8_FWD
+  return check_launch("tc_forward");
+}
+
+int mlp_forward_tc(const rl8_model* m, int which, const RowMap& map, int64_t rows, float* out,
+                   int tanh_col1, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (m->H != H || m->D > 8 || m->P > kMaxPT) return RL8_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < kW2Bytes) return RL8_ERR_WORKSPACE;
+  uint8_t* img = (uint8_t*)workspace;
+  int rc = launch_pack_w2(which ? m->vf_w2 : m->pi_w2, img, st);
+  if (rc) return rc;
+  return launch_forward(net_params(m, which, img), map, rows, out, tanh_col1, st);
+}
+
+int64_t collect_tc_workspace(const rl8_model*, int64_t, int32_t) { return 2 * kW2Bytes; }
+
+template <int KIND, int P>
+static int launch_rollout(const NetParams& np, const rl8_rollout* ro, cudaStream_t st) {
+  RolloutArgs a;
+  a.cfg = ro->env_cfg;
+  a.dist_kind = ro->dist_kind, a.deterministic = ro->deterministic, a.T = ro->T, a.N = ro->N;
+  a.gamma = ro->gamma;
+  a.state = ro->env_state, a.obs = ro->obs, a.actions = ro->actions, a.logp = ro->logp;
+  a.rewards = ro->rewards, a.rdr = ro->rdr, a.noise = ro->noise;
+  int rc = set_smem((const void*)tc_rollout_kernel<KIND, P>, sizeof(Smem));
+  if (rc) return rc;
+  const int64_t ntiles = ceil_div(ro->N, TILE);
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  tc_rollout_kernel<KIND, P><<<grid, 256, sizeof(Smem), st>>>(np, a);
+  return check_launch("tc_rollout");
+}
+
+int collect_tc(const rl8_model* model, const rl8_rollout* ro, void* workspace,
+               int64_t workspace_bytes, cudaStream_t st) {
+  if (model->H != H || model->P > kMaxPT) return RL8_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < 2 * kW2Bytes) return RL8_ERR_WORKSPACE;
+  uint8_t* img_pi = (uint8_t*)workspace;
+  uint8_t* img_vf = img_pi + kW2Bytes;
+  int rc;
+  if ((rc = launch_pack_w2(model->pi_w2, img_pi, st))) return rc;
+  if ((rc = launch_pack_w2(model->vf_w2, img_vf, st))) return rc;
+  const NetParams np = net_params(model, 0, img_pi);
+  switch (ro->env_kind) {
+    case RL8_ENV_DISCRETE_DUMMY: rc = launch_rollout<RL8_ENV_DISCRETE_DUMMY, 2>(np, ro, st); break;
+    case RL8_ENV_CONTINUOUS_DUMMY: rc = launch_rollout<RL8_ENV_CONTINUOUS_DUMMY, 2>(np, ro, st); break;
+    case RL8_ENV_CARTPOLE: rc = launch_rollout<RL8_ENV_CARTPOLE, 3>(np, ro, st); break;
+    case RL8_ENV_MOUNTAIN_CAR: rc = launch_rollout<RL8_ENV_MOUNTAIN_CAR, 3>(np, ro, st); break;
+    case RL8_ENV_PENDULUM: rc = launch_rollout<RL8_ENV_PENDULUM, 2>(np, ro, st); break;
+    default: return RL8_ERR_ARG;
+  }
+  if (rc) return rc;
+  // values of all T+1 observation slabs in one launch (rows r = t*N + n)
+  RowMap map{};
+  map.obs = ro->obs, map.mode = 2, map.D = model->D, map.N = ro->N, map.T = ro->T;
+  return launch_forward(net_params(model, 1, img_vf), map, (int64_t)(ro->T + 1) * ro->N, ro->values,
+                        0, st);
+}
+
 int64_t ppo_tc_workspace(const rl8_model*, int64_t) { return RL8_ERR_UNSUPPORTED; }
 int ppo_minibatch_tc(const rl8_model*, const rl8_model*, const rl8_batch*, const int64_t*, int64_t,
                      int64_t, double, const rl8_ppo_hparams*, double*, void*, int64_t,
                      cudaStream_t) {
   return RL8_ERR_UNSUPPORTED;
 }
-int mlp_forward_tc(const rl8_model*, int, const RowMap&, int64_t, float*, int, void*, int64_t,
-                   cudaStream_t) {
-  return RL8_ERR_UNSUPPORTED;
-}
 
 }  // namespace rl8
+
+using namespace rl8;
+
+// Test hook: one tcgen05 GEMM through the operand format of tc.cuh (see tests/test_gpu_tc.py).
+extern "C" int rl8_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                               int a_mn_major, int b_mn_major, rl8_stream_t stream) {
+  if (!A || !B || !D || N < 8 || N > 256 || (N % 8) || K < 16 || K > 256 || (K % 16)) return RL8_ERR_ARG;
+  const size_t bytes = 65536 + 131072 + 64;
+  int rc = set_smem((const void*)tc_selftest_kernel, bytes);
+  if (rc) return rc;
+  tc_selftest_kernel<<<1, 256, bytes, (cudaStream_t)stream>>>(A, B, D, N, K, a_mn_major, b_mn_major);
+  return check_launch("tc_selftest");
+}

@@ -1,0 +1,210 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy primitives for sm_100a (inline PTX) and the one
+// shared-memory operand format every tensor-core kernel in this library uses.
+//
+// Operand tiles ("chunked" format, no swizzle)
+// -------------------------------------------
+// A bf16 matrix T[ROWS][COLS] is stored in shared memory as 16-byte chunks of 8
+// consecutive columns, chunks of one column-group contiguous over rows:
+//
+//     byte_offset(row, col) = row * 16 + (col / 8) * (ROWS * 16) + (col % 8) * 2
+//
+// This is the canonical SWIZZLE_NONE ("interleaved") UMMA layout for BOTH majors:
+//   * rows = M/N index, cols = K index  -> K-major operand:  SBO = 128 B (next 8-row group),
+//                                          LBO = ROWS*16 B (next 8-column K group)
+//   * rows = K index, cols = M/N index  -> MN-major operand: SBO = ROWS*16 B (next 8 M/N
+//                                          elements), LBO = 128 B (next 8 K rows)
+// (core matrix = 8 rows x 16 bytes = 128 contiguous bytes in either reading).  A warp that
+// writes one chunk per lane with consecutive rows stores 512 contiguous bytes: no bank
+// conflicts, and the tile written for one GEMM (e.g. H1 as the K-major A of the forward
+// pass) is read by another as its transpose (H1^T as the MN-major A of the weight-gradient
+// GEMM) without being rewritten.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace rl8 {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// try_wait suspends the thread for a hardware-bounded time per attempt; the attempt cap turns
+// a protocol bug (a barrier that never completes) into a trap instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 24)) __trap();
+  }
+}
+
+// ---- bulk async copy global -> shared (TMA, non-tensor form; SASS: UBLKCP) ----------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- TMEM -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread `lane` of the warp gets row
+// (lane field of taddr) + lane, columns [col, col + 32).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 8 columns (small accumulators)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors --------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (SWIZZLE_NONE, sm_100 version field = 1).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// Instruction descriptor, kind::f16: bf16 x bf16 -> f32, dense.
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ |
+         ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA.
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when every MMA issued so far by this thread has completed (implies
+// tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// ---- chunked operand tiles ------------------------------------------------------------------------
+template <int ROWS>
+__device__ __forceinline__ uint32_t chunk_offset(int row, int col8 /* col / 8 */) {
+  return (uint32_t)row * 16u + (uint32_t)col8 * (uint32_t)(ROWS * 16);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// store 8 consecutive columns of one row
+__device__ __forceinline__ void store_chunk(uint8_t* tile, uint32_t off, const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + off) = q;
+}
+
+// Issue the K loop of one GEMM whose operands are chunked tiles.
+//   a_rows_is_k / b_rows_is_k: operand tile rows index K (MN-major) instead of M/N (K-major)
+//   A tile has A_ROWS rows, B tile B_ROWS rows; k_total = contraction length (multiple of 16)
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_saddr, int A_ROWS,
+                                           bool a_rows_is_k, uint32_t b_saddr, int B_ROWS,
+                                           bool b_rows_is_k, int M, int N, int k_total,
+                                           bool accumulate_first) {
+  const uint32_t idesc = instr_desc(M, N, a_rows_is_k ? 1 : 0, b_rows_is_k ? 1 : 0);
+  // K-major: LBO = ROWS*16, SBO = 128, 16 K elements = 2 column groups -> advance 2*ROWS*16
+  // MN-major: LBO = 128, SBO = ROWS*16, 16 K elements = 16 rows -> advance 256
+  const uint32_t a_lbo = a_rows_is_k ? 128u : (uint32_t)A_ROWS * 16u;
+  const uint32_t a_sbo = a_rows_is_k ? (uint32_t)A_ROWS * 16u : 128u;
+  const uint32_t b_lbo = b_rows_is_k ? 128u : (uint32_t)B_ROWS * 16u;
+  const uint32_t b_sbo = b_rows_is_k ? (uint32_t)B_ROWS * 16u : 128u;
+  const uint32_t a_step = a_rows_is_k ? 256u : 2u * A_ROWS * 16u;
+  const uint32_t b_step = b_rows_is_k ? 256u : 2u * B_ROWS * 16u;
+  const int steps = k_total / 16;
+  for (int s = 0; s < steps; ++s) {
+    uint64_t ad = smem_desc(a_saddr + s * a_step, a_lbo, a_sbo);
+    uint64_t bd = smem_desc(b_saddr + s * b_step, b_lbo, b_sbo);
+    mma_bf16(d_tmem, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+  }
+}
+
+}  // namespace tc
+}  // namespace rl8
