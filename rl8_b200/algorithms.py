@@ -378,7 +378,7 @@ class Algorithm:
         rc = self._lib.rl8_collect(m, ro, self.policy.precision, _lib.ptr(ws), ws.numel(), _lib.stream())
         _lib.check(rc, "rl8_collect")
         T = hp.horizon
-        self.last_launches["collect"] = (4 * T + 3 * (T + 1)) if self.policy.precision == _lib.PREC_FP32 else 2
+        self.last_launches["collect"] = (4 * T + 3 * (T + 1)) if self.policy.precision == _lib.PREC_FP32 else 4
 
     def _collect_generic(self, noise: None | torch.Tensor, deterministic: bool) -> None:
         """Rollout with a user-defined (Python / torch) environment: the policy forward,
@@ -482,6 +482,7 @@ class Algorithm:
         applied: list[bool] = []  # step boundary flags per minibatch
         stop_early = False
         mb_launches = 34 if prec == _lib.PREC_FP32 else 4
+        chunks = max(1, -(-M // 65536)) if prec == _lib.PREC_FP32 else 1
         for _ in range(hp.num_sgd_iters):
             perm = torch.randperm(N * T, device=self.device) if hp.shuffle_minibatches else None
             for i in range(hp.num_minibatches):
@@ -492,7 +493,7 @@ class Algorithm:
                     ctypes.c_void_p(sums.data_ptr() + 40 * k), prec, _lib.ptr(ws), ws.numel(), st,
                 )
                 _lib.check(rc, "rl8_ppo_minibatch")
-                launches += mb_launches * max(1, -(-M // 65536))
+                launches += mb_launches * chunks
                 applied.append(step_this_batch)
                 k += 1
                 if hp.target_kl_div is not None:

@@ -1,0 +1,170 @@
+// Shared pieces of the tensor-core kernels (mlp_tc.cu, update_tc.cu).
+#pragma once
+#include "dist.cuh"
+#include "mlp_fp32.cuh"
+#include "tc.cuh"
+
+namespace rl8 {
+
+using namespace tc;
+
+constexpr int H = 256;         // hidden width
+constexpr int TILE = 128;      // rows (envs / transitions) per CTA tile == UMMA M
+constexpr int kW2Bytes = H * H * 2;
+constexpr int kTileBytes = TILE * H * 2;
+constexpr int kMaxPT = 4;      // widest head on the tensor-core path
+
+struct NetParams {
+  const uint8_t* w2_img;  // bf16, chunked [j = 256 rows][i = 256 cols]
+  const float *w1, *b1, *b2, *w3, *b3;
+  int D, P;
+};
+
+// Shared-memory plan of the forward / rollout kernels (dynamic smem, 128-byte aligned).
+struct Smem {
+  uint8_t w2[kW2Bytes];        // 131072
+  uint8_t a_tile[kTileBytes];  //  65536  H1 tile: K-major A operand
+  float w1t[8][H];             //   8192  w1t[d][i]
+  float b1[H], b2[H];          //   2048
+  float w3[kMaxPT][H];         //   4096
+  float obs[8][TILE];          //   4096  obs[d][r]
+  float part[2][TILE][kMaxPT]; //   4096  head partial sums per column half
+  uint64_t bar_w, bar_mma[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Smem) <= 227 * 1024, "smem plan exceeds the 227 KB CTA limit");
+
+// ---- weight packing: fp32 [256][256] row-major -> bf16 chunked image ------------------------
+static __global__ void __launch_bounds__(256) pack_w2_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img) {
+  // one thread per 16-byte chunk: row j, column group c (8 consecutive i)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 256*32
+  if (idx >= H * (H / 8)) return;
+  const int j = idx % H, c = idx / H;
+  float v[8];
+  const float4 lo = *reinterpret_cast<const float4*>(w2 + j * H + c * 8);
+  const float4 hi = *reinterpret_cast<const float4*>(w2 + j * H + c * 8 + 4);
+  v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
+  store_chunk(img, chunk_offset<H>(j, c), v);
+}
+
+static inline int launch_pack_w2(const float* w2, uint8_t* img, cudaStream_t st) {
+  pack_w2_kernel<<<H * (H / 8) / 256, 256, 0, st>>>(w2, img);
+  return check_launch("pack_w2");
+}
+
+// ---- shared device pieces ------------------------------------------------------------------------
+template <class S>
+__device__ __forceinline__ void cta_setup(S& s, const NetParams& np, uint32_t tmem_cols) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&s.bar_w, 1);
+    mbar_init(&s.bar_mma[0], 1);
+    mbar_init(&s.bar_mma[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, tmem_cols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&s.bar_w, kW2Bytes);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      bulk_g2s(s.w2 + i * (kW2Bytes / 8), np.w2_img + i * (kW2Bytes / 8), kW2Bytes / 8, &s.bar_w);
+  }
+  for (int i = tid; i < 8 * H; i += blockDim.x) {
+    const int d = i / H, c = i - d * H;
+    s.w1t[d][c] = d < np.D ? np.w1[c * np.D + d] : 0.0f;
+  }
+  for (int i = tid; i < H; i += blockDim.x) s.b1[i] = np.b1[i], s.b2[i] = np.b2[i];
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  __syncthreads();
+  mbar_wait(&s.bar_w, 0);
+}
+
+// H1 = relu(b1 + obs @ w1^T) for the 128 rows staged in s.obs -> bf16 chunks in s.a_tile.
+// Thread -> row (tid & 127), 16 of the 32 column groups.
+template <class S>
+__device__ __forceinline__ void layer1_to_tile(S& s, int D) {
+  const int r = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  float o[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) o[d] = s.obs[d][r];
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const int c = half + 2 * k, i0 = c * 8;
+    float acc[8];
+    const float4 ba = *reinterpret_cast<const float4*>(&s.b1[i0]);
+    const float4 bb = *reinterpret_cast<const float4*>(&s.b1[i0 + 4]);
+    acc[0] = ba.x, acc[1] = ba.y, acc[2] = ba.z, acc[3] = ba.w;
+    acc[4] = bb.x, acc[5] = bb.y, acc[6] = bb.z, acc[7] = bb.w;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      if (d < D) {
+        const float4 wa = *reinterpret_cast<const float4*>(&s.w1t[d][i0]);
+        const float4 wb = *reinterpret_cast<const float4*>(&s.w1t[d][i0 + 4]);
+        acc[0] = fmaf(o[d], wa.x, acc[0]), acc[1] = fmaf(o[d], wa.y, acc[1]);
+        acc[2] = fmaf(o[d], wa.z, acc[2]), acc[3] = fmaf(o[d], wa.w, acc[3]);
+        acc[4] = fmaf(o[d], wb.x, acc[4]), acc[5] = fmaf(o[d], wb.y, acc[5]);
+        acc[6] = fmaf(o[d], wb.z, acc[6]), acc[7] = fmaf(o[d], wb.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.0f);
+    store_chunk(s.a_tile, chunk_offset<TILE>(r, c), acc);
+  }
+}
+
+// Head partial sums of one accumulator: thread -> row 32*(warp%4)+lane, column half warp/4.
+// dot[p] = sum_{j in half} relu(z[r][j] + b2[j]) * w3[p][j]  -> s.part[half][r][p]
+template <int P, class S>
+__device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane;
+  float dot[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) dot[p] = 0.0f;
+#pragma unroll 1
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const int col0 = half * 128 + c4 * 32;
+    float v[32];
+    tmem_ld32(acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float h2 = fmaxf(v[j] + s.b2[col0 + j], 0.0f);
+#pragma unroll
+      for (int p = 0; p < P; ++p) dot[p] = fmaf(h2, s.w3[p][col0 + j], dot[p]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) s.part[half][r][p] = dot[p];
+}
+
+
+static inline int set_smem(const void* fn, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_last_error("cudaFuncSetAttribute", e);
+    return RL8_ERR_CUDA;
+  }
+  return RL8_OK;
+}
+
+static inline NetParams net_params(const rl8_model* m, int which, const uint8_t* img) {
+  NetParams np;
+  np.w2_img = img;
+  np.w1 = which ? m->vf_w1 : m->pi_w1;
+  np.b1 = which ? m->vf_b1 : m->pi_b1;
+  np.b2 = which ? m->vf_b2 : m->pi_b2;
+  np.w3 = which ? m->vf_w3 : m->pi_w3;
+  np.b3 = which ? m->vf_b3 : m->pi_b3;
+  np.D = m->D;
+  np.P = which ? 1 : m->P;
+  return np;
+}
+
+}  // namespace rl8

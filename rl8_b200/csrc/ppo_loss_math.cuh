@@ -62,15 +62,15 @@ __device__ __forceinline__ float ppo_value_loss(float v, float ret, float vf_cli
   return clampf(l, 0.0f, vf_clip);
 }
 
-// One row.  `o` = policy head outputs (logits, or {mean, log_std}); `act` = stored action as
-// float (discrete index or continuous value).  Writes d(scaled total)/d(o) (for the
-// continuous head: w.r.t. {mean, raw log_std before tanh}) and d/d(v).
+// Policy half of one row.  `o` = policy head outputs (logits, or {mean, log_std}); `act` =
+// stored action as float (discrete index or continuous value).  Writes d(scaled total)/d(o)
+// (for the continuous head: w.r.t. {mean, raw log_std before tanh}); returns entropy, the
+// surrogate and the KL term in L.
 template <int P>
-__device__ __forceinline__ RowLoss ppo_row(int dist_kind, const float* o, float v, float act,
-                                           float logp_old, float adv, float ret,
-                                           const rl8_ppo_hparams& hp, float inv_denom, float* d_o,
-                                           float* d_v) {
-  RowLoss L;
+__device__ __forceinline__ void ppo_policy_row(int dist_kind, const float* o, float act,
+                                               float logp_old, float adv,
+                                               const rl8_ppo_hparams& hp, float inv_denom,
+                                               float* d_o, RowLoss& L) {
   float logp_new, dratio;
   const bool want_ent = hp.entropy_coeff != 0.0f;
   L.entropy = 0.0f;
@@ -125,9 +125,24 @@ __device__ __forceinline__ RowLoss ppo_row(int dist_kind, const float* o, float 
 #pragma unroll
     for (int k = 2; k < P; ++k) d_o[k] = 0.0f;
   }
+}
+
+// Value half of one row.
+__device__ __forceinline__ void ppo_value_row(float v, float ret, const rl8_ppo_hparams& hp,
+                                              float inv_denom, float* d_v, RowLoss& L) {
   float dv;
   L.vf = ppo_value_loss(v, ret, hp.vf_clip_param, &dv);
   *d_v = inv_denom * hp.vf_coeff * dv;
+}
+
+template <int P>
+__device__ __forceinline__ RowLoss ppo_row(int dist_kind, const float* o, float v, float act,
+                                           float logp_old, float adv, float ret,
+                                           const rl8_ppo_hparams& hp, float inv_denom, float* d_o,
+                                           float* d_v) {
+  RowLoss L;
+  ppo_policy_row<P>(dist_kind, o, act, logp_old, adv, hp, inv_denom, d_o, L);
+  ppo_value_row(v, ret, hp, inv_denom, d_v, L);
   return L;
 }
 
