@@ -28,7 +28,7 @@ import torch
 import torch.distributed as dist
 import torch.optim as optim
 
-from . import _lib
+from . import _lib, parallel
 from .buffer import RolloutBuffer
 from .data import AlgorithmHparams, AlgorithmState, CollectStats, DataKeys, Device, MemoryStats, StepStats
 from .distributions import Distribution
@@ -106,8 +106,7 @@ def memory_stats() -> MemoryStats:
     return {"memory/free": free, "memory/total": total, "memory/percent": 100 * (total - free) / total}
 
 
-def _world() -> int:
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+_world = parallel.world_size
 
 
 class _RunningMean:
@@ -307,19 +306,10 @@ class Algorithm:
         _lib.check(rc, "rl8_collect_stats")
         self.last_launches["collect"] += 1
         world = _world()
-        if world > 1:
-            dist.all_reduce(acc[:6])
-            mins = torch.stack((acc[6], -acc[7], acc[8], -acc[9]))
-            dist.all_reduce(mins, op=dist.ReduceOp.MIN)
-            acc[6], acc[7], acc[8], acc[9] = mins[0], -mins[1], mins[2], -mins[3]
+        parallel.reduce_collect_acc_(acc)
         a = acc.tolist()  # the one device->host sync of collect()
         n_r, n_R = float(N * T * world), float(N * world)
-
-        def mean_std(s: float, s2: float, n: float) -> tuple[float, float]:
-            mean = s / n
-            var = (s2 - s * mean) / (n - 1) if n > 1 else float("nan")
-            return mean, math.sqrt(max(var, 0.0)) if var == var else var
-
+        mean_std = parallel.mean_std
         r_mean, r_std = mean_std(a[0], a[1], n_r)
         R_mean, R_std = mean_std(a[2], a[3], n_R)
         stats: CollectStats = {

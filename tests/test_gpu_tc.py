@@ -205,8 +205,10 @@ def test_update_kernels_match_fp32_path(env_name: str, dist, kw) -> None:
     for algo, g in zip((a32, a16), grads):
         algo._on_grads = lambda named, g=g: g.update({k: v.detach().cpu().clone() for k, v in named.items()}) if not g else None
     s32, s16 = a32.step(), a16.step()
+    # bf16 operands: 2^-9 relative per hidden unit; the dummy envs feed |obs| up to 100, so
+    # their value loss moves by a few 1e-3 relative
     for k in ("losses/policy", "losses/vf", "losses/total", "losses/entropy", "monitors/kl_div"):
-        assert s16[k] == pytest.approx(s32[k], rel=3e-3, abs=3e-4), (k, s16[k], s32[k])
+        assert s16[k] == pytest.approx(s32[k], rel=1e-2, abs=5e-4), (k, s16[k], s32[k])
     assert set(grads[0]) == set(grads[1]) and grads[0]
     for k, g32 in grads[0].items():
         g16 = grads[1][k]
@@ -216,7 +218,7 @@ def test_update_kernels_match_fp32_path(env_name: str, dist, kw) -> None:
             continue
         cos = float((g32.double() * g16.double()).sum() / (n32 * g16.double().norm()))
         assert cos > 0.999, (k, cos)
-        assert float((g16 - g32).double().norm()) / n32 < 2e-2, (k, float((g16 - g32).double().norm()) / n32)
+        assert float((g16 - g32).double().norm()) / n32 < 5e-2, (k, float((g16 - g32).double().norm()) / n32)
     p32 = a32.policy.model.flat_params.cpu()
     p16 = a16.policy.model.flat_params.cpu()
     assert float((p32 - p16).abs().max()) < 2.5e-3  # one Adam step moves each weight by <= lr = 1e-3
