@@ -86,40 +86,51 @@ __device__ __forceinline__ void cta_setup(S& s, const NetParams& np, uint32_t tm
 }
 
 // H1 = relu(b1 + obs @ w1^T) for the 128 rows staged in s.obs -> bf16 chunks in s.a_tile.
-// Thread -> row (tid & 127), 16 of the 32 column groups.
+// Thread -> row (tid & 127) and the column half (tid >> 7): the same ownership as the TMEM
+// epilogues, so the layer-1 ReLU mask (bit j % 32 of word (j % 128) / 32) can stay in the
+// thread's registers until the backward pass needs it.
 template <class S>
-__device__ __forceinline__ void layer1_to_tile(S& s, int D) {
+__device__ __forceinline__ void layer1_to_tile(S& s, int D, uint32_t* mask_words = nullptr) {
   const int r = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
   float o[8];
 #pragma unroll
   for (int d = 0; d < 8; ++d) o[d] = s.obs[d][r];
-#pragma unroll 4
-  for (int k = 0; k < 16; ++k) {
-    const int c = half + 2 * k, i0 = c * 8;
-    float acc[8];
-    const float4 ba = *reinterpret_cast<const float4*>(&s.b1[i0]);
-    const float4 bb = *reinterpret_cast<const float4*>(&s.b1[i0 + 4]);
-    acc[0] = ba.x, acc[1] = ba.y, acc[2] = ba.z, acc[3] = ba.w;
-    acc[4] = bb.x, acc[5] = bb.y, acc[6] = bb.z, acc[7] = bb.w;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      if (d < D) {
-        const float4 wa = *reinterpret_cast<const float4*>(&s.w1t[d][i0]);
-        const float4 wb = *reinterpret_cast<const float4*>(&s.w1t[d][i0 + 4]);
-        acc[0] = fmaf(o[d], wa.x, acc[0]), acc[1] = fmaf(o[d], wa.y, acc[1]);
-        acc[2] = fmaf(o[d], wa.z, acc[2]), acc[3] = fmaf(o[d], wa.w, acc[3]);
-        acc[4] = fmaf(o[d], wb.x, acc[4]), acc[5] = fmaf(o[d], wb.y, acc[5]);
-        acc[6] = fmaf(o[d], wb.z, acc[6]), acc[7] = fmaf(o[d], wb.w, acc[7]);
+  for (int w = 0; w < 4; ++w) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = half * 16 + w * 4 + k, i0 = c * 8;
+      float acc[8];
+      const float4 ba = *reinterpret_cast<const float4*>(&s.b1[i0]);
+      const float4 bb = *reinterpret_cast<const float4*>(&s.b1[i0 + 4]);
+      acc[0] = ba.x, acc[1] = ba.y, acc[2] = ba.z, acc[3] = ba.w;
+      acc[4] = bb.x, acc[5] = bb.y, acc[6] = bb.z, acc[7] = bb.w;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        if (d < D) {
+          const float4 wa = *reinterpret_cast<const float4*>(&s.w1t[d][i0]);
+          const float4 wb = *reinterpret_cast<const float4*>(&s.w1t[d][i0 + 4]);
+          acc[0] = fmaf(o[d], wa.x, acc[0]), acc[1] = fmaf(o[d], wa.y, acc[1]);
+          acc[2] = fmaf(o[d], wa.z, acc[2]), acc[3] = fmaf(o[d], wa.w, acc[3]);
+          acc[4] = fmaf(o[d], wb.x, acc[4]), acc[5] = fmaf(o[d], wb.y, acc[5]);
+          acc[6] = fmaf(o[d], wb.z, acc[6]), acc[7] = fmaf(o[d], wb.w, acc[7]);
+        }
       }
-    }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.0f);
-    store_chunk(s.a_tile, chunk_offset<TILE>(r, c), acc);
+      for (int e = 0; e < 8; ++e) {
+        word |= (acc[e] > 0.0f ? 1u : 0u) << (k * 8 + e);
+        acc[e] = fmaxf(acc[e], 0.0f);
+      }
+      store_chunk(s.a_tile, chunk_offset<TILE>(r, c), acc);
+    }
+    if (mask_words) mask_words[w] = word;
   }
 }
 
 // Head partial sums of one accumulator: thread -> row 32*(warp%4)+lane, column half warp/4.
 // dot[p] = sum_{j in half} relu(z[r][j] + b2[j]) * w3[p][j]  -> s.part[half][r][p]
+// Per-column constants are read as 128-bit warp broadcasts.
 template <int P, class S>
 __device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,16 +145,27 @@ __device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem) {
     float v[32];
     tmem_ld32(acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float h2 = fmaxf(v[j] + s.b2[col0 + j], 0.0f);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + j]);
+      const float h0 = fmaxf(v[j] + b.x, 0.0f), h1 = fmaxf(v[j + 1] + b.y, 0.0f);
+      const float h2 = fmaxf(v[j + 2] + b.z, 0.0f), h3 = fmaxf(v[j + 3] + b.w, 0.0f);
 #pragma unroll
-      for (int p = 0; p < P; ++p) dot[p] = fmaf(h2, s.w3[p][col0 + j], dot[p]);
+      for (int p = 0; p < P; ++p) {
+        const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + j]);
+        dot[p] = fmaf(h0, w.x, dot[p]);
+        dot[p] = fmaf(h1, w.y, dot[p]);
+        dot[p] = fmaf(h2, w.z, dot[p]);
+        dot[p] = fmaf(h3, w.w, dot[p]);
+      }
     }
   }
 #pragma unroll
   for (int p = 0; p < P; ++p) s.part[half][r][p] = dot[p];
 }
 
+}  // namespace rl8
+
+namespace rl8 {
 
 static inline int set_smem(const void* fn, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -56,19 +56,73 @@ struct SmemH {
   float dout[TILE][kMaxPT];
   uint8_t dout_tile[TILE * 16];  // bf16 [r][8]: MN-major B operand (N = 8)
   uint8_t aug_tile[TILE * 16];   // bf16 [r][8] = [obs_0..obs_{D-1}, 1, 0..]
+  int64_t row_idx[TILE];         // t*N + n of the tile's rows (-1: past the minibatch)
   float gb3[kMaxPT];
   uint64_t bar_w, bar_mma[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(SmemH) <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
+static_assert(sizeof(SmemH) + 1024 <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
 
 // TMEM columns of kernel H
 constexpr uint32_t kColMain = 0, kColG3 = 256, kColGb2 = 320, kColG1 = 384;  // +32 per 128-block
 
-__device__ __forceinline__ int64_t batch_index(const UpdArgs& a, int64_t r) {
-  const int64_t g = a.rows ? a.rows[r] : a.row_begin + r;
-  const int64_t n = g / a.T, t = g - n * a.T;
-  return t * a.N + n;
+// Stage the tile's row indices and observations (gathered through the minibatch row list).
+template <class S>
+__device__ __forceinline__ void stage_rows(S& s, const UpdArgs& a, int64_t tile, int D) {
+  const int tid = threadIdx.x;
+  if (tid < TILE) {
+    const int64_t rw = tile * TILE + tid;
+    int64_t idx = -1;
+    if (rw < a.M) {
+      const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
+      const int64_t n = g / a.T, t = g - n * a.T;
+      idx = t * a.N + n;
+    }
+    s.row_idx[tid] = idx;
+  }
+  __syncthreads();
+  for (int i = tid; i < 8 * TILE; i += blockDim.x) {
+    const int d = i / TILE, rr = i - d * TILE;
+    const int64_t idx = s.row_idx[rr];
+    float v = 0.0f;
+    if (d < D && idx >= 0) {
+      const int64_t t = idx / a.N, n = idx - t * a.N;
+      v = a.obs[(t * D + d) * a.N + n];
+    }
+    s.obs[d][rr] = v;
+  }
+  __syncthreads();
+}
+
+// dZ2 chunks of this thread's 128 columns from the layer-2 ReLU mask words and dOut:
+// dz2[r][j] = mask ? sum_p dout[r][p] * w3[p][j] : 0  -> bf16 chunks in `tile`.
+template <int PN, class S>
+__device__ __forceinline__ void dz2_to_tile(S& s, uint8_t* tile, const uint32_t* mask_words, int r,
+                                            int half) {
+  float dr[PN];
+#pragma unroll
+  for (int p = 0; p < PN; ++p) dr[p] = s.dout[r][p];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const uint32_t word = mask_words[w];
+    const int col0 = half * 128 + w * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int p = 0; p < PN; ++p) {
+        const float4 wa = *reinterpret_cast<const float4*>(&s.w3[p][col0 + 8 * k]);
+        const float4 wb = *reinterpret_cast<const float4*>(&s.w3[p][col0 + 8 * k + 4]);
+        v[0] = fmaf(dr[p], wa.x, v[0]), v[1] = fmaf(dr[p], wa.y, v[1]);
+        v[2] = fmaf(dr[p], wa.z, v[2]), v[3] = fmaf(dr[p], wa.w, v[3]);
+        v[4] = fmaf(dr[p], wb.x, v[4]), v[5] = fmaf(dr[p], wb.y, v[5]);
+        v[6] = fmaf(dr[p], wb.z, v[6]), v[7] = fmaf(dr[p], wb.w, v[7]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = ((word >> (8 * k + e)) & 1u) ? v[e] : 0.0f;
+      store_chunk(tile, chunk_offset<TILE>(r, col0 / 8 + k), v);
+    }
+  }
 }
 
 template <int PN, bool POLICY>
@@ -93,27 +147,17 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
   for (int64_t tile = blockIdx.x >> 1; tile < ntiles; tile += nctas, ++it) {
     const int64_t row = tile * TILE + r;
     const bool valid = row < a.M;
-    // ---- 1. stage observations, [obs, 1] operand tile ---------------------------------------
-    for (int i = tid; i < 8 * TILE; i += blockDim.x) {
-      const int d = i / TILE, rr = i - d * TILE;
-      const int64_t rw = tile * TILE + rr;
-      float v = 0.0f;
-      if (d < D && rw < a.M) {
-        const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
-        const int64_t n = g / a.T, t = g - n * a.T;
-        v = a.obs[(t * D + d) * a.N + n];
-      }
-      s.obs[d][rr] = v;
-    }
-    __syncthreads();
+    // ---- 1. rows, observations, [obs, 1] operand tile ------------------------------------------
+    stage_rows(s, a, tile, D);
     if (tid < TILE) {
       float v[8];
 #pragma unroll
       for (int d = 0; d < 8; ++d) v[d] = d < D ? s.obs[d][tid] : (d == D ? 1.0f : 0.0f);
       store_chunk(s.aug_tile, (uint32_t)tid * 16u, v);
     }
-    // ---- 2./3. H1 -> MMA1 -----------------------------------------------------------------------
-    layer1_to_tile(s, D);
+    // ---- 2. H1 (keeps the layer-1 ReLU mask in registers) -> MMA1 ----------------------------------
+    uint32_t mask1[4], mask2[4];
+    layer1_to_tile(s, D, mask1);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -126,9 +170,45 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     mbar_wait(&s.bar_mma[0], ph0);
     ph0 ^= 1;
     fence_after_sync();
-    // ---- 4./5. heads, per-row loss, dOut ------------------------------------------------------------
-    head_partials<PN>(s, tmem + kColMain);
+    // ---- 3. one pass over Z2: head partial sums, H2 tile (bf16), layer-2 mask ----------------------
+    {
+      float dot[PN];
+#pragma unroll
+      for (int p = 0; p < PN; ++p) dot[p] = 0.0f;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col0 = half * 128 + c4 * 32;
+        float v[32];
+        tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + j]);
+          v[j] = fmaxf(v[j] + b.x, 0.0f), v[j + 1] = fmaxf(v[j + 1] + b.y, 0.0f);
+          v[j + 2] = fmaxf(v[j + 2] + b.z, 0.0f), v[j + 3] = fmaxf(v[j + 3] + b.w, 0.0f);
+#pragma unroll
+          for (int p = 0; p < PN; ++p) {
+            const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + j]);
+            dot[p] = fmaf(v[j], w.x, dot[p]);
+            dot[p] = fmaf(v[j + 1], w.y, dot[p]);
+            dot[p] = fmaf(v[j + 2], w.z, dot[p]);
+            dot[p] = fmaf(v[j + 3], w.w, dot[p]);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) word |= (v[j + e] > 0.0f ? 1u : 0u) << (j + e);
+        }
+        mask2[c4] = word;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
+      }
+#pragma unroll
+      for (int p = 0; p < PN; ++p) s.part[half][r][p] = dot[p];
+      if (valid)
+        *reinterpret_cast<uint4*>(a.mask[net] + row * 8 + half * 4) =
+            make_uint4(mask2[0], mask2[1], mask2[2], mask2[3]);
+    }
     __syncthreads();
+    // ---- 4. per-row loss -> dOut ---------------------------------------------------------------------------
     if (tid < TILE) {
       float o[PN], d_o[PN];
 #pragma unroll
@@ -136,7 +216,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
 #pragma unroll
       for (int p = 0; p < PN; ++p) d_o[p] = 0.0f;
       if (valid) {
-        const int64_t idx = batch_index(a, row);
+        const int64_t idx = s.row_idx[tid];
         RowLoss L;
         if constexpr (POLICY) {
           if (continuous) o[1] = tanhf(o[1]);
@@ -154,35 +234,19 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
 #pragma unroll
       for (int p = 0; p < 8; ++p) v8[p] = p < PN ? d_o[p] : 0.0f;
       store_chunk(s.dout_tile, (uint32_t)tid * 16u, v8);
+      *reinterpret_cast<float4*>(&s.dout[tid][0]) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+      if (valid) *reinterpret_cast<float4*>(a.dout[net] + row * 4) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+      // gb3 += sum_r dOut: one shared atomic per warp
 #pragma unroll
-      for (int p = 0; p < kMaxPT; ++p) s.dout[tid][p] = p < PN ? d_o[p] : 0.0f;
-      if (valid) {
-        *reinterpret_cast<float4*>(a.dout[net] + row * 4) = make_float4(v8[0], v8[1], v8[2], v8[3]);
-#pragma unroll
-        for (int p = 0; p < PN; ++p) atomicAdd(&s.gb3[p], d_o[p]);
+      for (int p = 0; p < PN; ++p) {
+        const float w = warp_sum(d_o[p]);
+        if ((tid & 31) == 0) atomicAdd(&s.gb3[p], w);
       }
-    }
-    __syncthreads();
-    // ---- 6. H2 tile (bf16) + mask bits --------------------------------------------------------------
-#pragma unroll 1
-    for (int c4 = 0; c4 < 4; ++c4) {
-      const int col0 = half * 128 + c4 * 32;
-      float v[32];
-      tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
-      uint32_t word = 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = fmaxf(v[j] + s.b2[col0 + j], 0.0f);
-        word |= (v[j] > 0.0f ? 1u : 0u) << j;
-      }
-      if (valid) a.mask[net][row * 8 + half * 4 + c4] = word;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    // ---- 7. gW3^T += H2^T * dOut ----------------------------------------------------------------------
+    // ---- 5. gW3^T += H2^T * dOut ----------------------------------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
@@ -194,32 +258,12 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     mbar_wait(&s.bar_mma[1], ph1);
     ph1 ^= 1;
     fence_after_sync();
-    // ---- 8. dZ2 tile ------------------------------------------------------------------------------------
-    {
-      float dr[PN];
-#pragma unroll
-      for (int p = 0; p < PN; ++p) dr[p] = s.dout[r][p];
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int col0 = half * 128 + c4 * 32;
-        float v[32];
-        tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool on = v[j] + s.b2[col0 + j] > 0.0f;
-          float g = 0.0f;
-#pragma unroll
-          for (int p = 0; p < PN; ++p) g = fmaf(dr[p], s.w3[p][col0 + j], g);
-          v[j] = on ? g : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
-      }
-    }
+    // ---- 6. dZ2 tile (from the mask words; no TMEM traffic) -----------------------------------------------------
+    dz2_to_tile<PN>(s, s.a_tile, mask2, r, half);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    // ---- 9. dH1 = dZ2 * W2 ; [., gb2] += dZ2^T * [obs, 1] ---------------------------------------------------
+    // ---- 7. dH1 = dZ2 * W2 ; [., gb2] += dZ2^T * [obs, 1] -----------------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
       issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, true, TILE, H, H,
@@ -233,32 +277,24 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     mbar_wait(&s.bar_mma[0], ph0);
     ph0 ^= 1;
     fence_after_sync();
-    // ---- 10. dZ1 tile (ReLU mask of layer 1 recomputed from the observation) ---------------------------------
-    {
-      float o[8];
-#pragma unroll
-      for (int d = 0; d < 8; ++d) o[d] = s.obs[d][r];
+    // ---- 8. dZ1 tile = dH1 masked by the layer-1 ReLU mask ------------------------------------------------------------
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int col0 = half * 128 + c4 * 32;
-        float v[32];
-        tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int col0 = half * 128 + c4 * 32;
+      float v[32];
+      tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
+      uint32_t word = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float h1 = s.b1[col0 + j];
+      for (int w = 0; w < 4; ++w) word = (c4 == w) ? mask1[w] : word;
 #pragma unroll
-          for (int d = 0; d < 8; ++d)
-            if (d < D) h1 = fmaf(o[d], s.w1t[d][col0 + j], h1);
-          v[j] = h1 > 0.0f ? v[j] : 0.0f;
-        }
+      for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] : 0.0f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
-      }
+      for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    // ---- 11. [gW1, gb1] += dZ1^T * [obs, 1] --------------------------------------------------------------------
+    // ---- 9. [gW1, gb1] += dZ1^T * [obs, 1] --------------------------------------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
@@ -290,6 +326,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       if (d < D) atomicAdd(a.gw1[net] + c * D + d, v[d]);
       if (d == D) atomicAdd(a.gb1[net] + c, v[d]);
     }
+    __syncthreads();
     if (tid < PN) atomicAdd(a.gb3[net] + tid, s.gb3[tid]);
   }
   __shared__ double red[32];
@@ -326,7 +363,7 @@ struct SmemW {
   float w3[kMaxPT][H];
   float obs[8][TILE];
   float dout[TILE][kMaxPT];
-  uint32_t mask[TILE][8];
+  int64_t row_idx[TILE];
   uint64_t bar_mma;
   uint32_t tmem_base;
 };
@@ -343,50 +380,19 @@ __device__ __forceinline__ void update_w_body(SmemW& s, const NetParams& np, con
   uint32_t ph = 0;
   int it = 0;
   for (int64_t tile = blockIdx.x >> 1; tile < ntiles; tile += nctas, ++it) {
-    for (int i = tid; i < 8 * TILE; i += blockDim.x) {
-      const int d = i / TILE, rr = i - d * TILE;
-      const int64_t rw = tile * TILE + rr;
-      float v = 0.0f;
-      if (d < D && rw < a.M) {
-        const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
-        const int64_t n = g / a.T, t = g - n * a.T;
-        v = a.obs[(t * D + d) * a.N + n];
-      }
-      s.obs[d][rr] = v;
+    const int64_t row = tile * TILE + r;
+    // mask words and dOut of this thread's row straight from the scratch (coalesced 16 B each)
+    uint4 mw = make_uint4(0u, 0u, 0u, 0u);
+    if (row < a.M) mw = *reinterpret_cast<const uint4*>(a.mask[net] + row * 8 + half * 4);
+    if (tid < TILE) {
+      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < a.M) d4 = *reinterpret_cast<const float4*>(a.dout[net] + row * 4);
+      *reinterpret_cast<float4*>(&s.dout[tid][0]) = d4;
     }
-    for (int i = tid; i < TILE * 8; i += blockDim.x) {
-      const int64_t rw = tile * TILE + (i >> 3);
-      s.mask[i >> 3][i & 7] = rw < a.M ? a.mask[net][rw * 8 + (i & 7)] : 0u;
-    }
-    for (int i = tid; i < TILE * kMaxPT; i += blockDim.x) {
-      const int64_t rw = tile * TILE + (i >> 2);
-      s.dout[i >> 2][i & 3] = rw < a.M ? a.dout[net][rw * 4 + (i & 3)] : 0.0f;
-    }
-    __syncthreads();
+    stage_rows(s, a, tile, D);  // ends with __syncthreads: s.dout visible too
     layer1_to_tile(s, D);
-    {
-      float dr[PN];
-#pragma unroll
-      for (int p = 0; p < PN; ++p) dr[p] = s.dout[r][p];
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int col0 = half * 128 + c4 * 32;
-        const uint32_t word = s.mask[r][half * 4 + c4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = col0 + 8 * k + e;
-            float g = 0.0f;
-#pragma unroll
-            for (int p = 0; p < PN; ++p) g = fmaf(dr[p], s.w3[p][j], g);
-            v[e] = ((word >> (8 * k + e)) & 1u) ? g : 0.0f;
-          }
-          store_chunk(s.dz_tile, chunk_offset<TILE>(r, col0 / 8 + k), v);
-        }
-      }
-    }
+    const uint32_t mask2[4] = {mw.x, mw.y, mw.z, mw.w};
+    dz2_to_tile<PN>(s, s.dz_tile, mask2, r, half);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
