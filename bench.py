@@ -295,15 +295,17 @@ def run_ours(a: argparse.Namespace) -> None:
     h2d = host_noise.numel() * 4
     d2h = 16 * 8 + algo2._loss_sums.numel() * 8
 
+    # ---- roofline of the update: every rank runs it (its collect() holds collectives) -------------
+    peaks = measured_peaks()
+    upd = update_roofline(algo, _lib, peaks, dtype, flush)
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- rooflines of the stream kernels + the update (rank 0) -----------------------------------
-    peaks = measured_peaks()
+    # ---- rooflines of the stream kernels (rank 0; no collectives) ----------------------------------
     roofs = stream_rooflines(lib, _lib, dev, peaks)
-    upd = update_roofline(algo, _lib, peaks, dtype, flush)
 
     line = {
         "metric": METRIC,

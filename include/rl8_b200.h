@@ -263,6 +263,15 @@ int rl8_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq
 int rl8_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K,
                     int a_mn_major, int b_mn_major, rl8_stream_t stream);
 
+/* D[128][N] = A[128][8] * B[N][8]^T through ONE kind::tf32 instruction (operands rounded to
+ * tf32, fp32 accumulate): the layer-1 contraction [obs, 1] * [W1, b1]^T of the tensor-core
+ * kernels.  N % 16 == 0, 16 <= N <= 256. */
+int rl8_tc_selftest_tf32(const float* A, const float* B, float* D, int32_t N, rl8_stream_t stream);
+
+/* out[128][128] = in[128][128] (32-bit words) through a tensor-memory store / load round trip
+ * (tcgen05.st / tcgen05.ld 32x32b.x32), as used to park packed bf16 activations in TMEM. */
+int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -474,7 +474,10 @@ class Algorithm:
         mb_launches = 34 if prec == _lib.PREC_FP32 else 4
         chunks = max(1, -(-M // 65536)) if prec == _lib.PREC_FP32 else 1
         for _ in range(hp.num_sgd_iters):
-            perm = torch.randperm(N * T, device=self.device) if hp.shuffle_minibatches else None
+            # A single minibatch is the whole buffer: its loss is a sum over all rows, so the
+            # reference's permutation (src/rl8/_utils.py:211-218) only reorders that sum.
+            shuffle = hp.shuffle_minibatches and hp.num_minibatches > 1
+            perm = torch.randperm(N * T, device=self.device) if shuffle else None
             for i in range(hp.num_minibatches):
                 step_this_batch = (i + 1) % accum == 0
                 rows = None if perm is None else perm[i * M : (i + 1) * M]

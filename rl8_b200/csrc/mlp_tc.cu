@@ -265,6 +265,89 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
   if (tid < 32) tmem_dealloc(tmem, 256);
 }
 
+// D[128][N] = A[128][8] * B[N][8]^T through kind::tf32 (one instruction, both operands K-major,
+// fp32 containers rounded onto the tf32 grid) -- the layer-1 contraction of the update kernels.
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_tf32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                        int N) {
+  __shared__ __align__(128) uint8_t a_tile[128 * 32];
+  __shared__ __align__(128) uint8_t b_tile[256 * 32];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&tmem_ptr, 256);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_ptr;
+  for (int i = tid; i < 128 * 8; i += blockDim.x) {
+    const int m = i >> 3, k = i & 7;
+    *reinterpret_cast<float*>(a_tile + m * 16 + (k >> 2) * (128 * 16) + (k & 3) * 4) = tf32_round(A[i]);
+  }
+  for (int i = tid; i < N * 8; i += blockDim.x) {
+    const int n = i >> 3, k = i & 7;
+    *reinterpret_cast<float*>(b_tile + n * 16 + (k >> 2) * (N * 16) + (k & 3) * 4) = tf32_round(B[i]);
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    fence_after_sync();
+    mma_tf32(tmem, smem_desc(smem_u32(a_tile), 128 * 16, 128), smem_desc(smem_u32(b_tile), N * 16, 128),
+             instr_desc_tf32(128, N), 0u);
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      for (int j = 0; j < 16; ++j) D[r * N + c0 + j] = v[j];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 256);
+}
+
+// TMEM round trip of raw 32-bit words next to a live accumulator: out[r][c] = in[r][c] for the
+// 32x32b.x32 store / load pair the update kernel parks its packed H1 copy with.
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_tmem_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x;
+  if (tid < 32) tmem_alloc(&tmem_ptr, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_ptr;
+  const int warp = tid >> 5;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    for (int j = 0; j < 32; ++j) v[j] = in[tid * 128 + c0 + j];
+    tmem_st32_raw(tmem + 256 + lane_base + (uint32_t)c0, v);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32_raw(tmem + 256 + lane_base + (uint32_t)c0, v);
+    for (int j = 0; j < 32; ++j) out[tid * 128 + c0 + j] = v[j];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 static int launch_forward(const NetParams& np, const RowMap& map, int64_t rows, float* out,
                           int tanh_col1, cudaStream_t st) {
@@ -351,4 +434,17 @@ extern "C" int rl8_tc_selftest(const float* A, const float* B, float* D, int32_t
   if (rc) return rc;
   tc_selftest_kernel<<<1, 256, bytes, (cudaStream_t)stream>>>(A, B, D, N, K, a_mn_major, b_mn_major);
   return check_launch("tc_selftest");
+}
+
+// Test hooks for the tf32 layer-1 instruction and the raw TMEM store / load pair.
+extern "C" int rl8_tc_selftest_tf32(const float* A, const float* B, float* D, int32_t N,
+                                    rl8_stream_t stream) {
+  if (!A || !B || !D || N < 16 || N > 256 || (N % 16)) return RL8_ERR_ARG;
+  tc_selftest_tf32_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(A, B, D, N);
+  return check_launch("tc_selftest_tf32");
+}
+extern "C" int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream) {
+  if (!in || !out) return RL8_ERR_ARG;
+  tc_selftest_tmem_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(in, out);
+  return check_launch("tc_selftest_tmem");
 }

@@ -73,6 +73,35 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- bulk async copy shared -> global (bulk-group completion; SASS: UBLKCP) -------------------
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// ... and have completed entirely (writes performed)
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// 128-bit vector reduction to global memory (sm_90+)
+__device__ __forceinline__ void red_add_v4(float* gptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -130,6 +159,49 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// raw 32-bit forms (packed bf16 pairs parked in TMEM next to the accumulators)
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32_raw(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (SWIZZLE_NONE, sm_100 version field = 1).
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -141,6 +213,31 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, 
   return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ |
          ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::tf32: fp32 containers in shared memory (10-bit mantissa used), K = 8 per instruction,
+// both operands K-major.  A 16-byte chunk holds 4 elements; the core matrix is still 8 rows x 16 B.
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+  return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// round-to-nearest (ties away) onto the tf32 grid: what the kernels store, so the tensor core
+// never sees mantissa bits it would drop
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA.
@@ -171,6 +268,25 @@ __device__ __forceinline__ uint32_t chunk_offset(int row, int col8 /* col / 8 */
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// relu + round-to-nearest pack of two floats (lo -> bits 0..15)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void store_chunk_relu(uint8_t* tile, uint32_t off, const float* v) {
+  uint4 q;
+  q.x = pack_relu_bf16x2(v[0], v[1]);
+  q.y = pack_relu_bf16x2(v[2], v[3]);
+  q.z = pack_relu_bf16x2(v[4], v[5]);
+  q.w = pack_relu_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + off) = q;
+}
+// 0xFFFF in each half whose bf16 value is > 0
+__device__ __forceinline__ uint32_t gt0_mask_bf16x2(uint32_t h) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&h);
+  return __hgt2_mask(v, __floats2bfloat162_rn(0.0f, 0.0f));
 }
 // store 8 consecutive columns of one row
 __device__ __forceinline__ void store_chunk(uint8_t* tile, uint32_t off, const float* v) {

@@ -1,32 +1,37 @@
 // PPO update on tensor cores (RL8_PREC_BF16): forward + clipped losses + hand-derived backward
-// of both default networks for one minibatch, as two persistent kernels.
+// of both default networks for one minibatch, as two persistent kernels per row chunk.
 //
-//   tc_update_h_kernel  ("activation" kernel; CTAs alternate between the policy and the value
-//     network, each with ITS W2 resident in smem).  Per 128-row tile:
-//       H1 (CUDA cores) -> MMA1  Z2 = H1 * W2^T            (K-major A, K-major B)
-//       heads + per-row PPO loss -> dOut                    (CUDA cores, fp32)
-//       H2 tile          -> MMA-G3  gW3^T += H2^T * dOut    (MN-major A, MN-major B, N = 8)
-//       dZ2 tile         -> MMA2  dH1 = dZ2 * W2            (K-major A, MN-major B: the SAME
-//                                                            W2 image read transposed)
-//                           MMA-Gb2 [.,gb2] += dZ2^T * [obs,1]
-//       dZ1 tile         -> MMA-G1  [gW1,gb1] += dZ1^T * [obs,1]
-//     The thin gradients (gW1, gb1, gb2, gW3) accumulate in TMEM over all tiles of the CTA and
-//     are flushed once.  The ReLU mask of layer 2 (256 bits / row) and dOut go to a small
-//     scratch (80 B / row / network) for the weight-gradient kernel.
-//   tc_update_w_kernel  ("weight" kernel).  gW2 needs a 256x256 fp32 accumulator = ALL 512 TMEM
-//     columns of an SM, so it cannot share an SM with the kernel above.  Per 128-row tile it
-//     recomputes H1 (K = D <= 8, cheap), rebuilds dZ2 from dOut and the mask bits, and issues
-//     gW2 += dZ2^T * H1 (both operands MN-major); accumulators stay in TMEM for the whole
-//     kernel and are flushed with one red.global.add per element.
+//   tc_update_h_kernel  ("activation" kernel, 16 warps; CTAs alternate between the policy and the
+//     value network, each with ITS W2 resident in smem).  Per 128-row tile, every contraction is
+//     a tcgen05.mma and the CUDA cores only convert, mask and evaluate the per-row loss:
+//       Z1  = [obs,1] * [W1,b1]^T          kind::tf32, K = 8 (one instruction)
+//       H1  = relu(Z1) -> bf16 tile (A operand) + a packed copy parked in TMEM for its mask
+//       Z2  = H1 * W2^T                     kind::f16 (bf16), K = 256
+//       H2  = relu(Z2 + b2) -> tile;  head dot products, per-row PPO loss -> dOut
+//       gW3^T += H2^T * dOut                thin GEMM (N = 16)
+//       dZ2 = [H2 > 0] .* (dOut * W3) -> tile -> one 64 KB bulk store to the dZ2 scratch
+//       dH1 = dZ2 * W2  (the SAME W2 image read MN-major);  [., gb2] += dZ2^T * [obs,1]
+//       dZ1 = [H1 > 0] .* dH1 -> tile;  [gW1, gb1] += dZ1^T * [obs,1]
+//     The thin gradients accumulate in TMEM over all tiles of the CTA and are flushed once.
+//   tc_update_w_kernel  ("weight" kernel).  gW2 = dZ2^T * H1 needs a 256x256 fp32 accumulator =
+//     all 512 TMEM columns, so each CTA owns HALF of the hidden units j of one network (256
+//     columns) and uses the other 256 columns to recompute Z1 -> H1 with the same tf32
+//     instruction (bit-identical to the activation kernel).  dZ2 half-tiles arrive by bulk
+//     async copy (double-buffered), so the loop is: TMA -> [tf32 MMA -> relu/pack epilogue]
+//     overlapped with the previous tile's gW2 MMAs.
 //
-// GEMM work per row and network: 3 x 256 x 256 MACs -- the minimum (forward, dH1, gW2); nothing
-// is recomputed on the tensor cores and no activation tile ever reaches HBM.
+// GEMM work per row and network: 3 x 256 x 256 MACs -- the minimum (forward, dH1, gW2).
+// Activations never reach HBM except the bf16 dZ2 tile (512 B / row / network, written once and
+// read once).
 #include "mlp_tc.cuh"
 #include "ppo_loss_math.cuh"
 
 namespace rl8 {
 
 using namespace tc;
+
+constexpr int kUpdThreads = 512;
+constexpr int64_t kChunkRows = 1 << 20;  // rows per kernel pair: bounds the dZ2 scratch at 1 GiB
 
 struct UpdArgs {
   const float* obs;      // [T+1][D][N]
@@ -35,300 +40,395 @@ struct UpdArgs {
   const float* adv;      // [T+1][N]
   const float* ret;      // [T+1][N]
   const int64_t* rows;   // minibatch row indices (n*T + t) or null
-  int64_t row_begin, M, N;
+  int64_t row_begin;     // first flattened row when rows == null
+  int64_t M;             // rows of the minibatch
+  int64_t row_off, Mc;   // this chunk: minibatch rows [row_off, row_off + Mc)
+  int64_t N;
+  int64_t slab_env0, slab_nenv;  // nenv > 0: order-free traversal t-major over envs [env0, env0+nenv)
   int T, dist_kind;
   rl8_ppo_hparams hp;
   float inv_denom;
-  uint32_t* mask[2];     // [M][8]   ReLU mask of layer 2, bit (j % 32) of word j / 32
-  float* dout[2];        // [M][4]   d(loss)/d(head outputs)
+  uint8_t* dz[2];        // [tiles of the chunk][64 KB] bf16 dZ2 tile images per network
   float *gw1[2], *gb1[2], *gw2[2], *gb2[2], *gw3[2], *gb3[2];
   double* sums;          // [5]
 };
 
+// Buffer index t*N + n of minibatch row `rw` (-1: past the minibatch).
+__device__ __forceinline__ int64_t row_to_idx(const UpdArgs& a, int64_t rw) {
+  if (rw >= a.M) return -1;
+  if (a.slab_nenv > 0) {
+    const int64_t t = rw / a.slab_nenv, n = a.slab_env0 + (rw - t * a.slab_nenv);
+    return t * a.N + n;
+  }
+  const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
+  const int64_t n = g / a.T, t = g - n * a.T;
+  return t * a.N + n;
+}
+
+// ---- shared pieces of both kernels -------------------------------------------------------------------
+// [W1 | b1] rounded to tf32, chunked fp32 [256 rows i][8]: off(i, d) = i*16 + (d/4)*4096 + (d%4)*4
+__device__ __forceinline__ void stage_w1aug(uint8_t* w1aug, const NetParams& np) {
+  for (int e = threadIdx.x; e < H * 8; e += blockDim.x) {
+    const int i = e >> 3, d = e & 7;
+    float v = 0.0f;
+    if (d < np.D) v = np.w1[i * np.D + d];
+    else if (d == np.D) v = np.b1[i];
+    *reinterpret_cast<float*>(w1aug + i * 16 + (d >> 2) * (H * 16) + (d & 3) * 4) = tf32_round(v);
+  }
+}
+
+// The two [obs, 1] slots (d = dsel, dsel + 4) of row rr this thread stages; loaded a tile ahead.
+struct ObsRegs {
+  float v0, v1;
+};
+__device__ __forceinline__ ObsRegs load_obs(const UpdArgs& a, int64_t idx, int D) {
+  const int d0 = threadIdx.x >> 7;  // 0..3
+  ObsRegs o;
+  o.v0 = d0 == D ? 1.0f : 0.0f;
+  o.v1 = d0 + 4 == D ? 1.0f : 0.0f;
+  if (idx >= 0) {
+    const int64_t t = idx / a.N, n = idx - t * a.N;
+    const float* base = a.obs + t * (int64_t)D * a.N + n;
+    if (d0 < D) o.v0 = __ldg(base + (int64_t)d0 * a.N);
+    if (d0 + 4 < D) o.v1 = __ldg(base + (int64_t)(d0 + 4) * a.N);
+  }
+  return o;
+}
+// aug32: fp32 (tf32-rounded) chunked [128 rows][8]: off(r, d) = r*16 + (d/4)*2048 + (d%4)*4
+__device__ __forceinline__ void store_aug32(uint8_t* aug32, const ObsRegs& o) {
+  const int rr = threadIdx.x & (TILE - 1), d0 = threadIdx.x >> 7;
+  *reinterpret_cast<float*>(aug32 + rr * 16 + d0 * 4) = tf32_round(o.v0);
+  *reinterpret_cast<float*>(aug32 + rr * 16 + TILE * 16 + d0 * 4) = tf32_round(o.v1);
+}
+
+__device__ __forceinline__ void issue_z1(uint32_t d_tmem, const uint8_t* aug32, const uint8_t* w1aug) {
+  mma_tf32(d_tmem, smem_desc(smem_u32(aug32), TILE * 16, 128), smem_desc(smem_u32(w1aug), H * 16, 128),
+           instr_desc_tf32(TILE, H), 0u);
+}
+
+// H1 = relu(Z1) of this thread's row and its 64 columns [64*cq, 64*cq + 64): bf16 chunks into
+// `tile`, packed pairs into hp[32].
+__device__ __forceinline__ void h1_epilogue(uint32_t z1_taddr /* lane + column base */, int r, int cq,
+                                            uint8_t* tile, uint32_t* hp) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v[32];
+    tmem_ld32(z1_taddr + (uint32_t)(cq * 64 + h * 32), v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 q;
+      q.x = pack_relu_bf16x2(v[8 * k + 0], v[8 * k + 1]);
+      q.y = pack_relu_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+      q.z = pack_relu_bf16x2(v[8 * k + 4], v[8 * k + 5]);
+      q.w = pack_relu_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+      hp[h * 16 + k * 4 + 0] = q.x, hp[h * 16 + k * 4 + 1] = q.y;
+      hp[h * 16 + k * 4 + 2] = q.z, hp[h * 16 + k * 4 + 3] = q.w;
+      *reinterpret_cast<uint4*>(tile + chunk_offset<TILE>(r, cq * 8 + h * 4 + k)) = q;
+    }
+  }
+}
+
+// ---- activation kernel ---------------------------------------------------------------------------------
 struct SmemH {
-  uint8_t w2[kW2Bytes];
-  uint8_t a_tile[kTileBytes];
-  float w1t[8][H];
-  float b1[H], b2[H];
-  float w3[kMaxPT][H];
-  float obs[8][TILE];
-  float part[2][TILE][kMaxPT];
-  float dout[TILE][kMaxPT];
-  uint8_t dout_tile[TILE * 16];  // bf16 [r][8]: MN-major B operand (N = 8)
-  uint8_t aug_tile[TILE * 16];   // bf16 [r][8] = [obs_0..obs_{D-1}, 1, 0..]
-  int64_t row_idx[TILE];         // t*N + n of the tile's rows (-1: past the minibatch)
+  uint8_t w2[kW2Bytes];        // 131072
+  uint8_t a_tile[kTileBytes];  //  65536  H1 -> H2 -> dZ2 -> dZ1
+  uint8_t w1aug[H * 32];       //   8192
+  uint8_t aug32[TILE * 32];    //   4096  tf32 [obs, 1] (A of the layer-1 MMA)
+  uint8_t aug16[TILE * 32];    //   4096  bf16 [r][16] = [obs, 1, 0..] (B of the thin GEMMs)
+  uint8_t dout16[TILE * 32];   //   4096  bf16 [r][16] = [dOut, 0..]
+  float b2[H];                 //   1024
+  float w3[kMaxPT][H];         //   4096
+  float part[3][TILE][kMaxPT]; //   6144  head partial sums of column quarters 1..3
+  float dout[TILE][kMaxPT];    //   2048
   float gb3[kMaxPT];
   uint64_t bar_w, bar_mma[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(SmemH) + 1024 <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
+static_assert(sizeof(SmemH) + 512 <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
 
-// TMEM columns of kernel H
-constexpr uint32_t kColMain = 0, kColG3 = 256, kColGb2 = 320, kColG1 = 384;  // +32 per 128-block
-
-// Stage the tile's row indices and observations (gathered through the minibatch row list).
-template <class S>
-__device__ __forceinline__ void stage_rows(S& s, const UpdArgs& a, int64_t tile, int D) {
-  const int tid = threadIdx.x;
-  if (tid < TILE) {
-    const int64_t rw = tile * TILE + tid;
-    int64_t idx = -1;
-    if (rw < a.M) {
-      const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
-      const int64_t n = g / a.T, t = g - n * a.T;
-      idx = t * a.N + n;
-    }
-    s.row_idx[tid] = idx;
-  }
-  __syncthreads();
-  for (int i = tid; i < 8 * TILE; i += blockDim.x) {
-    const int d = i / TILE, rr = i - d * TILE;
-    const int64_t idx = s.row_idx[rr];
-    float v = 0.0f;
-    if (d < D && idx >= 0) {
-      const int64_t t = idx / a.N, n = idx - t * a.N;
-      v = a.obs[(t * D + d) * a.N + n];
-    }
-    s.obs[d][rr] = v;
-  }
-  __syncthreads();
-}
-
-// dZ2 chunks of this thread's 128 columns from the layer-2 ReLU mask words and dOut:
-// dz2[r][j] = mask ? sum_p dout[r][p] * w3[p][j] : 0  -> bf16 chunks in `tile`.
-template <int PN, class S>
-__device__ __forceinline__ void dz2_to_tile(S& s, uint8_t* tile, const uint32_t* mask_words, int r,
-                                            int half) {
-  float dr[PN];
-#pragma unroll
-  for (int p = 0; p < PN; ++p) dr[p] = s.dout[r][p];
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    const uint32_t word = mask_words[w];
-    const int col0 = half * 128 + w * 32;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int p = 0; p < PN; ++p) {
-        const float4 wa = *reinterpret_cast<const float4*>(&s.w3[p][col0 + 8 * k]);
-        const float4 wb = *reinterpret_cast<const float4*>(&s.w3[p][col0 + 8 * k + 4]);
-        v[0] = fmaf(dr[p], wa.x, v[0]), v[1] = fmaf(dr[p], wa.y, v[1]);
-        v[2] = fmaf(dr[p], wa.z, v[2]), v[3] = fmaf(dr[p], wa.w, v[3]);
-        v[4] = fmaf(dr[p], wb.x, v[4]), v[5] = fmaf(dr[p], wb.y, v[5]);
-        v[6] = fmaf(dr[p], wb.z, v[6]), v[7] = fmaf(dr[p], wb.w, v[7]);
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = ((word >> (8 * k + e)) & 1u) ? v[e] : 0.0f;
-      store_chunk(tile, chunk_offset<TILE>(r, col0 / 8 + k), v);
-    }
-  }
-}
+// TMEM columns of the activation kernel
+constexpr uint32_t kColMain = 0;     // 256: Z1 / Z2 / dH1
+constexpr uint32_t kColH1 = 256;     // 128: packed bf16 H1 (for the layer-1 ReLU mask)
+constexpr uint32_t kColThin = 384;   // 6 x 16: gW3, gb2, [gW1 gb1], two 128-unit blocks each
+constexpr int kThinN = 16;
 
 template <int PN, bool POLICY>
-__device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, const UpdArgs& a,
-                                              int net) {
+__device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, const UpdArgs& a, int net) {
   const uint32_t tmem = s.tmem_base;
   const int tid = threadIdx.x;
-  const int r = tid & (TILE - 1), half = tid >> 7, q = (tid >> 5) & 3;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cq = warp >> 2;
+  const int r = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const int D = np.D;
-  const int64_t ntiles = (a.M + TILE - 1) / TILE;
+  const int64_t ntiles = (a.Mc + TILE - 1) / TILE;
   const int nctas = gridDim.x >> 1;
   float b3[PN];
 #pragma unroll
   for (int p = 0; p < PN; ++p) b3[p] = np.b3[p];
-  if (tid < kMaxPT) s.gb3[tid] = 0.0f;
   double s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;
   uint32_t ph0 = 0, ph1 = 0;
   int it = 0;
   const bool continuous = POLICY && a.dist_kind != RL8_DIST_CATEGORICAL;
 
-  for (int64_t tile = blockIdx.x >> 1; tile < ntiles; tile += nctas, ++it) {
-    const int64_t row = tile * TILE + r;
-    const bool valid = row < a.M;
-    // ---- 1. rows, observations, [obs, 1] operand tile ------------------------------------------
-    stage_rows(s, a, tile, D);
-    if (tid < TILE) {
-      float v[8];
-#pragma unroll
-      for (int d = 0; d < 8; ++d) v[d] = d < D ? s.obs[d][tid] : (d == D ? 1.0f : 0.0f);
-      store_chunk(s.aug_tile, (uint32_t)tid * 16u, v);
+  // prefetch of the first tile
+  int64_t tile = blockIdx.x >> 1;
+  int64_t idx_next = tile < ntiles ? row_to_idx(a, a.row_off + tile * TILE + (tid & (TILE - 1))) : -1;
+  ObsRegs obs_next = load_obs(a, idx_next, D);
+
+  for (; tile < ntiles; tile += nctas, ++it) {
+    // ---- A. operands of this tile: [obs, 1] in tf32 and bf16 ----------------------------------------------
+    const int64_t idx = idx_next;  // of row (tid & 127)
+    store_aug32(s.aug32, obs_next);
+    {
+      const int rr = tid & (TILE - 1), d0 = tid >> 7;
+      __nv_bfloat16* row16 = reinterpret_cast<__nv_bfloat16*>(s.aug16 + rr * 16);
+      row16[d0] = __float2bfloat16(obs_next.v0);
+      row16[d0 + 4] = __float2bfloat16(obs_next.v1);
     }
-    // ---- 2. H1 (keeps the layer-1 ReLU mask in registers) -> MMA1 ----------------------------------
-    uint32_t mask1[4], mask2[4];
-    layer1_to_tile(s, D, mask1);
+    // per-row loss inputs (threads 0..127), in flight until phase E
+    float in_act = 0.0f, in_logp = 0.0f, in_tgt = 0.0f;
+    if (tid < TILE && idx >= 0) {
+      if constexpr (POLICY) {
+        in_act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)((const long long*)a.actions)[idx]
+                                                     : ((const float*)a.actions)[idx];
+        in_logp = a.logp[idx];
+        in_tgt = a.adv[idx];
+      } else {
+        in_tgt = a.ret[idx];
+      }
+    }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
-      issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H,
-                 H, false);
+      issue_z1(tmem + kColMain, s.aug32, s.w1aug);
       mma_commit(&s.bar_mma[0]);
+    }
+    // ---- B. prefetch the next tile while the tensor core works ----------------------------------------------
+    {
+      const int64_t nt = tile + nctas;
+      idx_next = nt < ntiles ? row_to_idx(a, a.row_off + nt * TILE + (tid & (TILE - 1))) : -1;
+      obs_next = load_obs(a, idx_next, D);
     }
     mbar_wait(&s.bar_mma[0], ph0);
     ph0 ^= 1;
     fence_after_sync();
-    // ---- 3. one pass over Z2: head partial sums, H2 tile (bf16), layer-2 mask ----------------------
+    // ---- C. H1 tile + packed copy in TMEM -> Z2 = H1 * W2^T -----------------------------------------------------
     {
-      float dot[PN];
+      uint32_t hp[32];
+      h1_epilogue(tmem + kColMain + lane_base, r, cq, s.a_tile, hp);
+      tmem_st32_raw(tmem + kColH1 + lane_base + (uint32_t)(cq * 32), hp);
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H,
+                 false);
+      mma_commit(&s.bar_mma[1]);
+    }
+    mbar_wait(&s.bar_mma[1], ph1);
+    ph1 ^= 1;
+    fence_after_sync();
+    // ---- D. one pass over Z2: H2 tile (bf16) and head partial sums -----------------------------------------------
+    float dot[PN];
 #pragma unroll
-      for (int p = 0; p < PN; ++p) dot[p] = 0.0f;
+    for (int p = 0; p < PN; ++p) dot[p] = 0.0f;
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int col0 = half * 128 + c4 * 32;
-        float v[32];
-        tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
-        uint32_t word = 0;
+    for (int h = 0; h < 2; ++h) {
+      const int col0 = cq * 64 + h * 32;
+      float v[32];
+      tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + j]);
-          v[j] = fmaxf(v[j] + b.x, 0.0f), v[j + 1] = fmaxf(v[j + 1] + b.y, 0.0f);
-          v[j + 2] = fmaxf(v[j + 2] + b.z, 0.0f), v[j + 3] = fmaxf(v[j + 3] + b.w, 0.0f);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + j]);
+        v[j] = fmaxf(v[j] + b.x, 0.0f), v[j + 1] = fmaxf(v[j + 1] + b.y, 0.0f);
+        v[j + 2] = fmaxf(v[j + 2] + b.z, 0.0f), v[j + 3] = fmaxf(v[j + 3] + b.w, 0.0f);
 #pragma unroll
-          for (int p = 0; p < PN; ++p) {
-            const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + j]);
-            dot[p] = fmaf(v[j], w.x, dot[p]);
-            dot[p] = fmaf(v[j + 1], w.y, dot[p]);
-            dot[p] = fmaf(v[j + 2], w.z, dot[p]);
-            dot[p] = fmaf(v[j + 3], w.w, dot[p]);
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) word |= (v[j + e] > 0.0f ? 1u : 0u) << (j + e);
+        for (int p = 0; p < PN; ++p) {
+          const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + j]);
+          dot[p] = fmaf(v[j], w.x, dot[p]);
+          dot[p] = fmaf(v[j + 1], w.y, dot[p]);
+          dot[p] = fmaf(v[j + 2], w.z, dot[p]);
+          dot[p] = fmaf(v[j + 3], w.w, dot[p]);
         }
-        mask2[c4] = word;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
       }
 #pragma unroll
-      for (int p = 0; p < PN; ++p) s.part[half][r][p] = dot[p];
-      if (valid)
-        *reinterpret_cast<uint4*>(a.mask[net] + row * 8 + half * 4) =
-            make_uint4(mask2[0], mask2[1], mask2[2], mask2[3]);
+      for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
+    }
+    if (cq > 0) {
+#pragma unroll
+      for (int p = 0; p < PN; ++p) s.part[cq - 1][r][p] = dot[p];
     }
     __syncthreads();
-    // ---- 4. per-row loss -> dOut ---------------------------------------------------------------------------
+    // ---- E. per-row loss -> dOut (threads 0..127 own row tid and column quarter 0) -------------------------------------
     if (tid < TILE) {
       float o[PN], d_o[PN];
 #pragma unroll
-      for (int p = 0; p < PN; ++p) o[p] = s.part[0][tid][p] + s.part[1][tid][p] + b3[p];
+      for (int p = 0; p < PN; ++p)
+        o[p] = ((dot[p] + s.part[0][tid][p]) + s.part[1][tid][p]) + s.part[2][tid][p] + b3[p];
 #pragma unroll
       for (int p = 0; p < PN; ++p) d_o[p] = 0.0f;
-      if (valid) {
-        const int64_t idx = s.row_idx[tid];
+      if (idx >= 0) {
         RowLoss L;
         if constexpr (POLICY) {
           if (continuous) o[1] = tanhf(o[1]);
-          const float act = a.dist_kind == RL8_DIST_CATEGORICAL
-                                ? (float)((const long long*)a.actions)[idx]
-                                : ((const float*)a.actions)[idx];
-          ppo_policy_row<PN>(a.dist_kind, o, act, a.logp[idx], a.adv[idx], a.hp, a.inv_denom, d_o, L);
+          ppo_policy_row<PN>(a.dist_kind, o, in_act, in_logp, in_tgt, a.hp, a.inv_denom, d_o, L);
           s_ent += L.entropy, s_pol += L.policy, s_kl += L.kl;
         } else {
-          ppo_value_row(o[0], a.ret[idx], a.hp, a.inv_denom, d_o, L);
+          ppo_value_row(o[0], in_tgt, a.hp, a.inv_denom, d_o, L);
           s_vf += L.vf;
         }
       }
       float v8[8];
 #pragma unroll
       for (int p = 0; p < 8; ++p) v8[p] = p < PN ? d_o[p] : 0.0f;
-      store_chunk(s.dout_tile, (uint32_t)tid * 16u, v8);
+      store_chunk(s.dout16, (uint32_t)tid * 16u, v8);
       *reinterpret_cast<float4*>(&s.dout[tid][0]) = make_float4(v8[0], v8[1], v8[2], v8[3]);
-      if (valid) *reinterpret_cast<float4*>(a.dout[net] + row * 4) = make_float4(v8[0], v8[1], v8[2], v8[3]);
       // gb3 += sum_r dOut: one shared atomic per warp
 #pragma unroll
       for (int p = 0; p < PN; ++p) {
         const float w = warp_sum(d_o[p]);
-        if ((tid & 31) == 0) atomicAdd(&s.gb3[p], w);
+        if (lane == 0) atomicAdd(&s.gb3[p], w);
       }
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    // ---- 5. gW3^T += H2^T * dOut ----------------------------------------------------------------------------
+    // ---- F. gW3^T += H2^T * dOut ---------------------------------------------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb)
-        issue_gemm(tmem + kColG3 + 32 * jb, smem_u32(s.a_tile) + jb * 32768, TILE, true,
-                   smem_u32(s.dout_tile), TILE, true, TILE, 8, TILE, it > 0);
-      mma_commit(&s.bar_mma[1]);
+        issue_gemm(tmem + kColThin + kThinN * jb, smem_u32(s.a_tile) + jb * 32768, TILE, true,
+                   smem_u32(s.dout16), TILE, true, TILE, kThinN, TILE, it > 0);
+      mma_commit(&s.bar_mma[0]);
     }
-    mbar_wait(&s.bar_mma[1], ph1);
-    ph1 ^= 1;
-    fence_after_sync();
-    // ---- 6. dZ2 tile (from the mask words; no TMEM traffic) -----------------------------------------------------
-    dz2_to_tile<PN>(s, s.a_tile, mask2, r, half);
+    // ---- G. dZ2 = [H2 > 0] .* (dOut * W3), in place over H2 -----------------------------------------------------------------
+    {
+      float dr[PN];
+      {
+        const float4 d4 = *reinterpret_cast<const float4*>(&s.dout[r][0]);
+        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int p = 0; p < PN; ++p) dr[p] = dd[p];
+      }
+      mbar_wait(&s.bar_mma[0], ph0);  // the thin GEMM has read H2
+      ph0 ^= 1;
+      fence_after_sync();
+#pragma unroll 2
+      for (int c = 0; c < 8; ++c) {
+        const int cc = cq * 8 + c;
+        uint8_t* slot = s.a_tile + chunk_offset<TILE>(r, cc);
+        const uint4 h2 = *reinterpret_cast<const uint4*>(slot);
+        float g[8];
+        {
+          const float4 wa = *reinterpret_cast<const float4*>(&s.w3[0][cc * 8]);
+          const float4 wb = *reinterpret_cast<const float4*>(&s.w3[0][cc * 8 + 4]);
+          g[0] = dr[0] * wa.x, g[1] = dr[0] * wa.y, g[2] = dr[0] * wa.z, g[3] = dr[0] * wa.w;
+          g[4] = dr[0] * wb.x, g[5] = dr[0] * wb.y, g[6] = dr[0] * wb.z, g[7] = dr[0] * wb.w;
+        }
+#pragma unroll
+        for (int p = 1; p < PN; ++p) {
+          const float4 wa = *reinterpret_cast<const float4*>(&s.w3[p][cc * 8]);
+          const float4 wb = *reinterpret_cast<const float4*>(&s.w3[p][cc * 8 + 4]);
+          g[0] = fmaf(dr[p], wa.x, g[0]), g[1] = fmaf(dr[p], wa.y, g[1]);
+          g[2] = fmaf(dr[p], wa.z, g[2]), g[3] = fmaf(dr[p], wa.w, g[3]);
+          g[4] = fmaf(dr[p], wb.x, g[4]), g[5] = fmaf(dr[p], wb.y, g[5]);
+          g[6] = fmaf(dr[p], wb.z, g[6]), g[7] = fmaf(dr[p], wb.w, g[7]);
+        }
+        uint4 o4;
+        o4.x = pack_bf16x2(g[0], g[1]) & gt0_mask_bf16x2(h2.x);
+        o4.y = pack_bf16x2(g[2], g[3]) & gt0_mask_bf16x2(h2.y);
+        o4.z = pack_bf16x2(g[4], g[5]) & gt0_mask_bf16x2(h2.z);
+        o4.w = pack_bf16x2(g[6], g[7]) & gt0_mask_bf16x2(h2.w);
+        *reinterpret_cast<uint4*>(slot) = o4;
+      }
+    }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    // ---- 7. dH1 = dZ2 * W2 ; [., gb2] += dZ2^T * [obs, 1] -----------------------------------------------------------
+    // ---- H. dZ2 tile -> scratch;  dH1 = dZ2 * W2;  [., gb2] += dZ2^T * [obs, 1] -----------------------------------------------
     if (tid == 0) {
       fence_after_sync();
+      uint8_t* dst = a.dz[net] + tile * (int64_t)kTileBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bulk_s2g(dst + i * 16384, s.a_tile + i * 16384, 16384);
+      bulk_commit();
       issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, true, TILE, H, H,
                  false);
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb)
-        issue_gemm(tmem + kColGb2 + 32 * jb, smem_u32(s.a_tile) + jb * 32768, TILE, true,
-                   smem_u32(s.aug_tile), TILE, true, TILE, 8, TILE, it > 0);
-      mma_commit(&s.bar_mma[0]);
-    }
-    mbar_wait(&s.bar_mma[0], ph0);
-    ph0 ^= 1;
-    fence_after_sync();
-    // ---- 8. dZ1 tile = dH1 masked by the layer-1 ReLU mask ------------------------------------------------------------
-#pragma unroll 1
-    for (int c4 = 0; c4 < 4; ++c4) {
-      const int col0 = half * 128 + c4 * 32;
-      float v[32];
-      tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
-      uint32_t word = 0;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) word = (c4 == w) ? mask1[w] : word;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] : 0.0f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    // ---- 9. [gW1, gb1] += dZ1^T * [obs, 1] --------------------------------------------------------------------------------
-    if (tid == 0) {
-      fence_after_sync();
-#pragma unroll
-      for (int ib = 0; ib < 2; ++ib)
-        issue_gemm(tmem + kColG1 + 32 * ib, smem_u32(s.a_tile) + ib * 32768, TILE, true,
-                   smem_u32(s.aug_tile), TILE, true, TILE, 8, TILE, it > 0);
+        issue_gemm(tmem + kColThin + kThinN * (2 + jb), smem_u32(s.a_tile) + jb * 32768, TILE, true,
+                   smem_u32(s.aug16), TILE, true, TILE, kThinN, TILE, it > 0);
       mma_commit(&s.bar_mma[1]);
+      bulk_wait_read();  // the store engine has read the tile
     }
     mbar_wait(&s.bar_mma[1], ph1);
     ph1 ^= 1;
     fence_after_sync();
+    __syncthreads();  // thread 0's bulk_wait_read precedes every overwrite of the tile
+    // ---- I. dZ1 = [H1 > 0] .* dH1 ------------------------------------------------------------------------------------------------
+    {
+      uint32_t hp[32];
+      tmem_ld32_raw(tmem + kColH1 + lane_base + (uint32_t)(cq * 32), hp);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tmem_ld32(tmem + kColMain + lane_base + (uint32_t)(cq * 64 + h * 32), v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 o4;
+          o4.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 0]);
+          o4.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 1]);
+          o4.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 2]);
+          o4.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 3]);
+          *reinterpret_cast<uint4*>(s.a_tile + chunk_offset<TILE>(r, cq * 8 + h * 4 + k)) = o4;
+        }
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- J. [gW1, gb1] += dZ1^T * [obs, 1] ---------------------------------------------------------------------------------------
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int ib = 0; ib < 2; ++ib)
+        issue_gemm(tmem + kColThin + kThinN * (4 + ib), smem_u32(s.a_tile) + ib * 32768, TILE, true,
+                   smem_u32(s.aug16), TILE, true, TILE, kThinN, TILE, it > 0);
+      mma_commit(&s.bar_mma[0]);
+    }
+    mbar_wait(&s.bar_mma[0], ph0);  // tile, aug16 and aug32 are free again
+    ph0 ^= 1;
+    fence_after_sync();
   }
+  if (tid == 0) bulk_wait_all();  // dZ2 stores have landed before the kernel ends
 
-  // ---- flush the thin gradients (threads: warps 0-3 -> block 0, warps 4-7 -> block 1) ------------------------
-  if (it > 0) {
-    const int blk = half;
-    const int c = blk * 128 + q * 32 + (tid & 31);  // hidden unit of this thread
+  // ---- flush the thin gradients (warps 0-3 -> units 0..127, warps 4-7 -> units 128..255) ---------------------------------
+  if (it > 0 && warp < 8) {
+    const int blk = warp >> 2;
+    const int c = blk * 128 + q * 32 + lane;  // hidden unit of this thread
     float v[8];
-    tmem_ld8(tmem + kColG3 + 32 * blk + lane_base, v);
+    tmem_ld8(tmem + kColThin + kThinN * blk + lane_base, v);
 #pragma unroll
     for (int p = 0; p < PN; ++p) atomicAdd(a.gw3[net] + p * H + c, v[p]);
-    tmem_ld8(tmem + kColGb2 + 32 * blk + lane_base, v);
+    tmem_ld8(tmem + kColThin + kThinN * (2 + blk) + lane_base, v);
 #pragma unroll
     for (int d = 0; d < 8; ++d)
       if (d == D) atomicAdd(a.gb2[net] + c, v[d]);
-    tmem_ld8(tmem + kColG1 + 32 * blk + lane_base, v);
+    tmem_ld8(tmem + kColThin + kThinN * (4 + blk) + lane_base, v);
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
       if (d < D) atomicAdd(a.gw1[net] + c * D + d, v[d]);
       if (d == D) atomicAdd(a.gb1[net] + c, v[d]);
     }
-    __syncthreads();
-    if (tid < PN) atomicAdd(a.gb3[net] + tid, s.gb3[tid]);
   }
+  __syncthreads();
+  if (it > 0 && tid < PN) atomicAdd(a.gb3[net] + tid, s.gb3[tid]);
   __shared__ double red[32];
   double sv[4] = {s_ent, s_pol, s_vf, s_kl};
 #pragma unroll
@@ -336,119 +436,173 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     const double t = block_sum(sv[i], red);
     if (tid == 0 && t != 0.0) atomicAdd(a.sums + i, t);
   }
-  if (blockIdx.x == 0 && tid == 0) atomicAdd(a.sums + 4, (double)a.M);
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(a.sums + 4, (double)a.Mc);
 }
 
 template <int P>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kUpdThreads, 1)
 tc_update_h_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemH& s = *reinterpret_cast<SmemH*>(smem_raw);
   const int net = blockIdx.x & 1;
   const NetParams np = net ? np_vf : np_pi;
-  cta_setup(s, np, 512);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&s.bar_w, 1);
+    mbar_init(&s.bar_mma[0], 1);
+    mbar_init(&s.bar_mma[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&s.bar_w, kW2Bytes);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      bulk_g2s(s.w2 + i * (kW2Bytes / 8), np.w2_img + i * (kW2Bytes / 8), kW2Bytes / 8, &s.bar_w);
+  }
+  stage_w1aug(s.w1aug, np);
+  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  for (int i = tid; i < TILE * 32 / 4; i += blockDim.x) {
+    reinterpret_cast<uint32_t*>(s.aug16)[i] = 0u;
+    reinterpret_cast<uint32_t*>(s.dout16)[i] = 0u;
+  }
+  if (tid < kMaxPT) s.gb3[tid] = 0.0f;
+  __syncthreads();
+  mbar_wait(&s.bar_w, 0);
   if (net == 0) update_h_body<P, true>(s, np, a, 0);
   else update_h_body<1, false>(s, np, a, 1);
   fence_before_sync();
   __syncthreads();
-  if (threadIdx.x < 32) tmem_dealloc(s.tmem_base, 512);
+  if (tid < 32) tmem_dealloc(s.tmem_base, 512);
 }
 
 // ---- weight-gradient kernel -----------------------------------------------------------------------------------
 struct SmemW {
-  uint8_t a_tile[kTileBytes];   // H1 tile   (MN-major B: rows = K = r, cols = i)
-  uint8_t dz_tile[kTileBytes];  // dZ2 tile  (MN-major A: rows = K = r, cols = j)
-  float w1t[8][H];
-  float b1[H];
-  float w3[kMaxPT][H];
-  float obs[8][TILE];
-  float dout[TILE][kMaxPT];
-  int64_t row_idx[TILE];
-  uint64_t bar_mma;
+  uint8_t h1_tile[2][kTileBytes];      // 131072  H1 tiles (MN-major B: rows = K = r, cols = i)
+  uint8_t dz_tile[2][kTileBytes / 2];  //  65536  dZ2 half tiles (MN-major A: rows = K = r, cols = 128 units j)
+  uint8_t w1aug[H * 32];               //   8192
+  uint8_t aug32[2][TILE * 32];         //   8192
+  uint64_t bar_tma[2], bar_z, bar_g[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(SmemW) <= 227 * 1024, "SmemW exceeds the 227 KB CTA limit");
+static_assert(sizeof(SmemW) + 512 <= 227 * 1024, "SmemW exceeds the 227 KB CTA limit");
 
-template <int PN>
-__device__ __forceinline__ void update_w_body(SmemW& s, const NetParams& np, const UpdArgs& a, int net) {
-  const uint32_t tmem = s.tmem_base;
+// grid: blockIdx & 1 = network, (blockIdx >> 1) & 1 = half of the hidden units j, blockIdx >> 2 = CTA of the role
+__global__ void __launch_bounds__(kUpdThreads, 1)
+tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemW& s = *reinterpret_cast<SmemW*>(smem_raw);
+  const int net = blockIdx.x & 1, jh = (blockIdx.x >> 1) & 1;
+  const NetParams np = net ? np_vf : np_pi;
   const int tid = threadIdx.x;
-  const int r = tid & (TILE - 1), half = tid >> 7, q = (tid >> 5) & 3;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cq = warp >> 2;
+  const int r = q * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const int D = np.D;
-  const int64_t ntiles = (a.M + TILE - 1) / TILE;
-  const int nctas = gridDim.x >> 1;
-  uint32_t ph = 0;
-  int it = 0;
-  for (int64_t tile = blockIdx.x >> 1; tile < ntiles; tile += nctas, ++it) {
-    const int64_t row = tile * TILE + r;
-    // mask words and dOut of this thread's row straight from the scratch (coalesced 16 B each)
-    uint4 mw = make_uint4(0u, 0u, 0u, 0u);
-    if (row < a.M) mw = *reinterpret_cast<const uint4*>(a.mask[net] + row * 8 + half * 4);
-    if (tid < TILE) {
-      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < a.M) d4 = *reinterpret_cast<const float4*>(a.dout[net] + row * 4);
-      *reinterpret_cast<float4*>(&s.dout[tid][0]) = d4;
+  if (tid == 0) {
+    mbar_init(&s.bar_tma[0], 1);
+    mbar_init(&s.bar_tma[1], 1);
+    mbar_init(&s.bar_z, 1);
+    mbar_init(&s.bar_g[0], 1);
+    mbar_init(&s.bar_g[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
+  stage_w1aug(s.w1aug, np);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  constexpr uint32_t kColG = 0, kColZ = 256;
+
+  const int64_t ntiles = (a.Mc + TILE - 1) / TILE;
+  const int nctas = gridDim.x >> 2;
+  const int64_t tile0 = blockIdx.x >> 2;
+  const int64_t n_my = tile0 < ntiles ? (ntiles - tile0 + nctas - 1) / nctas : 0;
+  const uint8_t* dz_src = a.dz[net] + (int64_t)jh * (kTileBytes / 2);
+
+  auto tma_load = [&](int64_t k) {  // thread 0
+    const int st = (int)(k & 1);
+    const uint8_t* src = dz_src + (tile0 + k * nctas) * (int64_t)kTileBytes;
+    mbar_expect_tx(&s.bar_tma[st], kTileBytes / 2);
+    bulk_g2s(s.dz_tile[st], src, 16384, &s.bar_tma[st]);
+    bulk_g2s(s.dz_tile[st] + 16384, src + 16384, 16384, &s.bar_tma[st]);
+  };
+
+  if (n_my > 0) {
+    {
+      const int64_t idx = row_to_idx(a, a.row_off + tile0 * TILE + (tid & (TILE - 1)));
+      store_aug32(s.aug32[0], load_obs(a, idx, D));
     }
-    stage_rows(s, a, tile, D);  // ends with __syncthreads: s.dout visible too
-    layer1_to_tile(s, D);
-    const uint32_t mask2[4] = {mw.x, mw.y, mw.z, mw.w};
-    dz2_to_tile<PN>(s, s.dz_tile, mask2, r, half);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
-#pragma unroll
-      for (int jb = 0; jb < 2; ++jb)
-        issue_gemm(tmem + 256 * jb, smem_u32(s.dz_tile) + jb * 32768, TILE, true, smem_u32(s.a_tile),
-                   TILE, true, TILE, H, TILE, it > 0);
-      mma_commit(&s.bar_mma);
+      tma_load(0);
+      issue_z1(tmem + kColZ, s.aug32[0], s.w1aug);
+      mma_commit(&s.bar_z);
     }
-    mbar_wait(&s.bar_mma, ph);
-    ph ^= 1;
+    for (int64_t k = 0; k < n_my; ++k) {
+      const int st = (int)(k & 1);
+      const bool more = k + 1 < n_my;
+      ObsRegs nxt;
+      if (more) {
+        const int64_t idx = row_to_idx(a, a.row_off + (tile0 + (k + 1) * nctas) * TILE + (tid & (TILE - 1)));
+        nxt = load_obs(a, idx, D);
+      }
+      mbar_wait(&s.bar_z, (uint32_t)(k & 1));  // Z1(k) is in TMEM
+      if (k >= 2) mbar_wait(&s.bar_g[st], (uint32_t)(((k - 2) >> 1) & 1));  // gW2(k-2) has read stage st
+      fence_after_sync();
+      {
+        uint32_t hp[32];
+        h1_epilogue(tmem + kColZ + lane_base, r, cq, s.h1_tile[st], hp);
+      }
+      if (more) store_aug32(s.aug32[st ^ 1], nxt);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        if (more) {
+          issue_z1(tmem + kColZ, s.aug32[st ^ 1], s.w1aug);
+          mma_commit(&s.bar_z);
+        }
+        mbar_wait(&s.bar_tma[st], (uint32_t)((k >> 1) & 1));
+        // gW2[j half][i] += dZ2[:, j half]^T * H1: A = dz half tile (MN-major), B = H1 tile (MN-major)
+        issue_gemm(tmem + kColG, smem_u32(s.dz_tile[st]), TILE, true, smem_u32(s.h1_tile[st]), TILE, true,
+                   TILE, H, TILE, k > 0);
+        mma_commit(&s.bar_g[st]);
+        if (more) {
+          if (k >= 1) mbar_wait(&s.bar_g[st ^ 1], (uint32_t)(((k - 1) >> 1) & 1));  // gW2(k-1) done
+          tma_load(k + 1);
+        }
+      }
+    }
+    // all MMAs done: the last commit covers every earlier one
+    mbar_wait(&s.bar_g[(n_my - 1) & 1], (uint32_t)(((n_my - 1) >> 1) & 1));
     fence_after_sync();
-  }
-  if (it > 0) {
-    const int jb = half;
-    const int j = jb * 128 + q * 32 + (tid & 31);
-    float* dst = a.gw2[net] + (int64_t)j * H;
+    // flush: lane = unit j of this half, 256 columns i; warp (q, cq) -> lanes 32q.., columns 64cq..
+    {
+      const int j = jh * 128 + r;
+      float* dst = a.gw2[net] + (int64_t)j * H + cq * 64;
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      float v[32];
-      tmem_ld32(tmem + 256 * jb + ((uint32_t)(q * 32) << 16) + 32 * c, v);
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tmem_ld32(tmem + kColG + lane_base + (uint32_t)(cq * 64 + h * 32), v);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) atomicAdd(dst + 32 * c + e, v[e]);
+        for (int e = 0; e < 32; e += 4) red_add_v4(dst + h * 32 + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
     }
   }
-}
-
-template <int P>
-__global__ void __launch_bounds__(256, 1)
-tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  SmemW& s = *reinterpret_cast<SmemW*>(smem_raw);
-  const int net = blockIdx.x & 1;
-  const NetParams np = net ? np_vf : np_pi;
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    mbar_init(&s.bar_mma, 1);
-    fence_mbar_init();
-  }
-  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
-  for (int i = tid; i < 8 * H; i += blockDim.x) {
-    const int d = i / H, c = i - d * H;
-    s.w1t[d][c] = d < np.D ? np.w1[c * np.D + d] : 0.0f;
-  }
-  for (int i = tid; i < H; i += blockDim.x) s.b1[i] = np.b1[i];
-  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
-    const int p = i / H, c = i - p * H;
-    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  if (net == 0) update_w_body<P>(s, np, a, 0);
-  else update_w_body<1>(s, np, a, 1);
   fence_before_sync();
   __syncthreads();
   if (tid < 32) tmem_dealloc(s.tmem_base, 512);
@@ -456,7 +610,8 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
 
 // ---- host -----------------------------------------------------------------------------------------------------
 int64_t ppo_tc_workspace(const rl8_model*, int64_t max_rows) {
-  return 2 * (int64_t)kW2Bytes + 2 * max_rows * (8 * 4 + 4 * 4) + 256;
+  const int64_t chunk = max_rows < kChunkRows ? max_rows : kChunkRows;
+  return 2 * (int64_t)kW2Bytes + 2 * ceil_div(chunk, TILE) * (int64_t)kTileBytes + 256;
 }
 
 int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_batch* batch,
@@ -465,12 +620,12 @@ int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_b
                      int64_t workspace_bytes, cudaStream_t st) {
   if (model->H != H || model->P > kMaxPT || model->D > 7) return RL8_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < ppo_tc_workspace(model, M)) return RL8_ERR_WORKSPACE;
+  const int64_t chunk = M < kChunkRows ? M : kChunkRows;
+  const int64_t chunk_tiles = ceil_div(chunk, TILE);
   uint8_t* img_pi = (uint8_t*)workspace;
   uint8_t* img_vf = img_pi + kW2Bytes;
-  uint32_t* mask0 = (uint32_t*)(img_vf + kW2Bytes);
-  uint32_t* mask1 = mask0 + M * 8;
-  float* dout0 = (float*)(mask1 + M * 8);
-  float* dout1 = dout0 + M * 4;
+  uint8_t* dz0 = img_vf + kW2Bytes;
+  uint8_t* dz1 = dz0 + chunk_tiles * (int64_t)kTileBytes;
   int rc;
   if ((rc = launch_pack_w2(model->pi_w2, img_pi, st))) return rc;
   if ((rc = launch_pack_w2(model->vf_w2, img_vf, st))) return rc;
@@ -479,31 +634,45 @@ int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_b
   a.obs = batch->obs, a.actions = batch->actions, a.logp = batch->logp;
   a.adv = batch->advantages, a.ret = batch->returns;
   a.rows = rows, a.row_begin = row_begin, a.M = M, a.N = batch->N, a.T = batch->T;
+  // A contiguous run of whole environments may be visited in any order (the minibatch is a sum):
+  // walk it slab by slab so every load is coalesced in the horizon-major buffer.
+  a.slab_env0 = 0, a.slab_nenv = 0;
+  if (!rows && batch->T > 0 && row_begin % batch->T == 0 && M % batch->T == 0) {
+    a.slab_env0 = row_begin / batch->T;
+    a.slab_nenv = M / batch->T;
+  }
   a.dist_kind = batch->dist_kind, a.hp = *hp;
   a.inv_denom = (float)((double)hp->loss_scale / mean_denominator);
-  a.mask[0] = mask0, a.mask[1] = mask1, a.dout[0] = dout0, a.dout[1] = dout1;
+  a.dz[0] = dz0, a.dz[1] = dz1;
   a.gw1[0] = (float*)grads->pi_w1, a.gb1[0] = (float*)grads->pi_b1, a.gw2[0] = (float*)grads->pi_w2;
   a.gb2[0] = (float*)grads->pi_b2, a.gw3[0] = (float*)grads->pi_w3, a.gb3[0] = (float*)grads->pi_b3;
   a.gw1[1] = (float*)grads->vf_w1, a.gb1[1] = (float*)grads->vf_b1, a.gw2[1] = (float*)grads->vf_w2;
   a.gb2[1] = (float*)grads->vf_b2, a.gw3[1] = (float*)grads->vf_w3, a.gb3[1] = (float*)grads->vf_b3;
   a.sums = loss_sums;
-  const int64_t ntiles = ceil_div(M, TILE);
-  int grid = (int)(2 * ntiles < kNumSMs ? 2 * ntiles : kNumSMs);
-  grid &= ~1;
-#define RL8_UPD(PV)                                                                            \
-  case PV:                                                                                     \
-    if ((rc = set_smem((const void*)tc_update_h_kernel<PV>, sizeof(SmemH)))) return rc;         \
-    tc_update_h_kernel<PV><<<grid, 256, sizeof(SmemH), st>>>(np_pi, np_vf, a);                  \
-    if ((rc = check_launch("tc_update_h"))) return rc;                                          \
-    if ((rc = set_smem((const void*)tc_update_w_kernel<PV>, sizeof(SmemW)))) return rc;         \
-    tc_update_w_kernel<PV><<<grid, 256, sizeof(SmemW), st>>>(np_pi, np_vf, a);                  \
+  for (int64_t off = 0; off < M; off += chunk) {
+    a.row_off = off;
+    a.Mc = M - off < chunk ? M - off : chunk;
+    const int64_t ntiles = ceil_div(a.Mc, TILE);
+    int grid_h = (int)(2 * ntiles < kNumSMs ? 2 * ntiles : kNumSMs);
+    grid_h &= ~1;
+    int grid_w = (int)(4 * ntiles < kNumSMs ? 4 * ntiles : kNumSMs);
+    grid_w &= ~3;
+#define RL8_UPD(PV)                                                                              \
+  case PV:                                                                                       \
+    if ((rc = set_smem((const void*)tc_update_h_kernel<PV>, sizeof(SmemH)))) return rc;           \
+    tc_update_h_kernel<PV><<<grid_h, kUpdThreads, sizeof(SmemH), st>>>(np_pi, np_vf, a);          \
     break;
-  switch (model->P) {
-    RL8_UPD(2) RL8_UPD(3) RL8_UPD(4)
-    default: return RL8_ERR_UNSUPPORTED;
-  }
+    switch (model->P) {
+      RL8_UPD(2) RL8_UPD(3) RL8_UPD(4)
+      default: return RL8_ERR_UNSUPPORTED;
+    }
 #undef RL8_UPD
-  return check_launch("tc_update_w");
+    if ((rc = check_launch("tc_update_h"))) return rc;
+    if ((rc = set_smem((const void*)tc_update_w_kernel, sizeof(SmemW)))) return rc;
+    tc_update_w_kernel<<<grid_w, kUpdThreads, sizeof(SmemW), st>>>(np_pi, np_vf, a);
+    if ((rc = check_launch("tc_update_w"))) return rc;
+  }
+  return RL8_OK;
 }
 
 }  // namespace rl8
