@@ -24,6 +24,8 @@
 // Activations never reach HBM except the bf16 dZ2 tile (512 B / row / network, written once and
 // read once).
 #include "mlp_tc.cuh"
+#include <stdlib.h>
+
 #include "ppo_loss_math.cuh"
 
 namespace rl8 {
@@ -46,6 +48,8 @@ struct UpdArgs {
   int64_t N;
   int64_t slab_env0, slab_nenv;  // nenv > 0: order-free traversal t-major over envs [env0, env0+nenv)
   int T, dist_kind;
+  int small;             // every row count fits 31 bits: 32-bit index arithmetic
+  int n_pi;              // activation kernel: CTAs [0, n_pi) run the policy network, the rest the value network
   rl8_ppo_hparams hp;
   float inv_denom;
   uint8_t* dz[2];        // [tiles of the chunk][64 KB] bf16 dZ2 tile images per network
@@ -53,16 +57,28 @@ struct UpdArgs {
   double* sums;          // [5]
 };
 
-// Buffer index t*N + n of minibatch row `rw` (-1: past the minibatch).
-__device__ __forceinline__ int64_t row_to_idx(const UpdArgs& a, int64_t rw) {
-  if (rw >= a.M) return -1;
-  if (a.slab_nenv > 0) {
-    const int64_t t = rw / a.slab_nenv, n = a.slab_env0 + (rw - t * a.slab_nenv);
-    return t * a.N + n;
+// Buffer coordinates (slab t, env n) of minibatch row `rw`; false past the minibatch.
+__device__ __forceinline__ bool row_to_tn(const UpdArgs& a, int64_t rw, int64_t& t, int64_t& n) {
+  if (rw >= a.M) return false;
+  if (a.small) {
+    if (a.slab_nenv > 0) {
+      const uint32_t ne = (uint32_t)a.slab_nenv, rr = (uint32_t)rw;
+      const uint32_t tt = rr / ne;
+      t = tt, n = a.slab_env0 + (rr - tt * ne);
+    } else {
+      const uint32_t g = a.rows ? (uint32_t)a.rows[rw] : (uint32_t)(a.row_begin + rw);
+      const uint32_t TT = (uint32_t)a.T, nn = g / TT;
+      t = g - nn * TT, n = nn;
+    }
+    return true;
   }
-  const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
-  const int64_t n = g / a.T, t = g - n * a.T;
-  return t * a.N + n;
+  if (a.slab_nenv > 0) {
+    t = rw / a.slab_nenv, n = a.slab_env0 + (rw - t * a.slab_nenv);
+  } else {
+    const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
+    n = g / a.T, t = g - n * a.T;
+  }
+  return true;
 }
 
 // ---- shared pieces of both kernels -------------------------------------------------------------------
@@ -81,13 +97,12 @@ __device__ __forceinline__ void stage_w1aug(uint8_t* w1aug, const NetParams& np)
 struct ObsRegs {
   float v0, v1;
 };
-__device__ __forceinline__ ObsRegs load_obs(const UpdArgs& a, int64_t idx, int D) {
-  const int d0 = threadIdx.x >> 7;  // 0..3
+__device__ __forceinline__ ObsRegs load_obs(const UpdArgs& a, bool valid, int64_t t, int64_t n, int D) {
+  const int d0 = (threadIdx.x >> 7) & 3;  // 0..3
   ObsRegs o;
   o.v0 = d0 == D ? 1.0f : 0.0f;
   o.v1 = d0 + 4 == D ? 1.0f : 0.0f;
-  if (idx >= 0) {
-    const int64_t t = idx / a.N, n = idx - t * a.N;
+  if (valid) {
     const float* base = a.obs + t * (int64_t)D * a.N + n;
     if (d0 < D) o.v0 = __ldg(base + (int64_t)d0 * a.N);
     if (d0 + 4 < D) o.v1 = __ldg(base + (int64_t)(d0 + 4) * a.N);
@@ -96,7 +111,7 @@ __device__ __forceinline__ ObsRegs load_obs(const UpdArgs& a, int64_t idx, int D
 }
 // aug32: fp32 (tf32-rounded) chunked [128 rows][8]: off(r, d) = r*16 + (d/4)*2048 + (d%4)*4
 __device__ __forceinline__ void store_aug32(uint8_t* aug32, const ObsRegs& o) {
-  const int rr = threadIdx.x & (TILE - 1), d0 = threadIdx.x >> 7;
+  const int rr = threadIdx.x & (TILE - 1), d0 = (threadIdx.x >> 7) & 3;
   *reinterpret_cast<float*>(aug32 + rr * 16 + d0 * 4) = tf32_round(o.v0);
   *reinterpret_cast<float*>(aug32 + rr * 16 + TILE * 16 + d0 * 4) = tf32_round(o.v1);
 }
@@ -106,26 +121,21 @@ __device__ __forceinline__ void issue_z1(uint32_t d_tmem, const uint8_t* aug32, 
            instr_desc_tf32(TILE, H), 0u);
 }
 
-// H1 = relu(Z1) of this thread's row and its 64 columns [64*cq, 64*cq + 64): bf16 chunks into
-// `tile`, packed pairs into hp[32].
-__device__ __forceinline__ void h1_epilogue(uint32_t z1_taddr /* lane + column base */, int r, int cq,
-                                            uint8_t* tile, uint32_t* hp) {
+// Column ownership of the epilogues: thread (q = warp % 4, cq = warp / 4) owns row 32q + lane and the
+// two 32-column groups [32cq, 32cq + 32) and [128 + 32cq, 128 + 32cq + 32): one group per half of an
+// accumulator, so the epilogue of half 0 overlaps the MMAs of half 1.
+__device__ __forceinline__ int group_col0(int cq, int h) { return 128 * h + 32 * cq; }
+
+// relu + pack 32 fp32 columns -> 16 bf16 pairs
+__device__ __forceinline__ void relu_pack32(const float* v, uint32_t* hp) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    float v[32];
-    tmem_ld32(z1_taddr + (uint32_t)(cq * 64 + h * 32), v);
+  for (int i = 0; i < 16; ++i) hp[i] = pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ void store_group(uint8_t* tile, int r, int col0, const uint32_t* hp) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint4 q;
-      q.x = pack_relu_bf16x2(v[8 * k + 0], v[8 * k + 1]);
-      q.y = pack_relu_bf16x2(v[8 * k + 2], v[8 * k + 3]);
-      q.z = pack_relu_bf16x2(v[8 * k + 4], v[8 * k + 5]);
-      q.w = pack_relu_bf16x2(v[8 * k + 6], v[8 * k + 7]);
-      hp[h * 16 + k * 4 + 0] = q.x, hp[h * 16 + k * 4 + 1] = q.y;
-      hp[h * 16 + k * 4 + 2] = q.z, hp[h * 16 + k * 4 + 3] = q.w;
-      *reinterpret_cast<uint4*>(tile + chunk_offset<TILE>(r, cq * 8 + h * 4 + k)) = q;
-    }
-  }
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<uint4*>(tile + chunk_offset<TILE>(r, col0 / 8 + k)) =
+        make_uint4(hp[4 * k], hp[4 * k + 1], hp[4 * k + 2], hp[4 * k + 3]);
 }
 
 // ---- activation kernel ---------------------------------------------------------------------------------
@@ -133,27 +143,42 @@ struct SmemH {
   uint8_t w2[kW2Bytes];        // 131072
   uint8_t a_tile[kTileBytes];  //  65536  H1 -> H2 -> dZ2 -> dZ1
   uint8_t w1aug[H * 32];       //   8192
-  uint8_t aug32[TILE * 32];    //   4096  tf32 [obs, 1] (A of the layer-1 MMA)
-  uint8_t aug16[TILE * 32];    //   4096  bf16 [r][16] = [obs, 1, 0..] (B of the thin GEMMs)
-  uint8_t dout16[TILE * 32];   //   4096  bf16 [r][16] = [dOut, 0..]
+  uint8_t w3img[16 * H * 2];   //   8192  bf16 chunked [16 rows p][256 cols j]: off(p, c8) = p*16 + c8*256
+  union {
+    uint8_t aug32[TILE * 32];     //  tf32 [obs, 1] (A of the layer-1 MMA): dead once Z1 is in TMEM
+    float part[3][TILE][kMaxPT];  //  head partial sums of column quarters 1..3 (phases D, E)
+  } u;                         //   6144
+  uint8_t thin[3][TILE * 16];  //   6144  bf16 [r][8]: [0] = [obs, 1, 0..], [1] = [dOut, 0..], [2] = zeros (the
+                               //         second 8-column group of both N = 16 operands)
   float b2[H];                 //   1024
   float w3[kMaxPT][H];         //   4096
-  float part[3][TILE][kMaxPT]; //   6144  head partial sums of column quarters 1..3
-  float dout[TILE][kMaxPT];    //   2048
-  float gb3[kMaxPT];
-  uint64_t bar_w, bar_mma[2];
+  uint64_t bar_w, bar[7];
   uint32_t tmem_base;
 };
-static_assert(sizeof(SmemH) + 512 <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
+static_assert(sizeof(SmemH) + 1024 <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
 
 // TMEM columns of the activation kernel
-constexpr uint32_t kColMain = 0;     // 256: Z1 / Z2 / dH1
+constexpr uint32_t kColMain = 0;     // 256: Z1 / Z2 / G / dH1
 constexpr uint32_t kColH1 = 256;     // 128: packed bf16 H1 (for the layer-1 ReLU mask)
 constexpr uint32_t kColThin = 384;   // 6 x 16: gW3, gb2, [gW1 gb1], two 128-unit blocks each
 constexpr int kThinN = 16;
+// mbarriers: each completes exactly once per tile, so one phase bit (tile parity) serves all
+enum { kBZ1 = 0, kBZ2A, kBZ2B, kBT1, kBDA, kBDB, kBT2 };
+
+// D[128 units][16] (+)= X[:, 128-unit block]^T * Y with X the activation tile (MN-major A) and Y a
+// [r][16] operand whose second 8-column group is the shared zero block at b_saddr + b_sbo.
+__device__ __forceinline__ void issue_thin(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr,
+                                           uint32_t b_sbo, bool accumulate) {
+  const uint32_t idesc = instr_desc(TILE, kThinN, 1, 1);
+#pragma unroll
+  for (int k = 0; k < TILE / 16; ++k)
+    mma_bf16(d_tmem, smem_desc(a_saddr + k * 256, 128, TILE * 16), smem_desc(b_saddr + k * 256, 128, b_sbo),
+             idesc, (k > 0 || accumulate) ? 1u : 0u);
+}
 
 template <int PN, bool POLICY>
-__device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, const UpdArgs& a, int net) {
+__device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, const UpdArgs& a, int net,
+                                              int cta, int nctas) {
   const uint32_t tmem = s.tmem_base;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -162,27 +187,28 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const int D = np.D;
   const int64_t ntiles = (a.Mc + TILE - 1) / TILE;
-  const int nctas = gridDim.x >> 1;
-  float b3[PN];
+  float b3[PN], gb3_acc[PN];
 #pragma unroll
-  for (int p = 0; p < PN; ++p) b3[p] = np.b3[p];
-  double s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;
-  uint32_t ph0 = 0, ph1 = 0;
+  for (int p = 0; p < PN; ++p) b3[p] = np.b3[p], gb3_acc[p] = 0.0f;
+  float s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;  // per-thread partial sums (<= a few hundred rows)
   int it = 0;
   const bool continuous = POLICY && a.dist_kind != RL8_DIST_CATEGORICAL;
 
   // prefetch of the first tile
-  int64_t tile = blockIdx.x >> 1;
-  int64_t idx_next = tile < ntiles ? row_to_idx(a, a.row_off + tile * TILE + (tid & (TILE - 1))) : -1;
-  ObsRegs obs_next = load_obs(a, idx_next, D);
+  int64_t tile = cta;
+  int64_t tn = 0, nn = 0;
+  bool valid_next = tile < ntiles && row_to_tn(a, a.row_off + tile * TILE + (tid & (TILE - 1)), tn, nn);
+  ObsRegs obs_next = load_obs(a, valid_next, tn, nn, D);
+  int64_t idx_next = valid_next ? tn * a.N + nn : -1;
 
   for (; tile < ntiles; tile += nctas, ++it) {
+    const uint32_t ph = (uint32_t)(it & 1);
     // ---- A. operands of this tile: [obs, 1] in tf32 and bf16 ----------------------------------------------
     const int64_t idx = idx_next;  // of row (tid & 127)
-    store_aug32(s.aug32, obs_next);
+    store_aug32(s.u.aug32, obs_next);
     {
       const int rr = tid & (TILE - 1), d0 = tid >> 7;
-      __nv_bfloat16* row16 = reinterpret_cast<__nv_bfloat16*>(s.aug16 + rr * 16);
+      __nv_bfloat16* row16 = reinterpret_cast<__nv_bfloat16*>(s.thin[0] + rr * 16);
       row16[d0] = __float2bfloat16(obs_next.v0);
       row16[d0 + 4] = __float2bfloat16(obs_next.v1);
     }
@@ -190,7 +216,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     float in_act = 0.0f, in_logp = 0.0f, in_tgt = 0.0f;
     if (tid < TILE && idx >= 0) {
       if constexpr (POLICY) {
-        in_act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)((const long long*)a.actions)[idx]
+        in_act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)((const int*)a.actions)[2 * idx]
                                                      : ((const float*)a.actions)[idx];
         in_logp = a.logp[idx];
         in_tgt = a.adv[idx];
@@ -203,43 +229,62 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
-      issue_z1(tmem + kColMain, s.aug32, s.w1aug);
-      mma_commit(&s.bar_mma[0]);
+      issue_z1(tmem + kColMain, s.u.aug32, s.w1aug);
+      mma_commit(&s.bar[kBZ1]);
     }
     // ---- B. prefetch the next tile while the tensor core works ----------------------------------------------
     {
       const int64_t nt = tile + nctas;
-      idx_next = nt < ntiles ? row_to_idx(a, a.row_off + nt * TILE + (tid & (TILE - 1))) : -1;
-      obs_next = load_obs(a, idx_next, D);
+      valid_next = nt < ntiles && row_to_tn(a, a.row_off + nt * TILE + (tid & (TILE - 1)), tn, nn);
+      obs_next = load_obs(a, valid_next, tn, nn, D);
+      idx_next = valid_next ? tn * a.N + nn : -1;
     }
-    mbar_wait(&s.bar_mma[0], ph0);
-    ph0 ^= 1;
+    mbar_wait(&s.bar[kBZ1], ph);
     fence_after_sync();
-    // ---- C. H1 tile + packed copy in TMEM -> Z2 = H1 * W2^T -----------------------------------------------------
+    // ---- C. H1 = relu(Z1): bf16 tile + packed copy in TMEM;  Z2 = H1 * W2^T in two column halves --------------
     {
-      uint32_t hp[32];
-      h1_epilogue(tmem + kColMain + lane_base, r, cq, s.a_tile, hp);
-      tmem_st32_raw(tmem + kColH1 + lane_base + (uint32_t)(cq * 32), hp);
+      float v0[32], v1[32];
+      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, 0), v0);
+      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, 1), v1);
+      tmem_wait_ld();
+      reg_fence32(v0);
+      reg_fence32(v1);
+      uint32_t hp[16];
+      relu_pack32(v0, hp);
+      store_group(s.a_tile, r, group_col0(cq, 0), hp);
+      tmem_st16_raw(tmem + kColH1 + lane_base + (uint32_t)(group_col0(cq, 0) / 2), hp);
+      relu_pack32(v1, hp);
+      store_group(s.a_tile, r, group_col0(cq, 1), hp);
+      tmem_st16_raw(tmem + kColH1 + lane_base + (uint32_t)(group_col0(cq, 1) / 2), hp);
+      tmem_wait_st();
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
-      issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H,
-                 false);
-      mma_commit(&s.bar_mma[1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        issue_gemm(tmem + kColMain + 128 * h, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2) + h * 2048, H,
+                   false, TILE, 128, H, false);
+        mma_commit(&s.bar[kBZ2A + h]);
+      }
     }
-    mbar_wait(&s.bar_mma[1], ph1);
-    ph1 ^= 1;
-    fence_after_sync();
-    // ---- D. one pass over Z2: H2 tile (bf16) and head partial sums -----------------------------------------------
+    // ---- D. H2 = relu(Z2 + b2) -> tile, head partial sums; half 0 is processed under the MMAs of half 1 -------
     float dot[PN];
 #pragma unroll
     for (int p = 0; p < PN; ++p) dot[p] = 0.0f;
-#pragma unroll 1
+    uint32_t held[16];
+#pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int col0 = cq * 64 + h * 32;
+      const int col0 = group_col0(cq, h);
+      if (h == 0) {
+        mbar_wait(&s.bar[kBZ2A], ph);
+      } else {
+        mbar_wait(&s.bar[kBZ2B], ph);  // every MMA that reads H1 is done: the tile may be overwritten
+      }
+      fence_after_sync();
+      if (h == 1) store_group(s.a_tile, r, group_col0(cq, 0), held);
       float v[32];
       tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
 #pragma unroll
@@ -256,12 +301,19 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
           dot[p] = fmaf(v[j + 3], w.w, dot[p]);
         }
       }
+      if (h == 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) store_chunk(s.a_tile, chunk_offset<TILE>(r, col0 / 8 + k), v + 8 * k);
+        for (int i = 0; i < 16; ++i) held[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      } else {
+        uint32_t hp[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hp[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        store_group(s.a_tile, r, col0, hp);
+      }
     }
     if (cq > 0) {
 #pragma unroll
-      for (int p = 0; p < PN; ++p) s.part[cq - 1][r][p] = dot[p];
+      for (int p = 0; p < PN; ++p) s.u.part[cq - 1][r][p] = dot[p];
     }
     __syncthreads();
     // ---- E. per-row loss -> dOut (threads 0..127 own row tid and column quarter 0) -------------------------------------
@@ -269,7 +321,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       float o[PN], d_o[PN];
 #pragma unroll
       for (int p = 0; p < PN; ++p)
-        o[p] = ((dot[p] + s.part[0][tid][p]) + s.part[1][tid][p]) + s.part[2][tid][p] + b3[p];
+        o[p] = ((dot[p] + s.u.part[0][tid][p]) + s.u.part[1][tid][p]) + s.u.part[2][tid][p] + b3[p];
 #pragma unroll
       for (int p = 0; p < PN; ++p) d_o[p] = 0.0f;
       if (idx >= 0) {
@@ -286,109 +338,96 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       float v8[8];
 #pragma unroll
       for (int p = 0; p < 8; ++p) v8[p] = p < PN ? d_o[p] : 0.0f;
-      store_chunk(s.dout16, (uint32_t)tid * 16u, v8);
-      *reinterpret_cast<float4*>(&s.dout[tid][0]) = make_float4(v8[0], v8[1], v8[2], v8[3]);
-      // gb3 += sum_r dOut: one shared atomic per warp
+      store_chunk(s.thin[1], (uint32_t)tid * 16u, v8);
 #pragma unroll
-      for (int p = 0; p < PN; ++p) {
-        const float w = warp_sum(d_o[p]);
-        if (lane == 0) atomicAdd(&s.gb3[p], w);
-      }
+      for (int p = 0; p < PN; ++p) gb3_acc[p] += d_o[p];
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    // ---- F. gW3^T += H2^T * dOut ---------------------------------------------------------------------------------------
+    // ---- F. gW3^T += H2^T * dOut;  G = dOut * W3 (K = 16: one instruction) ------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb)
-        issue_gemm(tmem + kColThin + kThinN * jb, smem_u32(s.a_tile) + jb * 32768, TILE, true,
-                   smem_u32(s.dout16), TILE, true, TILE, kThinN, TILE, it > 0);
-      mma_commit(&s.bar_mma[0]);
+        issue_thin(tmem + kColThin + kThinN * jb, smem_u32(s.a_tile) + jb * 32768, smem_u32(s.thin[1]),
+                   TILE * 16, it > 0);
+      mma_bf16(tmem + kColMain, smem_desc(smem_u32(s.thin[1]), TILE * 16, 128),
+               smem_desc(smem_u32(s.w3img), 128, 16 * 16), instr_desc(TILE, H, 0, 1), 0u);
+      mma_commit(&s.bar[kBT1]);
     }
-    // ---- G. dZ2 = [H2 > 0] .* (dOut * W3), in place over H2 -----------------------------------------------------------------
+    mbar_wait(&s.bar[kBT1], ph);
+    fence_after_sync();
+    // ---- G. dZ2 = [H2 > 0] .* G, in place over H2 -----------------------------------------------------------------------------
     {
-      float dr[PN];
-      {
-        const float4 d4 = *reinterpret_cast<const float4*>(&s.dout[r][0]);
-        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      float v0[32], v1[32];
+      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, 0), v0);
+      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, 1), v1);
+      tmem_wait_ld();
+      reg_fence32(v0);
+      reg_fence32(v1);
 #pragma unroll
-        for (int p = 0; p < PN; ++p) dr[p] = dd[p];
-      }
-      mbar_wait(&s.bar_mma[0], ph0);  // the thin GEMM has read H2
-      ph0 ^= 1;
-      fence_after_sync();
-#pragma unroll 2
-      for (int c = 0; c < 8; ++c) {
-        const int cc = cq * 8 + c;
-        uint8_t* slot = s.a_tile + chunk_offset<TILE>(r, cc);
-        const uint4 h2 = *reinterpret_cast<const uint4*>(slot);
-        float g[8];
-        {
-          const float4 wa = *reinterpret_cast<const float4*>(&s.w3[0][cc * 8]);
-          const float4 wb = *reinterpret_cast<const float4*>(&s.w3[0][cc * 8 + 4]);
-          g[0] = dr[0] * wa.x, g[1] = dr[0] * wa.y, g[2] = dr[0] * wa.z, g[3] = dr[0] * wa.w;
-          g[4] = dr[0] * wb.x, g[5] = dr[0] * wb.y, g[6] = dr[0] * wb.z, g[7] = dr[0] * wb.w;
-        }
+      for (int h = 0; h < 2; ++h) {
+        const float* v = h ? v1 : v0;
 #pragma unroll
-        for (int p = 1; p < PN; ++p) {
-          const float4 wa = *reinterpret_cast<const float4*>(&s.w3[p][cc * 8]);
-          const float4 wb = *reinterpret_cast<const float4*>(&s.w3[p][cc * 8 + 4]);
-          g[0] = fmaf(dr[p], wa.x, g[0]), g[1] = fmaf(dr[p], wa.y, g[1]);
-          g[2] = fmaf(dr[p], wa.z, g[2]), g[3] = fmaf(dr[p], wa.w, g[3]);
-          g[4] = fmaf(dr[p], wb.x, g[4]), g[5] = fmaf(dr[p], wb.y, g[5]);
-          g[6] = fmaf(dr[p], wb.z, g[6]), g[7] = fmaf(dr[p], wb.w, g[7]);
+        for (int k = 0; k < 4; ++k) {
+          uint8_t* slot = s.a_tile + chunk_offset<TILE>(r, group_col0(cq, h) / 8 + k);
+          const uint4 h2 = *reinterpret_cast<const uint4*>(slot);
+          uint4 o4;
+          o4.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]) & gt0_mask_bf16x2(h2.x);
+          o4.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]) & gt0_mask_bf16x2(h2.y);
+          o4.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]) & gt0_mask_bf16x2(h2.z);
+          o4.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]) & gt0_mask_bf16x2(h2.w);
+          *reinterpret_cast<uint4*>(slot) = o4;
         }
-        uint4 o4;
-        o4.x = pack_bf16x2(g[0], g[1]) & gt0_mask_bf16x2(h2.x);
-        o4.y = pack_bf16x2(g[2], g[3]) & gt0_mask_bf16x2(h2.y);
-        o4.z = pack_bf16x2(g[4], g[5]) & gt0_mask_bf16x2(h2.z);
-        o4.w = pack_bf16x2(g[6], g[7]) & gt0_mask_bf16x2(h2.w);
-        *reinterpret_cast<uint4*>(slot) = o4;
       }
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    // ---- H. dZ2 tile -> scratch;  dH1 = dZ2 * W2;  [., gb2] += dZ2^T * [obs, 1] -----------------------------------------------
+    // ---- H. dZ2 tile -> scratch;  dH1 = dZ2 * W2 in two column halves;  [., gb2] += dZ2^T * [obs, 1] --------------------------
     if (tid == 0) {
       fence_after_sync();
       uint8_t* dst = a.dz[net] + tile * (int64_t)kTileBytes;
 #pragma unroll
       for (int i = 0; i < 4; ++i) bulk_s2g(dst + i * 16384, s.a_tile + i * 16384, 16384);
       bulk_commit();
-      issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, true, TILE, H, H,
+      issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, true, TILE, 128, H,
                  false);
+      mma_commit(&s.bar[kBDA]);
+      issue_gemm(tmem + kColMain + 128, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2) + 16 * (H * 16), H,
+                 true, TILE, 128, H, false);
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb)
-        issue_gemm(tmem + kColThin + kThinN * (2 + jb), smem_u32(s.a_tile) + jb * 32768, TILE, true,
-                   smem_u32(s.aug16), TILE, true, TILE, kThinN, TILE, it > 0);
-      mma_commit(&s.bar_mma[1]);
+        issue_thin(tmem + kColThin + kThinN * (2 + jb), smem_u32(s.a_tile) + jb * 32768, smem_u32(s.thin[0]),
+                   2 * TILE * 16, it > 0);
+      mma_commit(&s.bar[kBDB]);
       bulk_wait_read();  // the store engine has read the tile
     }
-    mbar_wait(&s.bar_mma[1], ph1);
-    ph1 ^= 1;
-    fence_after_sync();
-    __syncthreads();  // thread 0's bulk_wait_read precedes every overwrite of the tile
-    // ---- I. dZ1 = [H1 > 0] .* dH1 ------------------------------------------------------------------------------------------------
-    {
-      uint32_t hp[32];
-      tmem_ld32_raw(tmem + kColH1 + lane_base + (uint32_t)(cq * 32), hp);
+    // ---- I. dZ1 = [H1 > 0] .* dH1; half 0 is processed under the MMAs of half 1 -----------------------------------------------
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tmem_ld32(tmem + kColMain + lane_base + (uint32_t)(cq * 64 + h * 32), v);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4 o4;
-          o4.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 0]);
-          o4.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 1]);
-          o4.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 2]);
-          o4.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]) & gt0_mask_bf16x2(hp[h * 16 + k * 4 + 3]);
-          *reinterpret_cast<uint4*>(s.a_tile + chunk_offset<TILE>(r, cq * 8 + h * 4 + k)) = o4;
-        }
+    for (int h = 0; h < 2; ++h) {
+      const int col0 = group_col0(cq, h);
+      if (h == 0) {
+        mbar_wait(&s.bar[kBDA], ph);
+        fence_after_sync();
+      } else {
+        mbar_wait(&s.bar[kBDB], ph);
+        fence_after_sync();
+        __syncthreads();  // thread 0's bulk_wait_read precedes every overwrite of the tile
+        store_group(s.a_tile, r, group_col0(cq, 0), held);
       }
+      uint32_t hp[16];
+      float v[32];
+      tmem_ld16_raw(tmem + kColH1 + lane_base + (uint32_t)(col0 / 2), hp);
+      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)col0, v);
+      tmem_wait_ld();
+      reg_fence16(hp);
+      reg_fence32(v);
+      uint32_t* out = h == 0 ? held : hp;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]) & gt0_mask_bf16x2(hp[i]);
+      if (h == 1) store_group(s.a_tile, r, col0, hp);
     }
     fence_async_smem();
     fence_before_sync();
@@ -398,12 +437,11 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       fence_after_sync();
 #pragma unroll
       for (int ib = 0; ib < 2; ++ib)
-        issue_gemm(tmem + kColThin + kThinN * (4 + ib), smem_u32(s.a_tile) + ib * 32768, TILE, true,
-                   smem_u32(s.aug16), TILE, true, TILE, kThinN, TILE, it > 0);
-      mma_commit(&s.bar_mma[0]);
+        issue_thin(tmem + kColThin + kThinN * (4 + ib), smem_u32(s.a_tile) + ib * 32768, smem_u32(s.thin[0]),
+                   2 * TILE * 16, it > 0);
+      mma_commit(&s.bar[kBT2]);
     }
-    mbar_wait(&s.bar_mma[0], ph0);  // tile, aug16 and aug32 are free again
-    ph0 ^= 1;
+    mbar_wait(&s.bar[kBT2], ph);  // tile and operand tiles are free again
     fence_after_sync();
   }
   if (tid == 0) bulk_wait_all();  // dZ2 stores have landed before the kernel ends
@@ -427,10 +465,15 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       if (d == D) atomicAdd(a.gb1[net] + c, v[d]);
     }
   }
-  __syncthreads();
-  if (it > 0 && tid < PN) atomicAdd(a.gb3[net] + tid, s.gb3[tid]);
+  if (it > 0 && tid < TILE) {
+#pragma unroll
+    for (int p = 0; p < PN; ++p) {
+      const float w = warp_sum(gb3_acc[p]);
+      if (lane == 0) atomicAdd(a.gb3[net] + p, w);
+    }
+  }
   __shared__ double red[32];
-  double sv[4] = {s_ent, s_pol, s_vf, s_kl};
+  double sv[4] = {(double)s_ent, (double)s_pol, (double)s_vf, (double)s_kl};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const double t = block_sum(sv[i], red);
@@ -444,13 +487,15 @@ __global__ void __launch_bounds__(kUpdThreads, 1)
 tc_update_h_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemH& s = *reinterpret_cast<SmemH*>(smem_raw);
-  const int net = blockIdx.x & 1;
+  const int net = (int)blockIdx.x < a.n_pi ? 0 : 1;
+  const int cta = net ? (int)blockIdx.x - a.n_pi : (int)blockIdx.x;
+  const int nctas = net ? (int)gridDim.x - a.n_pi : a.n_pi;
   const NetParams np = net ? np_vf : np_pi;
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&s.bar_w, 1);
-    mbar_init(&s.bar_mma[0], 1);
-    mbar_init(&s.bar_mma[1], 1);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) mbar_init(&s.bar[i], 1);
     fence_mbar_init();
   }
   if (tid < 32) tmem_alloc(&s.tmem_base, 512);
@@ -469,15 +514,16 @@ tc_update_h_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
   }
-  for (int i = tid; i < TILE * 32 / 4; i += blockDim.x) {
-    reinterpret_cast<uint32_t*>(s.aug16)[i] = 0u;
-    reinterpret_cast<uint32_t*>(s.dout16)[i] = 0u;
+  for (int i = tid; i < 16 * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    *reinterpret_cast<__nv_bfloat16*>(s.w3img + p * 16 + (c >> 3) * 256 + (c & 7) * 2) =
+        __float2bfloat16(p < np.P ? np.w3[p * H + c] : 0.0f);
   }
-  if (tid < kMaxPT) s.gb3[tid] = 0.0f;
+  for (int i = tid; i < 3 * TILE * 16 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s.thin)[i] = 0u;
   __syncthreads();
   mbar_wait(&s.bar_w, 0);
-  if (net == 0) update_h_body<P, true>(s, np, a, 0);
-  else update_h_body<1, false>(s, np, a, 1);
+  if (net == 0) update_h_body<P, true>(s, np, a, 0, cta, nctas);
+  else update_h_body<1, false>(s, np, a, 1, cta, nctas);
   fence_before_sync();
   __syncthreads();
   if (tid < 32) tmem_dealloc(s.tmem_base, 512);
@@ -539,8 +585,9 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
 
   if (n_my > 0) {
     {
-      const int64_t idx = row_to_idx(a, a.row_off + tile0 * TILE + (tid & (TILE - 1)));
-      store_aug32(s.aug32[0], load_obs(a, idx, D));
+      int64_t t0 = 0, n0 = 0;
+      const bool valid = row_to_tn(a, a.row_off + tile0 * TILE + (tid & (TILE - 1)), t0, n0);
+      store_aug32(s.aug32[0], load_obs(a, valid, t0, n0, D));
     }
     fence_async_smem();
     fence_before_sync();
@@ -556,15 +603,25 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
       const bool more = k + 1 < n_my;
       ObsRegs nxt;
       if (more) {
-        const int64_t idx = row_to_idx(a, a.row_off + (tile0 + (k + 1) * nctas) * TILE + (tid & (TILE - 1)));
-        nxt = load_obs(a, idx, D);
+        int64_t t1 = 0, n1 = 0;
+        const bool valid = row_to_tn(a, a.row_off + (tile0 + (k + 1) * nctas) * TILE + (tid & (TILE - 1)), t1, n1);
+        nxt = load_obs(a, valid, t1, n1, D);
       }
       mbar_wait(&s.bar_z, (uint32_t)(k & 1));  // Z1(k) is in TMEM
       if (k >= 2) mbar_wait(&s.bar_g[st], (uint32_t)(((k - 2) >> 1) & 1));  // gW2(k-2) has read stage st
       fence_after_sync();
       {
-        uint32_t hp[32];
-        h1_epilogue(tmem + kColZ + lane_base, r, cq, s.h1_tile[st], hp);
+        float v0[32], v1[32];
+        tmem_ld32_nowait(tmem + kColZ + lane_base + (uint32_t)group_col0(cq, 0), v0);
+        tmem_ld32_nowait(tmem + kColZ + lane_base + (uint32_t)group_col0(cq, 1), v1);
+        tmem_wait_ld();
+        reg_fence32(v0);
+        reg_fence32(v1);
+        uint32_t hp[16];
+        relu_pack32(v0, hp);
+        store_group(s.h1_tile[st], r, group_col0(cq, 0), hp);
+        relu_pack32(v1, hp);
+        store_group(s.h1_tile[st], r, group_col0(cq, 1), hp);
       }
       if (more) store_aug32(s.aug32[st ^ 1], nxt);
       fence_async_smem();
@@ -609,6 +666,16 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------
+static int policy_ctas() {
+  static int n = 0;
+  if (!n) {
+    const char* e = getenv("RL8_H_POLICY_CTAS");  // tuning knob; default measured on B200
+    n = e ? atoi(e) : 78;
+    if (n < 1 || n > kNumSMs - 1) n = kNumSMs / 2;
+  }
+  return n;
+}
+
 int64_t ppo_tc_workspace(const rl8_model*, int64_t max_rows) {
   const int64_t chunk = max_rows < kChunkRows ? max_rows : kChunkRows;
   return 2 * (int64_t)kW2Bytes + 2 * ceil_div(chunk, TILE) * (int64_t)kTileBytes + 256;
@@ -641,6 +708,7 @@ int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_b
     a.slab_env0 = row_begin / batch->T;
     a.slab_nenv = M / batch->T;
   }
+  a.small = (M < (1ll << 31) && (int64_t)(batch->T + 1) * batch->N < (1ll << 31)) ? 1 : 0;
   a.dist_kind = batch->dist_kind, a.hp = *hp;
   a.inv_denom = (float)((double)hp->loss_scale / mean_denominator);
   a.dz[0] = dz0, a.dz[1] = dz1;
@@ -655,6 +723,8 @@ int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_b
     const int64_t ntiles = ceil_div(a.Mc, TILE);
     int grid_h = (int)(2 * ntiles < kNumSMs ? 2 * ntiles : kNumSMs);
     grid_h &= ~1;
+    // a policy tile costs more CUDA-core work than a value tile (wider head, heavier row loss)
+    a.n_pi = grid_h == kNumSMs ? policy_ctas() : grid_h / 2;
     int grid_w = (int)(4 * ntiles < kNumSMs ? 4 * ntiles : kNumSMs);
     grid_w &= ~3;
 #define RL8_UPD(PV)                                                                              \
