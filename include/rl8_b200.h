@@ -272,6 +272,12 @@ int rl8_tc_selftest_tf32(const float* A, const float* B, float* D, int32_t N, rl
  * (tcgen05.st / tcgen05.ld 32x32b.x32), as used to park packed bf16 activations in TMEM. */
 int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream);
 
+/* Microbenchmark: out_cycles[0] = SM cycles for `iters` rounds of tensor-memory reads by `nwarps`
+ * warps of one CTA (mode 0: 32x32b.x32 + wait; 1: two loads per wait; 2: x16 loads).  Sizes the
+ * epilogue budgets in DESIGN.md. */
+int rl8_tc_bench_tmem(long long* out_cycles, int32_t nwarps, int32_t iters, int32_t mode,
+                      rl8_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -348,6 +348,52 @@ tc_selftest_tmem_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ 
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+// Microbenchmark: cycles for `iters` rounds of tensor-memory reads by `blockDim.x / 32` warps,
+// each warp reading 32 lanes x (32 * width) columns per round.  mode 0: one 32x32b.x32 load +
+// wait per round; mode 1: two loads in flight per wait; mode 2: x16 loads.
+__global__ void __launch_bounds__(512, 1) tc_bench_tmem_kernel(long long* out, int iters, int mode) {
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid < 32) tmem_alloc(&tmem_ptr, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_ptr;
+  const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+  float acc = 0.0f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    if (mode == 0) {
+      float v[32];
+      tmem_ld32(base + (uint32_t)((i & 1) * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc += v[j];
+    } else if (mode == 1) {
+      float v0[32], v1[32];
+      tmem_ld32_nowait(base, v0);
+      tmem_ld32_nowait(base + 32, v1);
+      tmem_wait_ld();
+      reg_fence32(v0);
+      reg_fence32(v1);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc += v0[j] + v1[j];
+    } else {
+      float v[16];
+      tmem_ld16(base + (uint32_t)((i & 3) * 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc += v[j];
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) out[0] = t1 - t0;
+  if (acc == 123.456f) out[1] = 1;
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 static int launch_forward(const NetParams& np, const RowMap& map, int64_t rows, float* out,
                           int tanh_col1, cudaStream_t st) {
@@ -447,4 +493,12 @@ extern "C" int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_strea
   if (!in || !out) return RL8_ERR_ARG;
   tc_selftest_tmem_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(in, out);
   return check_launch("tc_selftest_tmem");
+}
+
+// Microbenchmark hook: SM cycles for `iters` rounds of TMEM reads with `nwarps` warps (see kernel).
+extern "C" int rl8_tc_bench_tmem(long long* out_cycles, int32_t nwarps, int32_t iters, int32_t mode,
+                                 rl8_stream_t stream) {
+  if (!out_cycles || nwarps < 1 || nwarps > 16 || iters < 1) return RL8_ERR_ARG;
+  tc_bench_tmem_kernel<<<1, 32 * nwarps, 0, (cudaStream_t)stream>>>(out_cycles, iters, mode);
+  return check_launch("tc_bench_tmem");
 }
