@@ -68,6 +68,19 @@ def golden_case(request: pytest.FixtureRequest) -> Golden:
     return Golden(request.param)
 
 
+RECURRENT_GOLDEN_CASES = [
+    "rec_discrete_dummy",
+    "rec_cartpole",
+    "rec_pendulum_squashed",
+    "rec_continuous_dummy_normal",
+]
+
+
+@pytest.fixture(params=RECURRENT_GOLDEN_CASES)
+def recurrent_golden_case(request: pytest.FixtureRequest) -> Golden:
+    return Golden(request.param)
+
+
 @pytest.fixture
 def kat() -> Golden:
     return Golden("kat")
