@@ -169,6 +169,11 @@ int rl8_gae_normalize(float* advantages, int64_t N, int32_t T, int64_t stride_n,
  *   6 min r, 7 max r, 8 min R, 9 max R) where R = per-env sum of rewards over t < T. */
 int rl8_collect_stats(const float* rewards, const float* rdr, int64_t N, int32_t T, double* acc,
                       rl8_stream_t stream);
+/* Same, with the reward statistics (acc 0..3, 6..9) taken over slots reward_t0 <= t < T: the
+ * recurrent algorithm summarises `rewards[:, 1:-1]` (src/rl8/algorithms/_recurrent.py:449), i.e.
+ * reward_t0 = 1; the rdr moments still cover slots 1..T. */
+int rl8_collect_stats_from(const float* rewards, const float* rdr, int64_t N, int32_t T,
+                           int32_t reward_t0, double* acc, rl8_stream_t stream);
 
 /* ---- policy / value networks ------------------------------------------------------- */
 
@@ -243,6 +248,73 @@ int rl8_ppo_losses(int dist_kind, const float* features, int32_t P, const float*
                    const float* returns, int64_t B, double mean_denominator,
                    const rl8_ppo_hparams* hp, double* loss_sums, float* d_features,
                    float* d_values, rl8_stream_t stream);
+
+/* ---- recurrent policy: RecurrentAlgorithm (src/rl8/algorithms/_recurrent.py) ----------------- */
+
+/* Default recurrent models (src/rl8/models/_recurrent.py:169-341): ONE nn.LSTM(D, H) whose
+ * latent h_t feeds the policy head ([P,H]: A logits, or {action_mean; action_log_std} stacked)
+ * and the value head ([1,H]).  torch's gate packing: rows [0,H) input, [H,2H) forget,
+ * [2H,3H) cell ("g"), [3H,4H) output.  All pointers address one flat fp32 buffer. */
+typedef struct {
+  int32_t D, H, P;
+  const float *w_ih, *w_hh, *b_ih, *b_hh; /* [4H,D] [4H,H] [4H] [4H] */
+  const float *pi_w, *pi_b;               /* [P,H] [P] */
+  const float *vf_w, *vf_b;               /* [1,H] [1] */
+} rl8_lstm_model;
+
+/* RecurrentAlgorithm.collect (src/rl8/algorithms/_recurrent.py:356-445).  `ro` is the
+ * feedforward rollout block (same fields, same layouts).  hidden / cell are horizon-major
+ * [T+1][N][H]: slab t is the state the policy CONSUMES at step t (slab 0 is an input: the host
+ * copies slab T of the previous collect into it, :380-382); slab t+1 receives the state the
+ * LSTM produced at step t.  Slab t is zeroed first when `t % seq_len == 0 and (seqs + t /
+ * seq_len) % seqs_per_state_reset == 0` -- unless seqs_per_state_reset < 0 and the running
+ * count is non-zero (:384-392).  `seqs` is RecurrentAlgorithmState.seqs at entry; the host
+ * advances it by T / seq_len afterwards (:430-431). */
+typedef struct {
+  rl8_rollout ro;
+  float* hidden; /* [T+1][N][H] */
+  float* cell;   /* [T+1][N][H] */
+  int32_t seq_len, seqs_per_state_reset;
+  int64_t seqs;
+} rl8_recurrent_rollout;
+
+int64_t rl8_lstm_collect_workspace(const rl8_lstm_model* model, int64_t N, int32_t T, int precision);
+int rl8_lstm_collect(const rl8_lstm_model* model, const rl8_recurrent_rollout* rro, int precision,
+                     void* workspace, int64_t workspace_bytes, rl8_stream_t stream);
+
+/* One step of the LSTM + heads on B rows (RecurrentPolicy.sample with a length-1 sequence,
+ * src/rl8/policies/_recurrent.py:68-164): obs (r, d) at obs[r*obs_stride_r + d*obs_stride_d],
+ * h_in/c_in [B][H] -> h_out/c_out [B][H] (may alias the inputs), features[B][P] (log_std
+ * column tanh'ed when apply_tanh_log_std), values[B].  workspace: B*4H floats. */
+int rl8_lstm_forward(const rl8_lstm_model* model, const float* obs, int64_t obs_stride_r,
+                     int64_t obs_stride_d, const float* h_in, const float* c_in, float* h_out,
+                     float* c_out, float* features, float* values, int64_t B,
+                     int apply_tanh_log_std, int precision, void* workspace,
+                     int64_t workspace_bytes, rl8_stream_t stream);
+
+/* One PPO minibatch of SEQUENCES with truncated back-propagation through time
+ * (src/rl8/algorithms/_recurrent.py:517-600).  The [N, T] transitions are cut into
+ * N*T/seq_len sequences, sequence s = n*(T/seq_len) + chunk covering steps chunk*seq_len ..
+ * +seq_len-1 of env n (`buffer.reshape(-1, seq_len)`, :518).  The M sequences seqs[0..M)
+ * (int64 device array; seq_begin.. when NULL) are replayed from their stored chunk-start state
+ * hidden/cell[chunk*seq_len][n] (no gradient flows into stored states), the PPO losses are
+ * taken over all M*seq_len rows, and gradients of `loss_scale * total / world` are ACCUMULATED
+ * into `grads`.  mean_denominator = global number of ROWS the means divide by (M*seq_len on
+ * one GPU).  loss_sums as rl8_ppo_minibatch. */
+typedef struct {
+  rl8_batch b;
+  const float* hidden; /* [T+1][N][H] */
+  const float* cell;   /* [T+1][N][H] */
+  int32_t seq_len;
+} rl8_recurrent_batch;
+
+int64_t rl8_lstm_ppo_workspace(const rl8_lstm_model* model, int64_t max_seqs, int32_t seq_len,
+                               int precision);
+int rl8_lstm_ppo_minibatch(const rl8_lstm_model* model, const rl8_lstm_model* grads,
+                           const rl8_recurrent_batch* batch, const int64_t* seqs,
+                           int64_t seq_begin, int64_t M, double mean_denominator,
+                           const rl8_ppo_hparams* hp, double* loss_sums, int precision,
+                           void* workspace, int64_t workspace_bytes, rl8_stream_t stream);
 
 /* ---- optimizer: clip_grad_norm_ + Adam (src/rl8/algorithms/_feedforward.py:586-593) ----- */
 

@@ -2,7 +2,16 @@
 
 from .algorithms import Algorithm, AlgorithmConfig
 from .env import Env
+from .recurrent import RecurrentAlgorithm, RecurrentAlgorithmConfig, RecurrentTrainer
 from .trainers import Trainer
 
-__all__ = ["Algorithm", "AlgorithmConfig", "Env", "Trainer"]
+__all__ = [
+    "Algorithm",
+    "AlgorithmConfig",
+    "Env",
+    "RecurrentAlgorithm",
+    "RecurrentAlgorithmConfig",
+    "RecurrentTrainer",
+    "Trainer",
+]
 __version__ = "0.1.0"

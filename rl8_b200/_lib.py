@@ -88,6 +88,33 @@ class Batch(C.Structure):
     ]
 
 
+class LstmModel(C.Structure):
+    _fields_ = [("D", C.c_int32), ("H", C.c_int32), ("P", C.c_int32)] + [
+        (name, C.c_void_p)
+        for name in ("w_ih", "w_hh", "b_ih", "b_hh", "pi_w", "pi_b", "vf_w", "vf_b")
+    ]
+
+
+class RecurrentRollout(C.Structure):
+    _fields_ = [
+        ("ro", Rollout),
+        ("hidden", C.c_void_p),
+        ("cell", C.c_void_p),
+        ("seq_len", C.c_int32),
+        ("seqs_per_state_reset", C.c_int32),
+        ("seqs", C.c_int64),
+    ]
+
+
+class RecurrentBatch(C.Structure):
+    _fields_ = [
+        ("b", Batch),
+        ("hidden", C.c_void_p),
+        ("cell", C.c_void_p),
+        ("seq_len", C.c_int32),
+    ]
+
+
 _i32, _i64, _f32, _f64, _vp, _int = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p, C.c_int
 
 # name -> (restype, argtypes); mirrors include/rl8_b200.h one for one.
@@ -105,6 +132,22 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     ),
     "rl8_gae_normalize": (_int, [_vp, _i64, _i32, _i64, _i64, _vp, _vp]),
     "rl8_collect_stats": (_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "rl8_collect_stats_from": (_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "rl8_lstm_collect_workspace": (_i64, [C.POINTER(LstmModel), _i64, _i32, _int]),
+    "rl8_lstm_collect": (
+        _int, [C.POINTER(LstmModel), C.POINTER(RecurrentRollout), _int, _vp, _i64, _vp]
+    ),
+    "rl8_lstm_forward": (
+        _int,
+        [C.POINTER(LstmModel), _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int,
+         _vp, _i64, _vp],
+    ),
+    "rl8_lstm_ppo_workspace": (_i64, [C.POINTER(LstmModel), _i64, _i32, _int]),
+    "rl8_lstm_ppo_minibatch": (
+        _int,
+        [C.POINTER(LstmModel), C.POINTER(LstmModel), C.POINTER(RecurrentBatch), _vp, _i64, _i64,
+         _f64, C.POINTER(PpoHparams), _vp, _int, _vp, _i64, _vp],
+    ),
     "rl8_mlp_forward_workspace": (_i64, [_i32, _i64]),
     "rl8_mlp_forward": (
         _int,

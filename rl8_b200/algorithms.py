@@ -285,6 +285,7 @@ class Algorithm:
             env_was_reset = True
             if rdr_hm is not None:
                 rdr_hm[0].zero_()
+        self._pre_collect()
 
         P = self.policy.model.head_width
         dist_cls = self.policy.distribution_cls
@@ -300,17 +301,19 @@ class Algorithm:
         # statistics + reward scale: one reduction kernel, one readback
         acc = self._stats_acc
         acc.copy_(self._stats_init)
-        rc = self._lib.rl8_collect_stats(
-            _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(rdr_hm), N, T, _lib.ptr(acc), _lib.stream()
+        t0 = self._stats_reward_t0
+        rc = self._lib.rl8_collect_stats_from(
+            _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(rdr_hm), N, T, t0, _lib.ptr(acc),
+            _lib.stream(),
         )
-        _lib.check(rc, "rl8_collect_stats")
+        _lib.check(rc, "rl8_collect_stats_from")
         self.last_launches["collect"] += 1
         world = _world()
         parallel.reduce_collect_acc_(acc)
         a = acc.tolist()  # the one device->host sync of collect()
         n_r, n_R = float(N * T * world), float(N * world)
         mean_std = parallel.mean_std
-        r_mean, r_std = mean_std(a[0], a[1], n_r)
+        r_mean, r_std = mean_std(a[0], a[1], float(N * (T - t0) * world))
         R_mean, R_std = mean_std(a[2], a[3], n_R)
         stats: CollectStats = {
             "returns/min": a[8],
@@ -324,6 +327,7 @@ class Algorithm:
         }
         self.state.horizons += 1
         self.state.buffered = True
+        self._post_collect()
         if hp.normalize_rewards:
             # float(torch.std(rdr[:, 1:])) -- an f32 value in the reference
             self.state.reward_scale = float(torch.tensor(mean_std(a[4], a[5], n_r)[1], dtype=torch.float32))
@@ -333,6 +337,15 @@ class Algorithm:
         stats["env/steps"] = hp.num_envs * hp.horizon
         stats["profiling/collect_ms"] = (time.perf_counter_ns() - start) / 1e6
         return stats
+
+    #: first reward slot of the collect statistics (the recurrent algorithm uses 1)
+    _stats_reward_t0 = 0
+
+    def _pre_collect(self) -> None:
+        """Hook between the env reset / carry-over and the rollout."""
+
+    def _post_collect(self) -> None:
+        """Hook after the rollout (counters)."""
 
     def _rollout_struct(self, noise: None | torch.Tensor, deterministic: bool) -> _lib.Rollout:
         hp, buf, env = self.hparams, self.buffer, self.env
@@ -439,26 +452,15 @@ class Algorithm:
 
         # -- PPO epochs ---------------------------------------------------------------------
         model = self.policy.model
-        m = model.struct_for(model.flat_params)
-        g = model.struct_for(self._grads)
         prec = self.policy.precision
         M = hp.sgd_minibatch_size
-        nbytes = int(lib.rl8_ppo_workspace(m, M, prec))
-        if nbytes < 0:
-            _lib.check(nbytes, "rl8_ppo_workspace")
-        ws = self._workspace("ppo", nbytes)
-        batch = _lib.Batch()
-        batch.dist_kind = self.policy.distribution_cls.rl8_kind
-        batch.T, batch.N = T, N
-        batch.obs = buf.hm[DataKeys.OBS].data_ptr()
-        batch.actions = buf.hm[DataKeys.ACTIONS].data_ptr()
-        batch.logp = buf.hm[DataKeys.LOGP].data_ptr()
-        batch.advantages = buf.hm[DataKeys.ADVANTAGES].data_ptr()
-        batch.returns = buf.hm[DataKeys.RETURNS].data_ptr()
+        batch = self._batch_struct()
+        launch_minibatch, mb_launches = self._minibatch_launcher(batch, M)
+        units, rows_per_unit = self._update_units()
 
         accum = hp.num_minibatches if hp.accumulate_grads else 1
         entropy_coeff = self.entropy_scheduler.coeff
-        if entropy_coeff != 0 and batch.dist_kind == _lib.DIST_SQUASHED_NORMAL:
+        if entropy_coeff != 0 and self.policy.distribution_cls.rl8_kind == _lib.DIST_SQUASHED_NORMAL:
             self.policy.distribution_cls({}, model).entropy()  # raises like the reference
         ppo = _lib.PpoHparams(
             hp.clip_param, hp.dual_clip_param or 0.0, entropy_coeff, hp.vf_clip_param,
@@ -471,22 +473,19 @@ class Algorithm:
         k = 0  # minibatches processed
         applied: list[bool] = []  # step boundary flags per minibatch
         stop_early = False
-        mb_launches = 34 if prec == _lib.PREC_FP32 else 4
-        chunks = max(1, -(-M // 65536)) if prec == _lib.PREC_FP32 else 1
         for _ in range(hp.num_sgd_iters):
             # A single minibatch is the whole buffer: its loss is a sum over all rows, so the
             # reference's permutation (src/rl8/_utils.py:211-218) only reorders that sum.
             shuffle = hp.shuffle_minibatches and hp.num_minibatches > 1
-            perm = torch.randperm(N * T, device=self.device) if shuffle else None
+            perm = torch.randperm(units, device=self.device) if shuffle else None
             for i in range(hp.num_minibatches):
                 step_this_batch = (i + 1) % accum == 0
                 rows = None if perm is None else perm[i * M : (i + 1) * M]
-                rc = lib.rl8_ppo_minibatch(
-                    m, g, batch, _lib.ptr(rows), i * M, M, float(M * world), ppo,
-                    ctypes.c_void_p(sums.data_ptr() + 40 * k), prec, _lib.ptr(ws), ws.numel(), st,
+                launch_minibatch(
+                    rows, i * M, float(M * rows_per_unit * world), ppo,
+                    ctypes.c_void_p(sums.data_ptr() + 40 * k),
                 )
-                _lib.check(rc, "rl8_ppo_minibatch")
-                launches += mb_launches * chunks
+                launches += mb_launches
                 applied.append(step_this_batch)
                 k += 1
                 if hp.target_kl_div is not None:
@@ -548,10 +547,7 @@ class Algorithm:
         self.lr_scheduler.step(hp.num_envs * self.state.horizons)
         self.entropy_scheduler.step(hp.num_envs * self.state.horizons)
 
-        # Fresh (zeroed) buffer that only keeps the final observation (:603-610).
-        final_obs = buf.hm[DataKeys.OBS][T].clone()
-        buf.zero_()
-        buf.hm[DataKeys.OBS][T].copy_(final_obs)
+        self._reset_buffer()
         self.state.buffered = False
         self.last_launches["step"] = launches
 
@@ -563,6 +559,50 @@ class Algorithm:
         torch.cuda.current_stream().synchronize()
         stats["profiling/step_ms"] = (time.perf_counter_ns() - start) / 1e6
         return stats
+
+    # -- pieces of step() the recurrent algorithm overrides --------------------------------------
+    def _batch_struct(self) -> _lib.Batch:
+        hp, buf = self.hparams, self.buffer
+        batch = _lib.Batch()
+        batch.dist_kind = self.policy.distribution_cls.rl8_kind
+        batch.T, batch.N = hp.horizon, hp.num_envs
+        batch.obs = buf.hm[DataKeys.OBS].data_ptr()
+        batch.actions = buf.hm[DataKeys.ACTIONS].data_ptr()
+        batch.logp = buf.hm[DataKeys.LOGP].data_ptr()
+        batch.advantages = buf.hm[DataKeys.ADVANTAGES].data_ptr()
+        batch.returns = buf.hm[DataKeys.RETURNS].data_ptr()
+        return batch
+
+    def _update_units(self) -> tuple[int, int]:
+        """(number of minibatch units in the buffer, transitions per unit)."""
+        return self.hparams.num_envs * self.hparams.horizon, 1
+
+    def _minibatch_launcher(self, batch: Any, M: int) -> tuple[Any, int]:
+        """Returns ``(launch(rows, begin, denominator, ppo, sums_ptr), kernel launches per call)``."""
+        lib, model, prec = self._lib, self.policy.model, self.policy.precision
+        m = model.struct_for(model.flat_params)
+        g = model.struct_for(self._grads)
+        nbytes = int(lib.rl8_ppo_workspace(m, M, prec))
+        if nbytes < 0:
+            _lib.check(nbytes, "rl8_ppo_workspace")
+        ws = self._workspace("ppo", nbytes)
+
+        def launch(rows: Any, begin: int, denom: float, ppo: Any, sums_ptr: Any) -> None:
+            rc = lib.rl8_ppo_minibatch(
+                m, g, batch, _lib.ptr(rows), begin, M, denom, ppo, sums_ptr, prec, _lib.ptr(ws),
+                ws.numel(), _lib.stream(),
+            )
+            _lib.check(rc, "rl8_ppo_minibatch")
+
+        per_call = 34 * max(1, -(-M // 65536)) if prec == _lib.PREC_FP32 else 4
+        return launch, per_call
+
+    def _reset_buffer(self) -> None:
+        """Fresh (zeroed) buffer that only keeps the final observation (:603-610)."""
+        buf, T = self.buffer, self.hparams.horizon
+        final_obs = buf.hm[DataKeys.OBS][T].clone()
+        buf.zero_()
+        buf.hm[DataKeys.OBS][T].copy_(final_obs)
 
     # ------------------------------------------------------------------------------------
     def validate(self) -> None:

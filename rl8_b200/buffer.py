@@ -13,7 +13,7 @@ unchanged.  Fields start 16-byte aligned; slabs stay aligned (and the kernels us
 
 from __future__ import annotations
 
-from typing import Iterator
+from typing import Any, Iterator
 
 import torch
 
@@ -37,8 +37,15 @@ class RolloutBuffer:
             DataKeys.OBS: T1 * self.obs_dim * N,
             DataKeys.ACTIONS: T1 * N * (2 if self.discrete else 1),
         }
+        self.state_dim = 0
         for k in spec.keys():
-            if k not in words:
+            if k == DataKeys.STATES:
+                # LSTM states of the recurrent algorithm: [T+1][N][H] per state tensor, so the
+                # slab of one step is the row-major [N, H] operand of that step's GEMM.
+                for sk, sspec in spec[k].items():
+                    self.state_dim = int(sspec.shape[-1])
+                    words[sk] = T1 * N * self.state_dim
+            elif k not in words:
                 words[k] = T1 * N
         self._raw = torch.zeros(sum((w + 3) // 4 * 4 for w in words.values()), device=device)
         self.hm: dict[str, torch.Tensor] = {}
@@ -49,10 +56,22 @@ class RolloutBuffer:
                 self.hm[k] = seg.view(T1, self.obs_dim, N)
             elif k == DataKeys.ACTIONS and self.discrete:
                 self.hm[k] = seg.view(torch.int64).view(T1, N)
+            elif k in (DataKeys.HIDDEN_STATES, DataKeys.CELL_STATES):
+                self.hm[k] = seg.view(T1, N, self.state_dim)
             else:
                 self.hm[k] = seg.view(T1, N)
             off += (w + 3) // 4 * 4
-        self._views = {k: self._env_major(k) for k in self.hm}
+        self._views: dict[str, Any] = {
+            k: self._env_major(k)
+            for k in self.hm
+            if k not in (DataKeys.HIDDEN_STATES, DataKeys.CELL_STATES)
+        }
+        if self.state_dim:
+            # buffer["states"]["hidden_states"]: [N, T+1, num_layers=1, H] like the reference
+            self._views[DataKeys.STATES] = {
+                k: self.hm[k].permute(1, 0, 2).unsqueeze(2)
+                for k in (DataKeys.HIDDEN_STATES, DataKeys.CELL_STATES)
+            }
         self.batch_size = torch.Size([N, T1])
 
     def _env_major(self, key: str) -> torch.Tensor:
@@ -62,7 +81,7 @@ class RolloutBuffer:
         return t.permute(1, 0).unsqueeze(-1)  # [N, T+1, 1]
 
     # -- mapping protocol (env-major views) -------------------------------------------------
-    def __getitem__(self, key: str) -> torch.Tensor:
+    def __getitem__(self, key: str) -> Any:
         return self._views[key]
 
     def __contains__(self, key: str) -> bool:

@@ -97,20 +97,25 @@ int env_dims(int env_kind, int* S, int* D, int* P_discrete) {
   return RL8_ERR_ARG;
 }
 
-int validate_rollout(const rl8_model* model, const rl8_rollout* ro) {
-  if (!model || !ro || !ro->env_state || !ro->obs || !ro->actions || !ro->logp || !ro->values ||
+int validate_rollout_dims(int mD, int mH, int mP, const rl8_rollout* ro) {
+  if (!ro || !ro->env_state || !ro->obs || !ro->actions || !ro->logp || !ro->values ||
       !ro->rewards || ro->N <= 0 || ro->T <= 0)
     return RL8_ERR_ARG;
   if (!ro->deterministic && !ro->noise) return RL8_ERR_ARG;
   int S, D, Pd;
   if (env_dims(ro->env_kind, &S, &D, &Pd)) return RL8_ERR_ARG;
-  if (model->D != D || model->H != 256) return RL8_ERR_UNSUPPORTED;
+  if (mD != D || mH != 256) return RL8_ERR_UNSUPPORTED;
   if (Pd) {
-    if (ro->dist_kind != RL8_DIST_CATEGORICAL || model->P != Pd) return RL8_ERR_UNSUPPORTED;
+    if (ro->dist_kind != RL8_DIST_CATEGORICAL || mP != Pd) return RL8_ERR_UNSUPPORTED;
   } else {
-    if (ro->dist_kind == RL8_DIST_CATEGORICAL || model->P != 2) return RL8_ERR_UNSUPPORTED;
+    if (ro->dist_kind == RL8_DIST_CATEGORICAL || mP != 2) return RL8_ERR_UNSUPPORTED;
   }
   return RL8_OK;
+}
+
+int validate_rollout(const rl8_model* model, const rl8_rollout* ro) {
+  if (!model) return RL8_ERR_ARG;
+  return validate_rollout_dims(model->D, model->H, model->P, ro);
 }
 
 int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st) {

@@ -266,14 +266,14 @@ gae_normalize_kernel(float* __restrict__ adv, int64_t N, int T, int64_t sn, int6
 // Horizon-major rewards[T+1][N], rdr[T+1][N]; one env per thread, coalesced along n.
 __global__ void __launch_bounds__(256)
 collect_stats_kernel(const float* __restrict__ rewards, const float* __restrict__ rdr, int64_t N,
-                     int T, double* __restrict__ acc) {
+                     int T, int t0, double* __restrict__ acc) {
   __shared__ double red[32];
   double sr = 0, sr2 = 0, sR = 0, sR2 = 0, sd = 0, sd2 = 0;
   double mnr = INFINITY, mxr = -INFINITY, mnR = INFINITY, mxR = -INFINITY;
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
        n += (int64_t)gridDim.x * blockDim.x) {
     float R = 0.0f;  // torch.sum(rewards, dim=1): sequential f32 accumulation over t
-    for (int t = 0; t < T; ++t) {
+    for (int t = t0; t < T; ++t) {
       float r = rewards[(int64_t)t * N + n];
       R = add(R, r);
       sr += r;
@@ -360,10 +360,16 @@ extern "C" int rl8_gae_normalize(float* advantages, int64_t N, int32_t T, int64_
   return check_launch("rl8_gae_normalize");
 }
 
+extern "C" int rl8_collect_stats_from(const float* rewards, const float* rdr, int64_t N,
+                                      int32_t T, int32_t reward_t0, double* acc,
+                                      rl8_stream_t stream) {
+  if (!rewards || !acc || N <= 0 || T <= 0 || reward_t0 < 0 || reward_t0 >= T) return RL8_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  collect_stats_kernel<<<grid_for(N, 256, 4, 2), 256, 0, st>>>(rewards, rdr, N, T, reward_t0, acc);
+  return check_launch("rl8_collect_stats");
+}
+
 extern "C" int rl8_collect_stats(const float* rewards, const float* rdr, int64_t N, int32_t T,
                                  double* acc, rl8_stream_t stream) {
-  if (!rewards || !acc || N <= 0 || T <= 0) return RL8_ERR_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  collect_stats_kernel<<<grid_for(N, 256, 4, 2), 256, 0, st>>>(rewards, rdr, N, T, acc);
-  return check_launch("rl8_collect_stats");
+  return rl8_collect_stats_from(rewards, rdr, N, T, 0, acc, stream);
 }

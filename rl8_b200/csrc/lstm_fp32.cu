@@ -1,0 +1,474 @@
+// Recurrent (LSTM) policy, fp32 CUDA-core path (RL8_PREC_FP32; reference `enable_amp=False`).
+//
+//   rollout  (src/rl8/algorithms/_recurrent.py:356-445): per step  SGEMM h.W_hh^T -> cell kernel
+//            (adds x.W_ih^T + biases, gate non-linearities, writes the state slabs) -> heads ->
+//            the feedforward path's fused [sample + logp + env.step + buffer writes] tail.
+//   update   (:517-600): minibatches of seq_len-step sequences replayed from the stored
+//            chunk-start states; hand-derived back-propagation through time.
+//
+// Gate packing follows torch.nn.LSTM: [i | f | g | o] blocks of H rows; c' = sig(f) c + sig(i)
+// tanh(g), h' = sig(o) tanh(c') (restated in oracle/recurrent_oracle.py:lstm_cell).
+#include "dist.cuh"
+#include "mlp_fp32.cuh"
+#include "ppo_loss.cuh"
+
+namespace rl8 {
+
+// collect.cu
+int validate_rollout_dims(int mD, int mH, int mP, const rl8_rollout* ro);
+int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st);
+
+constexpr int kLH = 256;   // hidden width of the default recurrent models
+constexpr int kLD = 8;     // widest observation on the fused path
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- forward cell --------------------------------------------------------------------------------
+// Block = H threads (hidden unit j, its 4 x D input weights and 8 biases in registers), rows
+// grid-strided.  G[r][4H] holds h_prev.W_hh^T on entry; on exit `act` (may alias G) holds the
+// gate ACTIVATIONS i, f, g, o (kept for the backward pass; NULL in the rollout).
+__global__ void __launch_bounds__(kLH)
+lstm_cell_fwd_kernel(const float* G, RowMap xmap, int D, int64_t rows,
+                     const float* __restrict__ w_ih, const float* __restrict__ b_ih,
+                     const float* __restrict__ b_hh, const float* c_prev, float* act, float* c_out,
+                     float* __restrict__ h_out) {
+  const int j = threadIdx.x;
+  float w[4][kLD], bi[4], bh[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+#pragma unroll
+    for (int d = 0; d < kLD; ++d) w[g][d] = d < D ? w_ih[(g * kLH + j) * D + d] : 0.0f;
+    bi[g] = b_ih[g * kLH + j];
+    bh[g] = b_hh[g * kLH + j];
+  }
+  const int64_t ds = xmap.dstride();
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int64_t xo = xmap.offset(r);
+    float x[kLD];
+#pragma unroll
+    for (int d = 0; d < kLD; ++d) x[d] = d < D ? xmap.obs[xo + d * ds] : 0.0f;
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float a = bi[g];
+#pragma unroll
+      for (int d = 0; d < kLD; ++d)
+        if (d < D) a = fmaf(x[d], w[g][d], a);
+      pre[g] = a + (G[r * 4 * kLH + g * kLH + j] + bh[g]);
+    }
+    const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]),
+                og = sigmoidf_(pre[3]);
+    const float c = fg * c_prev[r * kLH + j] + ig * gg;
+    const float h = og * tanhf(c);
+    if (act) {
+      act[r * 4 * kLH + 0 * kLH + j] = ig;
+      act[r * 4 * kLH + 1 * kLH + j] = fg;
+      act[r * 4 * kLH + 2 * kLH + j] = gg;
+      act[r * 4 * kLH + 3 * kLH + j] = og;
+    }
+    c_out[r * kLH + j] = c;
+    h_out[r * kLH + j] = h;
+  }
+}
+
+static int launch_cell_fwd(const rl8_lstm_model* m, const float* G, const RowMap& xmap, int64_t rows,
+                           const float* c_prev, float* act, float* c_out, float* h_out,
+                           cudaStream_t st) {
+  int grid = (int)(rows < (int64_t)kNumSMs * 16 ? rows : (int64_t)kNumSMs * 16);
+  lstm_cell_fwd_kernel<<<grid, kLH, 0, st>>>(G, xmap, m->D, rows, m->w_ih, m->b_ih, m->b_hh, c_prev,
+                                             act, c_out, h_out);
+  return check_launch("lstm_cell_fwd");
+}
+
+// One LSTM step + heads.  G: [rows][4H] scratch.
+static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t rows,
+                          const float* h_in, const float* c_in, float* h_out, float* c_out,
+                          float* act, float* G, float* features, float* values, int tanh_col1,
+                          cudaStream_t st) {
+  int rc = launch_sgemm(true, true, EPI_STORE, h_in, m->w_hh, G, rows, 4 * kLH, kLH, kLH, kLH,
+                        4 * kLH, nullptr, 1, st);
+  if (rc) return rc;
+  if ((rc = launch_cell_fwd(m, G, xmap, rows, c_in, act, c_out, h_out, st))) return rc;
+  if (features &&
+      (rc = launch_head_fwd(h_out, rows, kLH, m->P, m->pi_w, m->pi_b, features, tanh_col1, st)))
+    return rc;
+  if (values && (rc = launch_head_fwd(h_out, rows, kLH, 1, m->vf_w, m->vf_b, values, 0, st)))
+    return rc;
+  return RL8_OK;
+}
+
+static int check_model(const rl8_lstm_model* m) {
+  if (!m || !m->w_ih || !m->w_hh || !m->b_ih || !m->b_hh || !m->pi_w || !m->pi_b || !m->vf_w ||
+      !m->vf_b)
+    return RL8_ERR_ARG;
+  if (m->H != kLH || m->D < 1 || m->D > kLD || m->P < 2 || m->P > kMaxP) return RL8_ERR_UNSUPPORTED;
+  return RL8_OK;
+}
+
+// Does step t of this collect start from re-initialised (zero) states?  (:384-392)
+static bool state_reset_at(const rl8_recurrent_rollout* rro, int t) {
+  if (t % rro->seq_len) return false;
+  const int64_t seqs = rro->seqs + t / rro->seq_len;
+  if (seqs && rro->seqs_per_state_reset < 0) return false;
+  return (seqs % rro->seqs_per_state_reset) == 0;
+}
+
+int lstm_collect_fp32(const rl8_lstm_model* m, const rl8_recurrent_rollout* rro, void* workspace,
+                      int64_t workspace_bytes, cudaStream_t st) {
+  const rl8_rollout* ro = &rro->ro;
+  const int64_t N = ro->N;
+  const int T = ro->T, D = m->D;
+  const int64_t need = (N * 4 * kLH + 2 * N * kLH + N * kMaxP) * 4;
+  if (!workspace || workspace_bytes < need) return RL8_ERR_WORKSPACE;
+  float* G = (float*)workspace;
+  float* hs = G + N * 4 * kLH;  // scratch state for the bootstrap value
+  float* cs = hs + N * kLH;
+  float* feat = cs + N * kLH;
+  const bool continuous = ro->dist_kind != RL8_DIST_CATEGORICAL;
+  RowMap map{};
+  map.mode = 0, map.stride_r = 1, map.stride_d = N, map.D = D;
+  const int64_t slab = N * kLH;
+  for (int t = 0; t < T; ++t) {
+    float* h_t = rro->hidden + (int64_t)t * slab;
+    float* c_t = rro->cell + (int64_t)t * slab;
+    if (state_reset_at(rro, t)) {
+      cudaMemsetAsync(h_t, 0, slab * 4, st);
+      cudaMemsetAsync(c_t, 0, slab * 4, st);
+    }
+    map.obs = ro->obs + (int64_t)t * D * N;
+    int rc = lstm_step_fp32(m, map, N, h_t, c_t, h_t + slab, c_t + slab, nullptr, G, feat,
+                            ro->values + (int64_t)t * N, continuous, st);
+    if (rc) return rc;
+    if ((rc = collect_tail(ro, t, feat, st))) return rc;
+  }
+  // bootstrap value from the last observation and the final states (:433-445)
+  map.obs = ro->obs + (int64_t)T * D * N;
+  return lstm_step_fp32(m, map, N, rro->hidden + (int64_t)T * slab, rro->cell + (int64_t)T * slab,
+                        hs, cs, nullptr, G, nullptr, ro->values + (int64_t)T * N, 0, st);
+}
+
+// ---- update ----------------------------------------------------------------------------------------
+
+// rows_k[k*C + r] = seq(r)*L + k (flattened transition, row = n*T + t);  h0/c0[r] = stored
+// chunk-start state of sequence r.
+__global__ void __launch_bounds__(256)
+seq_setup_kernel(const int64_t* __restrict__ seqs, int64_t seq_begin, int64_t C, int L, int T,
+                 int64_t N, const float* __restrict__ hidden, const float* __restrict__ cell,
+                 int64_t* __restrict__ rows_k, float* __restrict__ h0, float* __restrict__ c0) {
+  const int Q = kLH / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C * Q;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Q;
+    const int q = (int)(i - r * Q);
+    const int64_t s = seqs ? seqs[r] : seq_begin + r;
+    if (q < L) rows_k[(int64_t)q * C + r] = s * L + q;
+    if (q == 0)
+      for (int k = Q; k < L; ++k) rows_k[(int64_t)k * C + r] = s * L + k;  // L > 64 (rare)
+    const int64_t g = s * L, n = g / T, t = g - n * T;
+    const int64_t src = (t * N + n) * kLH + q * 4;
+    *reinterpret_cast<float4*>(h0 + r * kLH + q * 4) = *reinterpret_cast<const float4*>(hidden + src);
+    *reinterpret_cast<float4*>(c0 + r * kLH + q * 4) = *reinterpret_cast<const float4*>(cell + src);
+  }
+}
+
+// dh[r][j] = sum_p dpi[r][p] pi_w[p][j] + dvf[r] vf_w[j] (+ dh[r][j] when accumulate)
+template <int P>
+__global__ void __launch_bounds__(256)
+lstm_dh_kernel(const float* __restrict__ dpi, const float* __restrict__ dvf, int64_t rows,
+               const float* __restrict__ pi_w, const float* __restrict__ vf_w, int accumulate,
+               float* __restrict__ dh) {
+  constexpr int Q = kLH / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * Q;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Q;
+    const int j = (int)(i - r * Q) * 4;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float d = dpi[r * P + p];
+      const float4 w = *reinterpret_cast<const float4*>(pi_w + p * kLH + j);
+      g[0] = fmaf(d, w.x, g[0]), g[1] = fmaf(d, w.y, g[1]);
+      g[2] = fmaf(d, w.z, g[2]), g[3] = fmaf(d, w.w, g[3]);
+    }
+    const float dv = dvf[r];
+    const float4 wv = *reinterpret_cast<const float4*>(vf_w + j);
+    g[0] = fmaf(dv, wv.x, g[0]), g[1] = fmaf(dv, wv.y, g[1]);
+    g[2] = fmaf(dv, wv.z, g[2]), g[3] = fmaf(dv, wv.w, g[3]);
+    float4* out = reinterpret_cast<float4*>(dh + r * kLH + j);
+    if (accumulate) {
+      const float4 o = *out;
+      g[0] += o.x, g[1] += o.y, g[2] += o.z, g[3] += o.w;
+    }
+    *out = make_float4(g[0], g[1], g[2], g[3]);
+  }
+}
+
+static int launch_dh(int P, const float* dpi, const float* dvf, int64_t rows, const float* pi_w,
+                     const float* vf_w, int accumulate, float* dh, cudaStream_t st) {
+  int grid = grid_for(rows * 64, 256, 8, 4);
+#define RL8_DH(PV)                                                                          \
+  case PV:                                                                                  \
+    lstm_dh_kernel<PV><<<grid, 256, 0, st>>>(dpi, dvf, rows, pi_w, vf_w, accumulate, dh);    \
+    break;
+  switch (P) {
+    RL8_DH(2) RL8_DH(3) RL8_DH(4) RL8_DH(5) RL8_DH(6) RL8_DH(7) RL8_DH(8)
+    default: return RL8_ERR_UNSUPPORTED;
+  }
+#undef RL8_DH
+  return check_launch("lstm_dh");
+}
+
+// Cell backward, one (row, unit) per thread.  act holds i,f,g,o and is overwritten with the
+// PRE-activation gate gradients; dc (in/out) carries dL/dc across steps (has_dc_in = 0 for the
+// last step of a sequence).
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ c, const float* __restrict__ c_prev,
+                     const float* __restrict__ dh, float* __restrict__ dc, int has_dc_in,
+                     int64_t rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * kLH;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kLH;
+    const int j = (int)(i - r * kLH);
+    float* a = act + r * 4 * kLH + j;
+    const float ig = a[0], fg = a[kLH], gg = a[2 * kLH], og = a[3 * kLH];
+    const float tc = tanhf(c[i]);
+    const float dhv = dh[i];
+    float dcv = dhv * og * (1.0f - tc * tc);
+    if (has_dc_in) dcv += dc[i];
+    a[0] = dcv * gg * ig * (1.0f - ig);
+    a[kLH] = dcv * c_prev[i] * fg * (1.0f - fg);
+    a[2 * kLH] = dcv * ig * (1.0f - gg * gg);
+    a[3 * kLH] = dhv * tc * og * (1.0f - og);
+    dc[i] = dcv * fg;
+  }
+}
+
+// gw_ih[g][d] += sum_r dG[r][g] x[r][d];  gb_ih[g], gb_hh[g] += sum_r dG[r][g]   (g < 4H)
+constexpr int kGrRows = 64;
+__global__ void __launch_bounds__(256)
+lstm_gate_reduce_kernel(const float* __restrict__ dG, int64_t rows, RowMap xmap, int D,
+                        float* __restrict__ gw_ih, float* __restrict__ gb_ih,
+                        float* __restrict__ gb_hh, int64_t rows_per_block) {
+  __shared__ float sx[kGrRows][kLD];
+  const int g = blockIdx.y * 256 + threadIdx.x;
+  float acc[kLD], accb = 0.0f;
+#pragma unroll
+  for (int d = 0; d < kLD; ++d) acc[d] = 0.0f;
+  const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t rend = min(rows, rbeg + rows_per_block);
+  const int64_t ds = xmap.dstride();
+  for (int64_t r0 = rbeg; r0 < rend; r0 += kGrRows) {
+    const int nr = (int)min((int64_t)kGrRows, rend - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kGrRows * D; i += blockDim.x) {
+      const int d = i / kGrRows, r = i - d * kGrRows;
+      sx[r][d] = r < nr ? xmap.obs[xmap.offset(r0 + r) + d * ds] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = 0; r < nr; ++r) {
+      const float v = dG[(r0 + r) * 4 * kLH + g];
+      accb += v;
+#pragma unroll
+      for (int d = 0; d < kLD; ++d)
+        if (d < D) acc[d] = fmaf(v, sx[r][d], acc[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kLD; ++d)
+    if (d < D) atomicAdd(gw_ih + (int64_t)g * D + d, acc[d]);
+  atomicAdd(gb_ih + g, accb);
+  atomicAdd(gb_hh + g, accb);
+}
+
+static int launch_gate_reduce(const float* dG, int64_t rows, const RowMap& xmap, int D, float* gw_ih,
+                              float* gb_ih, float* gb_hh, cudaStream_t st) {
+  int64_t blocks = min(ceil_div(rows, kGrRows), (int64_t)kNumSMs * 2);
+  int64_t rpb = round_up(ceil_div(rows, blocks), kGrRows);
+  blocks = ceil_div(rows, rpb);
+  lstm_gate_reduce_kernel<<<dim3((unsigned)blocks, 4), 256, 0, st>>>(dG, rows, xmap, D, gw_ih, gb_ih,
+                                                                    gb_hh, rpb);
+  return check_launch("lstm_gate_reduce");
+}
+
+// Sequences resident per update chunk: bounds the activation workspace (6H floats per row).
+static int64_t lstm_chunk_seqs(int64_t max_seqs, int L) {
+  int64_t cap = 32768 / L;
+  if (cap < 1) cap = 1;
+  return max_seqs < cap ? max_seqs : cap;
+}
+
+int64_t lstm_ppo_fp32_workspace(int64_t max_seqs, int L) {
+  const int64_t C = lstm_chunk_seqs(max_seqs, L);
+  // per step: act [C][4H], c [C][H], h [C][H], out_pi/dout_pi [C][kMaxP] x2, out_vf/dout_vf [C] x2
+  const int64_t per_step = C * (6 * kLH + 2 * kMaxP + 2);
+  // h0, c0, dh, dc [C][H] each; rows_k [L][C] int64
+  return (L * per_step + 4 * C * kLH) * 4 + L * C * 8 + 64;
+}
+
+int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
+                            const rl8_recurrent_batch* rb, const int64_t* seqs, int64_t seq_begin,
+                            int64_t M, double denom, const rl8_ppo_hparams* hp, double* loss_sums,
+                            void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  const rl8_batch* b = &rb->b;
+  const int L = rb->seq_len, D = m->D, P = m->P;
+  const int64_t C = lstm_chunk_seqs(M, L);
+  if (!workspace || workspace_bytes < lstm_ppo_fp32_workspace(M, L)) return RL8_ERR_WORKSPACE;
+  float* p = (float*)workspace;
+  auto take = [&](int64_t n) { float* q = p; p += n; return q; };
+  float* act = take((int64_t)L * C * 4 * kLH);
+  float* cbuf = take((int64_t)L * C * kLH);
+  float* hbuf = take((int64_t)L * C * kLH);
+  float* out_pi = take((int64_t)L * C * kMaxP);
+  float* dout_pi = take((int64_t)L * C * kMaxP);
+  float* out_vf = take((int64_t)L * C);
+  float* dout_vf = take((int64_t)L * C);
+  float* h0 = take(C * kLH);
+  float* c0 = take(C * kLH);
+  float* dh = take(C * kLH);
+  float* dc = take(C * kLH);
+  int64_t* rows_k = (int64_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  const bool continuous = b->dist_kind != RL8_DIST_CATEGORICAL;
+  const int splits = 64;
+
+  for (int64_t s0 = 0; s0 < M; s0 += C) {
+    const int64_t R = (M - s0) < C ? (M - s0) : C;
+    seq_setup_kernel<<<grid_for(R * 64, 256, 8, 4), 256, 0, st>>>(
+        seqs ? seqs + s0 : nullptr, seq_begin + s0, R, L, b->T, b->N, rb->hidden, rb->cell, rows_k,
+        h0, c0);
+    int rc = check_launch("seq_setup");
+    if (rc) return rc;
+    RowMap map{};
+    map.obs = b->obs, map.mode = 1, map.T = b->T, map.D = D, map.N = b->N;
+
+    // ---- forward through the sequence + per-step losses ------------------------------------
+    for (int k = 0; k < L; ++k) {
+      map.rows = rows_k + (int64_t)k * R;
+      float* act_k = act + (int64_t)k * C * 4 * kLH;
+      float* c_k = cbuf + (int64_t)k * C * kLH;
+      float* h_k = hbuf + (int64_t)k * C * kLH;
+      const float* h_prev = k ? h_k - C * kLH : h0;
+      const float* c_prev = k ? c_k - C * kLH : c0;
+      float* opi = out_pi + (int64_t)k * C * kMaxP;
+      float* ovf = out_vf + (int64_t)k * C;
+      if ((rc = lstm_step_fp32(m, map, R, h_prev, c_prev, h_k, c_k, act_k, act_k, opi, ovf,
+                               continuous, st)))
+        return rc;
+      LossArgs la{};
+      la.dist_kind = b->dist_kind, la.P = P, la.M = R;
+      la.out_pi = opi, la.out_vf = ovf;
+      la.actions = b->actions, la.logp_old = b->logp, la.advantages = b->advantages;
+      la.returns = b->returns, la.rows = map.rows, la.row_begin = 0;
+      la.T = b->T, la.N = b->N, la.hp = *hp;
+      la.inv_denom = (float)((double)hp->loss_scale / denom);
+      la.dout_pi = dout_pi + (int64_t)k * C * kMaxP, la.dout_vf = dout_vf + (int64_t)k * C;
+      la.gb3_pi = (float*)g->pi_b, la.gb3_vf = (float*)g->vf_b, la.sums = loss_sums;
+      if ((rc = launch_ppo_loss(la, st))) return rc;
+    }
+
+    // ---- back-propagation through time ------------------------------------------------------
+    for (int k = L - 1; k >= 0; --k) {
+      map.rows = rows_k + (int64_t)k * R;
+      float* act_k = act + (int64_t)k * C * 4 * kLH;
+      float* c_k = cbuf + (int64_t)k * C * kLH;
+      float* h_k = hbuf + (int64_t)k * C * kLH;
+      const float* h_prev = k ? h_k - C * kLH : h0;
+      const float* c_prev = k ? c_k - C * kLH : c0;
+      const float* dpi = dout_pi + (int64_t)k * C * kMaxP;
+      const float* dvf = dout_vf + (int64_t)k * C;
+      const int last = k == L - 1;
+      // dL/dh_k = heads' contribution (+ the recurrent term left in dh by step k+1)
+      if ((rc = launch_dh(P, dpi, dvf, R, m->pi_w, m->vf_w, !last, dh, st))) return rc;
+      // head weight gradients
+      if ((rc = launch_thin_reduce(h_k, R, kLH, dpi, nullptr, P, (float*)g->pi_w, kLH, 1, nullptr, st)))
+        return rc;
+      if ((rc = launch_thin_reduce(h_k, R, kLH, dvf, nullptr, 1, (float*)g->vf_w, kLH, 1, nullptr, st)))
+        return rc;
+      lstm_cell_bwd_kernel<<<grid_for(R * kLH, 256, 8, 4), 256, 0, st>>>(act_k, c_k, c_prev, dh, dc,
+                                                                         !last, R);
+      if ((rc = check_launch("lstm_cell_bwd"))) return rc;
+      // gw_hh[g][j] += sum_r dG[r][g] h_prev[r][j]   (split-K over rows)
+      if ((rc = launch_sgemm(false, false, EPI_ATOMIC, act_k, h_prev, (float*)g->w_hh, 4 * kLH, kLH, R,
+                             4 * kLH, kLH, kLH, nullptr, splits, st)))
+        return rc;
+      if ((rc = launch_gate_reduce(act_k, R, map, D, (float*)g->w_ih, (float*)g->b_ih,
+                                   (float*)g->b_hh, st)))
+        return rc;
+      // dL/dh_{k-1} (recurrent term) = dG . W_hh; nothing flows into the stored chunk-start state
+      if (k && (rc = launch_sgemm(true, false, EPI_STORE, act_k, m->w_hh, dh, R, kLH, 4 * kLH, 4 * kLH,
+                                  kLH, kLH, nullptr, 1, st)))
+        return rc;
+    }
+  }
+  return RL8_OK;
+}
+
+}  // namespace rl8
+
+using namespace rl8;
+
+extern "C" int64_t rl8_lstm_collect_workspace(const rl8_lstm_model* model, int64_t N, int32_t T,
+                                              int precision) {
+  if (check_model(model) || N <= 0 || T <= 0) return RL8_ERR_ARG;
+  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  return (N * 4 * kLH + 2 * N * kLH + N * kMaxP) * 4;
+}
+
+extern "C" int rl8_lstm_collect(const rl8_lstm_model* model, const rl8_recurrent_rollout* rro,
+                                int precision, void* workspace, int64_t workspace_bytes,
+                                rl8_stream_t stream) {
+  int rc = check_model(model);
+  if (rc) return rc;
+  if (!rro || !rro->hidden || !rro->cell || rro->seq_len <= 0 || rro->seqs_per_state_reset == 0 ||
+      rro->seqs < 0)
+    return RL8_ERR_ARG;
+  if ((rc = validate_rollout_dims(model->D, model->H, model->P, &rro->ro))) return rc;
+  if (rro->ro.T % rro->seq_len) return RL8_ERR_ARG;
+  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  return lstm_collect_fp32(model, rro, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rl8_lstm_forward(const rl8_lstm_model* model, const float* obs, int64_t obs_stride_r,
+                                int64_t obs_stride_d, const float* h_in, const float* c_in,
+                                float* h_out, float* c_out, float* features, float* values,
+                                int64_t B, int apply_tanh_log_std, int precision, void* workspace,
+                                int64_t workspace_bytes, rl8_stream_t stream) {
+  int rc = check_model(model);
+  if (rc) return rc;
+  if (!obs || !h_in || !c_in || !h_out || !c_out || B <= 0) return RL8_ERR_ARG;
+  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < B * 4 * kLH * 4) return RL8_ERR_WORKSPACE;
+  RowMap map{};
+  map.obs = obs, map.mode = 0, map.stride_r = obs_stride_r, map.stride_d = obs_stride_d;
+  map.D = model->D;
+  return lstm_step_fp32(model, map, B, h_in, c_in, h_out, c_out, nullptr, (float*)workspace,
+                        features, values, apply_tanh_log_std, (cudaStream_t)stream);
+}
+
+extern "C" int64_t rl8_lstm_ppo_workspace(const rl8_lstm_model* model, int64_t max_seqs,
+                                          int32_t seq_len, int precision) {
+  if (check_model(model) || max_seqs <= 0 || seq_len <= 0) return RL8_ERR_ARG;
+  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  return lstm_ppo_fp32_workspace(max_seqs, seq_len);
+}
+
+extern "C" int rl8_lstm_ppo_minibatch(const rl8_lstm_model* model, const rl8_lstm_model* grads,
+                                      const rl8_recurrent_batch* batch, const int64_t* seqs,
+                                      int64_t seq_begin, int64_t M, double mean_denominator,
+                                      const rl8_ppo_hparams* hp, double* loss_sums, int precision,
+                                      void* workspace, int64_t workspace_bytes,
+                                      rl8_stream_t stream) {
+  int rc = check_model(model);
+  if (rc) return rc;
+  if ((rc = check_model(grads))) return rc;
+  if (!batch || !hp || !loss_sums || M <= 0 || mean_denominator <= 0) return RL8_ERR_ARG;
+  const rl8_batch* b = &batch->b;
+  if (!b->obs || !b->actions || !b->logp || !b->advantages || !b->returns || !batch->hidden ||
+      !batch->cell || batch->seq_len <= 0 || b->T % batch->seq_len)
+    return RL8_ERR_ARG;
+  if (b->dist_kind != RL8_DIST_CATEGORICAL && model->P != 2) return RL8_ERR_UNSUPPORTED;
+  if (b->dist_kind == RL8_DIST_SQUASHED_NORMAL && hp->entropy_coeff != 0.0f)
+    return RL8_ERR_UNSUPPORTED;
+  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  return lstm_ppo_minibatch_fp32(model, grads, batch, seqs, seq_begin, M, mean_denominator, hp,
+                                 loss_sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}

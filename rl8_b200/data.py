@@ -129,6 +129,51 @@ class AlgorithmState:
     reward_scale: float = 1.0
 
 
+@dataclass(frozen=True, kw_only=True)
+class RecurrentAlgorithmHparams(AlgorithmHparams):
+    """Constants of one recurrent PPO run (src/rl8/data.py:273-326): ``sgd_minibatch_size``
+    counts SEQUENCES of ``seq_len`` transitions."""
+
+    #: Truncated back-propagation-through-time length.
+    seq_len: int
+    #: Sequences between recurrent-state re-initialisations (negative: never again).
+    seqs_per_state_reset: int
+
+    def __post_init__(self) -> None:
+        super().__post_init__()
+        _require(self.seq_len > 0, "`seq_len` must be > 0.")
+        _require(self.horizon % self.seq_len == 0, "`seq_len` must be a factor of `horizon`.")
+        _require(self.seqs_per_state_reset != 0, "`seqs_per_state_reset` must be nonzero.")
+        _require(
+            (self.horizon * self.horizons_per_env_reset)
+            % (self.seq_len * self.seqs_per_state_reset)
+            == 0,
+            "`seq_len * seqs_per_state_reset` must be a factor of `horizon *"
+            " horizons_per_env_reset`. As an example, if `horizon=8`,"
+            " `horizons_per_env_reset=1`, and `seq_len=2`, then"
+            " `seqs_per_state_reset` can be 1, 2, or 4.",
+        )
+
+    @property
+    def num_minibatches(self) -> int:
+        return (self.num_envs * (self.horizon // self.seq_len)) // self.sgd_minibatch_size
+
+    def validate(self) -> "RecurrentAlgorithmHparams":
+        _require(
+            (self.num_envs * (self.horizon // self.seq_len)) % self.sgd_minibatch_size == 0,
+            "`sgd_minibatch_size` must be a factor of `num_envs * (horizon // seq_len)`.",
+        )
+        return self
+
+
+@dataclass(kw_only=True)
+class RecurrentAlgorithmState(AlgorithmState):
+    """Mutable counters of a recurrent PPO run."""
+
+    #: Number of ``seq_len`` sequences transitioned so far (drives the state reset cadence).
+    seqs: int = 0
+
+
 TrainerState = TypedDict(
     "TrainerState", {"algorithm/collects": int, "algorithm/steps": int, "env/steps": int}
 )
