@@ -32,30 +32,51 @@ METRIC = "env transitions/sec (collect+PPO step)"
 UNIT = "transitions/s"
 
 
+#: workload -> (description, env, distribution, recurrent, num_envs per GPU, horizon, obs dim D, head width P)
+WORKLOADS = {
+    "cartpole": ("CartPole feedforward PPO (BASELINE.json configs[1])", "CartPole", "Categorical", False,
+                 65536, 32, 5, 3),
+    "dummy": ("DiscreteDummyEnv feedforward PPO (BASELINE.json configs[0])", "DiscreteDummyEnv", "Categorical",
+              False, 8192, 32, 1, 2),
+    "pendulum": ("Pendulum feedforward PPO, SquashedNormal (BASELINE.json configs[2])", "Pendulum",
+                 "SquashedNormal", False, 262144, 64, 3, 2),
+    "cartpole_lstm": ("CartPole RecurrentAlgorithm, LSTM policy (BASELINE.json configs[3])", "CartPole",
+                      "Categorical", True, 65536, 32, 5, 3),
+}
+
+
 def parse() -> argparse.Namespace:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--num-envs-per-gpu", type=int, default=65536)
-    ap.add_argument("--horizon", type=int, default=32)
+    ap.add_argument("--workload", default="cartpole", choices=sorted(WORKLOADS),
+                    help="cartpole = BASELINE.json configs[1] (the bench line); the others are extra"
+                         " measurements of configs[0], [2] and [3]")
+    ap.add_argument("--num-envs-per-gpu", type=int, default=0, help="0 = the workload's default")
+    ap.add_argument("--horizon", type=int, default=0, help="0 = the workload's default")
     ap.add_argument("--sgd-iters", type=int, default=4)
     ap.add_argument("--minibatch", type=int, default=0, help="0 = whole buffer (reference default)")
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    a.num_envs_per_gpu = a.num_envs_per_gpu or w[4]
+    a.horizon = a.horizon or w[5]
+    return a
 
 
 def workload_config(a: argparse.Namespace, world: int) -> dict:
+    w = WORKLOADS[a.workload]
     return {
-        "workload": "CartPole feedforward PPO (BASELINE.json configs[1])",
-        "env": "CartPole",
+        "workload": w[0],
+        "env": w[1],
         "num_envs_per_gpu": a.num_envs_per_gpu,
         "num_envs_total": a.num_envs_per_gpu * world,
         "horizon": a.horizon,
-        "distribution": "Categorical",
+        "distribution": w[2],
         "num_sgd_iters": a.sgd_iters,
         "sgd_minibatch_size": a.minibatch or a.num_envs_per_gpu * a.horizon,
         "parallelism": f"env-sharded dp{world}",
@@ -68,21 +89,49 @@ def workload_config(a: argparse.Namespace, world: int) -> dict:
 # ---------------------------------------------------------------------------------------
 
 
-def cpu_step_fn(N: int, T: int, sgd_iters: int, minibatch: int):
+_ORACLE_ENV = {"CartPole": "cartpole", "DiscreteDummyEnv": "discrete_dummy", "Pendulum": "pendulum"}
+_ORACLE_DIST = {"Categorical": "categorical", "Normal": "normal", "SquashedNormal": "squashed_normal"}
+
+
+def cpu_step_fn(workload: str, N: int, T: int, sgd_iters: int, minibatch: int):
     import torch
 
     from oracle import ppo_oracle as O
+    from oracle import recurrent_oracle as R
 
+    _, env_name, dist_name, recurrent, _, _, D, P = WORKLOADS[workload]
     torch.manual_seed(0)
-    params = O.init_params(5, "discrete", 3)
-    env = O.OracleEnv("cartpole", N)
-    buf = O.new_buffer(N, T, 5, "discrete")
-    dist = O.Dist("categorical")
+    env = O.OracleEnv(_ORACLE_ENV[env_name], N)
+    dist = O.Dist(_ORACLE_DIST[dist_name])
+    discrete = dist_name == "Categorical"
+    kind, n_act = ("discrete", P) if discrete else ("continuous", 1)
     opt: dict = {}
+    noise_shape = (T, N, 1, P) if discrete else (T, N, 1)
+
+    def draw() -> "torch.Tensor":
+        z = torch.empty(noise_shape)
+        return z.exponential_(1) if discrete else z.normal_()
+
+    if recurrent:
+        params = R.init_recurrent_params(D, kind, n_act)
+        buf = R.new_recurrent_buffer(N, T, D, kind)
+        seqs = [0]
+
+        def step() -> None:
+            stats, seqs[0] = R.collect_recurrent(params, env, buf, dist, draw(), seqs=seqs[0])
+            R.step_recurrent(params, buf, dist, opt, reward_scale=stats["reward_scale"],
+                             num_sgd_iters=sgd_iters, sgd_minibatch_size=minibatch or None,
+                             shuffle=bool(minibatch))
+            for v in buf.values():
+                v.zero_()
+
+        return step
+
+    params = O.init_params(D, kind, n_act)
+    buf = O.new_buffer(N, T, D, kind)
 
     def step() -> None:
-        noise_fn = lambda t: torch.empty(N, 1, 3).exponential_(1)  # noqa: E731
-        stats = O.collect(params, env, buf, dist, None, noise_fn=noise_fn)
+        stats = O.collect(params, env, buf, dist, draw())
         O.step(params, buf, dist, opt, reward_scale=stats["reward_scale"], num_sgd_iters=sgd_iters,
                sgd_minibatch_size=minibatch or None, shuffle=bool(minibatch))
 
@@ -93,7 +142,7 @@ def cpu_probe(a: argparse.Namespace, budget_s: float, iters: int) -> tuple[int, 
     """Pick the largest power-of-two num_envs (<= the workload's) whose `iters` steps fit the
     budget; returns (num_envs, seconds per transition estimate)."""
     N0 = 1024
-    fn = cpu_step_fn(N0, a.horizon, a.sgd_iters, 0)
+    fn = cpu_step_fn(a.workload, N0, a.horizon, a.sgd_iters, 0)
     fn()
     t0 = time.perf_counter()
     fn()
@@ -113,7 +162,7 @@ def run_reference(a: argparse.Namespace) -> None:
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     N, _ = cpu_probe(a, 150.0, a.steps + a.warmup)
-    fn = cpu_step_fn(N, a.horizon, a.sgd_iters, 0)
+    fn = cpu_step_fn(a.workload, N, a.horizon, a.sgd_iters, 0)
     for _ in range(a.warmup):
         fn()
     t0 = time.perf_counter()
@@ -121,7 +170,7 @@ def run_reference(a: argparse.Namespace) -> None:
         fn()
     dt = time.perf_counter() - t0
     value = N * a.horizon * a.steps / dt
-    sample = f"CartPole num_envs={N} (of {a.num_envs_per_gpu}), horizon={a.horizon}, {a.steps} collect+step"
+    sample = f"{WORKLOADS[a.workload][1]} num_envs={N} (of {a.num_envs_per_gpu}), horizon={a.horizon}, {a.steps} collect+step"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -206,9 +255,14 @@ def run_ours(a: argparse.Namespace) -> None:
     import torch
     import torch.distributed as dist
 
-    from rl8_b200 import AlgorithmConfig, Trainer, _lib
-    from rl8_b200.distributions import Categorical
-    from rl8_b200.env import CartPole
+    import rl8_b200.distributions as dists
+    import rl8_b200.env as envs
+    from rl8_b200 import AlgorithmConfig, RecurrentAlgorithmConfig, RecurrentTrainer, Trainer, _lib
+
+    _, env_name, dist_name, recurrent, _, _, D, P = WORKLOADS[a.workload]
+    env_cls, base_dist = getattr(envs, env_name), getattr(dists, dist_name)
+    config_cls = RecurrentAlgorithmConfig if recurrent else AlgorithmConfig
+    trainer_cls = RecurrentTrainer if recurrent else Trainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,18 +276,19 @@ def run_ours(a: argparse.Namespace) -> None:
 
     def make(dist_cls=None, precision=a.precision):  # noqa: ANN001, ANN202
         amp = precision in ("auto", "bf16")
+        dist_cls = dist_cls or base_dist
         try:
-            return AlgorithmConfig(
+            return config_cls(
                 num_envs=N, horizon=T, num_sgd_iters=a.sgd_iters, sgd_minibatch_size=a.minibatch or None,
                 enable_amp=amp, distribution_cls=dist_cls,
-            ).build(CartPole), ("bf16" if amp else "f32")
+            ).build(env_cls), ("bf16" if amp else "f32")
         except NotImplementedError:
             if precision != "auto":
                 raise
-            return AlgorithmConfig(
+            return config_cls(
                 num_envs=N, horizon=T, num_sgd_iters=a.sgd_iters, sgd_minibatch_size=a.minibatch or None,
                 enable_amp=False, distribution_cls=dist_cls,
-            ).build(CartPole), "f32"
+            ).build(env_cls), "f32"
 
     torch.manual_seed(rank)
     algo, dtype = make()
@@ -273,31 +328,36 @@ def run_ours(a: argparse.Namespace) -> None:
     value = N * T * world * a.steps / (ms / 1e3)
 
     # ---- e2e: Trainer.step() with host-supplied noise (pinned, H2D every step) + stats D2H --------
-    host_noise = torch.empty(T, N, 3).exponential_(1).pin_memory()
-    dev_noise = torch.empty(T, N, 3, device=dev)
+    discrete = dist_name == "Categorical"
+    width = P if discrete else 1
+    host_noise = torch.empty(T, N, width)
+    host_noise = (host_noise.exponential_(1) if discrete else host_noise.normal_()).pin_memory()
+    dev_noise = torch.empty(T, N, width, device=dev)
 
-    class HostNoise(Categorical):
+    class HostNoise(base_dist):  # type: ignore[misc, valid-type]
         @classmethod
         def draw_noise(cls, steps, num, width, device):  # noqa: ANN001, ANN206
+            if steps != T:  # build() -> validate()
+                return super().draw_noise(steps, num, width, device)
             dev_noise.copy_(host_noise, non_blocking=True)
             return dev_noise
 
     algo2, _ = make(HostNoise, "bf16" if dtype == "bf16" else "fp32")
-    trainer = Trainer(algo2)
+    trainer = trainer_cls(algo2)
 
     def e2e_step() -> int:
         stats = trainer.step()
         assert stats["losses/total"] == stats["losses/total"]
         return algo2.last_launches["collect"] + algo2.last_launches["step"]
 
-    ms2, _ = timed(e2e_step, max(2, a.steps // 2), 2)
-    e2e_value = N * T * world * max(2, a.steps // 2) / (ms2 / 1e3)
+    ms2, _ = timed(e2e_step, a.steps, 3)
+    e2e_value = N * T * world * a.steps / (ms2 / 1e3)
     h2d = host_noise.numel() * 4
     d2h = 16 * 8 + algo2._loss_sums.numel() * 8
 
     # ---- roofline of the update: every rank runs it (its collect() holds collectives) -------------
     peaks = measured_peaks()
-    upd = update_roofline(algo, _lib, peaks, dtype, flush)
+    upd = update_roofline(a, algo, _lib, peaks, dtype, flush)
     barrier()
     if rank != 0:
         if world > 1:
@@ -340,14 +400,14 @@ def cpu_baseline(a: argparse.Namespace) -> dict:
 
     torch.set_num_threads(os.cpu_count() or 1)
     n, _ = cpu_probe(a, a.cpu_budget_s, 2)
-    fn = cpu_step_fn(n, a.horizon, a.sgd_iters, 0)
+    fn = cpu_step_fn(a.workload, n, a.horizon, a.sgd_iters, 0)
     fn()
     t0 = time.perf_counter()
     fn()
     dt = time.perf_counter() - t0
     return {
         "value": n * a.horizon / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-        "sample": f"CartPole num_envs={n} (of {a.num_envs_per_gpu}), horizon={a.horizon}, 1 warm-up + 1 timed"
+        "sample": f"{WORKLOADS[a.workload][1]} num_envs={n} (of {a.num_envs_per_gpu}), horizon={a.horizon}, 1 warm-up + 1 timed"
                   " collect+step of oracle/ppo_oracle.py (torch fp32 eager)",
     }
 
@@ -414,24 +474,54 @@ def stream_rooflines(lib, L, dev, peaks: dict) -> list[dict]:  # noqa: ANN001
     return out
 
 
-def update_roofline(algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa: ANN001
-    """The update (forward + loss + backward over one minibatch) dominates a step: its GEMM
-    FLOPs are 3 x the forward's 2*2*H*H MACs per row (two networks)."""
-    import ctypes
+#: dram__bytes_read.sum + dram__bytes_write.sum of the four kernel launches of one CartPole
+#: N=65536 T=32 full-batch rl8_ppo_minibatch (2 x tc_update_h + 2 x tc_update_w), from the
+#: `ncu --set full` captures summarised in profiles/r01_update_v4_ncu_summary.md.
+NCU_TRAFFIC = {("cartpole", 2097152): 2 * (42.55e6 + 1015.5e6) + 2 * (1095.3e6 + 4.96e6)}
 
+
+def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa: ANN001
+    """The update (forward + loss + backward over one minibatch) dominates a step: its GEMM
+    FLOPs are 3 x the forward's (forward, input-gradient and weight-gradient contractions)."""
     import torch
 
+    _, _, _, recurrent, _, _, D, P = WORKLOADS[a.workload]
     hp = algo.hparams
     N, T = hp.num_envs, hp.horizon
+    peak = float(peaks["bf16_tflops_sustained"])
+    H = 256
+    if recurrent:
+        # one full step() = GAE + num_sgd_iters passes over every sequence (fp32 CUDA-core path)
+        def fn() -> None:
+            algo.collect()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            e0.record()
+            algo.step()
+            e1.record()
+            e1.synchronize()
+            fn.ms += e0.elapsed_time(e1)
+
+        fn.ms = 0.0
+        fn()
+        fn.ms = 0.0
+        for _ in range(3):
+            fn()
+        ms = fn.ms / 3
+        flops = hp.num_sgd_iters * N * T * 3.0 * 2.0 * ((D + H) * 4 * H + (P + 1) * H)
+        return {
+            "kernel": "RecurrentAlgorithm.step (rl8_lstm_ppo_minibatch x num_sgd_iters, fp32 CUDA-core GEMMs)",
+            "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
+            "frac": flops / ms / 1e9 / peak, "traffic": None, "ms": ms, "rows": N * T, "dtype": dtype,
+            "peak_source": peaks["source"] + " bf16 sustained (the recurrent path is fp32 on CUDA cores:"
+                           " the fraction shows the gap a tensor-core LSTM path would close)",
+        }
     algo.collect()
     model = algo.policy.model
     m, g = model.struct_for(model.flat_params), model.struct_for(algo._grads)
     M = hp.sgd_minibatch_size
     ws = algo._workspace("ppo", int(algo._lib.rl8_ppo_workspace(m, M, algo.policy.precision)))
-    batch = L.Batch()
-    batch.dist_kind, batch.T, batch.N = 0, T, N
-    for k in ("obs", "actions", "logp", "advantages", "returns"):
-        setattr(batch, k, algo.buffer.hm[k].data_ptr())
+    batch = algo._batch_struct()
     ppo = L.PpoHparams(0.2, 0.0, 0.0, 5.0, 1.0, 1.0)
     sums = torch.zeros(5, dtype=torch.float64, device=algo.device)
 
@@ -441,14 +531,15 @@ def update_roofline(algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa: A
         assert rc == 0, rc
 
     ms = _time_kernel(fn, flush, iters=5)
-    H, D, P = 256, 5, 3
     flops = M * 3.0 * 2.0 * (2 * H * H + 2 * D * H + (P + 1) * H)
-    peak = float(peaks["bf16_tflops_sustained"])
+    traffic = NCU_TRAFFIC.get((a.workload, M)) if dtype == "bf16" else None
     return {
-        "kernel": "rl8_ppo_minibatch (forward + losses + backward, one minibatch)",
+        "kernel": "rl8_ppo_minibatch (forward + losses + backward, one minibatch: tc_update_h_kernel +"
+                  " tc_update_w_kernel per 2^20-row chunk)",
         "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
-        "frac": flops / ms / 1e9 / peak, "traffic": None, "ms": ms, "rows": M, "dtype": dtype,
+        "frac": flops / ms / 1e9 / peak, "traffic": traffic, "ms": ms, "rows": M, "dtype": dtype,
         "peak_source": peaks["source"] + " bf16 sustained",
+        "traffic_source": "ncu --set full, profiles/r01_update_v4_ncu_summary.md" if traffic else None,
     }
 
 

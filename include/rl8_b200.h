@@ -350,6 +350,12 @@ int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream)
 int rl8_tc_bench_tmem(long long* out_cycles, int32_t nwarps, int32_t iters, int32_t mode,
                       rl8_stream_t stream);
 
+/* Debug hook: `device_counters` (16 x uint64 on the device, zeroed by the caller) receives the SM
+ * cycles CTA 0 of each network spends in the 8 phases of the tensor-core update's activation
+ * kernel ([0..7] policy, [8..15] value) for every later rl8_ppo_minibatch call; NULL switches the
+ * stamping off.  Feeds profiles/ (where the tile time goes), not the product path. */
+int rl8_tc_phase_buffer(unsigned long long* device_counters);
+
 #ifdef __cplusplus
 }
 #endif

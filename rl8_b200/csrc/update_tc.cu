@@ -55,6 +55,24 @@ struct UpdArgs {
   uint8_t* dz[2];        // [tiles of the chunk][64 KB] bf16 dZ2 tile images per network
   float *gw1[2], *gb1[2], *gw2[2], *gb2[2], *gw3[2], *gb3[2];
   double* sums;          // [5]
+  unsigned long long* phase;  // debug: [16] cycle sums of the activation kernel's phases, or null
+};
+
+// Phase timing (debug hook rl8_tc_phase_buffer): one observer thread stamps the clock at every phase
+// boundary it passes together with the rest of the CTA.
+struct PhaseClock {
+  unsigned long long* dst;
+  long long last;
+  __device__ __forceinline__ PhaseClock(unsigned long long* d) : dst(d), last(0) {
+    if (dst) last = clock64();
+  }
+  __device__ __forceinline__ void mark(int i) {
+    if (dst) {
+      const long long now = clock64();
+      atomicAdd(dst + i, (unsigned long long)(now - last));
+      last = now;
+    }
+  }
 };
 
 // Buffer coordinates (slab t, env n) of minibatch row `rw`; false past the minibatch.
@@ -201,6 +219,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
   ObsRegs obs_next = load_obs(a, valid_next, tn, nn, D);
   int64_t idx_next = valid_next ? tn * a.N + nn : -1;
 
+  PhaseClock pc(a.phase && tid == kUpdThreads - 1 && cta == 0 ? a.phase + 8 * net : nullptr);
   for (; tile < ntiles; tile += nctas, ++it) {
     const uint32_t ph = (uint32_t)(it & 1);
     // ---- A. operands of this tile: [obs, 1] in tf32 and bf16 ----------------------------------------------
@@ -241,6 +260,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     }
     mbar_wait(&s.bar[kBZ1], ph);
     fence_after_sync();
+    pc.mark(0);  // A + B: staging, Z1
     // ---- C. H1 = relu(Z1): bf16 tile + packed copy in TMEM;  Z2 = H1 * W2^T in two column halves --------------
     {
       float v0[32], v1[32];
@@ -270,6 +290,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
         mma_commit(&s.bar[kBZ2A + h]);
       }
     }
+    pc.mark(1);  // C: H1 epilogue
     // ---- D. H2 = relu(Z2 + b2) -> tile, head partial sums; half 0 is processed under the MMAs of half 1 -------
     float dot[PN];
 #pragma unroll
@@ -316,6 +337,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       for (int p = 0; p < PN; ++p) s.u.part[cq - 1][r][p] = dot[p];
     }
     __syncthreads();
+    pc.mark(2);  // D: Z2 MMAs + H2 epilogue
     // ---- E. per-row loss -> dOut (threads 0..127 own row tid and column quarter 0) -------------------------------------
     if (tid < TILE) {
       float o[PN], d_o[PN];
@@ -345,6 +367,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    pc.mark(3);  // E: row loss
     // ---- F. gW3^T += H2^T * dOut;  G = dOut * W3 (K = 16: one instruction) ------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
@@ -358,6 +381,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     }
     mbar_wait(&s.bar[kBT1], ph);
     fence_after_sync();
+    pc.mark(4);  // F: thin gW3 + G MMAs
     // ---- G. dZ2 = [H2 > 0] .* G, in place over H2 -----------------------------------------------------------------------------
     {
       float v0[32], v1[32];
@@ -385,6 +409,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    pc.mark(5);  // G: dZ2 epilogue
     // ---- H. dZ2 tile -> scratch;  dH1 = dZ2 * W2 in two column halves;  [., gb2] += dZ2^T * [obs, 1] --------------------------
     if (tid == 0) {
       fence_after_sync();
@@ -432,6 +457,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    pc.mark(6);  // H + I: dH1 MMAs + dZ1 epilogue
     // ---- J. [gW1, gb1] += dZ1^T * [obs, 1] ---------------------------------------------------------------------------------------
     if (tid == 0) {
       fence_after_sync();
@@ -443,6 +469,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     }
     mbar_wait(&s.bar[kBT2], ph);  // tile and operand tiles are free again
     fence_after_sync();
+    pc.mark(7);  // J: thin gW1
   }
   if (tid == 0) bulk_wait_all();  // dZ2 stores have landed before the kernel ends
 
@@ -666,6 +693,15 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------
+static unsigned long long* g_phase_buffer = nullptr;
+
+// Debug hook: device buffer of 16 counters (8 phases x {policy, value} CTA 0) the activation kernel adds
+// its per-phase cycle counts to; null switches the stamping off.
+extern "C" int rl8_tc_phase_buffer(unsigned long long* device_counters) {
+  g_phase_buffer = device_counters;
+  return RL8_OK;
+}
+
 static int policy_ctas() {
   static int n = 0;
   if (!n) {
@@ -717,6 +753,7 @@ int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_b
   a.gw1[1] = (float*)grads->vf_w1, a.gb1[1] = (float*)grads->vf_b1, a.gw2[1] = (float*)grads->vf_w2;
   a.gb2[1] = (float*)grads->vf_b2, a.gw3[1] = (float*)grads->vf_w3, a.gb3[1] = (float*)grads->vf_b3;
   a.sums = loss_sums;
+  a.phase = g_phase_buffer;
   for (int64_t off = 0; off < M; off += chunk) {
     a.row_off = off;
     a.Mc = M - off < chunk ? M - off : chunk;
