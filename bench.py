@@ -299,11 +299,14 @@ def run_ours(a: argparse.Namespace) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_step: list[float] = []  # ms of every timed step of the last timed() call (this rank)
+
     def timed(step_fn, steps: int, warmup: int) -> tuple[float, int]:  # noqa: ANN001
         for _ in range(warmup):
             step_fn()
         barrier()
         total_ms, launches = 0.0, 0
+        per_step.clear()
         for _ in range(steps):
             flush.zero_()  # L2 flush, outside the timed bracket
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -312,6 +315,7 @@ def run_ours(a: argparse.Namespace) -> None:
             e1.record()
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
+            per_step.append(round(e0.elapsed_time(e1), 3))
         barrier()
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         if world > 1:
@@ -326,6 +330,7 @@ def run_ours(a: argparse.Namespace) -> None:
     with ClockSampler(local) as clocks:
         ms, launches = timed(core_step, a.steps, a.warmup)
     value = N * T * world * a.steps / (ms / 1e3)
+    core_per_step = list(per_step)
 
     # ---- e2e: Trainer.step() with host-supplied noise (pinned, H2D every step) + stats D2H --------
     discrete = dist_name == "Categorical"
@@ -352,6 +357,7 @@ def run_ours(a: argparse.Namespace) -> None:
 
     ms2, _ = timed(e2e_step, a.steps, 3)
     e2e_value = N * T * world * a.steps / (ms2 / 1e3)
+    e2e_per_step = list(per_step)
     h2d = host_noise.numel() * 4
     d2h = 16 * 8 + algo2._loss_sums.numel() * 8
 
@@ -384,6 +390,7 @@ def run_ours(a: argparse.Namespace) -> None:
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
+        "ms_each_step": {"value": core_per_step, "e2e": e2e_per_step},
         "roofline": upd,
         "stream_rooflines": roofs,
         "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
@@ -471,6 +478,18 @@ def stream_rooflines(lib, L, dev, peaks: dict) -> list[dict]:  # noqa: ANN001
     out.append({"kernel": "env_step_kernel<cartpole>", "bound": "hbm", "bytes": alg, "ms": ms,
                 "achieved": alg / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / hbm,
                 "shape": f"N={N}"})
+    del env, act
+    # Padded rolling windows (shift 3) over a horizon-major obs field: item read once, windows + mask written once
+    N, T1, D, size = 1 << 19, 33, 5, 4
+    x = torch.randn(T1, D, N, device=dev).permute(2, 0, 1)
+    o = torch.empty(N * T1, size, D, device=dev)
+    mk = torch.empty(N * T1, size, dtype=torch.bool, device=dev)
+    ms = _time_kernel(lambda: lib.rl8_view_windows(L.ptr(x), 4, N, T1, D, x.stride(0), x.stride(1), x.stride(2),
+                                                   size, -(size - 1), T1, L.ptr(o), L.ptr(mk), st), flush)
+    alg = 4.0 * N * T1 * D * (1 + size) + 1.0 * N * T1 * size
+    out.append({"kernel": "view_windows_kernel<u32> (PaddedRollingWindow.apply_all, shift 3)", "bound": "hbm",
+                "bytes": alg, "ms": ms, "achieved": alg / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                "frac": alg / ms / 1e6 / hbm, "shape": f"N={N} T+1={T1} D={D} size={size}"})
     return out
 
 

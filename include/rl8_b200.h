@@ -326,6 +326,28 @@ int rl8_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   double max_norm, double lr, double beta1, double beta2, double eps,
                   int64_t step, float* norm_out, rl8_stream_t stream);
 
+/* ---- view requirements (src/rl8/views.py) ------------------------------------------------ */
+
+/* Sliding windows over the time axis of one rollout field:
+ *
+ *     out[b][w][s][f] = x[b][t_first + w + s][f]      w < count, s < size, f < F
+ *     mask[b][w][s]   = (t_first + w + s < 0)          (zero-filled `out` there; mask may be NULL)
+ *
+ * `x` is [B][T][F] with element strides (stride_b, stride_t, stride_f) -- the horizon-major
+ * buffer ([T+1][F][N]: stride_b = 1) and env-major tensors ([N][T+1][F]: stride_f = 1) are both
+ * read coalesced; `out` is contiguous [B * count][size][F], `mask` contiguous [B * count][size]
+ * bytes.  elem_bytes is 4 or 8 (f32 / i64 fields).  Requires t_first + count + size - 2 < T.
+ * One call replaces the unfold + permute + reshape of
+ *   RollingWindow.apply_all        src/rl8/views.py:158-193   (t_first = 0, count = T - size + 1)
+ *   PaddedRollingWindow.apply_all  :245-281 incl. pad_whole_sequence :91-118
+ *                                                          (t_first = -(size - 1), count = T)
+ *   pad_last_sequence              :57-88                   (t_first = T - size, count = 1)
+ *   pad_whole_sequence             :91-118                  (size = 1, t_first = -pad, count = T + pad)
+ */
+int rl8_view_windows(const void* x, int32_t elem_bytes, int64_t B, int64_t T, int64_t F,
+                     int64_t stride_b, int64_t stride_t, int64_t stride_f, int32_t size,
+                     int64_t t_first, int64_t count, void* out, uint8_t* mask, rl8_stream_t stream);
+
 /* ---- test hook ------------------------------------------------------------------------ */
 
 /* D[128][N] = A[128][K] * B[N][K]^T through ONE tcgen05 GEMM (bf16 operands, fp32 accumulate)

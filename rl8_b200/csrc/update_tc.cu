@@ -170,7 +170,7 @@ struct SmemH {
                                //         second 8-column group of both N = 16 operands)
   float b2[H];                 //   1024
   float w3[kMaxPT][H];         //   4096
-  uint64_t bar_w, bar[7];
+  uint64_t bar_w, bar[6];
   uint32_t tmem_base;
 };
 static_assert(sizeof(SmemH) + 1024 <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
@@ -181,7 +181,7 @@ constexpr uint32_t kColH1 = 256;     // 128: packed bf16 H1 (for the layer-1 ReL
 constexpr uint32_t kColThin = 384;   // 6 x 16: gW3, gb2, [gW1 gb1], two 128-unit blocks each
 constexpr int kThinN = 16;
 // mbarriers: each completes exactly once per tile, so one phase bit (tile parity) serves all
-enum { kBZ1 = 0, kBZ2A, kBZ2B, kBT1, kBDA, kBDB, kBT2 };
+enum { kBZ1 = 0, kBZ2A, kBZ2B, kBT1, kBDA, kBDB };  // kBZ1: Z1 of a tile + phase J of the tile before it
 
 // D[128 units][16] (+)= X[:, 128-unit block]^T * Y with X the activation tile (MN-major A) and Y a
 // [r][16] operand whose second 8-column group is the shared zero block at b_saddr + b_sbo.
@@ -212,37 +212,22 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
   int it = 0;
   const bool continuous = POLICY && a.dist_kind != RL8_DIST_CATEGORICAL;
 
-  // prefetch of the first tile
+  // [obs, 1] of row (tid & 127) in bf16 -> thin[0] (B operand of the gb2 / gW1 thin GEMMs)
+  auto store_thin0 = [&](const ObsRegs& o) {
+    const int rr = tid & (TILE - 1), d0 = tid >> 7;
+    __nv_bfloat16* row16 = reinterpret_cast<__nv_bfloat16*>(s.thin[0] + rr * 16);
+    row16[d0] = __float2bfloat16(o.v0);
+    row16[d0 + 4] = __float2bfloat16(o.v1);
+  };
+  // prefetch of the first tile; its layer-1 MMA is issued here, every later one together with the
+  // previous tile's last thin GEMM (phase J), so a tile starts with Z1 already in flight
   int64_t tile = cta;
   int64_t tn = 0, nn = 0;
   bool valid_next = tile < ntiles && row_to_tn(a, a.row_off + tile * TILE + (tid & (TILE - 1)), tn, nn);
   ObsRegs obs_next = load_obs(a, valid_next, tn, nn, D);
   int64_t idx_next = valid_next ? tn * a.N + nn : -1;
-
-  PhaseClock pc(a.phase && tid == kUpdThreads - 1 && cta == 0 ? a.phase + 8 * net : nullptr);
-  for (; tile < ntiles; tile += nctas, ++it) {
-    const uint32_t ph = (uint32_t)(it & 1);
-    // ---- A. operands of this tile: [obs, 1] in tf32 and bf16 ----------------------------------------------
-    const int64_t idx = idx_next;  // of row (tid & 127)
+  if (tile < ntiles) {
     store_aug32(s.u.aug32, obs_next);
-    {
-      const int rr = tid & (TILE - 1), d0 = tid >> 7;
-      __nv_bfloat16* row16 = reinterpret_cast<__nv_bfloat16*>(s.thin[0] + rr * 16);
-      row16[d0] = __float2bfloat16(obs_next.v0);
-      row16[d0 + 4] = __float2bfloat16(obs_next.v1);
-    }
-    // per-row loss inputs (threads 0..127), in flight until phase E
-    float in_act = 0.0f, in_logp = 0.0f, in_tgt = 0.0f;
-    if (tid < TILE && idx >= 0) {
-      if constexpr (POLICY) {
-        in_act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)((const int*)a.actions)[2 * idx]
-                                                     : ((const float*)a.actions)[idx];
-        in_logp = a.logp[idx];
-        in_tgt = a.adv[idx];
-      } else {
-        in_tgt = a.ret[idx];
-      }
-    }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -251,16 +236,40 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       issue_z1(tmem + kColMain, s.u.aug32, s.w1aug);
       mma_commit(&s.bar[kBZ1]);
     }
-    // ---- B. prefetch the next tile while the tensor core works ----------------------------------------------
+  }
+
+  PhaseClock pc(a.phase && tid == kUpdThreads - 1 && cta == 0 ? a.phase + 8 * net : nullptr);
+  for (; tile < ntiles; tile += nctas, ++it) {
+    const uint32_t ph = (uint32_t)(it & 1);
+    // ---- A. this tile's per-row loss inputs (threads 0..127), in flight until phase E ---------------------
+    const int64_t idx = idx_next;  // of row (tid & 127)
+    const ObsRegs obs_cur = obs_next;
+    // (the action stays a raw 32-bit word until phase E: converting here would wait for the load)
+    uint32_t in_act_raw = 0u;
+    float in_logp = 0.0f, in_tgt = 0.0f;
+    if (tid < TILE && idx >= 0) {
+      if constexpr (POLICY) {
+        in_act_raw = a.dist_kind == RL8_DIST_CATEGORICAL ? ((const uint32_t*)a.actions)[2 * idx]
+                                                         : ((const uint32_t*)a.actions)[idx];
+        in_logp = a.logp[idx];
+        in_tgt = a.adv[idx];
+      } else {
+        in_tgt = a.ret[idx];
+      }
+    }
+    // ---- B. prefetch the next tile's observations (staged in phase G) ---------------------------------------
+    const bool has_next = tile + nctas < ntiles;
     {
       const int64_t nt = tile + nctas;
-      valid_next = nt < ntiles && row_to_tn(a, a.row_off + nt * TILE + (tid & (TILE - 1)), tn, nn);
+      valid_next = has_next && row_to_tn(a, a.row_off + nt * TILE + (tid & (TILE - 1)), tn, nn);
       obs_next = load_obs(a, valid_next, tn, nn, D);
       idx_next = valid_next ? tn * a.N + nn : -1;
     }
+    // Z1 of this tile is in TMEM and the previous tile's last thin GEMM has read the tile and thin[0]
     mbar_wait(&s.bar[kBZ1], ph);
     fence_after_sync();
-    pc.mark(0);  // A + B: staging, Z1
+    store_thin0(obs_cur);  // read by the MMAs of phases H and J, several barriers from here
+    pc.mark(0);  // A + B: loads, Z1 / previous J round trip
     // ---- C. H1 = relu(Z1): bf16 tile + packed copy in TMEM;  Z2 = H1 * W2^T in two column halves --------------
     {
       float v0[32], v1[32];
@@ -350,6 +359,8 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
         RowLoss L;
         if constexpr (POLICY) {
           if (continuous) o[1] = tanhf(o[1]);
+          const float in_act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)(int)in_act_raw
+                                                                   : __uint_as_float(in_act_raw);
           ppo_policy_row<PN>(a.dist_kind, o, in_act, in_logp, in_tgt, a.hp, a.inv_denom, d_o, L);
           s_ent += L.entropy, s_pol += L.policy, s_kl += L.kl;
         } else {
@@ -406,6 +417,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
         }
       }
     }
+    if (has_next) store_aug32(s.u.aug32, obs_next);  // `part` (same bytes) was last read in phase E
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -458,18 +470,21 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_before_sync();
     __syncthreads();
     pc.mark(6);  // H + I: dH1 MMAs + dZ1 epilogue
-    // ---- J. [gW1, gb1] += dZ1^T * [obs, 1] ---------------------------------------------------------------------------------------
+    // ---- J. [gW1, gb1] += dZ1^T * [obs, 1];  Z1 of the next tile -- one commit, awaited at the top of the next tile -----
     if (tid == 0) {
       fence_after_sync();
 #pragma unroll
       for (int ib = 0; ib < 2; ++ib)
         issue_thin(tmem + kColThin + kThinN * (4 + ib), smem_u32(s.a_tile) + ib * 32768, smem_u32(s.thin[0]),
                    2 * TILE * 16, it > 0);
-      mma_commit(&s.bar[kBT2]);
+      if (has_next) issue_z1(tmem + kColMain, s.u.aug32, s.w1aug);
+      mma_commit(&s.bar[kBZ1]);
     }
-    mbar_wait(&s.bar[kBT2], ph);  // tile and operand tiles are free again
+    pc.mark(7);  // J: issue only
+  }
+  if (it > 0) {  // the last tile's thin GEMM: accumulators complete, tile free
+    mbar_wait(&s.bar[kBZ1], (uint32_t)(it & 1));
     fence_after_sync();
-    pc.mark(7);  // J: thin gW1
   }
   if (tid == 0) bulk_wait_all();  // dZ2 stores have landed before the kernel ends
 
@@ -522,7 +537,7 @@ tc_update_h_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   if (tid == 0) {
     mbar_init(&s.bar_w, 1);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) mbar_init(&s.bar[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&s.bar[i], 1);
     fence_mbar_init();
   }
   if (tid < 32) tmem_alloc(&s.tmem_base, 512);
