@@ -372,6 +372,13 @@ int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream)
 int rl8_tc_bench_tmem(long long* out_cycles, int32_t nwarps, int32_t iters, int32_t mode,
                       rl8_stream_t stream);
 
+/* Microbenchmark: out_cycles[0] = SM cycles from the first issue to the mbarrier completion of `reps`
+ * back-to-back tcgen05 GEMMs D[128][N] += A[128][k_total] * B[N][k_total]^T (bf16, one commit at the end,
+ * operands in the library's chunked shared-memory format); out_cycles[1] = cycles of the issue loop.
+ * Gives the per-instruction pace by N / operand major and the fixed issue -> commit -> wait latency. */
+int rl8_tc_bench_mma(long long* out_cycles, int32_t N, int32_t k_total, int32_t reps, int a_mn_major,
+                     int b_mn_major, rl8_stream_t stream);
+
 /* Debug hook: `device_counters` (16 x uint64 on the device, zeroed by the caller) receives the SM
  * cycles CTA 0 of each network spends in the 8 phases of the tensor-core update's activation
  * kernel ([0..7] policy, [8..15] value) for every later rl8_ppo_minibatch call; NULL switches the

@@ -101,8 +101,22 @@ class _NoopGradScaler:
         return 1.0
 
 
+_mem_cache: dict[int, tuple[int, int, int]] = {}  # device -> (allocator bytes reserved, free, total)
+
+
 def memory_stats() -> MemoryStats:
-    free, total = torch.cuda.mem_get_info()
+    """Device memory like the reference's ``torch.cuda.mem_get_info()``
+    (src/rl8/_utils.py:102-115).  ``cudaMemGetInfo`` takes a driver lock and sporadically
+    stalls for milliseconds, and ``Trainer.step`` calls this every iteration, so the driver
+    is only asked again when this process's caching allocator has grown or shrunk since the
+    last query (the only way this process changes the device's free memory)."""
+    dev = torch.cuda.current_device()
+    reserved = torch.cuda.memory_reserved(dev)
+    hit = _mem_cache.get(dev)
+    if hit is None or hit[0] != reserved:
+        free, total = torch.cuda.mem_get_info(dev)
+        hit = _mem_cache[dev] = (reserved, free, total)
+    _, free, total = hit
     return {"memory/free": free, "memory/total": total, "memory/percent": 100 * (total - free) / total}
 
 

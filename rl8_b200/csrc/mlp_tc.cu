@@ -66,7 +66,7 @@ tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ ou
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (cta_issuer()) {
       fence_after_sync();
       issue_gemm(tmem + (uint32_t)(buf * H), smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H,
                  false, TILE, H, H, false);
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, 1) tc_rollout_kernel(NetParams np, Rollou
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (cta_issuer()) {
         fence_after_sync();
         issue_gemm(tmem, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H, false);
         mma_commit(&s.bar_mma[0]);
@@ -394,6 +394,47 @@ __global__ void __launch_bounds__(512, 1) tc_bench_tmem_kernel(long long* out, i
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+// Microbenchmark: cycles for `reps` back-to-back GEMMs D[128][N] (+)= A[128][k_total] * B[N][k_total]^T issued by
+// one thread with ONE commit at the end, operands in this library's chunked shared-memory format (zeros).
+// out[0] = issue -> mbarrier-wait round trip, out[1] = cycles the issuing loop itself took.
+struct SmemMmaBench {
+  uint8_t b[kW2Bytes];
+  uint8_t a[kTileBytes];
+  uint64_t bar;
+  uint32_t tmem_base;
+};
+__global__ void __launch_bounds__(128, 1)
+tc_bench_mma_kernel(long long* out, int N, int k_total, int reps, int a_mn, int b_mn) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemMmaBench& s = *reinterpret_cast<SmemMmaBench*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (kW2Bytes + kTileBytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s.b)[i] = 0u;
+  if (tid == 0) {
+    mbar_init(&s.bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid < 32 && elect_one()) {
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r)
+      issue_gemm(s.tmem_base, smem_u32(s.a), TILE, a_mn != 0, smem_u32(s.b), b_mn ? k_total : N, b_mn != 0, TILE, N,
+                 k_total, r > 0);
+    mma_commit(&s.bar);
+    const long long t1 = clock64();
+    mbar_wait(&s.bar, 0);
+    const long long t2 = clock64();
+    out[0] = t2 - t0;
+    out[1] = t1 - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(s.tmem_base, 512);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 static int launch_forward(const NetParams& np, const RowMap& map, int64_t rows, float* out,
                           int tanh_col1, cudaStream_t st) {
@@ -493,6 +534,18 @@ extern "C" int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_strea
   if (!in || !out) return RL8_ERR_ARG;
   tc_selftest_tmem_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(in, out);
   return check_launch("tc_selftest_tmem");
+}
+
+extern "C" int rl8_tc_bench_mma(long long* out_cycles, int32_t N, int32_t k_total, int32_t reps, int a_mn_major,
+                                int b_mn_major, rl8_stream_t stream) {
+  if (!out_cycles || N < 16 || N > 256 || N % 16 || k_total < 16 || k_total > 256 || k_total % 16 || reps < 1)
+    return RL8_ERR_ARG;
+  if (a_mn_major && k_total > TILE) return RL8_ERR_ARG;
+  int rc;
+  if ((rc = set_smem((const void*)tc_bench_mma_kernel, sizeof(SmemMmaBench)))) return rc;
+  tc_bench_mma_kernel<<<1, 128, sizeof(SmemMmaBench), (cudaStream_t)stream>>>(out_cycles, N, k_total, reps,
+                                                                           a_mn_major, b_mn_major);
+  return check_launch("tc_bench_mma");
 }
 
 // Microbenchmark hook: SM cycles for `iters` rounds of TMEM reads with `nwarps` warps (see kernel).

@@ -255,6 +255,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One lane of a CONVERGED warp (the lowest active one).  Guard single-thread tcgen05 / bulk-copy issue
+// with `warp == k && elect_one()` rather than `tid == 32k`: behind a thread-index test the compiler
+// wraps every tcgen05.mma in its own ELECT / BRA.U.ANY serialisation loop (~75 cycles per
+// instruction, measured with rl8_tc_bench_mma); behind elect.sync it knows one lane is active.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// The CTA's single issuing thread: one elected lane of warp 0 (call it from converged code).
+__device__ __forceinline__ bool cta_issuer() { return threadIdx.x < 32 && elect_one(); }
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (SWIZZLE_NONE, sm_100 version field = 1).
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -368,10 +387,16 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_saddr, in
   const uint32_t a_step = a_rows_is_k ? 256u : 2u * A_ROWS * 16u;
   const uint32_t b_step = b_rows_is_k ? 256u : 2u * B_ROWS * 16u;
   const int steps = k_total / 16;
+  // The start-address field is the low 14 bits of the descriptor (bytes >> 4): stepping K is one
+  // 64-bit add per operand, so the issuing thread spends its cycles on tcgen05.mma, not on
+  // rebuilding descriptors (a tile never crosses the 256 KB the field spans).
+  uint64_t ad = smem_desc(a_saddr, a_lbo, a_sbo);
+  uint64_t bd = smem_desc(b_saddr, b_lbo, b_sbo);
+  const uint64_t a_inc = a_step >> 4, b_inc = b_step >> 4;
+#pragma unroll 4
   for (int s = 0; s < steps; ++s) {
-    uint64_t ad = smem_desc(a_saddr + s * a_step, a_lbo, a_sbo);
-    uint64_t bd = smem_desc(b_saddr + s * b_step, b_lbo, b_sbo);
     mma_bf16(d_tmem, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    ad += a_inc, bd += b_inc;
   }
 }
 

@@ -188,10 +188,12 @@ enum { kBZ1 = 0, kBZ2A, kBZ2B, kBT1, kBDA, kBDB };  // kBZ1: Z1 of a tile + phas
 __device__ __forceinline__ void issue_thin(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr,
                                            uint32_t b_sbo, bool accumulate) {
   const uint32_t idesc = instr_desc(TILE, kThinN, 1, 1);
+  uint64_t ad = smem_desc(a_saddr, 128, TILE * 16), bd = smem_desc(b_saddr, 128, b_sbo);
 #pragma unroll
-  for (int k = 0; k < TILE / 16; ++k)
-    mma_bf16(d_tmem, smem_desc(a_saddr + k * 256, 128, TILE * 16), smem_desc(b_saddr + k * 256, 128, b_sbo),
-             idesc, (k > 0 || accumulate) ? 1u : 0u);
+  for (int k = 0; k < TILE / 16; ++k) {
+    mma_bf16(d_tmem, ad, bd, idesc, (k > 0 || accumulate) ? 1u : 0u);
+    ad += 256 >> 4, bd += 256 >> 4;  // 16 rows of K per instruction
+  }
 }
 
 template <int PN, bool POLICY>
@@ -231,7 +233,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (cta_issuer()) {
       fence_after_sync();
       issue_z1(tmem + kColMain, s.u.aug32, s.w1aug);
       mma_commit(&s.bar[kBZ1]);
@@ -290,7 +292,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (cta_issuer()) {
       fence_after_sync();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -380,7 +382,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     __syncthreads();
     pc.mark(3);  // E: row loss
     // ---- F. gW3^T += H2^T * dOut;  G = dOut * W3 (K = 16: one instruction) ------------------------------------------------
-    if (tid == 0) {
+    if (cta_issuer()) {
       fence_after_sync();
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb)
@@ -423,7 +425,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     __syncthreads();
     pc.mark(5);  // G: dZ2 epilogue
     // ---- H. dZ2 tile -> scratch;  dH1 = dZ2 * W2 in two column halves;  [., gb2] += dZ2^T * [obs, 1] --------------------------
-    if (tid == 0) {
+    if (cta_issuer()) {
       fence_after_sync();
       uint8_t* dst = a.dz[net] + tile * (int64_t)kTileBytes;
 #pragma unroll
@@ -471,7 +473,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     __syncthreads();
     pc.mark(6);  // H + I: dH1 MMAs + dZ1 epilogue
     // ---- J. [gW1, gb1] += dZ1^T * [obs, 1];  Z1 of the next tile -- one commit, awaited at the top of the next tile -----
-    if (tid == 0) {
+    if (cta_issuer()) {
       fence_after_sync();
 #pragma unroll
       for (int ib = 0; ib < 2; ++ib)
@@ -486,7 +488,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     mbar_wait(&s.bar[kBZ1], (uint32_t)(it & 1));
     fence_after_sync();
   }
-  if (tid == 0) bulk_wait_all();  // dZ2 stores have landed before the kernel ends
+  if (cta_issuer()) bulk_wait_all();  // dZ2 stores have landed before the kernel ends
 
   // ---- flush the thin gradients (warps 0-3 -> units 0..127, warps 4-7 -> units 128..255) ---------------------------------
   if (it > 0 && warp < 8) {
@@ -634,7 +636,7 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (cta_issuer()) {
       fence_after_sync();
       tma_load(0);
       issue_z1(tmem + kColZ, s.aug32[0], s.w1aug);
@@ -669,7 +671,7 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (cta_issuer()) {
         fence_after_sync();
         if (more) {
           issue_z1(tmem + kColZ, s.aug32[st ^ 1], s.w1aug);
@@ -721,7 +723,7 @@ static int policy_ctas() {
   static int n = 0;
   if (!n) {
     const char* e = getenv("RL8_H_POLICY_CTAS");  // tuning knob; default measured on B200
-    n = e ? atoi(e) : 78;
+    n = e ? atoi(e) : 80;
     if (n < 1 || n > kNumSMs - 1) n = kNumSMs / 2;
   }
   return n;

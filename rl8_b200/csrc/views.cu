@@ -30,6 +30,8 @@ struct ViewArgs {
   int tb;     // sequences per CTA
   int tw;     // windows per CTA
   int pitch;  // staged elements per sequence (odd, >= (tw + size - 1) * F)
+  int tb_shift;       // log2(tb), or -1 when tb is not a power of two
+  uint32_t f_magic;   // floor(2^32 / F) + 1: n / F == umulhi(n, f_magic) for n * F < 2^32 (n < 2^14 here); 0 when F == 1
   int vec;    // 128-bit store path: out 16-byte aligned and size * F a multiple of the vector width
 };
 
@@ -63,8 +65,13 @@ __global__ void __launch_bounds__(kViewThreads) view_windows_kernel(ViewArgs a) 
         const int e = e0 + k * kViewThreads;
         v[k] = 0, dst[k] = -1;
         if (e < total) {
-          const int bl = e % a.tb, tf = e / a.tb;
-          const int tl = tf / F, f = tf - tl * F;
+          int bl, tf;
+          if (a.tb_shift >= 0) {
+            bl = e & (a.tb - 1), tf = e >> a.tb_shift;
+          } else {
+            bl = e % a.tb, tf = e / a.tb;
+          }
+          const int tl = a.f_magic ? (int)__umulhi((uint32_t)tf, a.f_magic) : tf, f = tf - tl * F;
           const int64_t t = t0 + tl;
           dst[k] = bl * a.pitch + tf;
           if (bl < nb && t >= 0) v[k] = x[(b0 + bl) * a.sb + t * a.st + (int64_t)f * a.sf];
@@ -86,7 +93,7 @@ __global__ void __launch_bounds__(kViewThreads) view_windows_kernel(ViewArgs a) 
           const int tf = tf0 + k * 32;
           v[k] = 0;
           if (tf < per_seq) {
-            const int tl = tf / F, f = tf - tl * F;
+            const int tl = a.f_magic ? (int)__umulhi((uint32_t)tf, a.f_magic) : tf, f = tf - tl * F;
             const int64_t t = t0 + tl;
             if (t >= 0) v[k] = xb[t * a.st + (int64_t)f * a.sf];
           }
@@ -184,6 +191,10 @@ extern "C" int rl8_view_windows(const void* x, int32_t elem_bytes, int64_t B, in
   int64_t pitch = (tw + size - 1) * F;
   pitch |= 1;  // odd: conflict-free when lanes walk the sequence axis
   a.pitch = (int)pitch;
+  a.tb_shift = -1;
+  for (int sft = 0; sft < 6; ++sft)
+    if ((1 << sft) == tb) a.tb_shift = sft;
+  a.f_magic = F == 1 ? 0u : (uint32_t)((1ull << 32) / (uint64_t)F + 1);
   a.vec = ((uintptr_t)out % 16 == 0 && (size * F) % (16 / elem_bytes) == 0) ? 1 : 0;
   const int64_t gx = ceil_div(B, tb), gy = ceil_div(count, tw);
   if (gy > 65535) return RL8_ERR_UNSUPPORTED;

@@ -57,3 +57,31 @@ print("step                  %.3f ms" % (sum(t) / len(t)))
 print("H2D 25 MB pinned      %.3f ms" % clock(lambda: dev_noise.copy_(host_noise, non_blocking=True)))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 print("flush.zero_ 256 MB    %.3f ms" % clock(flush.zero_))
+
+
+def per_step(fn, n=12):  # noqa: ANN001, ANN201
+    out = []
+    for _ in range(n):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        out.append(round(1e3 * (time.perf_counter() - t0), 2))
+    return out
+
+
+print("Trainer.step each            ", per_step(tr.step))
+print("memory_stats each            ", per_step(algo.memory_stats))
+real_mem = algo.memory_stats
+algo.memory_stats = lambda: {}
+print("Trainer.step w/o memory_stats", per_step(tr.step))
+algo.memory_stats = real_mem
+HostNoise.draw_noise = classmethod(lambda cls, steps, num, width, device: dev_noise)
+print("Trainer.step w/o H2D copy    ", per_step(tr.step))
+algo.memory_stats = lambda: {}
+print("Trainer.step w/o both        ", per_step(tr.step))
+import gc  # noqa: E402
+
+gc.disable()
+print("  ... and gc disabled        ", per_step(tr.step))
