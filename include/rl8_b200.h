@@ -379,9 +379,10 @@ int rl8_tc_bench_tmem(long long* out_cycles, int32_t nwarps, int32_t iters, int3
 int rl8_tc_bench_mma(long long* out_cycles, int32_t N, int32_t k_total, int32_t reps, int a_mn_major,
                      int b_mn_major, rl8_stream_t stream);
 
-/* Debug hook: `device_counters` (16 x uint64 on the device, zeroed by the caller) receives the SM
+/* Debug hook: `device_counters` (24 x uint64 on the device, zeroed by the caller) receives the SM
  * cycles CTA 0 of each network spends in the 8 phases of the tensor-core update's activation
- * kernel ([0..7] policy, [8..15] value) for every later rl8_ppo_minibatch call; NULL switches the
+ * kernel ([0..7] policy, [8..15] value; [16..20] weight-gradient kernel CTA 0) for every later
+ * rl8_ppo_minibatch call; NULL switches the
  * stamping off.  Feeds profiles/ (where the tile time goes), not the product path. */
 int rl8_tc_phase_buffer(unsigned long long* device_counters);
 

@@ -78,6 +78,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // ---- bulk async copy shared -> global (bulk-group completion; SASS: UBLKCP) -------------------
+// pull `bytes` of global memory into L2 ahead of the bulk copy that will stage it (no smem needed)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
                "r"(smem_u32(smem_src)), "r"(bytes)

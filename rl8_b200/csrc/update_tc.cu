@@ -585,7 +585,11 @@ struct SmemW {
 static_assert(sizeof(SmemW) + 512 <= 227 * 1024, "SmemW exceeds the 227 KB CTA limit");
 
 // grid: blockIdx & 1 = network, (blockIdx >> 1) & 1 = half of the hidden units j, blockIdx >> 2 = CTA of the role
-__global__ void __launch_bounds__(kUpdThreads, 1)
+// block: 16 epilogue warps (Z1 -> H1 tiles) + ONE issuing warp (warp 16: bulk copies and every tcgen05.mma),
+// so the issue / wait chain of the tensor pipe runs beside the epilogue instead of in series with it.
+constexpr int kUpdWThreads = kUpdThreads + 32;
+
+__global__ void __launch_bounds__(kUpdWThreads, 1)
 tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemW& s = *reinterpret_cast<SmemW*>(smem_raw);
@@ -593,6 +597,7 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   const NetParams np = net ? np_vf : np_pi;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const bool epi = tid < kUpdThreads;  // epilogue thread (the rest is the issuing warp)
   const int q = warp & 3, cq = warp >> 2;
   const int r = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -619,7 +624,7 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   const int64_t n_my = tile0 < ntiles ? (ntiles - tile0 + nctas - 1) / nctas : 0;
   const uint8_t* dz_src = a.dz[net] + (int64_t)jh * (kTileBytes / 2);
 
-  auto tma_load = [&](int64_t k) {  // thread 0
+  auto tma_load = [&](int64_t k) {  // issuing lane
     const int st = (int)(k & 1);
     const uint8_t* src = dz_src + (tile0 + k * nctas) * (int64_t)kTileBytes;
     mbar_expect_tx(&s.bar_tma[st], kTileBytes / 2);
@@ -628,7 +633,7 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   };
 
   if (n_my > 0) {
-    {
+    if (epi) {
       int64_t t0 = 0, n0 = 0;
       const bool valid = row_to_tn(a, a.row_off + tile0 * TILE + (tid & (TILE - 1)), t0, n0);
       store_aug32(s.aug32[0], load_obs(a, valid, t0, n0, D));
@@ -636,63 +641,74 @@ tc_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (cta_issuer()) {
+    if (!epi && elect_one()) {
       fence_after_sync();
       tma_load(0);
       issue_z1(tmem + kColZ, s.aug32[0], s.w1aug);
       mma_commit(&s.bar_z);
     }
+    // debug stamps (CTA 0): [16] wait for Z1 / stage, [17] H1 epilogue + barrier, and on the issuing
+    // lane [18] wait for the dZ2 bulk copy, [19] wait for the previous gW2, [20] issue
+    PhaseClock pc(a.phase && tid == kUpdThreads - 1 && blockIdx.x == 0 ? a.phase + 16 : nullptr);
     for (int64_t k = 0; k < n_my; ++k) {
       const int st = (int)(k & 1);
       const bool more = k + 1 < n_my;
-      ObsRegs nxt;
-      if (more) {
-        int64_t t1 = 0, n1 = 0;
-        const bool valid = row_to_tn(a, a.row_off + (tile0 + (k + 1) * nctas) * TILE + (tid & (TILE - 1)), t1, n1);
-        nxt = load_obs(a, valid, t1, n1, D);
+      if (epi) {
+        ObsRegs nxt;
+        if (more) {
+          int64_t t1 = 0, n1 = 0;
+          const bool valid =
+              row_to_tn(a, a.row_off + (tile0 + (k + 1) * nctas) * TILE + (tid & (TILE - 1)), t1, n1);
+          nxt = load_obs(a, valid, t1, n1, D);
+        }
+        mbar_wait(&s.bar_z, (uint32_t)(k & 1));  // Z1(k) is in TMEM
+        if (k >= 2) mbar_wait(&s.bar_g[st], (uint32_t)(((k - 2) >> 1) & 1));  // gW2(k-2) has read stage st
+        fence_after_sync();
+        pc.mark(0);
+        {
+          float v0[32], v1[32];
+          tmem_ld32_nowait(tmem + kColZ + lane_base + (uint32_t)group_col0(cq, 0), v0);
+          tmem_ld32_nowait(tmem + kColZ + lane_base + (uint32_t)group_col0(cq, 1), v1);
+          tmem_wait_ld();
+          reg_fence32(v0);
+          reg_fence32(v1);
+          uint32_t hp[16];
+          relu_pack32(v0, hp);
+          store_group(s.h1_tile[st], r, group_col0(cq, 0), hp);
+          relu_pack32(v1, hp);
+          store_group(s.h1_tile[st], r, group_col0(cq, 1), hp);
+        }
+        if (more) store_aug32(s.aug32[st ^ 1], nxt);
+        fence_async_smem();
       }
-      mbar_wait(&s.bar_z, (uint32_t)(k & 1));  // Z1(k) is in TMEM
-      if (k >= 2) mbar_wait(&s.bar_g[st], (uint32_t)(((k - 2) >> 1) & 1));  // gW2(k-2) has read stage st
-      fence_after_sync();
-      {
-        float v0[32], v1[32];
-        tmem_ld32_nowait(tmem + kColZ + lane_base + (uint32_t)group_col0(cq, 0), v0);
-        tmem_ld32_nowait(tmem + kColZ + lane_base + (uint32_t)group_col0(cq, 1), v1);
-        tmem_wait_ld();
-        reg_fence32(v0);
-        reg_fence32(v1);
-        uint32_t hp[16];
-        relu_pack32(v0, hp);
-        store_group(s.h1_tile[st], r, group_col0(cq, 0), hp);
-        relu_pack32(v1, hp);
-        store_group(s.h1_tile[st], r, group_col0(cq, 1), hp);
-      }
-      if (more) store_aug32(s.aug32[st ^ 1], nxt);
-      fence_async_smem();
       fence_before_sync();
       __syncthreads();
-      if (cta_issuer()) {
+      pc.mark(1);
+      if (!epi && elect_one()) {
+        PhaseClock pi(a.phase && blockIdx.x == 0 ? a.phase + 18 : nullptr);
         fence_after_sync();
         if (more) {
           issue_z1(tmem + kColZ, s.aug32[st ^ 1], s.w1aug);
           mma_commit(&s.bar_z);
+          // refill the other dZ2 stage as early as possible: gW2(k-1), issued one iteration ago, was its reader
+          if (k >= 1) mbar_wait(&s.bar_g[st ^ 1], (uint32_t)(((k - 1) >> 1) & 1));
+          pi.mark(1);
+          tma_load(k + 1);
         }
         mbar_wait(&s.bar_tma[st], (uint32_t)((k >> 1) & 1));
+        pi.mark(0);
         // gW2[j half][i] += dZ2[:, j half]^T * H1: A = dz half tile (MN-major), B = H1 tile (MN-major)
         issue_gemm(tmem + kColG, smem_u32(s.dz_tile[st]), TILE, true, smem_u32(s.h1_tile[st]), TILE, true,
                    TILE, H, TILE, k > 0);
         mma_commit(&s.bar_g[st]);
-        if (more) {
-          if (k >= 1) mbar_wait(&s.bar_g[st ^ 1], (uint32_t)(((k - 1) >> 1) & 1));  // gW2(k-1) done
-          tma_load(k + 1);
-        }
+        pi.mark(2);
       }
     }
     // all MMAs done: the last commit covers every earlier one
     mbar_wait(&s.bar_g[(n_my - 1) & 1], (uint32_t)(((n_my - 1) >> 1) & 1));
     fence_after_sync();
     // flush: lane = unit j of this half, 256 columns i; warp (q, cq) -> lanes 32q.., columns 64cq..
-    {
+    if (epi) {
       const int j = jh * 128 + r;
       float* dst = a.gw2[net] + (int64_t)j * H + cq * 64;
 #pragma unroll 1
@@ -793,7 +809,7 @@ int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_b
 #undef RL8_UPD
     if ((rc = check_launch("tc_update_h"))) return rc;
     if ((rc = set_smem((const void*)tc_update_w_kernel, sizeof(SmemW)))) return rc;
-    tc_update_w_kernel<<<grid_w, kUpdThreads, sizeof(SmemW), st>>>(np_pi, np_vf, a);
+    tc_update_w_kernel<<<grid_w, kUpdWThreads, sizeof(SmemW), st>>>(np_pi, np_vf, a);
     if ((rc = check_launch("tc_update_w"))) return rc;
   }
   return RL8_OK;

@@ -30,7 +30,7 @@ for k in ("obs", "actions", "logp", "advantages", "returns"):
     setattr(batch, k, algo.buffer.hm[k].data_ptr())
 ppo = L.PpoHparams(0.2, 0.0, 0.0, 5.0, 1.0, 1.0)
 sums = torch.zeros(5, dtype=torch.float64, device=algo.device)
-counters = torch.zeros(16, dtype=torch.int64, device=algo.device)
+counters = torch.zeros(24, dtype=torch.int64, device=algo.device)
 
 
 def run() -> None:
@@ -53,7 +53,7 @@ names = ["A+B stage, Z1 MMA", "C   H1 epilogue", "D   Z2 MMA + H2 epi", "E   row
          "G   dZ2 epilogue", "H+I dH1 MMA + dZ1 epi", "J   gW1 thin MMA"]
 chunk = min(M, 1 << 20)
 ntiles = -(-chunk // 128)
-n_pi = 78
+n_pi = int(__import__('os').environ.get('RL8_H_POLICY_CTAS', 80))
 for net, label, nct in ((0, "policy", n_pi), (1, "value", 148 - n_pi)):
     tiles = reps * (-(-M // chunk)) * (-(-ntiles // nct))  # tiles CTA 0 of this network processed
     tot = sum(c[8 * net: 8 * net + 8])
@@ -61,3 +61,10 @@ for net, label, nct in ((0, "policy", n_pi), (1, "value", 148 - n_pi)):
     for i, nm in enumerate(names):
         v = c[8 * net + i]
         print(f"   {nm:24s} {v / tiles:8.0f}  {100 * v / tot:5.1f}%")
+
+# weight-gradient kernel, CTA 0 (policy network, unit half 0): 37 CTAs per role
+tiles = reps * (-(-M // chunk)) * (-(-ntiles // 37))
+print(f"tc_update_w CTA 0 ({tiles} tiles):")
+for i, nm in ((16, "wait Z1 / free stage"), (17, "H1 epilogue + barrier"), (18, "issuer: wait dZ2 bulk copy"),
+              (19, "issuer: wait previous gW2"), (20, "issuer: issue Z1 + gW2")):
+    print(f"   {nm:28s} {c[i] / tiles:8.0f}")
