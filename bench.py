@@ -529,11 +529,11 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
         ms = fn.ms / 3
         flops = hp.num_sgd_iters * N * T * 3.0 * 2.0 * ((D + H) * 4 * H + (P + 1) * H)
         return {
-            "kernel": "RecurrentAlgorithm.step (rl8_lstm_ppo_minibatch x num_sgd_iters, fp32 CUDA-core GEMMs)",
+            "kernel": "RecurrentAlgorithm.step (rl8_lstm_ppo_minibatch x num_sgd_iters; LSTM GEMMs: "
+                      + ("tcgen05 bf16, tc_gemm_kernel)" if dtype == "bf16" else "fp32 CUDA cores)"),
             "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
             "frac": flops / ms / 1e9 / peak, "traffic": None, "ms": ms, "rows": N * T, "dtype": dtype,
-            "peak_source": peaks["source"] + " bf16 sustained (the recurrent path is fp32 on CUDA cores:"
-                           " the fraction shows the gap a tensor-core LSTM path would close)",
+            "peak_source": peaks["source"] + " bf16 sustained (whole step() incl. its elementwise kernels)",
         }
     algo.collect()
     model = algo.policy.model

@@ -372,6 +372,14 @@ int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream)
 int rl8_tc_bench_tmem(long long* out_cycles, int32_t nwarps, int32_t iters, int32_t mode,
                       rl8_stream_t stream);
 
+/* C[M][N] (ldc) = (accumulate ? C : 0) + sum_k A(m, k) * B(k, n) on tcgen05: fp32 operands converted to bf16
+ * while staged, fp32 accumulation.  a_kmajor: A(m, k) = A[m * lda + k] else A[k * lda + m]; b_kmajor:
+ * B(k, n) = B[n * ldb + k] else B[k * ldb + n].  accumulate splits K over `splits` CTAs (vector
+ * reductions into C).  The GEMM the recurrent path uses for `enable_amp=True`; exported for the tests. */
+int rl8_tc_gemm(int a_kmajor, int b_kmajor, int accumulate, const float* A, const float* B, float* C,
+                int64_t M, int32_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int32_t splits,
+                rl8_stream_t stream);
+
 /* Microbenchmark: out_cycles[0] = SM cycles from the first issue to the mbarrier completion of `reps`
  * back-to-back tcgen05 GEMMs D[128][N] += A[128][k_total] * B[N][k_total]^T (bf16, one commit at the end,
  * operands in the library's chunked shared-memory format); out_cycles[1] = cycles of the issue loop.

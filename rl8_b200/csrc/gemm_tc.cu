@@ -1,0 +1,232 @@
+// Generic tensor-core GEMM for the recurrent path's three contractions (RL8_PREC_BF16):
+//
+//     C[M][N] (ldc)  =  or  +=   sum_k A(m, k) * B(k, n)        fp32 in global memory, either major
+//
+// The operands are fp32 in HBM (LSTM states, gate activations / gradients, W_hh); a CTA converts
+// each K chunk to bf16 WHILE staging it into the library's chunked shared-memory format -- eight
+// consecutive elements along the operand's unit-stride axis are one 16-byte chunk in either major,
+// so both layouts are read with 128-bit loads and written with 128-bit stores -- and one elected
+// lane feeds tcgen05 (fp32 accumulation in TMEM).  Two stages: the loads of chunk k+1 run under
+// the MMAs of chunk k.  Grid = (M tiles of 128, N tiles of 256, K splits); split-K accumulates
+// with vector reductions (EPI_ATOMIC), otherwise the tile is stored (EPI_STORE).
+//
+// Replaces, for `enable_amp=True`, the cuBLAS / ATen GEMMs inside nn.LSTM's forward and autograd
+// backward that the reference runs (src/rl8/models/_recurrent.py:259-341 through
+// src/rl8/algorithms/_recurrent.py:517-600): gates = h W_hh^T, dh = dG W_hh, gW_hh += dG^T h.
+#include "mlp_fp32.cuh"
+#include "tc.cuh"
+
+namespace rl8 {
+
+using namespace tc;
+
+constexpr int kGM = 128;        // rows of C per CTA (MMA M)
+constexpr int kGN = 256;        // columns of C per CTA (MMA N)
+constexpr int kGK = 64;         // K elements per stage
+constexpr int kGThreads = 256;  // 8 warps: all stage operands; warp 0 elects the issuer
+
+struct SmemGemm {
+  uint8_t a[2][kGM * kGK * 2];  // 2 x 16 KB
+  uint8_t b[2][kGN * kGK * 2];  // 2 x 32 KB
+  uint64_t bar[2];
+  uint32_t tmem_base;
+};
+
+struct GemmArgs {
+  const float *A, *B;
+  float* C;
+  int64_t M, K, lda, ldb, ldc, kchunk;
+  int N;
+};
+
+// Eight consecutive fp32 elements at p (the first `valid` of them inside the matrix) -> one bf16 chunk.
+struct Chunk8 {
+  float4 lo, hi;
+};
+__device__ __forceinline__ Chunk8 load8(const float* p, bool in_range, int64_t valid) {
+  Chunk8 c;
+  c.lo = make_float4(0.f, 0.f, 0.f, 0.f), c.hi = c.lo;
+  if (in_range) {
+    if (valid >= 8) {
+      c.lo = __ldg(reinterpret_cast<const float4*>(p));
+      c.hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    } else {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = j < valid ? p[j] : 0.0f;
+      c.lo = make_float4(v[0], v[1], v[2], v[3]), c.hi = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  return c;
+}
+__device__ __forceinline__ uint4 pack8(const Chunk8& c) {
+  uint4 q;
+  q.x = pack_bf16x2(c.lo.x, c.lo.y), q.y = pack_bf16x2(c.lo.z, c.lo.w);
+  q.z = pack_bf16x2(c.hi.x, c.hi.y), q.w = pack_bf16x2(c.hi.z, c.hi.w);
+  return q;
+}
+constexpr int kGBatch = 4;  // chunks a thread has in flight: the staging loop is latency-, not issue-bound
+
+// Stage ROWS x kGK of an operand whose unit-stride axis is K (X(i, k) = X[i * ld + k]) as a K-major tile.
+template <int ROWS>
+__device__ __forceinline__ void stage_kmajor(uint8_t* tile, const float* X, int64_t ld, int64_t i0, int64_t imax,
+                                             int64_t k0, int64_t kmax) {
+  // 8 chunks of 8 k per row: consecutive threads read 256 contiguous bytes of one row
+  constexpr int kTasks = ROWS * (kGK / 8);
+  static_assert(kTasks % (kGBatch * kGThreads) == 0, "tile tasks must divide evenly");
+  for (int e0 = threadIdx.x; e0 < kTasks; e0 += kGBatch * kGThreads) {
+    Chunk8 c[kGBatch];
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kGThreads, row = e >> 3, kc = e & 7;
+      const int64_t i = i0 + row, k = k0 + kc * 8;
+      c[b] = load8(X + i * ld + k, i < imax && k < kmax, kmax - k);
+    }
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kGThreads, row = e >> 3, kc = e & 7;
+      *reinterpret_cast<uint4*>(tile + chunk_offset<ROWS>(row, kc)) = pack8(c[b]);
+    }
+  }
+}
+// Stage kGK x COLS of an operand whose unit-stride axis is M/N (X(i, k) = X[k * ld + i]) as an MN-major tile
+// (tile rows = K, 16-byte chunks = 8 consecutive i).
+template <int COLS>
+__device__ __forceinline__ void stage_mnmajor(uint8_t* tile, const float* X, int64_t ld, int64_t i0, int64_t imax,
+                                              int64_t k0, int64_t kmax) {
+  constexpr int CG = COLS / 8;  // column groups per K row: consecutive threads read one row of X contiguously
+  constexpr int kTasks = kGK * CG;
+  static_assert(kTasks % (kGBatch * kGThreads) == 0, "tile tasks must divide evenly");
+  for (int e0 = threadIdx.x; e0 < kTasks; e0 += kGBatch * kGThreads) {
+    Chunk8 c[kGBatch];
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kGThreads, kr = e / CG, cg = e - kr * CG;
+      const int64_t k = k0 + kr, i = i0 + cg * 8;
+      c[b] = load8(X + k * ld + i, k < kmax && i < imax, imax - i);
+    }
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kGThreads, kr = e / CG, cg = e - kr * CG;
+      *reinterpret_cast<uint4*>(tile + chunk_offset<kGK>(kr, cg)) = pack8(c[b]);
+    }
+  }
+}
+
+template <bool AK, bool BK, bool ATOMIC>
+__global__ void __launch_bounds__(kGThreads, 2) tc_gemm_kernel(GemmArgs g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemGemm& s = *reinterpret_cast<SmemGemm*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * kGM;
+  const int64_t n0 = (int64_t)blockIdx.y * kGN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.kchunk;
+  const int64_t kend = kbeg + g.kchunk < g.K ? kbeg + g.kchunk : g.K;
+  if (tid == 0) {
+    mbar_init(&s.bar[0], 1);
+    mbar_init(&s.bar[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, kGN);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  const int nchunks = (int)((kend - kbeg + kGK - 1) / kGK);
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    const int64_t k0 = kbeg + (int64_t)c * kGK;
+    if (c >= 2) {  // the MMAs of chunk c-2 have read this stage
+      mbar_wait(&s.bar[st], (uint32_t)(((c - 2) >> 1) & 1));
+      fence_after_sync();
+    }
+    if constexpr (AK) stage_kmajor<kGM>(s.a[st], g.A, g.lda, m0, g.M, k0, kend);
+    else stage_mnmajor<kGM>(s.a[st], g.A, g.lda, m0, g.M, k0, kend);
+    if constexpr (BK) stage_kmajor<kGN>(s.b[st], g.B, g.ldb, n0, g.N, k0, kend);
+    else stage_mnmajor<kGN>(s.b[st], g.B, g.ldb, n0, g.N, k0, kend);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (cta_issuer()) {
+      fence_after_sync();
+      issue_gemm(tmem, smem_u32(s.a[st]), AK ? kGM : kGK, !AK, smem_u32(s.b[st]), BK ? kGN : kGK, !BK, kGM, kGN,
+                 kGK, c > 0);
+      mma_commit(&s.bar[st]);
+    }
+  }
+  if (nchunks > 0) {  // the last commit covers every earlier MMA
+    mbar_wait(&s.bar[(nchunks - 1) & 1], (uint32_t)(((nchunks - 1) >> 1) & 1));
+    fence_after_sync();
+    // epilogue: warp (q = warp & 3, half = warp >> 2) -> rows 32q + lane, columns [128 half, 128 half + 128)
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t m = m0 + q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      float v[32];
+      const int col = half * 128 + j * 32;
+      tmem_ld32(tmem + lane_base + (uint32_t)col, v);
+      if (m < g.M) {
+        float* dst = g.C + m * g.ldc + n0 + col;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          if (n0 + col + e < g.N) {
+            if constexpr (ATOMIC) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+            else *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, kGN);
+}
+
+// Same contract as launch_sgemm (mlp_fp32.cuh) for EPI_STORE / EPI_ATOMIC, bf16 operands on tcgen05.
+// Requires 16-byte aligned operands, lda / ldb / ldc % 4 == 0 and N % 4 == 0 (the vector epilogue).
+int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const float* B, float* C, int64_t M,
+                   int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int splits, cudaStream_t st) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return RL8_ERR_ARG;
+  if ((lda | ldb | ldc | N) & 3) return RL8_ERR_UNSUPPORTED;
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return RL8_ERR_UNSUPPORTED;
+  if (epi != EPI_STORE && epi != EPI_ATOMIC) return RL8_ERR_UNSUPPORTED;
+  if (epi == EPI_STORE) splits = 1;
+  if (splits < 1) splits = 1;
+  GemmArgs g;
+  g.A = A, g.B = B, g.C = C, g.M = M, g.N = N, g.K = K, g.lda = lda, g.ldb = ldb, g.ldc = ldc;
+  g.kchunk = round_up(ceil_div(K, splits), kGK);
+  splits = (int)ceil_div(K, g.kchunk);
+  dim3 grid((unsigned)ceil_div(M, kGM), (unsigned)ceil_div(N, kGN), (unsigned)splits);
+  const size_t smem = sizeof(SmemGemm);
+#define RL8_GEMM(AKV, BKV, ATV)                                                                          \
+  {                                                                                                      \
+    static bool attr = false;                                                                            \
+    if (!attr) {                                                                                         \
+      cudaFuncSetAttribute(tc_gemm_kernel<AKV, BKV, ATV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           (int)smem);                                                                   \
+      attr = true;                                                                                       \
+    }                                                                                                    \
+    tc_gemm_kernel<AKV, BKV, ATV><<<grid, kGThreads, smem, st>>>(g);                                     \
+  }
+  const bool at = epi == EPI_ATOMIC;
+  if (a_kmajor && b_kmajor && !at) RL8_GEMM(true, true, false)
+  else if (a_kmajor && b_kmajor && at) RL8_GEMM(true, true, true)
+  else if (a_kmajor && !b_kmajor && !at) RL8_GEMM(true, false, false)
+  else if (a_kmajor && !b_kmajor && at) RL8_GEMM(true, false, true)
+  else if (!a_kmajor && !b_kmajor && !at) RL8_GEMM(false, false, false)
+  else if (!a_kmajor && !b_kmajor && at) RL8_GEMM(false, false, true)
+  else return RL8_ERR_UNSUPPORTED;
+#undef RL8_GEMM
+  return check_launch("tc_gemm");
+}
+
+}  // namespace rl8
+
+// Test hook (C ABI): the generic tensor-core GEMM with the launch_sgemm contract.
+extern "C" int rl8_tc_gemm(int a_kmajor, int b_kmajor, int accumulate, const float* A, const float* B, float* C,
+                           int64_t M, int32_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int32_t splits,
+                           rl8_stream_t stream) {
+  return rl8::launch_tc_gemm(a_kmajor != 0, b_kmajor != 0, accumulate ? rl8::EPI_ATOMIC : rl8::EPI_STORE, A, B, C,
+                             M, N, K, lda, ldb, ldc, splits, (cudaStream_t)stream);
+}

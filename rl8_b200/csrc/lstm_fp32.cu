@@ -1,4 +1,7 @@
-// Recurrent (LSTM) policy, fp32 CUDA-core path (RL8_PREC_FP32; reference `enable_amp=False`).
+// Recurrent (LSTM) policy.  RL8_PREC_FP32 (reference `enable_amp=False`): every GEMM in fp32 on CUDA
+// cores, bit-comparable with the reference.  RL8_PREC_BF16 (`enable_amp=True`): the three 256 x 1024
+// contractions (gates = h W_hh^T, dh = dG W_hh, gW_hh += dG^T h) run on tcgen05 with bf16 operands and
+// fp32 accumulation (gemm_tc.cu); everything else is unchanged fp32.
 //
 //   rollout  (src/rl8/algorithms/_recurrent.py:356-445): per step  SGEMM h.W_hh^T -> cell kernel
 //            (adds x.W_ih^T + biases, gate non-linearities, writes the state slabs) -> heads ->
@@ -17,6 +20,15 @@ namespace rl8 {
 // collect.cu
 int validate_rollout_dims(int mD, int mH, int mP, const rl8_rollout* ro);
 int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st);
+
+// The recurrent path's GEMM: CUDA-core fp32 or tcgen05 bf16 by precision.
+static int lstm_gemm(int prec, bool a_kmajor, bool b_kmajor, int epi, const float* A, const float* B, float* C,
+                     int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int splits,
+                     cudaStream_t st) {
+  if (prec == RL8_PREC_BF16)
+    return launch_tc_gemm(a_kmajor, b_kmajor, epi, A, B, C, M, N, K, lda, ldb, ldc, splits, st);
+  return launch_sgemm(a_kmajor, b_kmajor, epi, A, B, C, M, N, K, lda, ldb, ldc, nullptr, splits, st);
+}
 
 constexpr int kLH = 256;   // hidden width of the default recurrent models
 constexpr int kLD = 8;     // widest observation on the fused path
@@ -42,39 +54,55 @@ lstm_cell_fwd_kernel(const float* G, RowMap xmap, int D, int64_t rows,
     bh[g] = b_hh[g * kLH + j];
   }
   const int64_t ds = xmap.dstride();
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int64_t xo = xmap.offset(r);
-    float x[kLD];
+  // kRows rows per iteration: their loads are all in flight before the first gate is evaluated
+  constexpr int kRows = 4;
+  for (int64_t r0 = (int64_t)blockIdx.x * kRows; r0 < rows; r0 += (int64_t)gridDim.x * kRows) {
+    float pre[kRows][4], cp[kRows];
 #pragma unroll
-    for (int d = 0; d < kLD; ++d) x[d] = d < D ? xmap.obs[xo + d * ds] : 0.0f;
-    float pre[4];
+    for (int i = 0; i < kRows; ++i) {
+      const int64_t r = r0 + i;
+      if (r < rows) {
+        const int64_t xo = xmap.offset(r);
+        float x[kLD];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float a = bi[g];
+        for (int d = 0; d < kLD; ++d) x[d] = d < D ? xmap.obs[xo + d * ds] : 0.0f;
 #pragma unroll
-      for (int d = 0; d < kLD; ++d)
-        if (d < D) a = fmaf(x[d], w[g][d], a);
-      pre[g] = a + (G[r * 4 * kLH + g * kLH + j] + bh[g]);
+        for (int g = 0; g < 4; ++g) {
+          float a = bi[g];
+#pragma unroll
+          for (int d = 0; d < kLD; ++d)
+            if (d < D) a = fmaf(x[d], w[g][d], a);
+          pre[i][g] = a + (G[r * 4 * kLH + g * kLH + j] + bh[g]);
+        }
+        cp[i] = c_prev[r * kLH + j];
+      }
     }
-    const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]),
-                og = sigmoidf_(pre[3]);
-    const float c = fg * c_prev[r * kLH + j] + ig * gg;
-    const float h = og * tanhf(c);
-    if (act) {
-      act[r * 4 * kLH + 0 * kLH + j] = ig;
-      act[r * 4 * kLH + 1 * kLH + j] = fg;
-      act[r * 4 * kLH + 2 * kLH + j] = gg;
-      act[r * 4 * kLH + 3 * kLH + j] = og;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      const int64_t r = r0 + i;
+      if (r < rows) {
+        const float ig = sigmoidf_(pre[i][0]), fg = sigmoidf_(pre[i][1]), gg = tanhf(pre[i][2]),
+                    og = sigmoidf_(pre[i][3]);
+        const float c = fg * cp[i] + ig * gg;
+        const float h = og * tanhf(c);
+        if (act) {
+          act[r * 4 * kLH + 0 * kLH + j] = ig;
+          act[r * 4 * kLH + 1 * kLH + j] = fg;
+          act[r * 4 * kLH + 2 * kLH + j] = gg;
+          act[r * 4 * kLH + 3 * kLH + j] = og;
+        }
+        c_out[r * kLH + j] = c;
+        h_out[r * kLH + j] = h;
+      }
     }
-    c_out[r * kLH + j] = c;
-    h_out[r * kLH + j] = h;
   }
 }
 
 static int launch_cell_fwd(const rl8_lstm_model* m, const float* G, const RowMap& xmap, int64_t rows,
                            const float* c_prev, float* act, float* c_out, float* h_out,
                            cudaStream_t st) {
-  int grid = (int)(rows < (int64_t)kNumSMs * 16 ? rows : (int64_t)kNumSMs * 16);
+  const int64_t groups = ceil_div(rows, 4);  // 4 rows per block iteration
+  int grid = (int)(groups < (int64_t)kNumSMs * 16 ? groups : (int64_t)kNumSMs * 16);
   lstm_cell_fwd_kernel<<<grid, kLH, 0, st>>>(G, xmap, m->D, rows, m->w_ih, m->b_ih, m->b_hh, c_prev,
                                              act, c_out, h_out);
   return check_launch("lstm_cell_fwd");
@@ -84,9 +112,9 @@ static int launch_cell_fwd(const rl8_lstm_model* m, const float* G, const RowMap
 static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t rows,
                           const float* h_in, const float* c_in, float* h_out, float* c_out,
                           float* act, float* G, float* features, float* values, int tanh_col1,
-                          cudaStream_t st) {
-  int rc = launch_sgemm(true, true, EPI_STORE, h_in, m->w_hh, G, rows, 4 * kLH, kLH, kLH, kLH,
-                        4 * kLH, nullptr, 1, st);
+                          int prec, cudaStream_t st) {
+  int rc = lstm_gemm(prec, true, true, EPI_STORE, h_in, m->w_hh, G, rows, 4 * kLH, kLH, kLH, kLH,
+                     4 * kLH, 1, st);
   if (rc) return rc;
   if ((rc = launch_cell_fwd(m, G, xmap, rows, c_in, act, c_out, h_out, st))) return rc;
   if (features &&
@@ -113,7 +141,7 @@ static bool state_reset_at(const rl8_recurrent_rollout* rro, int t) {
   return (seqs % rro->seqs_per_state_reset) == 0;
 }
 
-int lstm_collect_fp32(const rl8_lstm_model* m, const rl8_recurrent_rollout* rro, void* workspace,
+int lstm_collect_fp32(const rl8_lstm_model* m, const rl8_recurrent_rollout* rro, int prec, void* workspace,
                       int64_t workspace_bytes, cudaStream_t st) {
   const rl8_rollout* ro = &rro->ro;
   const int64_t N = ro->N;
@@ -137,14 +165,14 @@ int lstm_collect_fp32(const rl8_lstm_model* m, const rl8_recurrent_rollout* rro,
     }
     map.obs = ro->obs + (int64_t)t * D * N;
     int rc = lstm_step_fp32(m, map, N, h_t, c_t, h_t + slab, c_t + slab, nullptr, G, feat,
-                            ro->values + (int64_t)t * N, continuous, st);
+                            ro->values + (int64_t)t * N, continuous, prec, st);
     if (rc) return rc;
     if ((rc = collect_tail(ro, t, feat, st))) return rc;
   }
   // bootstrap value from the last observation and the final states (:433-445)
   map.obs = ro->obs + (int64_t)T * D * N;
   return lstm_step_fp32(m, map, N, rro->hidden + (int64_t)T * slab, rro->cell + (int64_t)T * slab,
-                        hs, cs, nullptr, G, nullptr, ro->values + (int64_t)T * N, 0, st);
+                        hs, cs, nullptr, G, nullptr, ro->values + (int64_t)T * N, 0, prec, st);
 }
 
 // ---- update ----------------------------------------------------------------------------------------
@@ -290,9 +318,10 @@ static int launch_gate_reduce(const float* dG, int64_t rows, const RowMap& xmap,
   return check_launch("lstm_gate_reduce");
 }
 
-// Sequences resident per update chunk: bounds the activation workspace (6H floats per row).
+// Sequences resident per update chunk: bounds the activation workspace (6H floats per row and step:
+// 1.6 GB at the cap, sized for 180 GB of HBM) while keeping every kernel of a step at >= 512 row tiles.
 static int64_t lstm_chunk_seqs(int64_t max_seqs, int L) {
-  int64_t cap = 32768 / L;
+  int64_t cap = 262144 / L;
   if (cap < 1) cap = 1;
   return max_seqs < cap ? max_seqs : cap;
 }
@@ -308,7 +337,7 @@ int64_t lstm_ppo_fp32_workspace(int64_t max_seqs, int L) {
 int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
                             const rl8_recurrent_batch* rb, const int64_t* seqs, int64_t seq_begin,
                             int64_t M, double denom, const rl8_ppo_hparams* hp, double* loss_sums,
-                            void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                            int prec, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   const rl8_batch* b = &rb->b;
   const int L = rb->seq_len, D = m->D, P = m->P;
   const int64_t C = lstm_chunk_seqs(M, L);
@@ -351,7 +380,7 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
       float* opi = out_pi + (int64_t)k * C * kMaxP;
       float* ovf = out_vf + (int64_t)k * C;
       if ((rc = lstm_step_fp32(m, map, R, h_prev, c_prev, h_k, c_k, act_k, act_k, opi, ovf,
-                               continuous, st)))
+                               continuous, prec, st)))
         return rc;
       LossArgs la{};
       la.dist_kind = b->dist_kind, la.P = P, la.M = R;
@@ -387,15 +416,15 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
                                                                          !last, R);
       if ((rc = check_launch("lstm_cell_bwd"))) return rc;
       // gw_hh[g][j] += sum_r dG[r][g] h_prev[r][j]   (split-K over rows)
-      if ((rc = launch_sgemm(false, false, EPI_ATOMIC, act_k, h_prev, (float*)g->w_hh, 4 * kLH, kLH, R,
-                             4 * kLH, kLH, kLH, nullptr, splits, st)))
+      if ((rc = lstm_gemm(prec, false, false, EPI_ATOMIC, act_k, h_prev, (float*)g->w_hh, 4 * kLH, kLH, R,
+                          4 * kLH, kLH, kLH, splits, st)))
         return rc;
       if ((rc = launch_gate_reduce(act_k, R, map, D, (float*)g->w_ih, (float*)g->b_ih,
                                    (float*)g->b_hh, st)))
         return rc;
       // dL/dh_{k-1} (recurrent term) = dG . W_hh; nothing flows into the stored chunk-start state
-      if (k && (rc = launch_sgemm(true, false, EPI_STORE, act_k, m->w_hh, dh, R, kLH, 4 * kLH, 4 * kLH,
-                                  kLH, kLH, nullptr, 1, st)))
+      if (k && (rc = lstm_gemm(prec, true, false, EPI_STORE, act_k, m->w_hh, dh, R, kLH, 4 * kLH, 4 * kLH,
+                               kLH, kLH, 1, st)))
         return rc;
     }
   }
@@ -409,7 +438,7 @@ using namespace rl8;
 extern "C" int64_t rl8_lstm_collect_workspace(const rl8_lstm_model* model, int64_t N, int32_t T,
                                               int precision) {
   if (check_model(model) || N <= 0 || T <= 0) return RL8_ERR_ARG;
-  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  if (precision != RL8_PREC_FP32 && precision != RL8_PREC_BF16) return RL8_ERR_UNSUPPORTED;
   return (N * 4 * kLH + 2 * N * kLH + N * kMaxP) * 4;
 }
 
@@ -423,8 +452,8 @@ extern "C" int rl8_lstm_collect(const rl8_lstm_model* model, const rl8_recurrent
     return RL8_ERR_ARG;
   if ((rc = validate_rollout_dims(model->D, model->H, model->P, &rro->ro))) return rc;
   if (rro->ro.T % rro->seq_len) return RL8_ERR_ARG;
-  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
-  return lstm_collect_fp32(model, rro, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (precision != RL8_PREC_FP32 && precision != RL8_PREC_BF16) return RL8_ERR_UNSUPPORTED;
+  return lstm_collect_fp32(model, rro, precision, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int rl8_lstm_forward(const rl8_lstm_model* model, const float* obs, int64_t obs_stride_r,
@@ -435,19 +464,19 @@ extern "C" int rl8_lstm_forward(const rl8_lstm_model* model, const float* obs, i
   int rc = check_model(model);
   if (rc) return rc;
   if (!obs || !h_in || !c_in || !h_out || !c_out || B <= 0) return RL8_ERR_ARG;
-  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  if (precision != RL8_PREC_FP32 && precision != RL8_PREC_BF16) return RL8_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < B * 4 * kLH * 4) return RL8_ERR_WORKSPACE;
   RowMap map{};
   map.obs = obs, map.mode = 0, map.stride_r = obs_stride_r, map.stride_d = obs_stride_d;
   map.D = model->D;
   return lstm_step_fp32(model, map, B, h_in, c_in, h_out, c_out, nullptr, (float*)workspace,
-                        features, values, apply_tanh_log_std, (cudaStream_t)stream);
+                        features, values, apply_tanh_log_std, precision, (cudaStream_t)stream);
 }
 
 extern "C" int64_t rl8_lstm_ppo_workspace(const rl8_lstm_model* model, int64_t max_seqs,
                                           int32_t seq_len, int precision) {
   if (check_model(model) || max_seqs <= 0 || seq_len <= 0) return RL8_ERR_ARG;
-  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  if (precision != RL8_PREC_FP32 && precision != RL8_PREC_BF16) return RL8_ERR_UNSUPPORTED;
   return lstm_ppo_fp32_workspace(max_seqs, seq_len);
 }
 
@@ -468,7 +497,7 @@ extern "C" int rl8_lstm_ppo_minibatch(const rl8_lstm_model* model, const rl8_lst
   if (b->dist_kind != RL8_DIST_CATEGORICAL && model->P != 2) return RL8_ERR_UNSUPPORTED;
   if (b->dist_kind == RL8_DIST_SQUASHED_NORMAL && hp->entropy_coeff != 0.0f)
     return RL8_ERR_UNSUPPORTED;
-  if (precision != RL8_PREC_FP32) return RL8_ERR_UNSUPPORTED;
+  if (precision != RL8_PREC_FP32 && precision != RL8_PREC_BF16) return RL8_ERR_UNSUPPORTED;
   return lstm_ppo_minibatch_fp32(model, grads, batch, seqs, seq_begin, M, mean_denominator, hp,
-                                 loss_sums, workspace, workspace_bytes, (cudaStream_t)stream);
+                                 loss_sums, precision, workspace, workspace_bytes, (cudaStream_t)stream);
 }

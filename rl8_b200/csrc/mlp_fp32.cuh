@@ -45,6 +45,12 @@ int launch_sgemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const fl
                  int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
                  const float* bias, int splits, cudaStream_t st);
 
+// The same contract on tcgen05 (gemm_tc.cu): operands converted to bf16 while staged, fp32 accumulate;
+// EPI_STORE / EPI_ATOMIC only; 16-byte aligned pointers, lda / ldb / ldc / N multiples of 4.
+int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const float* B, float* C,
+                   int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int splits,
+                   cudaStream_t st);
+
 // out[rows][P] = b3 + h2 @ w3^T; column 1 is tanh'ed when tanh_col1 (continuous log_std).
 int launch_head_fwd(const float* h2, int64_t rows, int H, int P, const float* w3, const float* b3,
                     float* out, int tanh_col1, cudaStream_t st);

@@ -236,7 +236,7 @@ class RecurrentPolicy:
         rc = self._lib.rl8_lstm_forward(
             m, _lib.ptr(obs), obs.stride(0), obs.stride(1), _lib.ptr(h), _lib.ptr(c), _lib.ptr(h2),
             _lib.ptr(c2), _lib.ptr(head), _lib.ptr(values), B, int(self._continuous()),
-            _lib.PREC_FP32, _lib.ptr(self._ws), self._ws.numel(), _lib.stream(),
+            self.precision, _lib.ptr(self._ws), self._ws.numel(), _lib.stream(),
         )
         _lib.check(rc, "rl8_lstm_forward")
         return head, values, h2, c2
@@ -322,6 +322,8 @@ class RecurrentAlgorithmConfig:
     optimizer_cls: type[optim.Optimizer] = optim.Adam
     optimizer_config: None | dict[str, Any] = None
     accumulate_grads: bool = False
+    #: ``True``: the LSTM's hidden-to-hidden GEMMs (forward and both backward contractions) run in
+    #: bf16 on tcgen05 with fp32 accumulation; ``False``: everything in fp32 on CUDA cores.
     enable_amp: bool = False
     lr_schedule: None | list[tuple[int, float]] = None
     lr_schedule_kind: ScheduleKind = "step"
@@ -369,11 +371,6 @@ class RecurrentAlgorithm(Algorithm):
         if device == "cuda":
             device = f"cuda:{torch.cuda.current_device()}"
         self._lib = _lib.load()
-        if config.enable_amp:
-            raise NotImplementedError(
-                "the recurrent path runs its GEMMs in fp32 (enable_amp=False); the bf16 tcgen05"
-                " path covers the feedforward algorithm"
-            )
         max_num_envs = getattr(env_cls, "max_num_envs", config.num_envs)
         num_envs = min(config.num_envs, max_num_envs)
         horizon = min(config.horizon, getattr(env_cls, "max_horizon", 1_000_000))
@@ -391,6 +388,8 @@ class RecurrentAlgorithm(Algorithm):
             distribution_cls=config.distribution_cls,
             device=device,
         )
+        # enable_amp: the 256 x 1024 LSTM contractions in bf16 on tcgen05 (fp32 accumulate)
+        self.policy.precision = _lib.PREC_BF16 if config.enable_amp else _lib.PREC_FP32
         self.buffer_spec = Composite(
             {
                 DataKeys.OBS: self.env.observation_spec,
