@@ -170,7 +170,7 @@ struct SmemH {
                                //         second 8-column group of both N = 16 operands)
   float b2[H];                 //   1024
   float w3[kMaxPT][H];         //   4096
-  uint64_t bar_w, bar[6];
+  uint64_t bar_w, bar[7];
   uint32_t tmem_base;
 };
 static_assert(sizeof(SmemH) + 1024 <= 227 * 1024, "SmemH exceeds the 227 KB CTA limit");
@@ -181,7 +181,7 @@ constexpr uint32_t kColH1 = 256;     // 128: packed bf16 H1 (for the layer-1 ReL
 constexpr uint32_t kColThin = 384;   // 6 x 16: gW3, gb2, [gW1 gb1], two 128-unit blocks each
 constexpr int kThinN = 16;
 // mbarriers: each completes exactly once per tile, so one phase bit (tile parity) serves all
-enum { kBZ1 = 0, kBZ2A, kBZ2B, kBT1, kBDA, kBDB };  // kBZ1: Z1 of a tile + phase J of the tile before it
+enum { kBZ1 = 0, kBZ2A, kBZ2B, kBT1, kBDA, kBDB, kBT3 };  // kBZ1: Z1 of a tile + phase J of the tile before it
 
 // D[128 units][16] (+)= X[:, 128-unit block]^T * Y with X the activation tile (MN-major A) and Y a
 // [r][16] operand whose second 8-column group is the shared zero block at b_saddr + b_sbo.
@@ -381,43 +381,41 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_before_sync();
     __syncthreads();
     pc.mark(3);  // E: row loss
-    // ---- F. gW3^T += H2^T * dOut;  G = dOut * W3 (K = 16: one instruction) ------------------------------------------------
+    // ---- F. G = dOut * W3 (K = 16: one instruction), awaited;  gW3^T += H2^T * dOut completes under phase G ---------
     if (cta_issuer()) {
       fence_after_sync();
+      mma_bf16(tmem + kColMain, smem_desc(smem_u32(s.thin[1]), TILE * 16, 128),
+               smem_desc(smem_u32(s.w3img), 128, 16 * 16), instr_desc(TILE, H, 0, 1), 0u);
+      mma_commit(&s.bar[kBT1]);
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb)
         issue_thin(tmem + kColThin + kThinN * jb, smem_u32(s.a_tile) + jb * 32768, smem_u32(s.thin[1]),
                    TILE * 16, it > 0);
-      mma_bf16(tmem + kColMain, smem_desc(smem_u32(s.thin[1]), TILE * 16, 128),
-               smem_desc(smem_u32(s.w3img), 128, 16 * 16), instr_desc(TILE, H, 0, 1), 0u);
-      mma_commit(&s.bar[kBT1]);
+      mma_commit(&s.bar[kBT3]);
     }
     mbar_wait(&s.bar[kBT1], ph);
     fence_after_sync();
-    pc.mark(4);  // F: thin gW3 + G MMAs
-    // ---- G. dZ2 = [H2 > 0] .* G, in place over H2 -----------------------------------------------------------------------------
-    {
-      float v0[32], v1[32];
-      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, 0), v0);
-      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, 1), v1);
-      tmem_wait_ld();
-      reg_fence32(v0);
-      reg_fence32(v1);
+    pc.mark(4);  // F: G MMA round trip
+    // ---- G. dZ2 = [H2 > 0] .* G over H2: the first column group is computed while the thin GEMM still reads H2 ---------
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float* v = h ? v1 : v0;
+    for (int h = 0; h < 2; ++h) {
+      float v[32];
+      tmem_ld32(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, h), v);
+      uint32_t o[16];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint8_t* slot = s.a_tile + chunk_offset<TILE>(r, group_col0(cq, h) / 8 + k);
-          const uint4 h2 = *reinterpret_cast<const uint4*>(slot);
-          uint4 o4;
-          o4.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]) & gt0_mask_bf16x2(h2.x);
-          o4.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]) & gt0_mask_bf16x2(h2.y);
-          o4.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]) & gt0_mask_bf16x2(h2.z);
-          o4.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]) & gt0_mask_bf16x2(h2.w);
-          *reinterpret_cast<uint4*>(slot) = o4;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const uint4 h2 =
+            *reinterpret_cast<const uint4*>(s.a_tile + chunk_offset<TILE>(r, group_col0(cq, h) / 8 + k));
+        o[4 * k + 0] = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]) & gt0_mask_bf16x2(h2.x);
+        o[4 * k + 1] = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]) & gt0_mask_bf16x2(h2.y);
+        o[4 * k + 2] = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]) & gt0_mask_bf16x2(h2.z);
+        o[4 * k + 3] = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]) & gt0_mask_bf16x2(h2.w);
       }
+      if (h == 0) {  // gW3's MMAs have read H2: the tile may be overwritten
+        mbar_wait(&s.bar[kBT3], ph);
+        fence_after_sync();
+      }
+      store_group(s.a_tile, r, group_col0(cq, h), o);
     }
     if (has_next) store_aug32(s.u.aug32, obs_next);  // `part` (same bytes) was last read in phase E
     fence_async_smem();
@@ -539,7 +537,7 @@ tc_update_h_kernel(NetParams np_pi, NetParams np_vf, UpdArgs a) {
   if (tid == 0) {
     mbar_init(&s.bar_w, 1);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) mbar_init(&s.bar[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&s.bar[i], 1);
     fence_mbar_init();
   }
   if (tid < 32) tmem_alloc(&s.tmem_base, 512);
