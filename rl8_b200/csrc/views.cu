@@ -32,6 +32,8 @@ struct ViewArgs {
   int pitch;  // staged elements per sequence (odd, >= (tw + size - 1) * F)
   int tb_shift;       // log2(tb), or -1 when tb is not a power of two
   uint32_t f_magic;   // floor(2^32 / F) + 1: n / F == umulhi(n, f_magic) for n * F < 2^32 (n < 2^14 here); 0 when F == 1
+  int ld_vec;    // 128-bit staging loads: unit sequence stride, 4-byte elements, 16-byte aligned rows
+  int mask_vec;  // every (sequence, window block) run of the mask is a whole number of aligned 32-bit words
   int vec;    // 128-bit store path: out 16-byte aligned and size * F a multiple of the vector width
 };
 
@@ -54,7 +56,37 @@ __global__ void __launch_bounds__(kViewThreads) view_windows_kernel(ViewArgs a) 
   // ---- stage x[b0 .. b0+nb)[t0 .. t0+rows)[:] -> tile[bl * pitch + tl * F + f] -----------------------
   // (kLd independent loads per thread in flight: the staging loop is latency-, not issue-bound)
   constexpr int kLd = 8;
-  if (a.sb <= a.sf) {
+  if (a.ld_vec) {
+    // horizon-major buffer, 4-byte elements, everything 16-byte aligned: each lane reads four consecutive
+    // sequences with one 128-bit load (a quarter of the index arithmetic per element)
+    if constexpr (sizeof(U) == 4) {
+      const int tb4 = a.tb >> 2;
+      const int total = per_seq * tb4;
+      for (int e0 = tid; e0 < total; e0 += kLd * kViewThreads) {
+        uint4 v[kLd];
+        int dst[kLd];
+#pragma unroll
+        for (int k = 0; k < kLd; ++k) {
+          const int e = e0 + k * kViewThreads;
+          v[k] = make_uint4(0u, 0u, 0u, 0u), dst[k] = -1;
+          if (e < total) {
+            const int tf = a.tb_shift >= 2 ? e >> (a.tb_shift - 2) : e / tb4, bl = (e - tf * tb4) << 2;
+            const int tl = a.f_magic ? (int)__umulhi((uint32_t)tf, a.f_magic) : tf, f = tf - tl * F;
+            const int64_t t = t0 + tl;
+            dst[k] = bl * a.pitch + tf;
+            if (bl < nb && t >= 0)
+              v[k] = __ldg(reinterpret_cast<const uint4*>(x + (b0 + bl) + t * a.st + (int64_t)f * a.sf));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kLd; ++k)
+          if (dst[k] >= 0) {
+            tile[dst[k]] = v[k].x, tile[dst[k] + a.pitch] = v[k].y;
+            tile[dst[k] + 2 * a.pitch] = v[k].z, tile[dst[k] + 3 * a.pitch] = v[k].w;
+          }
+      }
+    }
+  } else if (a.sb <= a.sf) {
     // sequence axis is the fast one (horizon-major buffer): lanes walk b
     const int total = per_seq * a.tb;
     for (int e0 = tid; e0 < total; e0 += kLd * kViewThreads) {
@@ -148,12 +180,28 @@ __global__ void __launch_bounds__(kViewThreads) view_windows_kernel(ViewArgs a) 
     }
   }
   // ---- padding mask: true where the window element lies before the start of the sequence -----------------------
+  // (a function of (w, s) only: one 32-bit word of four flags per store when every sequence's run is word-aligned)
   if (a.mask) {
-    const int per = nw * a.size;
-    for (int e = tid; e < nb * per; e += kViewThreads) {
-      const int bl = e / per, ws = e - bl * per;
-      const int w = ws / a.size, s = ws - w * a.size;
-      a.mask[((b0 + bl) * a.count + w0) * a.size + ws] = (t0 + w + s) < 0 ? 1 : 0;
+    const int per = nw * a.size;  // mask bytes of one sequence in this window block
+    if (a.mask_vec) {
+      const int words = per >> 2;
+      for (int e = tid; e < nb * words; e += kViewThreads) {
+        const int bl = e / words, i = e - bl * words;
+        int w = (4 * i) / a.size, sft = 4 * i - w * a.size;
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          word |= (uint32_t)((t0 + w + sft) < 0) << (8 * j);
+          if (++sft == a.size) sft = 0, ++w;
+        }
+        reinterpret_cast<uint32_t*>(a.mask + ((b0 + bl) * a.count + w0) * a.size)[i] = word;
+      }
+    } else {
+      for (int e = tid; e < nb * per; e += kViewThreads) {
+        const int bl = e / per, ws = e - bl * per;
+        const int w = ws / a.size, sft = ws - w * a.size;
+        a.mask[((b0 + bl) * a.count + w0) * a.size + ws] = (t0 + w + sft) < 0 ? 1 : 0;
+      }
     }
   }
 }
@@ -196,6 +244,9 @@ extern "C" int rl8_view_windows(const void* x, int32_t elem_bytes, int64_t B, in
     if ((1 << sft) == tb) a.tb_shift = sft;
   a.f_magic = F == 1 ? 0u : (uint32_t)((1ull << 32) / (uint64_t)F + 1);
   a.vec = ((uintptr_t)out % 16 == 0 && (size * F) % (16 / elem_bytes) == 0) ? 1 : 0;
+  a.ld_vec = (elem_bytes == 4 && stride_b == 1 && tb % 4 == 0 && B % 4 == 0 && stride_t % 4 == 0 &&
+              stride_f % 4 == 0 && (uintptr_t)x % 16 == 0) ? 1 : 0;
+  a.mask_vec = (mask && (uintptr_t)mask % 4 == 0 && (count * size) % 4 == 0 && (tw * size) % 4 == 0) ? 1 : 0;
   const int64_t gx = ceil_div(B, tb), gy = ceil_div(count, tw);
   if (gy > 65535) return RL8_ERR_UNSUPPORTED;
   const size_t smem = (size_t)tb * pitch * elem_bytes;
