@@ -23,7 +23,7 @@ using namespace tc;
 
 // ---- forward kernel ---------------------------------------------------------------------------------
 template <int P>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ out, int tanh_col1) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -43,7 +43,7 @@ tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ ou
       if (row < rows) {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-          float v = s.part[0][tid][p] + s.part[1][tid][p] + b3[p];
+          float v = head_sum(s, tid, p) + b3[p];
           if (tanh_col1 && p == 1) v = tanhf(v);
           out[row * P + p] = v;
         }
@@ -99,7 +99,7 @@ struct RolloutArgs {
 };
 
 template <int KIND, int P>
-__global__ void __launch_bounds__(256, 1) tc_rollout_kernel(NetParams np, RolloutArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np, RolloutArgs a) {
   using Tr = EnvTraits<KIND>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, 1) tc_rollout_kernel(NetParams np, Rollou
       if (owner) {
         float o[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) o[p] = s.part[0][tid][p] + s.part[1][tid][p] + b3[p];
+        for (int p = 0; p < P; ++p) o[p] = head_sum(s, tid, p) + b3[p];
         float act, lp;
         if constexpr (Tr::discrete) {
           float norm[P], probs[P];
@@ -444,7 +444,7 @@ static int launch_forward(const NetParams& np, const RowMap& map, int64_t rows, 
 #define RL8_FWD(PV)                                                                       \
   case PV:                                                                                \
     if ((rc = set_smem((const void*)tc_forward_kernel<PV>, sizeof(Smem)))) return rc;      \
-    tc_forward_kernel<PV><<<grid, 256, sizeof(Smem), st>>>(np, map, rows, out, tanh_col1);  \
+    tc_forward_kernel<PV><<<grid, kFwdThreads, sizeof(Smem), st>>>(np, map, rows, out, tanh_col1);  \
     break;
   switch (np.P) {
     RL8_FWD(1) RL8_FWD(2) RL8_FWD(3) RL8_FWD(4)
@@ -478,7 +478,7 @@ static int launch_rollout(const NetParams& np, const rl8_rollout* ro, cudaStream
   if (rc) return rc;
   const int64_t ntiles = ceil_div(ro->N, TILE);
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
-  tc_rollout_kernel<KIND, P><<<grid, 256, sizeof(Smem), st>>>(np, a);
+  tc_rollout_kernel<KIND, P><<<grid, kFwdThreads, sizeof(Smem), st>>>(np, a);
   return check_launch("tc_rollout");
 }
 

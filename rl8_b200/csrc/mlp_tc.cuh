@@ -28,7 +28,7 @@ struct Smem {
   float b1[H], b2[H];          //   2048
   float w3[kMaxPT][H];         //   4096
   float obs[8][TILE];          //   4096  obs[d][r]
-  float part[2][TILE][kMaxPT]; //   4096  head partial sums per column half
+  float part[4][TILE][kMaxPT]; //   8192  head partial sums per column quarter
   uint64_t bar_w, bar_mma[2];
   uint32_t tmem_base;
 };
@@ -85,65 +85,60 @@ __device__ __forceinline__ void cta_setup(S& s, const NetParams& np, uint32_t tm
   mbar_wait(&s.bar_w, 0);
 }
 
+constexpr int kFwdThreads = 512;  // 16 warps: thread -> row (tid & 127), column quarter (tid >> 7)
+
 // H1 = relu(b1 + obs @ w1^T) for the 128 rows staged in s.obs -> bf16 chunks in s.a_tile.
-// Thread -> row (tid & 127) and the column half (tid >> 7): the same ownership as the TMEM
-// epilogues, so the layer-1 ReLU mask (bit j % 32 of word (j % 128) / 32) can stay in the
-// thread's registers until the backward pass needs it.
+// Thread -> row (tid & 127) and the column quarter (tid >> 7): 8 chunks of 8 columns each.
 template <class S>
-__device__ __forceinline__ void layer1_to_tile(S& s, int D, uint32_t* mask_words = nullptr) {
-  const int r = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+__device__ __forceinline__ void layer1_to_tile(S& s, int D) {
+  const int r = threadIdx.x & (TILE - 1), part = threadIdx.x >> 7;
   float o[8];
 #pragma unroll
   for (int d = 0; d < 8; ++d) o[d] = s.obs[d][r];
+#pragma unroll 2
+  for (int k = 0; k < 8; ++k) {
+    const int c = part * 8 + k, i0 = c * 8;
+    float acc[8];
+    const float4 ba = *reinterpret_cast<const float4*>(&s.b1[i0]);
+    const float4 bb = *reinterpret_cast<const float4*>(&s.b1[i0 + 4]);
+    acc[0] = ba.x, acc[1] = ba.y, acc[2] = ba.z, acc[3] = ba.w;
+    acc[4] = bb.x, acc[5] = bb.y, acc[6] = bb.z, acc[7] = bb.w;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    uint32_t word = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = half * 16 + w * 4 + k, i0 = c * 8;
-      float acc[8];
-      const float4 ba = *reinterpret_cast<const float4*>(&s.b1[i0]);
-      const float4 bb = *reinterpret_cast<const float4*>(&s.b1[i0 + 4]);
-      acc[0] = ba.x, acc[1] = ba.y, acc[2] = ba.z, acc[3] = ba.w;
-      acc[4] = bb.x, acc[5] = bb.y, acc[6] = bb.z, acc[7] = bb.w;
-#pragma unroll
-      for (int d = 0; d < 8; ++d) {
-        if (d < D) {
-          const float4 wa = *reinterpret_cast<const float4*>(&s.w1t[d][i0]);
-          const float4 wb = *reinterpret_cast<const float4*>(&s.w1t[d][i0 + 4]);
-          acc[0] = fmaf(o[d], wa.x, acc[0]), acc[1] = fmaf(o[d], wa.y, acc[1]);
-          acc[2] = fmaf(o[d], wa.z, acc[2]), acc[3] = fmaf(o[d], wa.w, acc[3]);
-          acc[4] = fmaf(o[d], wb.x, acc[4]), acc[5] = fmaf(o[d], wb.y, acc[5]);
-          acc[6] = fmaf(o[d], wb.z, acc[6]), acc[7] = fmaf(o[d], wb.w, acc[7]);
-        }
+    for (int d = 0; d < 8; ++d) {
+      if (d < D) {
+        const float4 wa = *reinterpret_cast<const float4*>(&s.w1t[d][i0]);
+        const float4 wb = *reinterpret_cast<const float4*>(&s.w1t[d][i0 + 4]);
+        acc[0] = fmaf(o[d], wa.x, acc[0]), acc[1] = fmaf(o[d], wa.y, acc[1]);
+        acc[2] = fmaf(o[d], wa.z, acc[2]), acc[3] = fmaf(o[d], wa.w, acc[3]);
+        acc[4] = fmaf(o[d], wb.x, acc[4]), acc[5] = fmaf(o[d], wb.y, acc[5]);
+        acc[6] = fmaf(o[d], wb.z, acc[6]), acc[7] = fmaf(o[d], wb.w, acc[7]);
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        word |= (acc[e] > 0.0f ? 1u : 0u) << (k * 8 + e);
-        acc[e] = fmaxf(acc[e], 0.0f);
-      }
-      store_chunk(s.a_tile, chunk_offset<TILE>(r, c), acc);
     }
-    if (mask_words) mask_words[w] = word;
+    store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, c), acc);
   }
 }
 
-// Head partial sums of one accumulator: thread -> row 32*(warp%4)+lane, column half warp/4.
-// dot[p] = sum_{j in half} relu(z[r][j] + b2[j]) * w3[p][j]  -> s.part[half][r][p]
+// Head partial sums of one accumulator: thread -> row 32*(warp%4)+lane, column quarter warp/4.
+// dot[p] = sum_{j in quarter} relu(z[r][j] + b2[j]) * w3[p][j]  -> s.part[quarter][r][p]
 // Per-column constants are read as 128-bit warp broadcasts.
 template <int P, class S>
 __device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, part = warp >> 2;
   const int r = q * 32 + lane;
   float dot[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) dot[p] = 0.0f;
-#pragma unroll 1
-  for (int c4 = 0; c4 < 4; ++c4) {
-    const int col0 = half * 128 + c4 * 32;
-    float v[32];
-    tmem_ld32(acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+  float v0[32], v1[32];
+  tmem_ld32_nowait(acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 64), v0);
+  tmem_ld32_nowait(acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 64 + 32), v1);
+  tmem_wait_ld();
+  reg_fence32(v0);
+  reg_fence32(v1);
+#pragma unroll
+  for (int c2 = 0; c2 < 2; ++c2) {
+    const int col0 = part * 64 + c2 * 32;
+    const float* v = c2 ? v1 : v0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + j]);
@@ -160,7 +155,12 @@ __device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem) {
     }
   }
 #pragma unroll
-  for (int p = 0; p < P; ++p) s.part[half][r][p] = dot[p];
+  for (int p = 0; p < P; ++p) s.part[part][r][p] = dot[p];
+}
+// sum of the four column quarters' partial sums of row r (in a fixed order)
+template <class S>
+__device__ __forceinline__ float head_sum(const S& s, int r, int p) {
+  return (s.part[0][r][p] + s.part[1][r][p]) + (s.part[2][r][p] + s.part[3][r][p]);
 }
 
 }  // namespace rl8
