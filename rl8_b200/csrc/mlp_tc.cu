@@ -5,11 +5,12 @@
 //                       rl8_mlp_forward): persistent CTAs, 128-row tiles, W2 resident in smem
 //                       (one 128 KB bulk-async copy per CTA), TMEM double-buffered so the
 //                       epilogue of tile i overlaps the MMAs of tile i+1.
-//   tc_rollout_kernel   the whole T-step rollout of a 128-env tile inside one persistent CTA:
-//                       layer 1 on CUDA cores -> 256x256 layer on tcgen05 -> head dot products,
-//                       sampling, log-prob, env transition (state in registers) and the
-//                       horizon-major buffer writes in the epilogue.  No grid-wide sync: envs
-//                       are independent.
+//   tc_rollout_kernel   the whole T-step rollout of TWO 128-env tiles inside one persistent CTA,
+//                       half a step apart: layer 1 on CUDA cores -> 256x256 layer on tcgen05 ->
+//                       head dot products -> sampling, log-prob, env transition (state in
+//                       registers) and the horizon-major buffer writes, the last stage of one
+//                       tile running under the MMAs of the other.  No grid-wide sync: envs are
+//                       independent.
 //   tc_selftest_kernel  one 128xNxK GEMM with either operand major, used by the parity tests to
 //                       pin the descriptor encodings.
 //
@@ -98,71 +99,63 @@ struct RolloutArgs {
   const float* noise;  // [T][N][P] | [T][N]
 };
 
+// Two env tiles per CTA, half a step apart: while the tensor core works on one tile's 256x256 layer, the
+// 128 owner threads of the OTHER tile sample its actions and step its environments, so the serial chain
+// layer 1 -> MMA -> head -> sample / env-step of a tile is hidden behind its partner's.
+//   threads   0..127 own the rows of tile A (accumulator columns   0..255, s.part[0])
+//   threads 128..255 own the rows of tile B (accumulator columns 256..511, s.part[1])
+// One s.obs / a_tile serves both: every producer runs strictly between the consumers (see the cycle below).
 template <int KIND, int P>
 __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np, RolloutArgs a) {
   using Tr = EnvTraits<KIND>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-  cta_setup(s, np, 256);
+  cta_setup(s, np, 512);
   const uint32_t tmem = s.tmem_base;
   const int tid = threadIdx.x;
+  const int slot = tid >> 7, row = tid & (TILE - 1);  // slot 0 / 1: owner of tile A / B; 2, 3: helpers
   const int64_t N = a.N;
   const int64_t ntiles = (N + TILE - 1) / TILE;
+  const int64_t npairs = (ntiles + 1) / 2;
   float b3[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) b3[p] = np.b3[p];
-  uint32_t phase = 0;
+  uint32_t phase[2] = {0u, 0u};
+  constexpr int kNz = Tr::discrete ? P : 1;  // noise values per env and step
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t n = tile * TILE + tid;  // env of this thread (threads 0..127)
-    const bool owner = tid < TILE && n < N;
-    float st[Tr::S], rdr_prev = 0.0f;
+  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const bool has_b = 2 * pair + 1 < ntiles;
+    const int64_t n = (2 * pair + slot) * TILE + row;  // env of this thread when it is an owner
+    const bool owner = slot < 2 && n < N;
+    float st[Tr::S], rdr_prev = 0.0f, nz[kNz];
     if (owner) {
 #pragma unroll
       for (int i = 0; i < Tr::S; ++i) st[i] = a.state[(int64_t)i * N + n];
       if (a.rdr) rdr_prev = a.rdr[n];
     }
-    if (tid < TILE) {
+    auto load_noise = [&](int t) {
+      if (owner && !a.deterministic && t < a.T) {
+        const float* src = a.noise + ((int64_t)t * N + n) * kNz;
+#pragma unroll
+        for (int k = 0; k < kNz; ++k) nz[k] = src[k];
+      }
+    };
+    auto stage_obs = [&](int t) {  // this slot's observations of step t: buffer -> s.obs
 #pragma unroll
       for (int d = 0; d < 8; ++d)
-        s.obs[d][tid] = (d < Tr::D && n < N) ? a.obs[(int64_t)d * N + n] : 0.0f;
-    }
-    __syncthreads();
-
-    for (int t = 0; t < a.T; ++t) {
-      layer1_to_tile(s, Tr::D);
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (cta_issuer()) {
-        fence_after_sync();
-        issue_gemm(tmem, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H, false);
-        mma_commit(&s.bar_mma[0]);
-      }
-      mbar_wait(&s.bar_mma[0], phase);
-      phase ^= 1;
-      fence_after_sync();
-      head_partials<P>(s, tmem);
-      fence_before_sync();
-      __syncthreads();
+        s.obs[d][row] = (d < Tr::D && n < N) ? a.obs[((int64_t)t * Tr::D + d) * N + n] : 0.0f;
+    };
+    // sample the action of step t from this slot's head outputs, step the env, write slab t (+ obs, rdr of t+1)
+    auto env_phase = [&](int t) {
       if (owner) {
         float o[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) o[p] = head_sum(s, tid, p) + b3[p];
+        for (int p = 0; p < P; ++p) o[p] = head_sum(s, row, p, slot) + b3[p];
         float act, lp;
         if constexpr (Tr::discrete) {
           float norm[P], probs[P];
           categorical_norm<P>(o, norm, probs);
-          int ai;
-          if (a.deterministic) {
-            ai = categorical_mode<P>(probs);
-          } else {
-            float q[P];
-            const float* nz = a.noise + ((int64_t)t * N + n) * P;
-#pragma unroll
-            for (int k = 0; k < P; ++k) q[k] = nz[k];
-            ai = categorical_sample<P>(probs, q);
-          }
+          const int ai = a.deterministic ? categorical_mode<P>(probs) : categorical_sample<P>(probs, nz);
           lp = norm[0];
 #pragma unroll
           for (int k = 1; k < P; ++k) lp = (ai == k) ? norm[k] : lp;
@@ -170,7 +163,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np
           ((long long*)a.actions)[(int64_t)t * N + n] = ai;
         } else {
           const float mean = o[0], scale = expf(tanhf(o[1]));
-          float x = a.deterministic ? mean : add(mul(a.noise[(int64_t)t * N + n], scale), mean);
+          float x = a.deterministic ? mean : add(mul(nz[0], scale), mean);
           if (a.dist_kind == RL8_DIST_SQUASHED_NORMAL) {
             x = tanhf(x);
             lp = squashed_logp(mean, scale, x, nullptr);
@@ -191,19 +184,73 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np
 #pragma unroll
         for (int d = 0; d < Tr::D; ++d) {
           a.obs[((int64_t)(t + 1) * Tr::D + d) * N + n] = ob[d];
-          s.obs[d][tid] = ob[d];
+          s.obs[d][row] = ob[d];
         }
+      } else if (slot < 2) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) s.obs[d][row] = 0.0f;
       }
+    };
+    auto mma_tile = [&](int sl) {  // H1 tile -> accumulator of slot sl (elected lane of warp 0)
+      if (cta_issuer()) {
+        fence_after_sync();
+        issue_gemm(tmem + (uint32_t)(sl * H), smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H,
+                   false);
+        mma_commit(&s.bar_mma[sl]);
+      }
+    };
+    auto wait_head = [&](int sl) {  // accumulator of slot sl -> head partial sums
+      mbar_wait(&s.bar_mma[sl], phase[sl]);
+      phase[sl] ^= 1u;
+      fence_after_sync();
+      head_partials<P>(s, tmem + (uint32_t)(sl * H), sl);
+    };
+
+    if (slot == 0) {
+      stage_obs(0);
+      load_noise(0);
+    }
+    __syncthreads();
+    // cycle of step t:  a. L1(A)  b. env(B, t-1) under MMA(A)  c. head(A)  d. L1(B)  e. env(A, t) under MMA(B)  f. head(B)
+    for (int t = 0; t < a.T; ++t) {
+      layer1_to_tile(s, Tr::D);  // a. s.obs holds A's observations of step t
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      mma_tile(0);
+      if (slot == 1) {  // b. B's observations of step t: from its previous env step, or the buffer at t = 0
+        if (t == 0) stage_obs(0);
+        else env_phase(t - 1);
+        load_noise(t);
+      }
+      wait_head(0);  // c.
+      fence_before_sync();
+      __syncthreads();
+      if (has_b) {
+        layer1_to_tile(s, Tr::D);  // d. s.obs holds B's observations of step t
+        fence_async_smem();
+      }
+      fence_before_sync();
+      __syncthreads();
+      if (has_b) mma_tile(1);
+      if (slot == 0) {  // e.
+        env_phase(t);
+        load_noise(t + 1);
+      }
+      if (has_b) wait_head(1);  // f.
+      fence_before_sync();
       __syncthreads();
     }
+    if (slot == 1 && has_b) env_phase(a.T - 1);  // B's last step
     if (owner) {
 #pragma unroll
       for (int i = 0; i < Tr::S; ++i) a.state[(int64_t)i * N + n] = st[i];
     }
+    __syncthreads();
   }
   fence_before_sync();
   __syncthreads();
-  if (tid < 32) tmem_dealloc(tmem, 256);
+  if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
 // ---- descriptor self-test --------------------------------------------------------------------------------
@@ -476,8 +523,8 @@ static int launch_rollout(const NetParams& np, const rl8_rollout* ro, cudaStream
   a.rewards = ro->rewards, a.rdr = ro->rdr, a.noise = ro->noise;
   int rc = set_smem((const void*)tc_rollout_kernel<KIND, P>, sizeof(Smem));
   if (rc) return rc;
-  const int64_t ntiles = ceil_div(ro->N, TILE);
-  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  const int64_t npairs = ceil_div(ceil_div(ro->N, TILE), 2);  // a CTA rolls two env tiles out at a time
+  const int grid = (int)(npairs < kNumSMs ? npairs : kNumSMs);
   tc_rollout_kernel<KIND, P><<<grid, kFwdThreads, sizeof(Smem), st>>>(np, a);
   return check_launch("tc_rollout");
 }

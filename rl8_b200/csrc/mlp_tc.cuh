@@ -28,7 +28,7 @@ struct Smem {
   float b1[H], b2[H];          //   2048
   float w3[kMaxPT][H];         //   4096
   float obs[8][TILE];          //   4096  obs[d][r]
-  float part[4][TILE][kMaxPT]; //   8192  head partial sums per column quarter
+  float part[2][4][TILE][kMaxPT]; // 16384  head partial sums per column quarter, one set per accumulator
   uint64_t bar_w, bar_mma[2];
   uint32_t tmem_base;
 };
@@ -122,7 +122,7 @@ __device__ __forceinline__ void layer1_to_tile(S& s, int D) {
 // dot[p] = sum_{j in quarter} relu(z[r][j] + b2[j]) * w3[p][j]  -> s.part[quarter][r][p]
 // Per-column constants are read as 128-bit warp broadcasts.
 template <int P, class S>
-__device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem) {
+__device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem, int set = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3, part = warp >> 2;
   const int r = q * 32 + lane;
@@ -155,12 +155,12 @@ __device__ __forceinline__ void head_partials(S& s, uint32_t acc_tmem) {
     }
   }
 #pragma unroll
-  for (int p = 0; p < P; ++p) s.part[part][r][p] = dot[p];
+  for (int p = 0; p < P; ++p) s.part[set][part][r][p] = dot[p];
 }
 // sum of the four column quarters' partial sums of row r (in a fixed order)
 template <class S>
-__device__ __forceinline__ float head_sum(const S& s, int r, int p) {
-  return (s.part[0][r][p] + s.part[1][r][p]) + (s.part[2][r][p] + s.part[3][r][p]);
+__device__ __forceinline__ float head_sum(const S& s, int r, int p, int set = 0) {
+  return (s.part[set][0][r][p] + s.part[set][1][r][p]) + (s.part[set][2][r][p] + s.part[set][3][r][p]);
 }
 
 }  // namespace rl8
