@@ -194,3 +194,43 @@ def test_learning_improves_dummy_env_returns() -> None:
     for _ in range(30):
         last = trainer.step(env_config={"bounds": 4.0})["returns/mean"]
     assert last > first + 1.0, (first, last)
+
+
+def test_state_dicts_are_interchangeable_with_the_reference() -> None:
+    """Policy export round trip: ``state_dict()`` of every default model carries exactly the
+    reference's parameter names and shapes (tests/golden/state_dict_shapes.json, recorded from the unmodified
+    upstream models by tests/golden/generate_state_dict_golden.py), and ``load_state_dict`` writes through to
+    the flat kernel buffer."""
+    import json
+    import os
+
+    import rl8_b200.env as E
+    from rl8_b200 import AlgorithmConfig, RecurrentAlgorithmConfig
+    from rl8_b200.distributions import SquashedNormal
+
+    from .conftest import GOLDEN_DIR
+
+    with open(os.path.join(GOLDEN_DIR, "state_dict_shapes.json")) as f:
+        want = json.load(f)
+    builds = {
+        "ff_discrete_cartpole": lambda: AlgorithmConfig(num_envs=8, horizon=4).build(E.CartPole),
+        "ff_discrete_dummy": lambda: AlgorithmConfig(num_envs=8, horizon=4).build(E.DiscreteDummyEnv),
+        "ff_continuous_pendulum": lambda: AlgorithmConfig(
+            num_envs=8, horizon=4, distribution_cls=SquashedNormal).build(E.Pendulum),
+        "rec_discrete_cartpole": lambda: RecurrentAlgorithmConfig(
+            num_envs=8, horizon=4, seq_len=2, seqs_per_state_reset=2).build(E.CartPole),
+        "rec_continuous_pendulum": lambda: RecurrentAlgorithmConfig(
+            num_envs=8, horizon=4, seq_len=2, seqs_per_state_reset=2, distribution_cls=SquashedNormal).build(E.Pendulum),
+    }
+    assert set(builds) == set(want)
+    for name, make in builds.items():
+        algo = make()
+        model = algo.policy.model
+        sd = model.state_dict()
+        assert {k: list(v.shape) for k, v in sd.items()} == want[name], name
+        # a checkpoint (e.g. one written by the reference) loads into the flat buffer the kernels read
+        new = {k: torch.full_like(v, 0.25) for k, v in sd.items()}
+        model.load_state_dict(new)
+        flat = model.flat_params
+        n_params = sum(v.numel() for v in sd.values())
+        assert int((flat == 0.25).sum()) == n_params, name
