@@ -575,7 +575,7 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
     traffic = NCU_TRAFFIC.get((a.workload, M)) if dtype == "bf16" else None
     return {
         "kernel": "rl8_ppo_minibatch (forward + losses + backward, one minibatch: tc_update_h_kernel +"
-                  " tc_update_w_kernel per 2^20-row chunk)",
+                  " tc_update_w_kernel per 2^21-row chunk)",
         "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
         "frac": flops / ms / 1e9 / peak, "traffic": traffic, "ms": ms, "rows": M, "dtype": dtype,
         "peak_source": peaks["source"] + " bf16 sustained",

@@ -33,7 +33,7 @@ namespace rl8 {
 using namespace tc;
 
 constexpr int kUpdThreads = 512;
-constexpr int64_t kChunkRows = 1 << 20;  // rows per kernel pair: bounds the dZ2 scratch at 1 GiB
+constexpr int64_t kChunkRows = 1 << 21;  // rows per kernel pair: bounds the dZ2 scratch at 2 GiB (of 180 GB)
 
 struct UpdArgs {
   const float* obs;      // [T+1][D][N]

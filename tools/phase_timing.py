@@ -51,7 +51,7 @@ lib.rl8_tc_phase_buffer(None)
 c = counters.cpu().tolist()
 names = ["A+B stage, Z1 MMA", "C   H1 epilogue", "D   Z2 MMA + H2 epi", "E   row loss", "F   gW3 + G MMA",
          "G   dZ2 epilogue", "H+I dH1 MMA + dZ1 epi", "J   gW1 thin MMA"]
-chunk = min(M, 1 << 20)
+chunk = min(M, 1 << 21)
 ntiles = -(-chunk // 128)
 n_pi = int(__import__('os').environ.get('RL8_H_POLICY_CTAS', 80))
 for net, label, nct in ((0, "policy", n_pi), (1, "value", 148 - n_pi)):
