@@ -23,18 +23,89 @@ namespace rl8 {
 using namespace tc;
 
 // ---- forward kernel ---------------------------------------------------------------------------------
+// Per 128-row tile k (accumulator buf = k & 1):
+//   Z1 = [obs, 1] * [W1, b1]^T   one kind::tf32 instruction (K = 8) into acc[buf] -- the same layer-1
+//                                arithmetic as the update kernels, so stored values and their later
+//                                recomputation agree bit for bit
+//   H1 = relu(Z1) -> bf16 tile;  Z2 = H1 * W2^T into acc[buf];  head epilogue of tile k-1 (acc[buf ^ 1])
+//   runs under Z2(k);  then Z1(k+1) is issued into acc[buf ^ 1] behind Z2(k) on the in-order tensor pipe.
+struct SmemF {
+  uint8_t w2[kW2Bytes];           // 131072
+  uint8_t a_tile[kTileBytes];     //  65536  H1 tile: K-major A operand
+  uint8_t w1aug[H * 32];          //   8192  tf32 [W1 | b1]: off(i, d) = i*16 + (d/4)*4096 + (d%4)*4
+  uint8_t aug32[TILE * 32];       //   4096  tf32 [obs, 1]:  off(r, d) = r*16 + (d/4)*2048 + (d%4)*4
+  float b2[H];                    //   1024
+  float w3[kMaxPT][H];            //   4096
+  float part[1][4][TILE][kMaxPT]; //   8192  head partial sums per column quarter
+  uint64_t bar_w, bar_z, bar_mma[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SmemF) <= 227 * 1024, "smem plan exceeds the 227 KB CTA limit");
+
 template <int P>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ out, int tanh_col1) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-  cta_setup(s, np, 512);
+  SmemF& s = *reinterpret_cast<SmemF*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&s.bar_w, 1);
+    mbar_init(&s.bar_z, 1);
+    mbar_init(&s.bar_mma[0], 1);
+    mbar_init(&s.bar_mma[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&s.bar_w, kW2Bytes);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      bulk_g2s(s.w2 + i * (kW2Bytes / 8), np.w2_img + i * (kW2Bytes / 8), kW2Bytes / 8, &s.bar_w);
+  }
+  for (int e = tid; e < H * 8; e += blockDim.x) {
+    const int i = e >> 3, d = e & 7;
+    float v = 0.0f;
+    if (d < np.D) v = np.w1[i * np.D + d];
+    else if (d == np.D) v = np.b1[i];
+    *reinterpret_cast<float*>(s.w1aug + i * 16 + (d >> 2) * (H * 16) + (d & 3) * 4) = tf32_round(v);
+  }
+  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  __syncthreads();
+  mbar_wait(&s.bar_w, 0);
+
   const uint32_t tmem = s.tmem_base;
-  const int tid = threadIdx.x;
   const int64_t ntiles = (rows + TILE - 1) / TILE;
   const int64_t ds = map.dstride();
+  const int D = np.D;
   const float b3[kMaxPT] = {np.b3[0], P > 1 ? np.b3[1] : 0.f, P > 2 ? np.b3[2] : 0.f, P > 3 ? np.b3[3] : 0.f};
-
+  // this thread stages slots d0 and d0 + 4 of [obs, 1] of row rr
+  const int rr = tid & (TILE - 1), d0 = tid >> 7;
+  auto load_obs = [&](int64_t tile, float& v0, float& v1) {
+    v0 = d0 == D ? 1.0f : 0.0f;
+    v1 = d0 + 4 == D ? 1.0f : 0.0f;
+    const int64_t row = tile * TILE + rr;
+    if (row < rows) {
+      const float* base = map.obs + map.offset(row);
+      if (d0 < D) v0 = __ldg(base + (int64_t)d0 * ds);
+      if (d0 + 4 < D) v1 = __ldg(base + (int64_t)(d0 + 4) * ds);
+    }
+  };
+  auto store_aug = [&](float v0, float v1) {
+    *reinterpret_cast<float*>(s.aug32 + rr * 16 + d0 * 4) = tf32_round(v0);
+    *reinterpret_cast<float*>(s.aug32 + rr * 16 + TILE * 16 + d0 * 4) = tf32_round(v1);
+  };
+  auto issue_z1 = [&](int buf) {  // elected lane
+    mma_tf32(tmem + (uint32_t)(buf * H), smem_desc(smem_u32(s.aug32), TILE * 16, 128),
+             smem_desc(smem_u32(s.w1aug), H * 16, 128), instr_desc_tf32(TILE, H), 0u);
+    mma_commit(&s.bar_z);
+  };
   auto epilogue = [&](int64_t tile, int buf) {
     head_partials<P>(s, tmem + (uint32_t)(buf * H));
     fence_before_sync();
@@ -52,29 +123,63 @@ tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ ou
     }
   };
 
-  int it = 0;
-  int64_t prev_tile = -1;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    // stage observations (r fastest: coalesced for the SoA buffer)
-    for (int i = tid; i < 8 * TILE; i += blockDim.x) {
-      const int d = i / TILE, r = i - d * TILE;
-      const int64_t row = tile * TILE + r;
-      s.obs[d][r] = (d < np.D && row < rows) ? map.obs[map.offset(row) + d * ds] : 0.0f;
-    }
-    __syncthreads();
-    layer1_to_tile(s, np.D);
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) {
+    float v0, v1;
+    load_obs(tile, v0, v1);
+    store_aug(v0, v1);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (cta_issuer()) {
       fence_after_sync();
-      issue_gemm(tmem + (uint32_t)(buf * H), smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H,
-                 false, TILE, H, H, false);
+      issue_z1(0);
+    }
+  }
+  const int q = warp & 3, part = warp >> 2;
+  const int r = q * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  int it = 0;
+  int64_t prev_tile = -1;
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const bool has_next = tile + gridDim.x < ntiles;
+    float n0 = 0.0f, n1 = 0.0f;
+    if (has_next) load_obs(tile + gridDim.x, n0, n1);  // in flight until the staging below
+    mbar_wait(&s.bar_z, (uint32_t)(it & 1));  // Z1 of this tile is in acc[buf]
+    fence_after_sync();
+    {
+      float v0[32], v1[32];
+      tmem_ld32_nowait(tmem + (uint32_t)(buf * H) + lane_base + (uint32_t)(part * 64), v0);
+      tmem_ld32_nowait(tmem + (uint32_t)(buf * H) + lane_base + (uint32_t)(part * 64 + 32), v1);
+      tmem_wait_ld();
+      reg_fence32(v0);
+      reg_fence32(v1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, part * 8 + k), v0 + 8 * k);
+        store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, part * 8 + 4 + k), v1 + 8 * k);
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (cta_issuer()) {
+      fence_after_sync();
+      issue_gemm(tmem + (uint32_t)(buf * H), smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H,
+                 false);
       mma_commit(&s.bar_mma[buf]);
     }
-    if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1);  // overlaps the MMAs just issued
-    mbar_wait(&s.bar_mma[buf], (uint32_t)((it >> 1) & 1));
+    if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1);  // under the MMAs just issued
+    if (has_next) store_aug(n0, n1);                   // Z1 of this tile has read aug32
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();  // acc[buf ^ 1] has been read by the head epilogue: the next Z1 may overwrite it
+    if (has_next && cta_issuer()) {
+      fence_after_sync();
+      issue_z1(buf ^ 1);
+    }
+    mbar_wait(&s.bar_mma[buf], (uint32_t)((it >> 1) & 1));  // Z2 done: the H1 tile may be rewritten
     fence_after_sync();
     prev_tile = tile;
   }
@@ -490,8 +595,8 @@ static int launch_forward(const NetParams& np, const RowMap& map, int64_t rows, 
   int rc;
 #define RL8_FWD(PV)                                                                       \
   case PV:                                                                                \
-    if ((rc = set_smem((const void*)tc_forward_kernel<PV>, sizeof(Smem)))) return rc;      \
-    tc_forward_kernel<PV><<<grid, kFwdThreads, sizeof(Smem), st>>>(np, map, rows, out, tanh_col1);  \
+    if ((rc = set_smem((const void*)tc_forward_kernel<PV>, sizeof(SmemF)))) return rc;     \
+    tc_forward_kernel<PV><<<grid, kFwdThreads, sizeof(SmemF), st>>>(np, map, rows, out, tanh_col1); \
     break;
   switch (np.P) {
     RL8_FWD(1) RL8_FWD(2) RL8_FWD(3) RL8_FWD(4)
@@ -503,7 +608,7 @@ static int launch_forward(const NetParams& np, const RowMap& map, int64_t rows, 
 
 int mlp_forward_tc(const rl8_model* m, int which, const RowMap& map, int64_t rows, float* out,
                    int tanh_col1, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
-  if (m->H != H || m->D > 8 || m->P > kMaxPT) return RL8_ERR_UNSUPPORTED;
+  if (m->H != H || m->D > 7 || m->P > kMaxPT) return RL8_ERR_UNSUPPORTED;  // D + 1 <= 8 = K of the tf32 MMA
   if (!workspace || workspace_bytes < kW2Bytes) return RL8_ERR_WORKSPACE;
   uint8_t* img = (uint8_t*)workspace;
   int rc = launch_pack_w2(which ? m->vf_w2 : m->pi_w2, img, st);

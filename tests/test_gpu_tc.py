@@ -29,12 +29,18 @@ def tf32_round(x: torch.Tensor) -> torch.Tensor:
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def emulated_forward(p: dict[str, torch.Tensor], obs: torch.Tensor):
-    """Oracle forward with the tensor-core path's operand rounding: layer 1 in tf32 (update
-    kernels) is within a quarter bf16 ulp of the fp32 layer 1 (rollout kernels), so one
-    emulation serves both at the tolerances below."""
+def emulated_forward(p: dict[str, torch.Tensor], obs: torch.Tensor, tf32_layer1: bool = False):
+    """Oracle forward with the tensor-core path's operand rounding.  ``tf32_layer1``: layer 1 as the
+    forward / update kernels compute it (one kind::tf32 MMA: observations, W1 and b1 rounded to tf32,
+    fp32 accumulation); otherwise fp32 as the rollout kernel's CUDA-core layer 1.  The two differ by a
+    quarter of a bf16 ulp of H1."""
     def net(prefix: str) -> torch.Tensor:
-        h1 = F.relu(F.linear(obs, p[f"{prefix}.0.0.weight"], p[f"{prefix}.0.0.bias"]))
+        w1, b1 = p[f"{prefix}.0.0.weight"], p[f"{prefix}.0.0.bias"]
+        if tf32_layer1:
+            z1 = (tf32_round(obs).double() @ tf32_round(w1).double().T + tf32_round(b1).double()).float()
+            h1 = F.relu(z1)
+        else:
+            h1 = F.relu(F.linear(obs, w1, b1))
         z2 = F.linear(bf16_round(h1).double(), bf16_round(p[f"{prefix}.0.2.weight"]).double()).float()
         return F.relu(z2 + p[f"{prefix}.0.2.bias"])
 
@@ -108,7 +114,7 @@ def test_forward_matches_emulated_oracle(env_name: str, rows: int) -> None:
     params = {k: v.detach().cpu().clone() for k, v in pol.model.state_dict().items()}
     D = algo.env.observation_spec.shape[0]
     obs = torch.randn(rows, D) * 2
-    feats, value = emulated_forward(params, obs)
+    feats, value = emulated_forward(params, obs, tf32_layer1=True)
     out = pol.sample({"obs": obs.to(DEV).unsqueeze(1)}, return_actions=False, return_values=True)
     # An H1 element that sits on a bf16 rounding boundary may round the other way on the GPU
     # (fmaf chain vs the CPU's dot product): allow one bf16 ulp of one hidden unit.
@@ -182,7 +188,8 @@ def test_rollout_kernel_teacher_forced(env_name: str, oname: str, dist: str, n: 
             torch.testing.assert_close(buf["rewards"][:, t], o_r, rtol=1e-4, atol=1e-5)
     # (2) policy outputs recomputed on the recorded observations with the same operand rounding
     flat_obs = buf["obs"].reshape(n * (T + 1), -1)
-    feats, value = emulated_forward(params, flat_obs)
+    feats, _ = emulated_forward(params, flat_obs)  # rollout kernel: fp32 layer 1
+    _, value = emulated_forward(params, flat_obs, tf32_layer1=True)  # value pass: forward kernel
     torch.testing.assert_close(buf["values"].reshape(-1, 1), value, rtol=2e-3, atol=5e-4)
     d = O.Dist(dist).bind({k: v.reshape(n, T + 1, *v.shape[1:])[:, :T].reshape(n * T, *v.shape[1:]) for k, v in feats.items()})
     nz = noise.permute(1, 0, 2, 3).reshape(n * T, 1, P) if dist == "categorical" else noise.permute(1, 0, 2).reshape(n * T, 1)
