@@ -6,7 +6,7 @@
 //                       (one 128 KB bulk-async copy per CTA), TMEM double-buffered so the
 //                       epilogue of tile i overlaps the MMAs of tile i+1.
 //   tc_rollout_kernel   the whole T-step rollout of TWO 128-env tiles inside one persistent CTA,
-//                       half a step apart: layer 1 on CUDA cores -> 256x256 layer on tcgen05 ->
+//                       half a step apart: layer 1 (one tf32 MMA) -> 256x256 layer on tcgen05 ->
 //                       head dot products -> sampling, log-prob, env transition (state in
 //                       registers) and the horizon-major buffer writes, the last stage of one
 //                       tile running under the MMAs of the other.  No grid-wide sync: envs are
@@ -14,8 +14,8 @@
 //   tc_selftest_kernel  one 128xNxK GEMM with either operand major, used by the parity tests to
 //                       pin the descriptor encodings.
 //
-// The first layer (K = D <= 8) and the heads (N = P <= 4) are not GEMM-shaped: they stay on
-// CUDA cores in fp32.  Only the 256x256 contraction runs in bf16.
+// The first layer is one kind::tf32 instruction ([obs, 1] * [W1, b1]^T, K = 8); the heads (N = P <= 4)
+// are not GEMM-shaped and stay on CUDA cores in fp32.  Only the 256x256 contraction runs in bf16.
 #include "mlp_tc.cuh"
 
 namespace rl8 {
@@ -47,38 +47,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ out, int tanh_col1) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemF& s = *reinterpret_cast<SmemF*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&s.bar_w, 1);
-    mbar_init(&s.bar_z, 1);
-    mbar_init(&s.bar_mma[0], 1);
-    mbar_init(&s.bar_mma[1], 1);
-    fence_mbar_init();
-  }
-  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  if (tid == 0) {
-    mbar_expect_tx(&s.bar_w, kW2Bytes);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      bulk_g2s(s.w2 + i * (kW2Bytes / 8), np.w2_img + i * (kW2Bytes / 8), kW2Bytes / 8, &s.bar_w);
-  }
-  for (int e = tid; e < H * 8; e += blockDim.x) {
-    const int i = e >> 3, d = e & 7;
-    float v = 0.0f;
-    if (d < np.D) v = np.w1[i * np.D + d];
-    else if (d == np.D) v = np.b1[i];
-    *reinterpret_cast<float*>(s.w1aug + i * 16 + (d >> 2) * (H * 16) + (d & 3) * 4) = tf32_round(v);
-  }
-  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
-  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
-    const int p = i / H, c = i - p * H;
-    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
-  }
-  __syncthreads();
-  mbar_wait(&s.bar_w, 0);
+  const int tid = threadIdx.x;
+  cta_setup(s, np, 512);
 
   const uint32_t tmem = s.tmem_base;
   const int64_t ntiles = (rows + TILE - 1) / TILE;
@@ -101,11 +71,7 @@ tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ ou
     *reinterpret_cast<float*>(s.aug32 + rr * 16 + d0 * 4) = tf32_round(v0);
     *reinterpret_cast<float*>(s.aug32 + rr * 16 + TILE * 16 + d0 * 4) = tf32_round(v1);
   };
-  auto issue_z1 = [&](int buf) {  // elected lane
-    mma_tf32(tmem + (uint32_t)(buf * H), smem_desc(smem_u32(s.aug32), TILE * 16, 128),
-             smem_desc(smem_u32(s.w1aug), H * 16, 128), instr_desc_tf32(TILE, H), 0u);
-    mma_commit(&s.bar_z);
-  };
+  auto issue_z1 = [&](int buf) { issue_layer1(s, tmem + (uint32_t)(buf * H)); };  // elected lane
   auto epilogue = [&](int64_t tile, int buf) {
     head_partials<P>(s, tmem + (uint32_t)(buf * H));
     fence_before_sync();
@@ -136,9 +102,6 @@ tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ ou
       issue_z1(0);
     }
   }
-  const int q = warp & 3, part = warp >> 2;
-  const int r = q * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   int it = 0;
   int64_t prev_tile = -1;
   for (; tile < ntiles; tile += gridDim.x, ++it) {
@@ -148,19 +111,7 @@ tc_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ ou
     if (has_next) load_obs(tile + gridDim.x, n0, n1);  // in flight until the staging below
     mbar_wait(&s.bar_z, (uint32_t)(it & 1));  // Z1 of this tile is in acc[buf]
     fence_after_sync();
-    {
-      float v0[32], v1[32];
-      tmem_ld32_nowait(tmem + (uint32_t)(buf * H) + lane_base + (uint32_t)(part * 64), v0);
-      tmem_ld32_nowait(tmem + (uint32_t)(buf * H) + lane_base + (uint32_t)(part * 64 + 32), v1);
-      tmem_wait_ld();
-      reg_fence32(v0);
-      reg_fence32(v1);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, part * 8 + k), v0 + 8 * k);
-        store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, part * 8 + 4 + k), v1 + 8 * k);
-      }
-    }
+    h1_epilogue(s, tmem + (uint32_t)(buf * H));
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -209,7 +160,7 @@ struct RolloutArgs {
 // layer 1 -> MMA -> head -> sample / env-step of a tile is hidden behind its partner's.
 //   threads   0..127 own the rows of tile A (accumulator columns   0..255, s.part[0])
 //   threads 128..255 own the rows of tile B (accumulator columns 256..511, s.part[1])
-// One s.obs / a_tile serves both: every producer runs strictly between the consumers (see the cycle below).
+// One aug32 / a_tile serves both: every producer runs strictly between the consumers (see the cycle below).
 template <int KIND, int P>
 __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np, RolloutArgs a) {
   using Tr = EnvTraits<KIND>;
@@ -225,7 +176,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np
   float b3[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) b3[p] = np.b3[p];
-  uint32_t phase[2] = {0u, 0u};
+  uint32_t phase[2] = {0u, 0u}, zphase = 0u;
   constexpr int kNz = Tr::discrete ? P : 1;  // noise values per env and step
 
   for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -245,10 +196,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np
         for (int k = 0; k < kNz; ++k) nz[k] = src[k];
       }
     };
-    auto stage_obs = [&](int t) {  // this slot's observations of step t: buffer -> s.obs
+    // [obs, 1] of this slot's row in tf32 -> aug32 (the A operand of the layer-1 MMA); visible to the
+    // tensor core after the fence + the CTA barrier that always follows
+    auto put_obs = [&](const float* ob) {
+      float v[8];
 #pragma unroll
-      for (int d = 0; d < 8; ++d)
-        s.obs[d][row] = (d < Tr::D && n < N) ? a.obs[((int64_t)t * Tr::D + d) * N + n] : 0.0f;
+      for (int d = 0; d < 8; ++d) v[d] = d < Tr::D ? tf32_round(ob[d]) : (d == Tr::D ? 1.0f : 0.0f);
+      *reinterpret_cast<float4*>(s.aug32 + row * 16) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(s.aug32 + row * 16 + TILE * 16) = make_float4(v[4], v[5], v[6], v[7]);
+      fence_async_smem();
+    };
+    auto stage_obs = [&](int t) {  // this slot's observations of step t: buffer -> aug32
+      float ob[Tr::D];
+#pragma unroll
+      for (int d = 0; d < Tr::D; ++d) ob[d] = n < N ? a.obs[((int64_t)t * Tr::D + d) * N + n] : 0.0f;
+      put_obs(ob);
     };
     // sample the action of step t from this slot's head outputs, step the env, write slab t (+ obs, rdr of t+1)
     auto env_phase = [&](int t) {
@@ -287,20 +249,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np
           a.rdr[(int64_t)(t + 1) * N + n] = rdr_prev;
         }
 #pragma unroll
-        for (int d = 0; d < Tr::D; ++d) {
-          a.obs[((int64_t)(t + 1) * Tr::D + d) * N + n] = ob[d];
-          s.obs[d][row] = ob[d];
-        }
+        for (int d = 0; d < Tr::D; ++d) a.obs[((int64_t)(t + 1) * Tr::D + d) * N + n] = ob[d];
+        put_obs(ob);
       } else if (slot < 2) {
+        float ob[Tr::D];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) s.obs[d][row] = 0.0f;
+        for (int d = 0; d < Tr::D; ++d) ob[d] = 0.0f;
+        put_obs(ob);
       }
     };
-    auto mma_tile = [&](int sl) {  // H1 tile -> accumulator of slot sl (elected lane of warp 0)
+    // layers 1 and 2 of slot sl from aug32: Z1 (tf32 MMA) -> H1 tile -> Z2 issued into the slot's accumulator
+    auto layers = [&](int sl) {
+      const uint32_t acc = tmem + (uint32_t)(sl * H);
       if (cta_issuer()) {
         fence_after_sync();
-        issue_gemm(tmem + (uint32_t)(sl * H), smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H,
-                   false);
+        issue_layer1(s, acc);
+      }
+      mbar_wait(&s.bar_z, zphase);
+      zphase ^= 1u;
+      fence_after_sync();
+      h1_epilogue(s, acc);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (cta_issuer()) {
+        fence_after_sync();
+        issue_gemm(acc, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, false, TILE, H, H, false);
         mma_commit(&s.bar_mma[sl]);
       }
     };
@@ -316,13 +290,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np
       load_noise(0);
     }
     __syncthreads();
-    // cycle of step t:  a. L1(A)  b. env(B, t-1) under MMA(A)  c. head(A)  d. L1(B)  e. env(A, t) under MMA(B)  f. head(B)
+    // cycle of step t:  a. layers(A)  b. env(B, t-1) under MMA(A)  c. head(A)  d. layers(B)  e. env(A, t) under MMA(B)  f. head(B)
     for (int t = 0; t < a.T; ++t) {
-      layer1_to_tile(s, Tr::D);  // a. s.obs holds A's observations of step t
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      mma_tile(0);
+      layers(0);  // a. aug32 holds A's observations of step t
       if (slot == 1) {  // b. B's observations of step t: from its previous env step, or the buffer at t = 0
         if (t == 0) stage_obs(0);
         else env_phase(t - 1);
@@ -331,13 +301,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_rollout_kernel(NetParams np
       wait_head(0);  // c.
       fence_before_sync();
       __syncthreads();
-      if (has_b) {
-        layer1_to_tile(s, Tr::D);  // d. s.obs holds B's observations of step t
-        fence_async_smem();
-      }
-      fence_before_sync();
-      __syncthreads();
-      if (has_b) mma_tile(1);
+      if (has_b) layers(1);  // d. aug32 holds B's observations of step t
       if (slot == 0) {  // e.
         env_phase(t);
         load_noise(t + 1);

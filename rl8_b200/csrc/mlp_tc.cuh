@@ -20,16 +20,16 @@ struct NetParams {
   int D, P;
 };
 
-// Shared-memory plan of the forward / rollout kernels (dynamic smem, 128-byte aligned).
+// Shared-memory plan of the rollout kernel (dynamic smem, 128-byte aligned).
 struct Smem {
-  uint8_t w2[kW2Bytes];        // 131072
-  uint8_t a_tile[kTileBytes];  //  65536  H1 tile: K-major A operand
-  float w1t[8][H];             //   8192  w1t[d][i]
-  float b1[H], b2[H];          //   2048
-  float w3[kMaxPT][H];         //   4096
-  float obs[8][TILE];          //   4096  obs[d][r]
-  float part[2][4][TILE][kMaxPT]; // 16384  head partial sums per column quarter, one set per accumulator
-  uint64_t bar_w, bar_mma[2];
+  uint8_t w2[kW2Bytes];           // 131072
+  uint8_t a_tile[kTileBytes];     //  65536  H1 tile: K-major A operand
+  uint8_t w1aug[H * 32];          //   8192  tf32 [W1 | b1]: off(i, d) = i*16 + (d/4)*4096 + (d%4)*4
+  uint8_t aug32[TILE * 32];       //   4096  tf32 [obs, 1]:  off(r, d) = r*16 + (d/4)*2048 + (d%4)*4
+  float b2[H];                    //   1024
+  float w3[kMaxPT][H];            //   4096
+  float part[2][4][TILE][kMaxPT]; //  16384  head partial sums per column quarter, one set per accumulator
+  uint64_t bar_w, bar_z, bar_mma[2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Smem) <= 227 * 1024, "smem plan exceeds the 227 KB CTA limit");
@@ -53,11 +53,14 @@ static inline int launch_pack_w2(const float* w2, uint8_t* img, cudaStream_t st)
 }
 
 // ---- shared device pieces ------------------------------------------------------------------------
+// Barriers, TMEM, the resident W2 image (one bulk-async copy) and the per-network constants; works on any
+// plan with the members w2, w1aug, b2, w3, bar_w, bar_z, bar_mma[2], tmem_base.
 template <class S>
 __device__ __forceinline__ void cta_setup(S& s, const NetParams& np, uint32_t tmem_cols) {
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&s.bar_w, 1);
+    mbar_init(&s.bar_z, 1);
     mbar_init(&s.bar_mma[0], 1);
     mbar_init(&s.bar_mma[1], 1);
     fence_mbar_init();
@@ -72,11 +75,15 @@ __device__ __forceinline__ void cta_setup(S& s, const NetParams& np, uint32_t tm
     for (int i = 0; i < 8; ++i)
       bulk_g2s(s.w2 + i * (kW2Bytes / 8), np.w2_img + i * (kW2Bytes / 8), kW2Bytes / 8, &s.bar_w);
   }
-  for (int i = tid; i < 8 * H; i += blockDim.x) {
-    const int d = i / H, c = i - d * H;
-    s.w1t[d][c] = d < np.D ? np.w1[c * np.D + d] : 0.0f;
+  // [W1 | b1] rounded to tf32: the B operand of the layer-1 MMA  Z1 = [obs, 1] * [W1, b1]^T  (K = 8)
+  for (int e = tid; e < H * 8; e += blockDim.x) {
+    const int i = e >> 3, d = e & 7;
+    float v = 0.0f;
+    if (d < np.D) v = np.w1[i * np.D + d];
+    else if (d == np.D) v = np.b1[i];
+    *reinterpret_cast<float*>(s.w1aug + i * 16 + (d >> 2) * (H * 16) + (d & 3) * 4) = tf32_round(v);
   }
-  for (int i = tid; i < H; i += blockDim.x) s.b1[i] = np.b1[i], s.b2[i] = np.b2[i];
+  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
@@ -85,36 +92,32 @@ __device__ __forceinline__ void cta_setup(S& s, const NetParams& np, uint32_t tm
   mbar_wait(&s.bar_w, 0);
 }
 
-constexpr int kFwdThreads = 512;  // 16 warps: thread -> row (tid & 127), column quarter (tid >> 7)
+constexpr int kFwdThreads = 512;  // 16 warps: thread -> row 32 * (warp % 4) + lane, column quarter warp / 4
 
-// H1 = relu(b1 + obs @ w1^T) for the 128 rows staged in s.obs -> bf16 chunks in s.a_tile.
-// Thread -> row (tid & 127) and the column quarter (tid >> 7): 8 chunks of 8 columns each.
+// Z1 = [obs, 1] * [W1, b1]^T into the accumulator at acc_tmem (elected lane; commits to s.bar_z)
 template <class S>
-__device__ __forceinline__ void layer1_to_tile(S& s, int D) {
-  const int r = threadIdx.x & (TILE - 1), part = threadIdx.x >> 7;
-  float o[8];
+__device__ __forceinline__ void issue_layer1(S& s, uint32_t acc_tmem) {
+  mma_tf32(acc_tmem, smem_desc(smem_u32(s.aug32), TILE * 16, 128), smem_desc(smem_u32(s.w1aug), H * 16, 128),
+           instr_desc_tf32(TILE, H), 0u);
+  mma_commit(&s.bar_z);
+}
+// H1 = relu(Z1): accumulator -> bf16 chunks of the A tile (this thread's row and column quarter)
+template <class S>
+__device__ __forceinline__ void h1_epilogue(S& s, uint32_t acc_tmem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, part = warp >> 2;
+  const int r = q * 32 + lane;
+  const uint32_t base = acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 64);
+  float v0[32], v1[32];
+  tmem_ld32_nowait(base, v0);
+  tmem_ld32_nowait(base + 32, v1);
+  tmem_wait_ld();
+  reg_fence32(v0);
+  reg_fence32(v1);
 #pragma unroll
-  for (int d = 0; d < 8; ++d) o[d] = s.obs[d][r];
-#pragma unroll 2
-  for (int k = 0; k < 8; ++k) {
-    const int c = part * 8 + k, i0 = c * 8;
-    float acc[8];
-    const float4 ba = *reinterpret_cast<const float4*>(&s.b1[i0]);
-    const float4 bb = *reinterpret_cast<const float4*>(&s.b1[i0 + 4]);
-    acc[0] = ba.x, acc[1] = ba.y, acc[2] = ba.z, acc[3] = ba.w;
-    acc[4] = bb.x, acc[5] = bb.y, acc[6] = bb.z, acc[7] = bb.w;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      if (d < D) {
-        const float4 wa = *reinterpret_cast<const float4*>(&s.w1t[d][i0]);
-        const float4 wb = *reinterpret_cast<const float4*>(&s.w1t[d][i0 + 4]);
-        acc[0] = fmaf(o[d], wa.x, acc[0]), acc[1] = fmaf(o[d], wa.y, acc[1]);
-        acc[2] = fmaf(o[d], wa.z, acc[2]), acc[3] = fmaf(o[d], wa.w, acc[3]);
-        acc[4] = fmaf(o[d], wb.x, acc[4]), acc[5] = fmaf(o[d], wb.y, acc[5]);
-        acc[6] = fmaf(o[d], wb.z, acc[6]), acc[7] = fmaf(o[d], wb.w, acc[7]);
-      }
-    }
-    store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, c), acc);
+  for (int k = 0; k < 4; ++k) {
+    store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, part * 8 + k), v0 + 8 * k);
+    store_chunk_relu(s.a_tile, chunk_offset<TILE>(r, part * 8 + 4 + k), v1 + 8 * k);
   }
 }
 

@@ -31,9 +31,8 @@ def tf32_round(x: torch.Tensor) -> torch.Tensor:
 
 def emulated_forward(p: dict[str, torch.Tensor], obs: torch.Tensor, tf32_layer1: bool = False):
     """Oracle forward with the tensor-core path's operand rounding.  ``tf32_layer1``: layer 1 as the
-    forward / update kernels compute it (one kind::tf32 MMA: observations, W1 and b1 rounded to tf32,
-    fp32 accumulation); otherwise fp32 as the rollout kernel's CUDA-core layer 1.  The two differ by a
-    quarter of a bf16 ulp of H1."""
+    tensor-core kernels compute it (one kind::tf32 MMA: observations, W1 and b1 rounded to tf32, fp32
+    accumulation); otherwise plain fp32.  The two differ by a quarter of a bf16 ulp of H1."""
     def net(prefix: str) -> torch.Tensor:
         w1, b1 = p[f"{prefix}.0.0.weight"], p[f"{prefix}.0.0.bias"]
         if tf32_layer1:
@@ -188,8 +187,7 @@ def test_rollout_kernel_teacher_forced(env_name: str, oname: str, dist: str, n: 
             torch.testing.assert_close(buf["rewards"][:, t], o_r, rtol=1e-4, atol=1e-5)
     # (2) policy outputs recomputed on the recorded observations with the same operand rounding
     flat_obs = buf["obs"].reshape(n * (T + 1), -1)
-    feats, _ = emulated_forward(params, flat_obs)  # rollout kernel: fp32 layer 1
-    _, value = emulated_forward(params, flat_obs, tf32_layer1=True)  # value pass: forward kernel
+    feats, value = emulated_forward(params, flat_obs, tf32_layer1=True)  # every tensor-core kernel: tf32 layer 1
     torch.testing.assert_close(buf["values"].reshape(-1, 1), value, rtol=2e-3, atol=5e-4)
     d = O.Dist(dist).bind({k: v.reshape(n, T + 1, *v.shape[1:])[:, :T].reshape(n * T, *v.shape[1:]) for k, v in feats.items()})
     nz = noise.permute(1, 0, 2, 3).reshape(n * T, 1, P) if dist == "categorical" else noise.permute(1, 0, 2).reshape(n * T, 1)
