@@ -15,7 +15,21 @@ __global__ void __launch_bounds__(1024)
 grad_norm_kernel(const float* __restrict__ g, int64_t count, float* __restrict__ norm_out) {
   __shared__ double red[32];
   double s = 0.0;
-  for (int64_t i = threadIdx.x; i < count; i += blockDim.x) s += (double)g[i] * (double)g[i];
+  // 128-bit loads, four in flight per thread: one CTA (a fixed summation order) without a latency chain
+  const int64_t n4 = ((uintptr_t)g % 16 == 0) ? count / 4 : 0;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 4 * (int64_t)blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = i0 + k * (int64_t)blockDim.x;
+      v[k] = i < n4 ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      s += (double)v[k].x * v[k].x + (double)v[k].y * v[k].y + (double)v[k].z * v[k].z + (double)v[k].w * v[k].w;
+  }
+  for (int64_t i = 4 * n4 + threadIdx.x; i < count; i += blockDim.x) s += (double)g[i] * (double)g[i];
   s = block_sum(s, red);
   if (threadIdx.x == 0) norm_out[0] = (float)sqrt(s);
 }
