@@ -272,7 +272,9 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     fence_after_sync();
     store_thin0(obs_cur);  // read by the MMAs of phases H and J, several barriers from here
     pc.mark(0);  // A + B: loads, Z1 / previous J round trip
-    // ---- C. H1 = relu(Z1): bf16 tile + packed copy in TMEM;  Z2 = H1 * W2^T in two column halves --------------
+    // ---- C. H1 = relu(Z1) packed to bf16 in TMEM only: it is the A operand of Z2 = H1 * W2^T (read by the tensor
+    //         core straight from tensor memory: no shared-memory traffic, the activation tile stays free) and,
+    //         in phase I, the layer-1 ReLU mask --------------------------------------------------------------------
     {
       float v0[32], v1[32];
       tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)group_col0(cq, 0), v0);
@@ -282,22 +284,25 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       reg_fence32(v1);
       uint32_t hp[16];
       relu_pack32(v0, hp);
-      store_group(s.a_tile, r, group_col0(cq, 0), hp);
       tmem_st16_raw(tmem + kColH1 + lane_base + (uint32_t)(group_col0(cq, 0) / 2), hp);
       relu_pack32(v1, hp);
-      store_group(s.a_tile, r, group_col0(cq, 1), hp);
       tmem_st16_raw(tmem + kColH1 + lane_base + (uint32_t)(group_col0(cq, 1) / 2), hp);
       tmem_wait_st();
     }
-    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (cta_issuer()) {
       fence_after_sync();
+      const uint32_t idesc = instr_desc(TILE, 128, 0, 0);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        issue_gemm(tmem + kColMain + 128 * h, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2) + h * 2048, H,
-                   false, TILE, 128, H, false);
+        // B = W2 rows [128 h, 128 h + 128) K-major: LBO = H*16 (next 8 K), SBO = 128, 16 K = 2 * H * 16 bytes
+        uint64_t bd = smem_desc(smem_u32(s.w2) + h * 2048, H * 16, 128);
+#pragma unroll
+        for (int ks = 0; ks < H / 16; ++ks) {
+          mma_bf16_ts(tmem + kColMain + 128 * h, tmem + kColH1 + 8 * ks, bd, idesc, ks > 0 ? 1u : 0u);
+          bd += (2 * H * 16) >> 4;
+        }
         mma_commit(&s.bar[kBZ2A + h]);
       }
     }
@@ -306,17 +311,11 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     float dot[PN];
 #pragma unroll
     for (int p = 0; p < PN; ++p) dot[p] = 0.0f;
-    uint32_t held[16];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int col0 = group_col0(cq, h);
-      if (h == 0) {
-        mbar_wait(&s.bar[kBZ2A], ph);
-      } else {
-        mbar_wait(&s.bar[kBZ2B], ph);  // every MMA that reads H1 is done: the tile may be overwritten
-      }
+      mbar_wait(&s.bar[kBZ2A + h], ph);
       fence_after_sync();
-      if (h == 1) store_group(s.a_tile, r, group_col0(cq, 0), held);
       float v[32];
       tmem_ld32(tmem + kColMain + lane_base + (uint32_t)col0, v);
 #pragma unroll
@@ -333,15 +332,10 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
           dot[p] = fmaf(v[j + 3], w.w, dot[p]);
         }
       }
-      if (h == 0) {
+      uint32_t hp[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) held[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-      } else {
-        uint32_t hp[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) hp[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        store_group(s.a_tile, r, col0, hp);
-      }
+      for (int i = 0; i < 16; ++i) hp[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      store_group(s.a_tile, r, col0, hp);  // nothing reads the tile during this phase
     }
     if (cq > 0) {
 #pragma unroll
@@ -441,6 +435,7 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       mma_commit(&s.bar[kBDB]);
       bulk_wait_read();  // the store engine has read the tile
     }
+    uint32_t held[16];
     // ---- I. dZ1 = [H1 > 0] .* dH1; half 0 is processed under the MMAs of half 1 -----------------------------------------------
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -471,6 +466,8 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
     __syncthreads();
     pc.mark(6);  // H + I: dH1 MMAs + dZ1 epilogue
     // ---- J. [gW1, gb1] += dZ1^T * [obs, 1];  Z1 of the next tile -- one commit, awaited at the top of the next tile -----
+    // (Z1 first on its own barrier was measured: the thin GEMM then delays the next tile's Z2 on the in-order pipe
+    // by more than the shorter wait saves)
     if (cta_issuer()) {
       fence_after_sync();
 #pragma unroll
