@@ -423,11 +423,10 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
 #pragma unroll
       for (int i = 0; i < 4; ++i) bulk_s2g(dst + i * 16384, s.a_tile + i * 16384, 16384);
       bulk_commit();
-      issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, true, TILE, 128, H,
-                 false);
+      // one N = 256 GEMM: the phase is bound by shared-memory bandwidth (operand fetch + the bulk store + the
+      // dZ1 stores), and N = 256 fetches the A operand once per K step instead of once per column half
+      issue_gemm(tmem + kColMain, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2), H, true, TILE, H, H, false);
       mma_commit(&s.bar[kBDA]);
-      issue_gemm(tmem + kColMain + 128, smem_u32(s.a_tile), TILE, false, smem_u32(s.w2) + 16 * (H * 16), H,
-                 true, TILE, 128, H, false);
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb)
         issue_thin(tmem + kColThin + kThinN * (2 + jb), smem_u32(s.a_tile) + jb * 32768, smem_u32(s.thin[0]),
@@ -435,31 +434,29 @@ __device__ __forceinline__ void update_h_body(SmemH& s, const NetParams& np, con
       mma_commit(&s.bar[kBDB]);
       bulk_wait_read();  // the store engine has read the tile
     }
-    uint32_t held[16];
-    // ---- I. dZ1 = [H1 > 0] .* dH1; half 0 is processed under the MMAs of half 1 -----------------------------------------------
+    // ---- I. dZ1 = [H1 > 0] .* dH1 in registers while the thin gb2 GEMM still reads dZ2, then stored over it ----------------
+    {
+      uint32_t held[16], hp[16];
+      mbar_wait(&s.bar[kBDA], ph);
+      fence_after_sync();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col0 = group_col0(cq, h);
-      if (h == 0) {
-        mbar_wait(&s.bar[kBDA], ph);
-        fence_after_sync();
-      } else {
-        mbar_wait(&s.bar[kBDB], ph);
-        fence_after_sync();
-        __syncthreads();  // thread 0's bulk_wait_read precedes every overwrite of the tile
-        store_group(s.a_tile, r, group_col0(cq, 0), held);
+      for (int h = 0; h < 2; ++h) {
+        const int col0 = group_col0(cq, h);
+        float v[32];
+        uint32_t* out = h == 0 ? held : hp;
+        tmem_ld16_raw(tmem + kColH1 + lane_base + (uint32_t)(col0 / 2), out);
+        tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)col0, v);
+        tmem_wait_ld();
+        reg_fence16(out);
+        reg_fence32(v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]) & gt0_mask_bf16x2(out[i]);
       }
-      uint32_t hp[16];
-      float v[32];
-      tmem_ld16_raw(tmem + kColH1 + lane_base + (uint32_t)(col0 / 2), hp);
-      tmem_ld32_nowait(tmem + kColMain + lane_base + (uint32_t)col0, v);
-      tmem_wait_ld();
-      reg_fence16(hp);
-      reg_fence32(v);
-      uint32_t* out = h == 0 ? held : hp;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]) & gt0_mask_bf16x2(hp[i]);
-      if (h == 1) store_group(s.a_tile, r, col0, hp);
+      mbar_wait(&s.bar[kBDB], ph);  // every MMA that reads dZ2 is done
+      fence_after_sync();
+      __syncthreads();  // ... and the issuing lane's bulk_wait_read precedes every overwrite of the tile
+      store_group(s.a_tile, r, group_col0(cq, 0), held);
+      store_group(s.a_tile, r, group_col0(cq, 1), hp);
     }
     fence_async_smem();
     fence_before_sync();
