@@ -5,12 +5,13 @@
 //     value network, each with ITS W2 resident in smem).  Per 128-row tile, every contraction is
 //     a tcgen05.mma and the CUDA cores only convert, mask and evaluate the per-row loss:
 //       Z1  = [obs,1] * [W1,b1]^T          kind::tf32, K = 8 (one instruction)
-//       H1  = relu(Z1) -> bf16 tile (A operand) + a packed copy parked in TMEM for its mask
-//       Z2  = H1 * W2^T                     kind::f16 (bf16), K = 256
+//       H1  = relu(Z1) -> packed bf16 in 128 TMEM columns: the A operand of Z2 (read from tensor memory,
+//                                          no shared-memory traffic) and later the layer-1 ReLU mask
+//       Z2  = H1 * W2^T                     kind::f16 (bf16), K = 256, two N = 128 halves
 //       H2  = relu(Z2 + b2) -> tile;  head dot products, per-row PPO loss -> dOut
 //       gW3^T += H2^T * dOut                thin GEMM (N = 16)
 //       dZ2 = [H2 > 0] .* (dOut * W3) -> tile -> one 64 KB bulk store to the dZ2 scratch
-//       dH1 = dZ2 * W2  (the SAME W2 image read MN-major);  [., gb2] += dZ2^T * [obs,1]
+//       dH1 = dZ2 * W2  (the SAME W2 image read MN-major, one N = 256 GEMM);  [., gb2] += dZ2^T * [obs,1]
 //       dZ1 = [H1 > 0] .* dH1 -> tile;  [gW1, gb1] += dZ1^T * [obs,1]
 //     The thin gradients accumulate in TMEM over all tiles of the CTA and are flushed once.
 //   tc_update_w_kernel  ("weight" kernel).  gW2 = dZ2^T * H1 needs a 256x256 fp32 accumulator =
@@ -18,7 +19,7 @@
 //     columns) and uses the other 256 columns to recompute Z1 -> H1 with the same tf32
 //     instruction (bit-identical to the activation kernel).  dZ2 half-tiles arrive by bulk
 //     async copy (double-buffered), so the loop is: TMA -> [tf32 MMA -> relu/pack epilogue]
-//     overlapped with the previous tile's gW2 MMAs.
+//     overlapped with the previous tile's gW2 MMAs; a 17th warp issues every bulk copy and MMA.
 //
 // GEMM work per row and network: 3 x 256 x 256 MACs -- the minimum (forward, dH1, gW2).
 // Activations never reach HBM except the bf16 dZ2 tile (512 B / row / network, written once and
