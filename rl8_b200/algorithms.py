@@ -608,7 +608,8 @@ class Algorithm:
             )
             _lib.check(rc, "rl8_ppo_minibatch")
 
-        per_call = 34 * max(1, -(-M // 65536)) if prec == _lib.PREC_FP32 else 4
+        # bf16: 2 x W2 packing + (activation kernel + weight-gradient kernel) per 2^21-row chunk
+        per_call = 34 * max(1, -(-M // 65536)) if prec == _lib.PREC_FP32 else 2 + 2 * max(1, -(-M // (1 << 21)))
         return launch, per_call
 
     def _reset_buffer(self) -> None:
