@@ -36,65 +36,75 @@ constexpr int kLD = 8;     // widest observation on the fused path
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- forward cell --------------------------------------------------------------------------------
-// Block = H threads (hidden unit j, its 4 x D input weights and 8 biases in registers), rows
-// grid-strided.  G[r][4H] holds h_prev.W_hh^T on entry; on exit `act` (may alias G) holds the
-// gate ACTIVATIONS i, f, g, o (kept for the backward pass; NULL in the rollout).
-__global__ void __launch_bounds__(kLH)
+// HBM-bound stream: per row 4 KB of gate pre-activations in, 4 KB of activations + c + h out.  A thread
+// owns FOUR consecutive hidden units of one row (128-bit loads and stores throughout); a block of 256
+// threads walks 4 rows per iteration; W_ih (transposed, [gate][d][unit]) and the biases sit in shared
+// memory.  G[r][4H] holds h_prev.W_hh^T on entry; on exit `act` (may alias G) holds the gate ACTIVATIONS
+// i, f, g, o (kept for the backward pass; NULL in the rollout).  Arithmetic order per element:
+// pre = (b_ih + sum_d x_d w_d) + (G + b_hh), as oracle/recurrent_oracle.py:lstm_cell.
+__global__ void __launch_bounds__(256, 3)
 lstm_cell_fwd_kernel(const float* G, RowMap xmap, int D, int64_t rows,
                      const float* __restrict__ w_ih, const float* __restrict__ b_ih,
                      const float* __restrict__ b_hh, const float* c_prev, float* act, float* c_out,
                      float* __restrict__ h_out) {
-  const int j = threadIdx.x;
-  float w[4][kLD], bi[4], bh[4];
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-#pragma unroll
-    for (int d = 0; d < kLD; ++d) w[g][d] = d < D ? w_ih[(g * kLH + j) * D + d] : 0.0f;
-    bi[g] = b_ih[g * kLH + j];
-    bh[g] = b_hh[g * kLH + j];
+  __shared__ __align__(16) float wt[4][kLD][kLH];  // 32 KB
+  __shared__ __align__(16) float bi[4][kLH], bh[4][kLH];  // 8 KB
+  for (int i = threadIdx.x; i < 4 * kLD * kLH; i += blockDim.x) {
+    const int g = i / (kLD * kLH), d = (i / kLH) % kLD, j = i % kLH;
+    wt[g][d][j] = d < D ? w_ih[(g * kLH + j) * D + d] : 0.0f;
   }
+  for (int i = threadIdx.x; i < 4 * kLH; i += blockDim.x) {
+    (&bi[0][0])[i] = b_ih[i];
+    (&bh[0][0])[i] = b_hh[i];
+  }
+  __syncthreads();
+  const int rb = threadIdx.x >> 6, j0 = (threadIdx.x & 63) * 4;
   const int64_t ds = xmap.dstride();
-  // kRows rows per iteration: their loads are all in flight before the first gate is evaluated
-  constexpr int kRows = 4;
-  for (int64_t r0 = (int64_t)blockIdx.x * kRows; r0 < rows; r0 += (int64_t)gridDim.x * kRows) {
-    float pre[kRows][4], cp[kRows];
+  for (int64_t r = (int64_t)blockIdx.x * 4 + rb; r < rows; r += (int64_t)gridDim.x * 4) {
+    const float* Gr = G + r * 4 * kLH + j0;
+    float4 gq[4];
 #pragma unroll
-    for (int i = 0; i < kRows; ++i) {
-      const int64_t r = r0 + i;
-      if (r < rows) {
-        const int64_t xo = xmap.offset(r);
-        float x[kLD];
+    for (int g = 0; g < 4; ++g) gq[g] = *reinterpret_cast<const float4*>(Gr + g * kLH);
+    const float4 cp = *reinterpret_cast<const float4*>(c_prev + r * kLH + j0);
+    const int64_t xo = xmap.offset(r);
+    float x[kLD];
 #pragma unroll
-        for (int d = 0; d < kLD; ++d) x[d] = d < D ? xmap.obs[xo + d * ds] : 0.0f;
+    for (int d = 0; d < kLD; ++d) x[d] = d < D ? xmap.obs[xo + d * ds] : 0.0f;
+    float pre[4][4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float a = bi[g];
+    for (int g = 0; g < 4; ++g) {
+      const float4 b = *reinterpret_cast<const float4*>(&bi[g][j0]);
+      float a[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int d = 0; d < kLD; ++d)
-            if (d < D) a = fmaf(x[d], w[g][d], a);
-          pre[i][g] = a + (G[r * 4 * kLH + g * kLH + j] + bh[g]);
+      for (int d = 0; d < kLD; ++d) {
+        if (d < D) {
+          const float4 w = *reinterpret_cast<const float4*>(&wt[g][d][j0]);
+          a[0] = fmaf(x[d], w.x, a[0]), a[1] = fmaf(x[d], w.y, a[1]);
+          a[2] = fmaf(x[d], w.z, a[2]), a[3] = fmaf(x[d], w.w, a[3]);
         }
-        cp[i] = c_prev[r * kLH + j];
       }
+      const float4 h4 = *reinterpret_cast<const float4*>(&bh[g][j0]);
+      pre[g][0] = a[0] + (gq[g].x + h4.x), pre[g][1] = a[1] + (gq[g].y + h4.y);
+      pre[g][2] = a[2] + (gq[g].z + h4.z), pre[g][3] = a[3] + (gq[g].w + h4.w);
     }
+    const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+    float ig[4], fg[4], gg[4], og[4], c[4], h[4];
 #pragma unroll
-    for (int i = 0; i < kRows; ++i) {
-      const int64_t r = r0 + i;
-      if (r < rows) {
-        const float ig = sigmoidf_(pre[i][0]), fg = sigmoidf_(pre[i][1]), gg = tanhf(pre[i][2]),
-                    og = sigmoidf_(pre[i][3]);
-        const float c = fg * cp[i] + ig * gg;
-        const float h = og * tanhf(c);
-        if (act) {
-          act[r * 4 * kLH + 0 * kLH + j] = ig;
-          act[r * 4 * kLH + 1 * kLH + j] = fg;
-          act[r * 4 * kLH + 2 * kLH + j] = gg;
-          act[r * 4 * kLH + 3 * kLH + j] = og;
-        }
-        c_out[r * kLH + j] = c;
-        h_out[r * kLH + j] = h;
-      }
+    for (int u = 0; u < 4; ++u) {
+      ig[u] = sigmoidf_(pre[0][u]), fg[u] = sigmoidf_(pre[1][u]);
+      gg[u] = tanhf(pre[2][u]), og[u] = sigmoidf_(pre[3][u]);
+      c[u] = fg[u] * cpv[u] + ig[u] * gg[u];
+      h[u] = og[u] * tanhf(c[u]);
     }
+    if (act) {
+      float* ar = act + r * 4 * kLH + j0;
+      *reinterpret_cast<float4*>(ar) = make_float4(ig[0], ig[1], ig[2], ig[3]);
+      *reinterpret_cast<float4*>(ar + kLH) = make_float4(fg[0], fg[1], fg[2], fg[3]);
+      *reinterpret_cast<float4*>(ar + 2 * kLH) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      *reinterpret_cast<float4*>(ar + 3 * kLH) = make_float4(og[0], og[1], og[2], og[3]);
+    }
+    *reinterpret_cast<float4*>(c_out + r * kLH + j0) = make_float4(c[0], c[1], c[2], c[3]);
+    *reinterpret_cast<float4*>(h_out + r * kLH + j0) = make_float4(h[0], h[1], h[2], h[3]);
   }
 }
 
@@ -102,8 +112,8 @@ static int launch_cell_fwd(const rl8_lstm_model* m, const float* G, const RowMap
                            const float* c_prev, float* act, float* c_out, float* h_out,
                            cudaStream_t st) {
   const int64_t groups = ceil_div(rows, 4);  // 4 rows per block iteration
-  int grid = (int)(groups < (int64_t)kNumSMs * 16 ? groups : (int64_t)kNumSMs * 16);
-  lstm_cell_fwd_kernel<<<grid, kLH, 0, st>>>(G, xmap, m->D, rows, m->w_ih, m->b_ih, m->b_hh, c_prev,
+  int grid = (int)(groups < (int64_t)kNumSMs * 8 ? groups : (int64_t)kNumSMs * 8);
+  lstm_cell_fwd_kernel<<<grid, 256, 0, st>>>(G, xmap, m->D, rows, m->w_ih, m->b_ih, m->b_hh, c_prev,
                                              act, c_out, h_out);
   return check_launch("lstm_cell_fwd");
 }
