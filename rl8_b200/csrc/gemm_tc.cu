@@ -37,6 +37,7 @@ struct GemmArgs {
   float* C;
   int64_t M, K, lda, ldb, ldc, kchunk;
   int N;
+  unsigned ntn;  // column tiles
 };
 
 // Eight consecutive fp32 elements at p (the first `valid` of them inside the matrix) -> one bf16 chunk.
@@ -118,8 +119,10 @@ __global__ void __launch_bounds__(kGThreads, 2) tc_gemm_kernel(GemmArgs g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemGemm& s = *reinterpret_cast<SmemGemm*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * kGM;
-  const int64_t n0 = (int64_t)blockIdx.y * kGN;
+  // column tiles are the fast block index: the CTAs that share a 128-row strip of A are co-resident, so the
+  // strip comes from HBM once and from L2 for the other column tiles
+  const int64_t m0 = (int64_t)(blockIdx.x / g.ntn) * kGM;
+  const int64_t n0 = (int64_t)(blockIdx.x % g.ntn) * kGN;
   const int64_t kbeg = (int64_t)blockIdx.z * g.kchunk;
   const int64_t kend = kbeg + g.kchunk < g.K ? kbeg + g.kchunk : g.K;
   if (tid == 0) {
@@ -197,7 +200,8 @@ int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const 
   g.A = A, g.B = B, g.C = C, g.M = M, g.N = N, g.K = K, g.lda = lda, g.ldb = ldb, g.ldc = ldc;
   g.kchunk = round_up(ceil_div(K, splits), kGK);
   splits = (int)ceil_div(K, g.kchunk);
-  dim3 grid((unsigned)ceil_div(M, kGM), (unsigned)ceil_div(N, kGN), (unsigned)splits);
+  g.ntn = (unsigned)ceil_div(N, kGN);
+  dim3 grid((unsigned)(ceil_div(M, kGM) * g.ntn), 1, (unsigned)splits);
   const size_t smem = sizeof(SmemGemm);
 #define RL8_GEMM(AKV, BKV, ATV)                                                                          \
   {                                                                                                      \

@@ -303,12 +303,21 @@ lstm_gate_reduce_kernel(const float* __restrict__ dG, int64_t rows, RowMap xmap,
       sx[r][d] = r < nr ? xmap.obs[xmap.offset(r0 + r) + d * ds] : 0.0f;
     }
     __syncthreads();
-    for (int r = 0; r < nr; ++r) {
-      const float v = dG[(r0 + r) * 4 * kLH + g];
-      accb += v;
+    // four rows per trip: their loads are in flight together (the loop is latency-, not bandwidth-bound);
+    // the accumulation order over rows is unchanged
+    for (int rq = 0; rq < nr; rq += 4) {
+      float v4[4];
 #pragma unroll
-      for (int d = 0; d < kLD; ++d)
-        if (d < D) acc[d] = fmaf(v, sx[r][d], acc[d]);
+      for (int i = 0; i < 4; ++i) v4[i] = rq + i < nr ? dG[(r0 + rq + i) * 4 * kLH + g] : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (rq + i < nr) {
+          accb += v4[i];
+#pragma unroll
+          for (int d = 0; d < kLD; ++d)
+            if (d < D) acc[d] = fmaf(v4[i], sx[rq + i][d], acc[d]);
+        }
+      }
     }
   }
 #pragma unroll
