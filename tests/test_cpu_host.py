@@ -148,3 +148,30 @@ def test_specs_and_reduce_stats() -> None:
     assert list(comp) == ["obs", "actions"] and comp.to("cpu")["obs"].shape == u.shape
     r = reduce_stats({"a/min": [1, 2], "a/max": [1, 2], "a/mean": [1, 3], "a/std": [3, 4], "env/steps": [5, 5]})
     assert r == {"a/min": 1, "a/max": 2, "a/mean": 2, "a/std": (12.5) ** 0.5, "env/steps": 10}
+
+
+def test_bench_reference_arm_contract() -> None:
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints ONE JSON line with the
+    contract's keys; a tiny workload keeps this in seconds."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(
+        [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+         "--num-envs-per-gpu", "256", "--horizon", "8"],
+        capture_output=True, text=True, timeout=300, cwd=root,
+    )
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "transitions/s"
+    assert d["metric"].startswith("env transitions/sec")
+    for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d, k
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("CartPole")
