@@ -536,9 +536,14 @@ tc_bench_mma_kernel(long long* out, int N, int k_total, int reps, int a_mn, int 
   fence_after_sync();
   if (tid < 32 && elect_one()) {
     const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r)
-      issue_gemm(s.tmem_base, smem_u32(s.a), TILE, a_mn != 0, smem_u32(s.b), b_mn ? k_total : N, b_mn != 0, TILE, N,
-                 k_total, r > 0);
+    for (int r = 0; r < reps; ++r) {
+      if (k_total == 8)  // kind::tf32, K = 8: the layer-1 instruction of the tensor-core kernels
+        mma_tf32(s.tmem_base, smem_desc(smem_u32(s.a), TILE * 16, 128), smem_desc(smem_u32(s.b), N * 16, 128),
+                 instr_desc_tf32(TILE, N), r > 0 ? 1u : 0u);
+      else
+        issue_gemm(s.tmem_base, smem_u32(s.a), TILE, a_mn != 0, smem_u32(s.b), b_mn ? k_total : N, b_mn != 0, TILE,
+                   N, k_total, r > 0);
+    }
     mma_commit(&s.bar);
     const long long t1 = clock64();
     mbar_wait(&s.bar, 0);
@@ -654,8 +659,8 @@ extern "C" int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_strea
 
 extern "C" int rl8_tc_bench_mma(long long* out_cycles, int32_t N, int32_t k_total, int32_t reps, int a_mn_major,
                                 int b_mn_major, rl8_stream_t stream) {
-  if (!out_cycles || N < 16 || N > 256 || N % 16 || k_total < 16 || k_total > 256 || k_total % 16 || reps < 1)
-    return RL8_ERR_ARG;
+  if (!out_cycles || N < 16 || N > 256 || N % 16 || reps < 1) return RL8_ERR_ARG;
+  if (k_total != 8 && (k_total < 16 || k_total > 256 || k_total % 16)) return RL8_ERR_ARG;  // 8: one tf32 instruction
   if (a_mn_major && k_total > TILE) return RL8_ERR_ARG;
   int rc;
   if ((rc = set_smem((const void*)tc_bench_mma_kernel, sizeof(SmemMmaBench)))) return rc;
