@@ -43,3 +43,7 @@ print(f"  N=256 (gW2 shape, A and B MN-major): {t / 1024:7.1f} cycles/instr")
 print("kind::tf32, K=8 (the layer-1 instruction): round trip of one instruction, and pace over 256 instructions:")
 for N in (128, 256):
     print(f"  N={N:3d}: round trip {run(N, 8, 1, 0, 0)[0]} cycles, pace {run(N, 8, 256, 0, 0)[0] / 256:6.1f} cycles/instr")
+print("gW2 shape (A and B MN-major, K=128 rows) by N:")
+for N in (64, 128, 256):
+    t, i = run(N, 128, 128, 1, 1)
+    print(f"  N={N:3d}: {t / 1024:7.1f} cycles/instr, {128 * N * 16 * 2 * 1024 / t:7.0f} FLOP/cycle")
