@@ -515,9 +515,9 @@ def stream_rooflines(lib, L, dev, peaks: dict) -> list[dict]:  # noqa: ANN001
 
 
 #: dram__bytes_read.sum + dram__bytes_write.sum of the four kernel launches of one CartPole
-#: N=65536 T=32 full-batch rl8_ppo_minibatch (2 x tc_update_h + 2 x tc_update_w), from the
-#: `ncu --set full` captures summarised in profiles/r01_update_v5_ncu_summary.md.
-NCU_TRAFFIC = {("cartpole", 2097152): 2 * (42.39e6 + 1014.9e6) + 2 * (1095.3e6 + 4.59e6)}
+#: N=65536 T=32 full-batch rl8_ppo_minibatch (tc_update_h + tc_update_w over 2^21 rows), from the
+#: `ncu --set full` captures summarised in profiles/r01_update_v8_ncu_summary.md.
+NCU_TRAFFIC = {("cartpole", 2097152): (84.31e6 + 2089.0e6) + (2190.0e6 + 7.0e6)}
 
 
 def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa: ANN001
@@ -579,7 +579,7 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
         "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
         "frac": flops / ms / 1e9 / peak, "traffic": traffic, "ms": ms, "rows": M, "dtype": dtype,
         "peak_source": peaks["source"] + " bf16 sustained",
-        "traffic_source": "ncu --set full, profiles/r01_update_v5_ncu_summary.md" if traffic else None,
+        "traffic_source": "ncu --set full, profiles/r01_update_v8_ncu_summary.md" if traffic else None,
     }
 
 
