@@ -249,6 +249,15 @@ int rl8_ppo_losses(int dist_kind, const float* features, int32_t P, const float*
                    const rl8_ppo_hparams* hp, double* loss_sums, float* d_features,
                    float* d_values, rl8_stream_t stream);
 
+/* Same, for features produced by a user-defined model (the reference's `Model` plug-in point,
+ * src/rl8/models/_feedforward.py:146-162, whose `log_std` is the model's own output): the second
+ * column of d_features is the gradient w.r.t. log_std itself. */
+int rl8_ppo_losses_direct(int dist_kind, const float* features, int32_t P, const float* values,
+                          const void* actions, const float* logp_old, const float* advantages,
+                          const float* returns, int64_t B, double mean_denominator,
+                          const rl8_ppo_hparams* hp, double* loss_sums, float* d_features,
+                          float* d_values, rl8_stream_t stream);
+
 /* ---- recurrent policy: RecurrentAlgorithm (src/rl8/algorithms/_recurrent.py) ----------------- */
 
 /* Default recurrent models (src/rl8/models/_recurrent.py:169-341): ONE nn.LSTM(D, H) whose

@@ -179,6 +179,11 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         [_int, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f64, C.POINTER(PpoHparams), _vp, _vp,
          _vp, _vp],
     ),
+    "rl8_ppo_losses_direct": (
+        _int,
+        [_int, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f64, C.POINTER(PpoHparams), _vp, _vp,
+         _vp, _vp],
+    ),
     "rl8_view_windows": (_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp]),
     "rl8_tc_selftest": (_int, [_vp, _vp, _vp, _i32, _i32, _int, _int, _vp]),
     "rl8_tc_selftest_tf32": (_int, [_vp, _vp, _vp, _i32, _vp]),

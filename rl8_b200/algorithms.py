@@ -123,6 +123,13 @@ def memory_stats() -> MemoryStats:
 _world = parallel.world_size
 
 
+def _index_views(views: Any, idx: Any) -> Any:
+    """Rows ``idx`` of every tensor leaf of a (nested) views mapping."""
+    if isinstance(views, torch.Tensor):
+        return views[idx]
+    return {k: _index_views(v, idx) for k, v in views.items()}
+
+
 class _RunningMean:
     def __init__(self) -> None:
         self.avg, self.n = 0.0, 0
@@ -179,23 +186,28 @@ class Algorithm:
         if config.normalize_rewards:
             self.buffer_spec.set(DataKeys.REVERSED_DISCOUNTED_RETURNS, Unbounded(1, device=device))
         self.buffer = RolloutBuffer(self.buffer_spec, num_envs, horizon, device)
-        if config.optimizer_cls is not optim.Adam:
-            raise NotImplementedError(
-                "the fused update implements Adam (the reference default); other optimizer"
-                " classes are outside the fused hot path"
-            )
+        self._fused_model = self.policy.fused
         optimizer_config = dict(config.optimizer_config or {"lr": 1e-3})
-        unsupported = {k: v for k, v in optimizer_config.items()
-                       if k not in ("lr", "betas", "eps") and v}
-        if unsupported:
-            raise NotImplementedError(f"fused Adam does not implement {sorted(unsupported)}")
-        # A real torch optimizer object holds the param groups (lr schedules mutate them);
-        # the update itself runs in rl8_clip_adam on the flat buffers below.
-        self.optimizer = optim.Adam(self.policy.model.parameters(), **optimizer_config)
-        flat = self.policy.model.flat_params
-        self._grads = torch.zeros_like(flat)
-        self._exp_avg = torch.zeros_like(flat)
-        self._exp_avg_sq = torch.zeros_like(flat)
+        if self._fused_model:
+            if config.optimizer_cls is not optim.Adam:
+                raise NotImplementedError(
+                    "the fused update of the default models implements Adam (the reference default);"
+                    " other optimizer classes run with user-defined models (rl8_b200.models.GenericModel)"
+                )
+            unsupported = {k: v for k, v in optimizer_config.items()
+                           if k not in ("lr", "betas", "eps") and v}
+            if unsupported:
+                raise NotImplementedError(f"fused Adam does not implement {sorted(unsupported)}")
+            # A real torch optimizer object holds the param groups (lr schedules mutate them);
+            # the update itself runs in rl8_clip_adam on the flat buffers below.
+            self.optimizer = optim.Adam(self.policy.model.parameters(), **optimizer_config)
+            flat = self.policy.model.flat_params
+            self._grads = torch.zeros_like(flat)
+            self._exp_avg = torch.zeros_like(flat)
+            self._exp_avg_sq = torch.zeros_like(flat)
+        else:
+            # user-defined torch model: its parameters belong to torch, any optimizer class works
+            self.optimizer = config.optimizer_cls(self.policy.model.parameters(), **optimizer_config)
         self._grad_norm = torch.zeros(1, device=device)
         self._opt_steps = 0
         self.lr_scheduler = LRScheduler(
@@ -301,13 +313,15 @@ class Algorithm:
                 rdr_hm[0].zero_()
         self._pre_collect()
 
-        P = self.policy.model.head_width
+        P = self._head_width()
         dist_cls = self.policy.distribution_cls
         noise = None
         if not deterministic:
             noise = dist_cls.draw_noise(T, N, P, self.device).contiguous()
             assert noise.dtype == torch.float32 and noise.is_cuda
-        if self._fused_env:
+        if not self._fused_model:
+            self._collect_generic_model(noise, deterministic)
+        elif self._fused_env:
             self._collect_fused(noise, deterministic)
         else:
             self._collect_generic(noise, deterministic)
@@ -397,6 +411,48 @@ class Algorithm:
         T = hp.horizon
         self.last_launches["collect"] = (4 * T + 3 * (T + 1)) if self.policy.precision == _lib.PREC_FP32 else 4
 
+    def _head_width(self) -> int:
+        """Policy-head outputs the sampling kernels see: A logits, or 2 = {mean, log_std}."""
+        if self._fused_model:
+            return self.policy.model.head_width
+        spec = self.env.action_spec
+        return int(spec.space.n) if isinstance(spec, Categorical) else 2
+
+    def _collect_generic_model(self, noise: None | torch.Tensor, deterministic: bool) -> None:
+        """Rollout with a user-defined torch model (rl8_b200.models.GenericModel): the model's forward
+        runs through torch every step; sampling, log-probabilities, the env step (bundled envs) and the
+        buffer writes stay on this library's kernels."""
+        hp, buf = self.hparams, self.buffer
+        N, T = hp.num_envs, hp.horizon
+        obs_hm, act_hm = buf.hm[DataKeys.OBS], buf.hm[DataKeys.ACTIONS]
+        rdr_hm = buf.hm.get(DataKeys.REVERSED_DISCOUNTED_RETURNS)
+        model, kind = self.policy.model, self.policy.distribution_cls.rl8_kind
+        obs_em = buf[DataKeys.OBS]  # [N, T+1, D] view
+        launches = 0
+        model.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=hp.enable_amp):
+            for t in range(T + 1):
+                views = model.apply_view_requirements({DataKeys.OBS: obs_em[:, : t + 1]}, kind="last")
+                features = model(views)
+                buf.hm[DataKeys.VALUES][t].copy_(model.value_function().reshape(N))
+                if t == T:
+                    break
+                packed = self.policy.distribution_cls(features, model)._packed()
+                nz = None if noise is None else noise[t]
+                rc = self._lib.rl8_dist_sample(
+                    kind, _lib.ptr(packed), packed.shape[1], _lib.ptr(nz), int(deterministic),
+                    _lib.ptr(act_hm[t]), _lib.ptr(buf.hm[DataKeys.LOGP][t]), N, _lib.stream(),
+                )
+                _lib.check(rc, "rl8_dist_sample")
+                out = self.env.step(act_hm[t].view(N, 1))
+                rewards = out[DataKeys.REWARDS].reshape(N)
+                if rdr_hm is not None:
+                    torch.add(rewards, rdr_hm[t], alpha=hp.gamma, out=rdr_hm[t + 1])
+                buf.hm[DataKeys.REWARDS][t].copy_(rewards)
+                obs_hm[t + 1].copy_(out[DataKeys.OBS].reshape(N, -1).T)
+                launches += 2  # rl8_dist_sample + the env's step kernel
+        self.last_launches["collect"] = launches
+
     def _collect_generic(self, noise: None | torch.Tensor, deterministic: bool) -> None:
         """Rollout with a user-defined (Python / torch) environment: the policy forward,
         sampling and log-probabilities still run on this library's kernels; ``env.step`` is
@@ -463,6 +519,9 @@ class Algorithm:
             )
             _lib.check(rc, "rl8_gae_normalize")
             launches += 1
+
+        if not self._fused_model:
+            return self._step_generic_model(start, launches)
 
         # -- PPO epochs ---------------------------------------------------------------------
         model = self.policy.model
@@ -533,6 +592,14 @@ class Algorithm:
             if stop_early:
                 break
 
+        return self._finish_step(start, launches, k, applied, accum, entropy_coeff)
+
+    def _finish_step(self, start: int, launches: int, k: int, applied: list[bool], accum: int,
+                     entropy_coeff: float) -> StepStats:
+        """Statistics of the update (one readback), schedulers, buffer reset."""
+        hp = self.hparams
+        world = _world()
+        sums = self._loss_sums
         # -- statistics: one readback ----------------------------------------------------------
         used = sums[:k]
         if world > 1 and k:
@@ -573,6 +640,89 @@ class Algorithm:
         torch.cuda.current_stream().synchronize()
         stats["profiling/step_ms"] = (time.perf_counter_ns() - start) / 1e6
         return stats
+
+    def _step_generic_model(self, start: int, launches: int) -> StepStats:
+        """The PPO epochs for a user-defined torch model (src/rl8/algorithms/_feedforward.py:469-600):
+        per minibatch ``model(views)`` through torch, ``rl8_ppo_losses_direct`` for the clipped losses and
+        their gradients w.r.t. the model outputs, ``torch.autograd.backward`` through the model, then
+        ``clip_grad_norm_`` and the user's optimizer."""
+        hp, buf, lib = self.hparams, self.buffer, self._lib
+        N, T = hp.num_envs, hp.horizon
+        world = _world()
+        model, dist_cls = self.policy.model, self.policy.distribution_cls
+        kind = dist_cls.rl8_kind
+        views = model.apply_view_requirements(
+            {k: buf[k][:, :-1] for k in model.view_requirements}, kind="all"
+        )
+
+        def column(key: str) -> torch.Tensor:  # [N, T+1, 1] view -> contiguous [N * T], row = n * T + t
+            return buf[key][:, :-1].reshape(N * T).contiguous()
+
+        actions, logp_old = column(DataKeys.ACTIONS), column(DataKeys.LOGP)
+        advantages, returns = column(DataKeys.ADVANTAGES), column(DataKeys.RETURNS)
+        M = hp.sgd_minibatch_size
+        accum = hp.num_minibatches if hp.accumulate_grads else 1
+        entropy_coeff = self.entropy_scheduler.coeff
+        if entropy_coeff != 0 and kind == _lib.DIST_SQUASHED_NORMAL:
+            dist_cls({}, model).entropy()  # raises like the reference
+        ppo = _lib.PpoHparams(
+            hp.clip_param, hp.dual_clip_param or 0.0, entropy_coeff, hp.vf_clip_param, hp.vf_coeff, 1.0 / accum,
+        )
+        sums = self._loss_sums
+        sums.zero_()
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.optimizer.zero_grad(set_to_none=True)
+        model.train()
+        k = 0
+        applied: list[bool] = []
+        stop_early = False
+        for _ in range(hp.num_sgd_iters):
+            perm = torch.randperm(N * T, device=self.device) if hp.shuffle_minibatches else None
+            for i in range(hp.num_minibatches):
+                step_this_batch = (i + 1) % accum == 0
+                idx = perm[i * M : (i + 1) * M] if perm is not None else slice(i * M, (i + 1) * M)
+                mb_views = _index_views(views, idx)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=hp.enable_amp):
+                    features = model(mb_views)
+                    values = model.value_function()
+                packed = dist_cls(features, model)._packed()  # [M, P], differentiable
+                vflat = values.float().reshape(-1)
+                P = packed.shape[1]
+                d_feat, d_val = torch.empty_like(packed), torch.empty_like(vflat)
+                acts = actions[idx].contiguous()
+                rc = lib.rl8_ppo_losses_direct(
+                    kind, _lib.ptr(packed.detach()), P, _lib.ptr(vflat.detach().contiguous()), _lib.ptr(acts),
+                    _lib.ptr(logp_old[idx].contiguous()), _lib.ptr(advantages[idx].contiguous()),
+                    _lib.ptr(returns[idx].contiguous()), M, float(M * world), ppo,
+                    ctypes.c_void_p(sums.data_ptr() + 40 * k), _lib.ptr(d_feat), _lib.ptr(d_val), _lib.stream(),
+                )
+                _lib.check(rc, "rl8_ppo_losses_direct")
+                launches += 1
+                applied.append(step_this_batch)
+                k += 1
+                if hp.target_kl_div is not None:
+                    row = sums[k - 1].clone()
+                    if world > 1:
+                        dist.all_reduce(row)
+                    if float(row[3] / row[4]) > 1.5 * hp.target_kl_div:
+                        stop_early = True
+                        self.optimizer.zero_grad(set_to_none=True)
+                        break
+                torch.autograd.backward([packed, vflat], [d_feat, d_val])
+                if step_this_batch:
+                    if world > 1:
+                        for p in params:
+                            if p.grad is not None:
+                                dist.all_reduce(p.grad)  # already carries 1 / (M * world)
+                    if self._on_grads is not None:
+                        self._on_grads({n: p.grad for n, p in model.named_parameters() if p.grad is not None})
+                    torch.nn.utils.clip_grad_norm_(params, hp.max_grad_norm)
+                    self.optimizer.step()
+                    self.optimizer.zero_grad(set_to_none=True)
+                    self._opt_steps += 1
+            if stop_early:
+                break
+        return self._finish_step(start, launches, k, applied, accum, entropy_coeff)
 
     # -- pieces of step() the recurrent algorithm overrides --------------------------------------
     def _batch_struct(self) -> _lib.Batch:

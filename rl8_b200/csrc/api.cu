@@ -185,8 +185,8 @@ extern "C" int rl8_ppo_minibatch(const rl8_model* model, const rl8_model* grads,
   return RL8_ERR_ARG;
 }
 
-extern "C" int rl8_ppo_losses(int dist_kind, const float* features, int32_t P, const float* values,
-                              const void* actions, const float* logp_old, const float* advantages,
+static int ppo_losses_impl(int log_std_direct, int dist_kind, const float* features, int32_t P, const float* values,
+                           const void* actions, const float* logp_old, const float* advantages,
                               const float* returns, int64_t B, double mean_denominator,
                               const rl8_ppo_hparams* hp, double* loss_sums, float* d_features,
                               float* d_values, rl8_stream_t stream) {
@@ -204,5 +204,24 @@ extern "C" int rl8_ppo_losses(int dist_kind, const float* features, int32_t P, c
   la.inv_denom = (float)((double)hp->loss_scale / mean_denominator);
   la.dout_pi = d_features, la.dout_vf = d_values;
   la.gb3_pi = nullptr, la.gb3_vf = nullptr, la.sums = loss_sums;
+  la.log_std_direct = log_std_direct;
   return launch_ppo_loss(la, (cudaStream_t)stream);
+}
+
+extern "C" int rl8_ppo_losses(int dist_kind, const float* features, int32_t P, const float* values,
+                              const void* actions, const float* logp_old, const float* advantages,
+                              const float* returns, int64_t B, double mean_denominator,
+                              const rl8_ppo_hparams* hp, double* loss_sums, float* d_features,
+                              float* d_values, rl8_stream_t stream) {
+  return ppo_losses_impl(0, dist_kind, features, P, values, actions, logp_old, advantages, returns, B,
+                         mean_denominator, hp, loss_sums, d_features, d_values, stream);
+}
+
+extern "C" int rl8_ppo_losses_direct(int dist_kind, const float* features, int32_t P, const float* values,
+                                     const void* actions, const float* logp_old, const float* advantages,
+                                     const float* returns, int64_t B, double mean_denominator,
+                                     const rl8_ppo_hparams* hp, double* loss_sums, float* d_features,
+                                     float* d_values, rl8_stream_t stream) {
+  return ppo_losses_impl(1, dist_kind, features, P, values, actions, logp_old, advantages, returns, B,
+                         mean_denominator, hp, loss_sums, d_features, d_values, stream);
 }

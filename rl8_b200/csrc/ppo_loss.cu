@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(LossArgs a) {
     const float act = discrete ? (float)((const long long*)a.actions)[idx]
                                : ((const float*)a.actions)[idx];
     RowLoss L = ppo_row<P>(a.dist_kind, o, a.out_vf[r], act, a.logp_old[idx], a.advantages[idx],
-                           a.returns[idx], a.hp, a.inv_denom, d_o, &d_v);
+                           a.returns[idx], a.hp, a.inv_denom, d_o, &d_v, !a.log_std_direct);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       if (a.dout_pi) a.dout_pi[r * P + k] = d_o[k];

@@ -26,6 +26,7 @@ struct LossArgs {
   float* gb3_pi;       // [P]  += sum_r dout_pi
   float* gb3_vf;       // [1]
   double* sums;        // [5] += entropy, policy, vf, kl, count
+  int log_std_direct;  // continuous head: dout_pi[:, 1] is d/d(log_std) itself, not d/d(pre-tanh output)
 };
 
 int launch_ppo_loss(const LossArgs& a, cudaStream_t st);

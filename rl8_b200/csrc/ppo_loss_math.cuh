@@ -70,7 +70,7 @@ template <int P>
 __device__ __forceinline__ void ppo_policy_row(int dist_kind, const float* o, float act,
                                                float logp_old, float adv,
                                                const rl8_ppo_hparams& hp, float inv_denom,
-                                               float* d_o, RowLoss& L) {
+                                               float* d_o, RowLoss& L, bool tanh_chain = true) {
   float logp_new, dratio;
   const bool want_ent = hp.entropy_coeff != 0.0f;
   L.entropy = 0.0f;
@@ -121,7 +121,8 @@ __device__ __forceinline__ void ppo_policy_row(int dist_kind, const float* o, fl
       dls += -inv_denom * hp.entropy_coeff;
     }
     d_o[0] = dmean;
-    d_o[1] = dls * (1.0f - ls * ls);  // log_std = tanh(raw)
+    // default models: log_std = tanh(raw) and the gradient is w.r.t. raw; custom models get it w.r.t. log_std
+    d_o[1] = tanh_chain ? dls * (1.0f - ls * ls) : dls;
 #pragma unroll
     for (int k = 2; k < P; ++k) d_o[k] = 0.0f;
   }
@@ -139,9 +140,9 @@ template <int P>
 __device__ __forceinline__ RowLoss ppo_row(int dist_kind, const float* o, float v, float act,
                                            float logp_old, float adv, float ret,
                                            const rl8_ppo_hparams& hp, float inv_denom, float* d_o,
-                                           float* d_v) {
+                                           float* d_v, bool tanh_chain = true) {
   RowLoss L;
-  ppo_policy_row<P>(dist_kind, o, act, logp_old, adv, hp, inv_denom, d_o, L);
+  ppo_policy_row<P>(dist_kind, o, act, logp_old, adv, hp, inv_denom, d_o, L, tanh_chain);
   ppo_value_row(v, ret, hp, inv_denom, d_v, L);
   return L;
 }

@@ -41,6 +41,56 @@ def _small_head(in_dim: int, out_dim: int) -> nn.Linear:
     return head
 
 
+class GenericModel(nn.Module):
+    """User-defined feedforward model: the reference's ``Model`` plug-in point
+    (src/rl8/models/_feedforward.py:19-231).
+
+    Subclass it like the reference's ``Model``: build torch modules in ``__init__``, return the
+    distribution's features from ``forward(batch)`` (``{"logits": [B, 1, A]}`` for
+    ``Categorical``, ``{"mean": [B, 1], "log_std": [B, 1]}`` for ``Normal`` /
+    ``SquashedNormal``) and the value estimate ``[B, 1]`` from ``value_function()``.
+    ``view_requirements`` maps batch keys to :class:`~rl8_b200.views.ViewRequirement` (default: the
+    most recent observation).  Such a model runs through torch (autograd included) on the GPU while
+    everything around it -- env step, sampling, log-probabilities, GAE, the PPO losses and their
+    gradients w.r.t. the model outputs -- stays on this library's kernels; any ``torch.optim``
+    optimizer can drive it.  The default models below take the fully fused path instead.
+    """
+
+    def __init__(self, observation_spec: TensorSpec, action_spec: TensorSpec, /, **config: Any) -> None:
+        super().__init__()
+        from .views import ViewRequirement
+
+        self.observation_spec = observation_spec
+        self.action_spec = action_spec
+        self.config = config
+        self.view_requirements = {DataKeys.OBS: ViewRequirement(shift=0)}
+
+    def apply_view_requirements(self, batch: Any, /, *, kind: str = "last") -> dict[str, Any]:
+        """``{key: view}`` of ``batch [B, T, ...]``: ``kind="last"`` -> ``[B, ...]`` (sampling),
+        ``kind="all"`` -> ``[B * T, ...]`` (training); src/rl8/models/_feedforward.py:58-101."""
+        out = {}
+        for key, vr in self.view_requirements.items():
+            out[key] = vr.apply_all(key, batch) if kind == "all" else vr.apply_last(key, batch)
+        return out
+
+    @property
+    def drop_size(self) -> int:
+        return next(iter(vr.drop_size for vr in self.view_requirements.values()))
+
+    def validate_view_requirements(self) -> None:
+        drops = {k: vr.drop_size for k, vr in self.view_requirements.items()}
+        if len(set(drops.values())) > 1:
+            raise RuntimeError(
+                f"{self} view requirements with drop sizes {drops} result in an ambiguous batch size."
+            )
+
+    def forward(self, batch: Any, /) -> dict[str, torch.Tensor]:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def value_function(self) -> torch.Tensor:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
 class Model(nn.Module):
     """Base of the fused default models."""
 
@@ -225,4 +275,4 @@ class DefaultContinuousModel(Model):
         return {"mean": head[:, 0:1].contiguous(), "log_std": head[:, 1:2].contiguous()}
 
 
-__all__ = ["Model", "DefaultDiscreteModel", "DefaultContinuousModel", "DataKeys"]
+__all__ = ["GenericModel", "Model", "DefaultDiscreteModel", "DefaultContinuousModel", "DataKeys"]

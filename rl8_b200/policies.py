@@ -9,7 +9,7 @@ import torch
 from . import _lib
 from .data import DataKeys, Device
 from .distributions import Distribution
-from .models import Model
+from .models import GenericModel, Model
 from .specs import TensorSpec
 
 ViewKind = Literal["last", "all"]
@@ -46,11 +46,20 @@ class Policy:
         if model is None:
             model_cls = model_cls or Model.default_model_cls(observation_spec, action_spec)
             model = model_cls(observation_spec, action_spec, **self.model_config)
-        if not isinstance(model, Model):
-            raise NotImplementedError(
-                "custom model classes are outside the fused hot path; use the default models"
+        if isinstance(model, Model):
+            self.model = model.flatten_(device)
+        elif isinstance(model, GenericModel):
+            # a user-defined torch model: forward / backward through torch on the GPU, everything
+            # around it on this library's kernels (see GenericModel)
+            model.validate_view_requirements()
+            self.model = model.to(device)
+        else:
+            raise TypeError(
+                "`model` / `model_cls` must derive from rl8_b200.models.GenericModel (user-defined"
+                " torch models) or be one of the default models"
             )
-        self.model = model.flatten_(device)
+        #: ``True``: default model on the fully fused kernels; ``False``: user-defined torch model.
+        self.fused = isinstance(model, Model)
         self.distribution_cls = distribution_cls or Distribution.default_dist_cls(action_spec)
         if not (isinstance(self.distribution_cls, type) and issubclass(self.distribution_cls, Distribution)):
             raise NotImplementedError("custom distributions must subclass rl8_b200 distributions")
@@ -109,6 +118,12 @@ class Policy:
         ``kind="all"`` flattens ``B`` and ``T`` (row ``b * T + t``), as the shift-0 view
         requirements of the default models do (src/rl8/views.py:408-445).
         """
+        if not self.fused:
+            return self._sample_generic(
+                batch, kind=kind, deterministic=deterministic, inplace=inplace, requires_grad=requires_grad,
+                return_actions=return_actions, return_logp=return_logp, return_values=return_values,
+                return_views=return_views,
+            )
         if requires_grad:
             raise NotImplementedError(
                 "autograd through Policy.sample is not part of the fused path; gradients are"
@@ -135,4 +150,33 @@ class Policy:
             out[DataKeys.VALUES] = self.model._value
         if return_views:
             out[DataKeys.VIEWS] = {DataKeys.OBS: obs}
+        return out
+
+    def _sample_generic(
+        self, batch: Mapping[str, Any], /, *, kind: ViewKind, deterministic: bool, inplace: bool,
+        requires_grad: bool, return_actions: bool, return_logp: bool, return_values: bool,
+        return_views: bool,
+    ) -> dict[str, Any]:
+        """``sample`` for a user-defined torch model (src/rl8/policies/_feedforward.py:66-176): views ->
+        ``model(views)`` (with autograd when ``requires_grad``) -> this library's sampling / log-prob
+        kernels on the returned features."""
+        if DataKeys.VIEWS in batch:
+            views = batch[DataKeys.VIEWS]
+        else:
+            views = self.model.apply_view_requirements(batch, kind=kind)
+        self.model.train(requires_grad)
+        with torch.set_grad_enabled(requires_grad):
+            features = self.model(views)
+            out: dict[str, Any] = dict(batch) if inplace else {}
+            out[DataKeys.FEATURES] = features
+            if return_values:
+                out[DataKeys.VALUES] = self.model.value_function()
+        if return_actions:
+            dist = self.distribution_cls({k: v.detach() for k, v in features.items()}, self.model)
+            actions = dist.deterministic_sample() if deterministic else dist.sample()
+            out[DataKeys.ACTIONS] = actions
+            if return_logp:
+                out[DataKeys.LOGP] = dist.logp(actions)
+        if return_views:
+            out[DataKeys.VIEWS] = views
         return out

@@ -388,6 +388,7 @@ class RecurrentAlgorithm(Algorithm):
             distribution_cls=config.distribution_cls,
             device=device,
         )
+        self._fused_model = True  # the default recurrent models are always on the kernels
         # enable_amp: the 256 x 1024 LSTM contractions in bf16 on tcgen05 (fp32 accumulate)
         self.policy.precision = _lib.PREC_BF16 if config.enable_amp else _lib.PREC_FP32
         self.buffer_spec = Composite(

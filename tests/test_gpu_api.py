@@ -234,3 +234,129 @@ def test_state_dicts_are_interchangeable_with_the_reference() -> None:
         flat = model.flat_params
         n_params = sum(v.numel() for v in sd.values())
         assert int((flat == 0.25).sum()) == n_params, name
+
+
+def _custom_discrete_model_cls():
+    """A user-defined model with the default architecture, written the way a reference user would
+    (src/rl8/models/_feedforward.py:313-383) on top of GenericModel."""
+    import torch.nn as nn
+
+    from rl8_b200.models import GenericModel
+
+    class MyModel(GenericModel):
+        def __init__(self, observation_spec, action_spec, /, hidden: int = 256) -> None:  # noqa: ANN001
+            super().__init__(observation_spec, action_spec, hidden=hidden)
+            d, a = observation_spec.shape[0], action_spec.space.n
+            self.pi = nn.Sequential(nn.Linear(d, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                                    nn.Linear(hidden, a))
+            self.vf = nn.Sequential(nn.Linear(d, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                                    nn.Linear(hidden, 1))
+            self._obs = None
+
+        def forward(self, batch):  # noqa: ANN001, ANN201
+            self._obs = batch["obs"]
+            return {"logits": self.pi(self._obs).unsqueeze(1)}
+
+        def value_function(self):  # noqa: ANN201
+            return self.vf(self._obs)
+
+    return MyModel
+
+
+def test_user_defined_model_matches_the_fused_default_model() -> None:
+    """The reference's Model plug-in point: a user-written torch model with the default architecture and the
+    default model's weights goes through torch autograd + rl8_ppo_losses_direct and must reproduce the fully
+    fused fp32 path: identical actions, rollout values / log-probs to 1e-5, update statistics and the
+    parameters after one Adam step to 1e-4."""
+    import rl8_b200.env as E
+    from rl8_b200 import AlgorithmConfig
+    from rl8_b200 import distributions as Dm
+
+    N, T = 256, 8
+    torch.manual_seed(3)
+    noise = torch.empty(T, N, 3).exponential_(1)
+    state0 = torch.randn(4, N) * 0.05
+
+    class InjDist(Dm.Categorical):
+        @classmethod
+        def draw_noise(cls, steps, num, width, device):  # noqa: ANN001, ANN206
+            if steps != T:
+                return super().draw_noise(steps, num, width, device)
+            return noise.to(device)
+
+    class InjEnv(E.CartPole):
+        def reset(self, *, config=None):  # noqa: ANN001, ANN202
+            super().reset(config=config)
+            return self.set_state(state0.to("cuda"))
+
+    kw = dict(num_envs=N, horizon=T, distribution_cls=InjDist, num_sgd_iters=2, sgd_minibatch_size=512,
+              shuffle_minibatches=False, entropy_coeff=0.01)
+    fused = AlgorithmConfig(**kw).build(InjEnv)
+    custom = AlgorithmConfig(model_cls=_custom_discrete_model_cls(), **kw).build(InjEnv)
+    assert not custom.policy.fused and fused.policy.fused
+    sd = fused.policy.model.state_dict()
+    mapping = {"feature_model.0.0": "pi.0", "feature_model.0.2": "pi.2", "feature_model.2": "pi.4",
+               "vf_model.0.0": "vf.0", "vf_model.0.2": "vf.2", "vf_model.2": "vf.4"}
+    with torch.no_grad():
+        own = dict(custom.policy.model.named_parameters())
+        for src, dst in mapping.items():
+            own[f"{dst}.weight"].copy_(sd[f"{src}.weight"])
+            own[f"{dst}.bias"].copy_(sd[f"{src}.bias"])
+    cf, cc = fused.collect(), custom.collect()
+    assert torch.equal(fused.buffer["actions"], custom.buffer["actions"])
+    for k in ("obs", "rewards", "logp", "values"):
+        torch.testing.assert_close(custom.buffer[k], fused.buffer[k], rtol=1e-5, atol=2e-6, msg=k)
+    assert cc["returns/mean"] == pytest.approx(cf["returns/mean"], rel=1e-6)
+    sf, sc = fused.step(), custom.step()
+    for k in ("losses/policy", "losses/vf", "losses/entropy", "losses/total", "monitors/kl_div"):
+        assert sc[k] == pytest.approx(sf[k], rel=1e-4, abs=2e-6), k
+    sd2 = fused.policy.model.state_dict()
+    own = dict(custom.policy.model.named_parameters())
+    for src, dst in mapping.items():
+        torch.testing.assert_close(own[f"{dst}.weight"], sd2[f"{src}.weight"], rtol=1e-4, atol=2e-4)
+
+
+def test_user_defined_model_with_shifted_views_and_rmsprop_learns() -> None:
+    """A custom model over a padded rolling window of the last 3 observations (ViewRequirement(shift=2)),
+    trained with torch.optim.RMSprop -- neither exists on the fused path -- improves the dummy env's returns."""
+    import torch.nn as nn
+    import torch.optim as optim
+
+    import rl8_b200.env as E
+    from rl8_b200 import AlgorithmConfig, Trainer
+    from rl8_b200.models import GenericModel
+    from rl8_b200.views import ViewRequirement
+
+    class WindowModel(GenericModel):
+        def __init__(self, observation_spec, action_spec, /) -> None:  # noqa: ANN001
+            super().__init__(observation_spec, action_spec)
+            self.view_requirements["obs"] = ViewRequirement(shift=2, method="padded_rolling_window")
+            d = observation_spec.shape[0] * 3
+            self.body = nn.Sequential(nn.Linear(d, 64), nn.Tanh())
+            self.pi = nn.Linear(64, action_spec.space.n)
+            self.vf = nn.Linear(64, 1)
+            self._z = None
+
+        def forward(self, batch):  # noqa: ANN001, ANN201
+            item = batch["obs"]
+            x = item["inputs"].masked_fill(item["padding_mask"].unsqueeze(-1), 0.0) / 10.0
+            self._z = self.body(x.flatten(1))
+            return {"logits": self.pi(self._z).unsqueeze(1)}
+
+        def value_function(self):  # noqa: ANN201
+            return self.vf(self._z)
+
+    torch.manual_seed(0)
+    algo = AlgorithmConfig(num_envs=512, horizon=16, model_cls=WindowModel, optimizer_cls=optim.RMSprop,
+                           optimizer_config={"lr": 1e-3}, sgd_minibatch_size=2048).build(
+        E.DiscreteDummyEnv
+    )
+    assert isinstance(algo.optimizer, optim.RMSprop)
+    trainer = Trainer(algo)
+    first = trainer.step(env_config={"bounds": 4.0})["returns/mean"]
+    last = first
+    for _ in range(40):
+        s = trainer.step(env_config={"bounds": 4.0})
+        last = s["returns/mean"]
+        assert all(v == v for v in s.values() if isinstance(v, float))
+    assert last > first + 1.0, (first, last)
