@@ -327,8 +327,10 @@ def run_ours(a: argparse.Namespace) -> None:
         algo.step()
         return algo.last_launches["collect"] + algo.last_launches["step"]
 
-    with ClockSampler(local) as clocks:
-        ms, launches = timed(core_step, a.steps, a.warmup)
+    # clocks / throttle reasons are sampled while BOTH timed legs run (one nvidia-smi query takes ~0.2 s)
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    ms, launches = timed(core_step, a.steps, a.warmup)
     value = N * T * world * a.steps / (ms / 1e3)
     core_per_step = list(per_step)
 
@@ -377,6 +379,7 @@ def run_ours(a: argparse.Namespace) -> None:
         return algo2.last_launches["collect"] + algo2.last_launches["step"]
 
     ms2, _ = timed(e2e_step, a.steps, 3)
+    clocks.__exit__(None, None, None)
     e2e_value = N * T * world * a.steps / (ms2 / 1e3)
     e2e_per_step = list(per_step)
     h2d = host_noise.numel() * 4
