@@ -186,6 +186,130 @@ __global__ void __launch_bounds__(kGThreads, 2) tc_gemm_kernel(GemmArgs g) {
   if (tid < 32) tmem_dealloc(tmem, kGN);
 }
 
+// ---- B-resident variant: C[M][N] = A[M][256] * B[N][256]^T, both K-major, store --------------------------------
+// (the LSTM gate pre-activations h W_hh^T: M = rows, N = 4H = 1024, K = H = 256).  A CTA keeps ONE 256-column
+// block of B in shared memory (128 KB bf16, converted once) and walks 128-row tiles of A: per tile it converts
+// 128 x 256 of A in two K halves (each half is multiplied as soon as it is staged), accumulates in one of two
+// 256-column TMEM buffers and streams the PREVIOUS tile's accumulator to global memory under the MMAs of the
+// current one.  Per tile: 128 KB of A read, 128 KB of C written, 2 056 tensor cycles.
+constexpr int kRK = 256;         // K of the resident variant
+constexpr int kRThreads = 512;
+struct SmemGemmR {
+  uint8_t b[kGN * kRK * 2];      // 131072  B block, K-major tile of 256 rows
+  uint8_t a[2][kGM * 128 * 2];   //  65536  A tile in two K halves of 128 (K-major tiles of 128 rows, 16 chunks)
+  uint64_t bar_h[2], bar_acc[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kRThreads, 1) tc_gemm_bres_kernel(GemmArgs g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemGemmR& s = *reinterpret_cast<SmemGemmR*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = (int)(blockIdx.x % g.ntn);            // column block of this CTA
+  const int64_t n0 = (int64_t)nb * kGN;
+  const int64_t mt0 = blockIdx.x / g.ntn, mstride = gridDim.x / g.ntn;
+  const int64_t mtiles = (g.M + kGM - 1) / kGM;
+  if (tid == 0) {
+    mbar_init(&s.bar_h[0], 1), mbar_init(&s.bar_h[1], 1);
+    mbar_init(&s.bar_acc[0], 1), mbar_init(&s.bar_acc[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
+  // B block: 256 rows x 32 chunks of 8 k
+  for (int e0 = tid; e0 < kGN * (kRK / 8); e0 += kGBatch * kRThreads) {
+    Chunk8 c[kGBatch];
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kRThreads, row = e >> 5, kc = e & 31;
+      c[b] = load8(g.B + (n0 + row) * g.ldb + kc * 8, n0 + row < g.N, 8);
+    }
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kRThreads, row = e >> 5, kc = e & 31;
+      *reinterpret_cast<uint4*>(s.b + chunk_offset<kGN>(row, kc)) = pack8(c[b]);
+    }
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+
+  // K half h of the A tile at rows m0: 128 rows x 16 chunks = 2048 tasks, 4 per thread, all loads in flight
+  auto stage_a = [&](int h, int64_t m0) {
+    Chunk8 c[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int e = tid + b * kRThreads, row = e >> 4, kc = e & 15;
+      c[b] = load8(g.A + (m0 + row) * g.lda + h * 128 + kc * 8, m0 + row < g.M, 8);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int e = tid + b * kRThreads, row = e >> 4, kc = e & 15;
+      *reinterpret_cast<uint4*>(s.a[h] + chunk_offset<kGM>(row, kc)) = pack8(c[b]);
+    }
+  };
+  // accumulator buf -> C rows of tile mt: warp (q = warp & 3, part = warp >> 2) -> rows 32q + lane, 64 columns
+  auto epilogue = [&](int64_t mt, int buf) {
+    const int q = warp & 3, part = warp >> 2;
+    const int64_t m = mt * kGM + q * 32 + lane;
+    const uint32_t base = tmem + (uint32_t)(buf * kGN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 64);
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      float v[32];
+      tmem_ld32(base + (uint32_t)(j * 32), v);
+      if (m < g.M) {
+        float* dst = g.C + m * g.ldc + n0 + part * 64 + j * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          if (n0 + part * 64 + j * 32 + e < g.N)
+            *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
+    }
+  };
+
+  int it = 0;
+  int64_t prev = -1;
+  for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
+    const int buf = it & 1;
+    const uint32_t acc = tmem + (uint32_t)(buf * kGN);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (it > 0) {  // the MMAs of the previous tile have read this K half
+        mbar_wait(&s.bar_h[h], (uint32_t)((it - 1) & 1));
+        fence_after_sync();
+      }
+      stage_a(h, mt * kGM);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (cta_issuer()) {
+        fence_after_sync();
+        // 8 K steps of this half against the resident block: B advances 8 chunk groups of 256 rows per half
+        issue_gemm(acc, smem_u32(s.a[h]), kGM, false, smem_u32(s.b) + h * 16 * (kGN * 16), kGN, false, kGM, kGN, 128,
+                   h > 0);
+        mma_commit(&s.bar_h[h]);
+        if (h == 1) mma_commit(&s.bar_acc[buf]);
+      }
+      if (h == 0 && prev >= 0) {  // the previous tile's accumulator: its MMAs were committed one tile ago
+        mbar_wait(&s.bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));
+        fence_after_sync();
+        epilogue(prev, buf ^ 1);
+        fence_before_sync();  // its TMEM reads precede the next tile's MMAs into that buffer (barrier below)
+      }
+    }
+    prev = mt;
+  }
+  if (prev >= 0) {
+    mbar_wait(&s.bar_acc[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+    fence_after_sync();
+    epilogue(prev, (it - 1) & 1);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
 // Same contract as launch_sgemm (mlp_fp32.cuh) for EPI_STORE / EPI_ATOMIC, bf16 operands on tcgen05.
 // Requires 16-byte aligned operands, lda / ldb / ldc % 4 == 0 and N % 4 == 0 (the vector epilogue).
 int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const float* B, float* C, int64_t M,
@@ -198,6 +322,22 @@ int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const 
   if (splits < 1) splits = 1;
   GemmArgs g;
   g.A = A, g.B = B, g.C = C, g.M = M, g.N = N, g.K = K, g.lda = lda, g.ldb = ldb, g.ldc = ldc;
+  if (a_kmajor && b_kmajor && epi == EPI_STORE && K == kRK && M >= 4 * kGM) {
+    // the LSTM gate GEMM: one 256-column block of B resident per CTA, rows streamed
+    g.ntn = (unsigned)ceil_div(N, kGN);
+    g.kchunk = K;
+    const int64_t mtiles = ceil_div(M, kGM);
+    int64_t per_block = kNumSMs / g.ntn;  // CTAs per column block
+    if (per_block < 1) per_block = 1;
+    if (per_block > mtiles) per_block = mtiles;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(tc_gemm_bres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemGemmR));
+      attr = true;
+    }
+    tc_gemm_bres_kernel<<<(unsigned)(per_block * g.ntn), kRThreads, sizeof(SmemGemmR), st>>>(g);
+    return check_launch("tc_gemm_bres");
+  }
   g.kchunk = round_up(ceil_div(K, splits), kGK);
   splits = (int)ceil_div(K, g.kchunk);
   g.ntn = (unsigned)ceil_div(N, kGN);

@@ -310,6 +310,8 @@ def test_bf16_training_improves_returns() -> None:
     "a_k,b_k,M,N,K,splits",
     [
         (1, 1, 300, 1024, 256, 1),    # gates = h W_hh^T            (ragged M)
+        (1, 1, 1000, 1024, 256, 1),   # ... at M >= 512: the B-resident variant (ragged last tile)
+        (1, 1, 40000, 1000, 256, 1),  # ... many tiles per CTA, ragged N
         (1, 0, 257, 256, 1024, 1),    # dh = dG W_hh
         (0, 0, 1024, 256, 1000, 7),   # gW_hh += dG^T h             (split-K over ragged K)
         (1, 1, 128, 256, 64, 1),
