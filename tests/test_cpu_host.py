@@ -175,3 +175,31 @@ def test_bench_reference_arm_contract() -> None:
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("CartPole")
+
+
+def test_generic_model_host_logic() -> None:
+    """GenericModel (the reference's Model plug-in point, src/rl8/models/_feedforward.py:19-231): default view
+    requirement, drop size, ambiguous drop sizes rejected; no device needed."""
+    from rl8_b200.models import GenericModel
+    from rl8_b200.specs import Categorical, Unbounded
+    from rl8_b200.views import ViewRequirement
+
+    class M(GenericModel):
+        def forward(self, batch):  # noqa: ANN001, ANN201
+            return {}
+
+    m = M(Unbounded(3), Categorical(2, shape=(1,)), width=7)
+    assert m.config == {"width": 7}
+    assert list(m.view_requirements) == ["obs"] and m.view_requirements["obs"].shift == 0
+    assert m.drop_size == 0
+    m.validate_view_requirements()
+    m.view_requirements["obs"] = ViewRequirement(shift=2, method="rolling_window")
+    assert m.drop_size == 2
+    m.view_requirements["other"] = ViewRequirement(shift=1, method="padded_rolling_window")
+    with pytest.raises(RuntimeError, match="ambiguous"):
+        m.validate_view_requirements()
+    # shift-0 views are pure torch indexing: they work on CPU tensors too
+    m.view_requirements = {"obs": ViewRequirement(shift=0)}
+    x = torch.arange(24.0).reshape(2, 4, 3)
+    assert torch.equal(m.apply_view_requirements({"obs": x}, kind="last")["obs"], x[:, -1])
+    assert torch.equal(m.apply_view_requirements({"obs": x}, kind="all")["obs"], x.reshape(8, 3))
