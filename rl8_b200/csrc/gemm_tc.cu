@@ -310,6 +310,219 @@ __global__ void __launch_bounds__(kRThreads, 1) tc_gemm_bres_kernel(GemmArgs g) 
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+// ---- fused LSTM step: gates = h W_hh^T on tcgen05 with the cell in the epilogue -----------------------------
+// (nn.LSTM's forward cell, src/rl8/models/_recurrent.py:259-341; restated in oracle/recurrent_oracle.py:lstm_cell)
+// Same structure as the B-resident GEMM, but a CTA's 256 accumulator columns are the FOUR gates of 64 hidden
+// units (column g * 64 + u <-> W_hh row g * 256 + 64 nb + u), so the epilogue owns everything a unit needs:
+//   pre_g = (b_ih + x W_ih^T) + (acc + b_hh);  c' = sig(f) c + sig(i) tanh(g);  h' = sig(o) tanh(c')
+// and writes the gate activations (kept for the backward pass), c' and h' -- the 4 KB / row of pre-activations
+// never go to HBM and the separate cell kernel disappears.
+constexpr int kCellD = 8;  // widest observation
+struct SmemLstm {
+  uint8_t b[kGN * kRK * 2];      // 131072  W_hh block (4 gates x 64 units), K-major tile of 256 rows
+  uint8_t a[2][kGM * 128 * 2];   //  65536  h tile in two K halves
+  float wt[4][kCellD][64];       //   8192  W_ih of this block's units, [gate][d][unit]
+  float bi[4][64], bh[4][64];    //   2048
+  uint64_t bar_h[2], bar_acc[2];
+  uint32_t tmem_base;
+};
+struct LstmCellArgs {
+  const float *h_in, *w_hh, *w_ih, *b_ih, *b_hh, *c_prev;
+  float *act, *c_out, *h_out;  // act may be null (rollout)
+  RowMap xmap;
+  int64_t rows;
+  int D;
+};
+
+// SFU-based gate non-linearities (2-ulp exp, fast reciprocal): this is the bf16 path, whose gate pre-activations
+// already carry bf16 operand rounding; the fp32 path's cell kernel keeps the exact functions
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+  return __fdividef(e - 1.0f, e + 1.0f);
+}
+
+__global__ void __launch_bounds__(kRThreads, 1) tc_lstm_cell_kernel(LstmCellArgs g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemLstm& s = *reinterpret_cast<SmemLstm*>(smem_raw);
+  constexpr int LH = 256;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = (int)(blockIdx.x & 3);  // unit block: units [64 nb, 64 nb + 64)
+  const int64_t mt0 = blockIdx.x >> 2, mstride = gridDim.x >> 2;
+  const int64_t mtiles = (g.rows + kGM - 1) / kGM;
+  if (tid == 0) {
+    mbar_init(&s.bar_h[0], 1), mbar_init(&s.bar_h[1], 1);
+    mbar_init(&s.bar_acc[0], 1), mbar_init(&s.bar_acc[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
+  // W_hh block: tile row c = gate * 64 + u  <-  W_hh row gate * 256 + 64 nb + u
+  for (int e0 = tid; e0 < kGN * (kRK / 8); e0 += kGBatch * kRThreads) {
+    Chunk8 c[kGBatch];
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kRThreads, row = e >> 5, kc = e & 31;
+      const int src = (row >> 6) * LH + nb * 64 + (row & 63);
+      c[b] = load8(g.w_hh + (int64_t)src * LH + kc * 8, true, 8);
+    }
+#pragma unroll
+    for (int b = 0; b < kGBatch; ++b) {
+      const int e = e0 + b * kRThreads, row = e >> 5, kc = e & 31;
+      *reinterpret_cast<uint4*>(s.b + chunk_offset<kGN>(row, kc)) = pack8(c[b]);
+    }
+  }
+  for (int i = tid; i < 4 * kCellD * 64; i += kRThreads) {
+    const int gate = i / (kCellD * 64), d = (i / 64) % kCellD, u = i % 64;
+    s.wt[gate][d][u] = d < g.D ? g.w_ih[(int64_t)(gate * LH + nb * 64 + u) * g.D + d] : 0.0f;
+  }
+  for (int i = tid; i < 4 * 64; i += kRThreads) {
+    const int gate = i >> 6, u = i & 63;
+    s.bi[gate][u] = g.b_ih[gate * LH + nb * 64 + u];
+    s.bh[gate][u] = g.b_hh[gate * LH + nb * 64 + u];
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+
+  auto stage_a = [&](int h, int64_t m0) {
+    Chunk8 c[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int e = tid + b * kRThreads, row = e >> 4, kc = e & 15;
+      c[b] = load8(g.h_in + (m0 + row) * LH + h * 128 + kc * 8, m0 + row < g.rows, 8);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int e = tid + b * kRThreads, row = e >> 4, kc = e & 15;
+      *reinterpret_cast<uint4*>(s.a[h] + chunk_offset<kGM>(row, kc)) = pack8(c[b]);
+    }
+  };
+  // the cell of tile mt from accumulator buf: warp (q = warp & 3, part = warp >> 2) -> row 32q + lane, units
+  // [16 part, 16 part + 16) of this block, in two groups of 8 units
+  auto epilogue = [&](int64_t mt, int buf) {
+    const int q = warp & 3, part = warp >> 2;
+    const int64_t r = mt * kGM + q * 32 + lane;
+    const uint32_t base = tmem + (uint32_t)(buf * kGN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16);
+    const bool live = r < g.rows;
+    int64_t xo = 0;
+    const int64_t ds = g.xmap.dstride();
+    float x[kCellD];
+    if (live) xo = g.xmap.offset(r);
+#pragma unroll
+    for (int d = 0; d < kCellD; ++d) x[d] = (live && d < g.D) ? g.xmap.obs[xo + d * ds] : 0.0f;
+    // two groups of 8 units: 32 accumulator values live at a time
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int u0 = part * 16 + half * 8;  // first unit of the group inside the block
+      const int j0 = nb * 64 + u0;          // ... and in the layer
+      float pre[4][8];
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) tmem_ld8(base + (uint32_t)(gate * 64 + half * 8), pre[gate]);
+      if (!live) continue;
+      float cp[8];
+      {
+        const float4 c0 = *reinterpret_cast<const float4*>(g.c_prev + r * LH + j0);
+        const float4 c1 = *reinterpret_cast<const float4*>(g.c_prev + r * LH + j0 + 4);
+        cp[0] = c0.x, cp[1] = c0.y, cp[2] = c0.z, cp[3] = c0.w, cp[4] = c1.x, cp[5] = c1.y, cp[6] = c1.z, cp[7] = c1.w;
+      }
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float a = s.bi[gate][u0 + u];
+#pragma unroll
+          for (int d = 0; d < kCellD; ++d)
+            if (d < g.D) a = fmaf(x[d], s.wt[gate][d][u0 + u], a);
+          pre[gate][u] = a + (pre[gate][u] + s.bh[gate][u0 + u]);
+        }
+      }
+      float cn[8], hn[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float ig = sigmoid_fast(pre[0][u]), fg = sigmoid_fast(pre[1][u]);
+        const float gg = tanh_fast(pre[2][u]), og = sigmoid_fast(pre[3][u]);
+        pre[0][u] = ig, pre[1][u] = fg, pre[2][u] = gg, pre[3][u] = og;
+        cn[u] = fg * cp[u] + ig * gg;
+        hn[u] = og * tanh_fast(cn[u]);
+      }
+      if (g.act) {
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+          float* dst = g.act + r * 4 * LH + gate * LH + j0;
+          *reinterpret_cast<float4*>(dst) = make_float4(pre[gate][0], pre[gate][1], pre[gate][2], pre[gate][3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(pre[gate][4], pre[gate][5], pre[gate][6], pre[gate][7]);
+        }
+      }
+      *reinterpret_cast<float4*>(g.c_out + r * LH + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      *reinterpret_cast<float4*>(g.c_out + r * LH + j0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+      *reinterpret_cast<float4*>(g.h_out + r * LH + j0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      *reinterpret_cast<float4*>(g.h_out + r * LH + j0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+    }
+  };
+
+  int it = 0;
+  int64_t prev = -1;
+  for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
+    const int buf = it & 1;
+    const uint32_t acc = tmem + (uint32_t)(buf * kGN);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (it > 0) {
+        mbar_wait(&s.bar_h[h], (uint32_t)((it - 1) & 1));
+        fence_after_sync();
+      }
+      stage_a(h, mt * kGM);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (cta_issuer()) {
+        fence_after_sync();
+        issue_gemm(acc, smem_u32(s.a[h]), kGM, false, smem_u32(s.b) + h * 16 * (kGN * 16), kGN, false, kGM, kGN, 128,
+                   h > 0);
+        mma_commit(&s.bar_h[h]);
+        if (h == 1) mma_commit(&s.bar_acc[buf]);
+      }
+      if (h == 0 && prev >= 0) {
+        mbar_wait(&s.bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));
+        fence_after_sync();
+        epilogue(prev, buf ^ 1);
+        fence_before_sync();
+      }
+    }
+    prev = mt;
+  }
+  if (prev >= 0) {
+    mbar_wait(&s.bar_acc[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+    fence_after_sync();
+    epilogue(prev, (it - 1) & 1);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+// h' / c' / gate activations of one LSTM step for `rows` rows (H = 256); h_in must not alias h_out.
+int launch_lstm_cell_tc(const float* h_in, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh,
+                        const float* c_prev, const RowMap& xmap, int D, int64_t rows, float* act, float* c_out,
+                        float* h_out, cudaStream_t st) {
+  if (D < 1 || D > kCellD || rows <= 0) return RL8_ERR_ARG;
+  LstmCellArgs g;
+  g.h_in = h_in, g.w_hh = w_hh, g.w_ih = w_ih, g.b_ih = b_ih, g.b_hh = b_hh, g.c_prev = c_prev;
+  g.act = act, g.c_out = c_out, g.h_out = h_out, g.xmap = xmap, g.rows = rows, g.D = D;
+  const int64_t mtiles = ceil_div(rows, kGM);
+  int64_t per_block = kNumSMs / 4;
+  if (per_block > mtiles) per_block = mtiles;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc_lstm_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLstm));
+    attr = true;
+  }
+  tc_lstm_cell_kernel<<<(unsigned)(per_block * 4), kRThreads, sizeof(SmemLstm), st>>>(g);
+  return check_launch("tc_lstm_cell");
+}
+
 // Same contract as launch_sgemm (mlp_fp32.cuh) for EPI_STORE / EPI_ATOMIC, bf16 operands on tcgen05.
 // Requires 16-byte aligned operands, lda / ldb / ldc % 4 == 0 and N % 4 == 0 (the vector epilogue).
 int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const float* B, float* C, int64_t M,

@@ -1,7 +1,8 @@
 // Recurrent (LSTM) policy.  RL8_PREC_FP32 (reference `enable_amp=False`): every GEMM in fp32 on CUDA
 // cores, bit-comparable with the reference.  RL8_PREC_BF16 (`enable_amp=True`): the three 256 x 1024
 // contractions (gates = h W_hh^T, dh = dG W_hh, gW_hh += dG^T h) run on tcgen05 with bf16 operands and
-// fp32 accumulation (gemm_tc.cu); everything else is unchanged fp32.
+// fp32 accumulation (gemm_tc.cu) -- the forward one with the cell non-linearity in its epilogue
+// (tc_lstm_cell_kernel) -- everything else is unchanged fp32.
 //
 //   rollout  (src/rl8/algorithms/_recurrent.py:356-445): per step  SGEMM h.W_hh^T -> cell kernel
 //            (adds x.W_ih^T + biases, gate non-linearities, writes the state slabs) -> heads ->
@@ -123,10 +124,18 @@ static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t r
                           const float* h_in, const float* c_in, float* h_out, float* c_out,
                           float* act, float* G, float* features, float* values, int tanh_col1,
                           int prec, cudaStream_t st) {
-  int rc = lstm_gemm(prec, true, true, EPI_STORE, h_in, m->w_hh, G, rows, 4 * kLH, kLH, kLH, kLH,
-                     4 * kLH, 1, st);
-  if (rc) return rc;
-  if ((rc = launch_cell_fwd(m, G, xmap, rows, c_in, act, c_out, h_out, st))) return rc;
+  int rc;
+  if (prec == RL8_PREC_BF16 && rows >= 512 && h_in != h_out && c_in != c_out) {
+    // tensor-core path: the gate GEMM with the cell in its epilogue (no pre-activation round trip through HBM)
+    if ((rc = launch_lstm_cell_tc(h_in, m->w_hh, m->w_ih, m->b_ih, m->b_hh, c_in, xmap, m->D, rows, act, c_out,
+                                  h_out, st)))
+      return rc;
+  } else {
+    if ((rc = lstm_gemm(prec, true, true, EPI_STORE, h_in, m->w_hh, G, rows, 4 * kLH, kLH, kLH, kLH, 4 * kLH, 1,
+                        st)))
+      return rc;
+    if ((rc = launch_cell_fwd(m, G, xmap, rows, c_in, act, c_out, h_out, st))) return rc;
+  }
   if (features &&
       (rc = launch_head_fwd(h_out, rows, kLH, m->P, m->pi_w, m->pi_b, features, tanh_col1, st)))
     return rc;

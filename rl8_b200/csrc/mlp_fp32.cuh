@@ -51,6 +51,12 @@ int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const 
                    int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int splits,
                    cudaStream_t st);
 
+// One LSTM step on tensor cores (gemm_tc.cu): gates = h_in W_hh^T (bf16 operands, fp32 accumulate) with the cell
+// non-linearity in the epilogue; writes act [rows][4H] (may be NULL), c_out, h_out [rows][H].  H = 256.
+int launch_lstm_cell_tc(const float* h_in, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh,
+                        const float* c_prev, const RowMap& xmap, int D, int64_t rows, float* act, float* c_out,
+                        float* h_out, cudaStream_t st);
+
 // out[rows][P] = b3 + h2 @ w3^T; column 1 is tanh'ed when tanh_col1 (continuous log_std).
 int launch_head_fwd(const float* h2, int64_t rows, int H, int P, const float* w3, const float* b3,
                     float* out, int tanh_col1, cudaStream_t st);
