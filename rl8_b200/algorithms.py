@@ -208,6 +208,9 @@ class Algorithm:
         else:
             # user-defined torch model: its parameters belong to torch, any optimizer class works
             self.optimizer = config.optimizer_cls(self.policy.model.parameters(), **optimizer_config)
+        # Multi-GPU: replicas start from rank 0's parameters whatever each rank's RNG state was
+        # (seed env resets / sampling noise per rank; the model is made identical here).
+        parallel.sync_replicas(self.policy.model)
         self._grad_norm = torch.zeros(1, device=device)
         self._opt_steps = 0
         self.lr_scheduler = LRScheduler(

@@ -1,0 +1,152 @@
+// fp32-accurate GEMMs on the bf16 tensor pipe: every fp32 operand x is split into bf16 pieces
+//
+//     x = p0 + p1 + p2 (+ 2^-27 |x|),   p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1)
+//
+// (each subtraction is exact in fp32) and a product a*b is accumulated in fp32 TMEM as the sum of the
+// piece products that matter:
+//
+//     6 terms  a0b0 + a0b1 + a1b0 + a1b1 + a0b2 + a2b0     dropped terms <= 2^-25 |ab|   ("x3")
+//     3 terms  a0b0 + a0b1 + a1b0  (two pieces per operand)  dropped terms <= 2^-16 |ab|   ("x2")
+//
+// The x3 form reproduces an fp32 nn.Linear within fp32 rounding (the reference's arithmetic,
+// src/rl8/models/_feedforward.py:263-289, 336-362); the x2 form is used where the consumer is a gradient
+// (tests bound gradients at 1e-4).
+//
+// The MMAs are tcgen05.mma.cta_group::2: a pair of CTAs (one cluster) works on one 256-row tile, each CTA
+// stages ITS 128 rows of A and ITS 128-row half of B (the N index), so per CTA an N = 256 instruction reads
+// 4 KB + 4 KB of shared memory per 128 cycles instead of 4 KB + 8 KB -- with three pieces per operand the
+// single-CTA form would sit at the shared-memory bandwidth limit.  Accumulators: 128 lanes x 256 columns
+// in each CTA's tensor memory (rows of the leader = tile rows 0..127, of the peer = 128..255).
+#pragma once
+#include "tc.cuh"
+
+namespace rl8 {
+namespace tc {
+
+// ---- cluster / pair primitives --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// arrive on the mbarrier at the same offset in CTA `rank` (release at cluster scope: the smem writes and
+// proxy fences of this thread are ordered before the arrival)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  const uint32_t addr = map_to_cta(smem_u32(bar), rank);
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// waits with cluster-scope acquire (arrivals may come from the peer CTA or from a multicast commit)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins) {
+    if (spins > (1u << 24)) __trap();
+  }
+}
+
+// ---- tensor memory, pair form (one warp of EACH CTA of the pair calls these) -------------------------------
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), issued by one thread of the LEADER CTA.
+// The descriptors address the leader's shared memory; the peer's tensor core reads the same offsets of its own.
+__device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the mbarrier at this offset in BOTH CTAs receives one arrival when every MMA issued so far has completed
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+// ---- splitting ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float bf16lo_f32(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16hi_f32(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
+// two fp32 values -> NP packed bf16 pairs (piece k of both values in q[k]; x0 in the low half)
+template <int NP>
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t* q) {
+  q[0] = cvt_bf16x2(x0, x1);
+  if constexpr (NP > 1) {
+    x0 -= bf16lo_f32(q[0]), x1 -= bf16hi_f32(q[0]);
+    q[1] = cvt_bf16x2(x0, x1);
+  }
+  if constexpr (NP > 2) {
+    x0 -= bf16lo_f32(q[1]), x1 -= bf16hi_f32(q[1]);
+    q[2] = cvt_bf16x2(x0, x1);
+  }
+}
+// eight consecutive K (or MN) elements -> one 16-byte chunk per piece at tile_k + off
+template <int NP>
+__device__ __forceinline__ void store_split_chunk(uint8_t* const* piece_tiles, uint32_t off, const float* v) {
+  uint32_t q[4][NP];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_pair<NP>(v[2 * i], v[2 * i + 1], q[i]);
+#pragma unroll
+  for (int k = 0; k < NP; ++k)
+    *reinterpret_cast<uint4*>(piece_tiles[k] + off) = make_uint4(q[0][k], q[1][k], q[2][k], q[3][k]);
+}
+
+// piece pairs (a piece, b piece) in issue order: small products first within a K step
+//   x3: a2b0 a0b2 a1b1 a1b0 a0b1 a0b0     x2: a1b0 a0b1 a0b0
+template <int NP>
+struct Terms;
+template <>
+struct Terms<3> {
+  static constexpr int n = 6;
+  __host__ __device__ static constexpr int a(int i) { return i == 0 ? 2 : i == 1 ? 0 : i == 2 ? 1 : i == 3 ? 1 : 0; }
+  __host__ __device__ static constexpr int b(int i) { return i == 0 ? 0 : i == 1 ? 2 : i == 2 ? 1 : i == 3 ? 0 : i == 4 ? 1 : 0; }
+};
+template <>
+struct Terms<2> {
+  static constexpr int n = 3;
+  __host__ __device__ static constexpr int a(int i) { return i == 0 ? 1 : 0; }
+  __host__ __device__ static constexpr int b(int i) { return i == 1 ? 1 : 0; }
+};
+
+}  // namespace tc
+}  // namespace rl8

@@ -52,6 +52,25 @@ def shard_envs(total_envs: int, world: int, rk: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rk < extra else 0)
 
 
+def sync_replicas(model: torch.nn.Module, *extra: torch.Tensor) -> None:
+    """Make every rank's replica identical to rank 0's (SURVEY.md §8e "identical init (broadcast
+    once)"): the flat parameter buffer of a fused model in one broadcast, else every parameter and
+    buffer of the module, plus any ``extra`` tensors (optimizer moments).  A no-op on one rank.
+    Without it replicas seeded differently would apply the same averaged gradient to different
+    weights forever, with no error."""
+    if world_size() <= 1:
+        return
+    flat = getattr(model, "_flat", None)
+    with torch.no_grad():
+        if flat is not None:
+            dist.broadcast(flat, src=0)
+        else:
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=0)
+        for t in extra:
+            dist.broadcast(t, src=0)
+
+
 def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if world_size() > 1:
         dist.all_reduce(t)

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 import torch.optim as optim
 
-from . import _lib
+from . import _lib, parallel
 from .algorithms import Algorithm, _NoopGradScaler
 from .buffer import RolloutBuffer
 from .data import DataKeys, Device, RecurrentAlgorithmHparams, RecurrentAlgorithmState
@@ -421,6 +421,7 @@ class RecurrentAlgorithm(Algorithm):
         self._grads = torch.zeros_like(flat)
         self._exp_avg = torch.zeros_like(flat)
         self._exp_avg_sq = torch.zeros_like(flat)
+        parallel.sync_replicas(self.policy.model)  # replicas start from rank 0's parameters
         self._grad_norm = torch.zeros(1, device=device)
         self._opt_steps = 0
         self.lr_scheduler = LRScheduler(

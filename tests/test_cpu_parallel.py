@@ -55,6 +55,37 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
     g = rows.sum(0) / 4.0
     parallel.all_reduce_sum_(g)
     torch.testing.assert_close(g, grads_full.mean(0))
+    # replicas: ranks seeded differently must end up with rank 0's parameters (and buffers)
+    torch.manual_seed(100 + rank)
+    net = torch.nn.Sequential(torch.nn.Linear(3, 5), torch.nn.BatchNorm1d(5))
+    net[1].running_mean.normal_()
+    moments = torch.randn(7)
+
+    class Flat(torch.nn.Module):  # a fused model: every parameter is a view of ONE flat buffer
+        def __init__(self) -> None:
+            super().__init__()
+            self._flat = torch.randn(12)
+            self.w = torch.nn.Parameter(self._flat[:12].view(3, 4))
+
+    flat = Flat()
+    before = [t.detach().clone() for t in net.state_dict().values()] + [flat._flat.clone(), moments.clone()]
+    parallel.sync_replicas(net, moments)
+    parallel.sync_replicas(flat)
+    after = [t.detach().clone() for t in net.state_dict().values()] + [flat._flat.clone(), moments.clone()]
+    changed: list[bool] = []
+    for b4, now in zip(before, after):
+        if now.dtype != torch.float32:
+            continue
+        both = [torch.empty_like(now) for _ in range(world)]
+        dist.all_gather(both, now)
+        assert all(torch.equal(both[0], x) for x in both), "replicas differ after sync_replicas"
+        if rank == 0:
+            assert torch.equal(b4, now), "rank 0 must keep its own values"
+        else:
+            changed.append(not torch.equal(b4, now))
+    if rank != 0:  # Linear weight / bias, running_mean, the flat buffer and the moments were seeded per rank
+        assert sum(changed) >= 5, "test is vacuous: ranks started identical"
+    assert flat.w.data_ptr() == flat._flat.data_ptr()  # still a view of the flat buffer
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
