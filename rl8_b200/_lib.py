@@ -21,7 +21,18 @@ ABI_VERSION = 1
 # enums (include/rl8_b200.h)
 ENV_DISCRETE_DUMMY, ENV_CONTINUOUS_DUMMY, ENV_CARTPOLE, ENV_MOUNTAIN_CAR, ENV_PENDULUM = range(5)
 DIST_CATEGORICAL, DIST_NORMAL, DIST_SQUASHED_NORMAL = range(3)
-PREC_FP32, PREC_BF16 = range(2)
+PREC_FP32, PREC_BF16, PREC_FP32_TC = range(3)
+
+
+
+def precision_for(enable_amp: bool) -> int:
+    """Kernel precision of an ``enable_amp`` setting: ``True`` -> bf16 tcgen05 GEMMs; ``False`` -> fp32
+    results, on tcgen05 through split-bf16 operands (``PREC_FP32_TC``), or -- with ``RL8_FP32_SIMT=1`` in
+    the environment -- the CUDA-core fp32 GEMMs the split path is cross-checked against."""
+    if enable_amp:
+        return PREC_BF16
+    return PREC_FP32 if os.environ.get("RL8_FP32_SIMT", "0") == "1" else PREC_FP32_TC
+
 
 _ERRORS = {
     -1: "RL8_ERR_ARG (bad argument)",

@@ -171,7 +171,7 @@ class Algorithm:
             distribution_cls=config.distribution_cls,
             device=device,
         )
-        self.policy.precision = _lib.PREC_BF16 if config.enable_amp else _lib.PREC_FP32
+        self.policy.precision = _lib.precision_for(config.enable_amp)
         self.buffer_spec = Composite(
             {
                 DataKeys.OBS: self.env.observation_spec,
@@ -412,7 +412,11 @@ class Algorithm:
         rc = self._lib.rl8_collect(m, ro, self.policy.precision, _lib.ptr(ws), ws.numel(), _lib.stream())
         _lib.check(rc, "rl8_collect")
         T = hp.horizon
-        self.last_launches["collect"] = (4 * T + 3 * (T + 1)) if self.policy.precision == _lib.PREC_FP32 else 4
+        self.last_launches["collect"] = {
+            _lib.PREC_FP32: 4 * T + 3 * (T + 1),  # layer 1, SGEMM, head, tail per step; 3 per value slab
+            _lib.PREC_BF16: 4,                    # 2 x W2 packing, rollout kernel, value pass
+            _lib.PREC_FP32_TC: 2 + 2 * T + 1,     # 2 x W2 piece images, (split forward + tail) per step, value pass
+        }[self.policy.precision]
 
     def _head_width(self) -> int:
         """Policy-head outputs the sampling kernels see: A logits, or 2 = {mean, log_std}."""
@@ -762,7 +766,7 @@ class Algorithm:
             _lib.check(rc, "rl8_ppo_minibatch")
 
         # bf16: 2 x W2 packing + (activation kernel + weight-gradient kernel) per 2^21-row chunk
-        per_call = 34 * max(1, -(-M // 65536)) if prec == _lib.PREC_FP32 else 2 + 2 * max(1, -(-M // (1 << 21)))
+        per_call = 2 + 2 * max(1, -(-M // (1 << 21))) if prec == _lib.PREC_BF16 else 34 * max(1, -(-M // 65536))
         return launch, per_call
 
     def _reset_buffer(self) -> None:

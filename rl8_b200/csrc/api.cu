@@ -28,6 +28,17 @@ int ppo_minibatch_tc(const rl8_model* model, const rl8_model* grads, const rl8_b
                      int64_t workspace_bytes, cudaStream_t st);
 int mlp_forward_tc(const rl8_model* m, int which, const RowMap& map, int64_t rows, float* out,
                    int tanh_col1, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+// fp32-accurate tensor-core path (split_tc.cu)
+int64_t forward_x3_workspace();
+int mlp_forward_x3(const rl8_model* m, int which, const RowMap& map, int64_t rows, float* out, int tanh_col1,
+                   void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int64_t ppo_x3_workspace(const rl8_model* model, int64_t max_rows);
+int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_batch* batch, const int64_t* rows,
+                     int64_t row_begin, int64_t M, double mean_denominator, const rl8_ppo_hparams* hp,
+                     double* loss_sums, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int64_t collect_x3_workspace(const rl8_model* model, int64_t N, int32_t T);
+int collect_x3(const rl8_model* model, const rl8_rollout* ro, void* workspace, int64_t workspace_bytes,
+               cudaStream_t st);
 
 constexpr int64_t kChunkRows = 65536;  // rows of activations resident per update chunk (fp32)
 
@@ -114,7 +125,8 @@ extern "C" int rl8_abi_version(void) { return 1; }
 extern "C" const char* rl8_last_error(void) { return g_last_error; }
 
 extern "C" int64_t rl8_mlp_forward_workspace(int32_t H, int64_t rows) {
-  return 2 * rows * (int64_t)H * 4;
+  const int64_t simt = 2 * rows * (int64_t)H * 4, split = forward_x3_workspace();
+  return simt > split ? simt : split;
 }
 
 extern "C" int rl8_mlp_forward(const rl8_model* model, int which, const float* obs,
@@ -130,6 +142,8 @@ extern "C" int rl8_mlp_forward(const rl8_model* model, int which, const float* o
   if (precision == RL8_PREC_BF16)
     return mlp_forward_tc(model, which, map, rows, out, apply_tanh_log_std, workspace,
                           workspace_bytes, st);
+  if (precision == RL8_PREC_FP32_TC)
+    return mlp_forward_x3(model, which, map, rows, out, apply_tanh_log_std, workspace, workspace_bytes, st);
   if (precision != RL8_PREC_FP32) return RL8_ERR_ARG;
   if (!workspace || workspace_bytes < rl8_mlp_forward_workspace(model->H, rows))
     return RL8_ERR_WORKSPACE;
@@ -142,6 +156,7 @@ extern "C" int64_t rl8_collect_workspace(const rl8_model* model, int64_t N, int3
                                          int precision) {
   if (!model) return RL8_ERR_ARG;
   if (precision == RL8_PREC_BF16) return collect_tc_workspace(model, N, T);
+  if (precision == RL8_PREC_FP32_TC) return collect_x3_workspace(model, N, T);
   return 2 * N * (int64_t)model->H * 4 + N * 8 * 4;
 }
 
@@ -152,12 +167,14 @@ extern "C" int rl8_collect(const rl8_model* model, const rl8_rollout* ro, int pr
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == RL8_PREC_FP32) return collect_fp32(model, ro, workspace, workspace_bytes, st);
   if (precision == RL8_PREC_BF16) return collect_tc(model, ro, workspace, workspace_bytes, st);
+  if (precision == RL8_PREC_FP32_TC) return collect_x3(model, ro, workspace, workspace_bytes, st);
   return RL8_ERR_ARG;
 }
 
 extern "C" int64_t rl8_ppo_workspace(const rl8_model* model, int64_t max_rows, int precision) {
   if (!model || max_rows <= 0) return RL8_ERR_ARG;
   if (precision == RL8_PREC_BF16) return ppo_tc_workspace(model, max_rows);
+  if (precision == RL8_PREC_FP32_TC) return ppo_x3_workspace(model, max_rows);
   const int64_t C = ppo_fp32_chunk(max_rows);
   return (5 * C * model->H + C * (2 * 8 + 2)) * 4;
 }
@@ -181,6 +198,9 @@ extern "C" int rl8_ppo_minibatch(const rl8_model* model, const rl8_model* grads,
                               loss_sums, workspace, workspace_bytes, st);
   if (precision == RL8_PREC_BF16)
     return ppo_minibatch_tc(model, grads, batch, rows, row_begin, M, mean_denominator, hp,
+                            loss_sums, workspace, workspace_bytes, st);
+  if (precision == RL8_PREC_FP32_TC)
+    return ppo_minibatch_x3(model, grads, batch, rows, row_begin, M, mean_denominator, hp,
                             loss_sums, workspace, workspace_bytes, st);
   return RL8_ERR_ARG;
 }

@@ -1,0 +1,120 @@
+// Shared pieces of the split-bf16 pair kernels (split_tc.cu: forward / collect; update_x3.cu: PPO update).
+#pragma once
+#include "mlp_tc.cuh"
+#include "split_tc.cuh"
+
+namespace rl8 {
+
+using namespace tc;
+
+constexpr int kXKc = 32;                              // contraction values per ring stage (two K = 16 instructions)
+constexpr int kXPieceBytes = TILE * (kXKc / 8) * 16;  // 8192: one piece of one operand stage, [128 rows][4 column groups]
+constexpr int kXThreads = 544;                        // 16 worker warps + the TMEM / MMA warp
+constexpr int kXImgBytes = (H / kXKc) * 2 * 3 * kXPieceBytes;  // 393216: W2 piece image (three pieces)
+
+// One ring stage of a K-major operand pair: piece tiles [128 rows][4 column groups of 8 K values],
+// off(r, c) = r * 16 + c * 2048  (LBO 2048 = next K group, SBO 128 = next 8 rows).
+//
+// K ORDER.  Stage kc holds the global K groups {8 g + kc : g = 0..3} as its local column groups g, so the
+// worker thread (row, g) that fills local group g of every stage covers the 64 consecutive K values
+// [64 g, 64 g + 64) of its row over the 8 stages of a tile (its ReLU-mask bits are two whole words).
+// Any order works for a contraction as long as both operands use the same one.
+template <int NP>
+struct StageX {
+  uint8_t a[NP][kXPieceBytes];
+  uint8_t b[NP][kXPieceBytes];
+};
+__host__ __device__ constexpr int stage_kgroup(int kc, int g) { return g * 8 + kc; }  // global group of 8 K values
+
+// every piece product of one ring stage, M = 256 (pair), N = 256, both operands K-major
+template <int NP>
+__device__ __forceinline__ void issue_stage(uint32_t acc_tmem, const StageX<NP>& stg, uint32_t idesc,
+                                            bool accumulate_first) {
+  using T = Terms<NP>;
+#pragma unroll
+  for (int ks = 0; ks < kXKc / 16; ++ks) {
+#pragma unroll
+    for (int i = 0; i < T::n; ++i) {
+      const uint64_t ad = smem_desc(smem_u32(stg.a[T::a(i)]) + ks * 4096, 2048, 128);
+      const uint64_t bd = smem_desc(smem_u32(stg.b[T::b(i)]) + ks * 4096, 2048, 128);
+      mma_bf16_pair(acc_tmem, ad, bd, idesc, (accumulate_first || ks > 0 || i > 0) ? 1u : 0u);
+    }
+  }
+}
+
+// [W1 | b1] in fp32: w1s[i][d] = W1[i][d] (d < D <= 7, zero padded), w1s[i][7] = b1[i]
+__device__ __forceinline__ void stage_w1s(float (*w1s)[8], const NetParams& np) {
+  for (int e = threadIdx.x; e < H * 8; e += blockDim.x) {
+    const int i = e >> 3, d = e & 7;
+    w1s[i][d] = d < np.D ? np.w1[i * np.D + d] : (d == 7 ? np.b1[i] : 0.0f);
+  }
+}
+// Z1[row][c] = b1[c] + sum_d obs[d] W1[c][d] in fp32 (bias first, then d ascending; padded slots add 0)
+__device__ __forceinline__ float z1_value(const float* w1row, const float* ob) {
+  const float4 wa = *reinterpret_cast<const float4*>(w1row);
+  const float4 wb = *reinterpret_cast<const float4*>(w1row + 4);
+  float acc = wb.w;
+  acc = fmaf(ob[0], wa.x, acc), acc = fmaf(ob[1], wa.y, acc), acc = fmaf(ob[2], wa.z, acc);
+  acc = fmaf(ob[3], wa.w, acc), acc = fmaf(ob[4], wb.x, acc), acc = fmaf(ob[5], wb.y, acc);
+  acc = fmaf(ob[6], wb.z, acc);
+  return acc;
+}
+// H1[row][c0 .. c0 + 8) = relu(Z1); returns the 8 ReLU-mask bits (bit e: column c0 + e is positive)
+__device__ __forceinline__ uint32_t h1_chunk(const float (*w1s)[8], const float* ob, int c0, float* v) {
+  uint32_t bits = 0u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z = z1_value(w1s[c0 + j], ob);
+    bits |= (z > 0.0f ? 1u : 0u) << j;
+    v[j] = fmaxf(z, 0.0f);
+  }
+  return bits;
+}
+
+__device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// lane l of the warp returns sum over the 32 lanes m of x_m[l]  (x is destroyed): 31 shuffles
+__device__ __forceinline__ float transpose_reduce32(float* x, int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? x[i] : x[i + o];
+      const float keep = up ? x[i + o] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return x[0];
+}
+
+// Buffer coordinates (slab t, env n) of minibatch row `rw` (update kernels); false past the minibatch.
+// A needs: M, small, slab_nenv, slab_env0, rows, row_begin, T.
+template <class A>
+__device__ __forceinline__ bool minibatch_row_to_tn(const A& a, int64_t rw, int64_t& t, int64_t& n) {
+  if (rw >= a.M) return false;
+  if (a.small) {
+    if (a.slab_nenv > 0) {
+      const uint32_t ne = (uint32_t)a.slab_nenv, rr = (uint32_t)rw;
+      const uint32_t tt = rr / ne;
+      t = tt, n = a.slab_env0 + (rr - tt * ne);
+    } else {
+      const uint32_t g = a.rows ? (uint32_t)a.rows[rw] : (uint32_t)(a.row_begin + rw);
+      const uint32_t TT = (uint32_t)a.T, nn = g / TT;
+      t = g - nn * TT, n = nn;
+    }
+    return true;
+  }
+  if (a.slab_nenv > 0) {
+    t = rw / a.slab_nenv, n = a.slab_env0 + (rw - t * a.slab_nenv);
+  } else {
+    const int64_t g = a.rows ? a.rows[rw] : a.row_begin + rw;
+    n = g / a.T, t = g - n * a.T;
+  }
+  return true;
+}
+
+// split_tc.cu
+int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st);
+
+}  // namespace rl8

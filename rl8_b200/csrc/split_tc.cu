@@ -3,11 +3,13 @@
 //   tc3_selftest_kernel   D[256][256] = A[256][K] * B[256][K]^T with a selectable set of piece products: pins the
 //                         pair plumbing (cluster launch, pair TMEM allocation, N-split B operand, multicast commit)
 //                         and measures what each term set costs in accuracy.
-#include "split_tc.cuh"
+#include "split_common.cuh"
 
 namespace rl8 {
 
 using namespace tc;
+
+constexpr int kXStages = 4;  // ring depth of the forward kernel (48 KB stages)
 
 // ---- pair selftest ---------------------------------------------------------------------------------------------
 // One cluster of two CTAs, 256 threads each, synchronous K loop in chunks of 32: stage -> cluster barrier ->
@@ -90,6 +92,278 @@ tc3_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
   __syncthreads();
   cluster_sync_all();
   if (warp == 0) tmem_dealloc_pair(tmem, 512);
+}
+
+
+// ---- W2 piece images ------------------------------------------------------------------------------------------------
+// The weight operand of a 256x256 contraction, split once per call into NP bf16 pieces and laid out so that the half
+// a CTA of the pair needs for one ring stage (its 128 rows, the stage's four K groups, every piece) is one contiguous
+// run of NP x 8 KB:
+//     img[kc][half = n / 128][piece][ (n % 128) * 16 + g * 2048 + (k % 8) * 2 ]     with  k / 8 = 8 g + kc
+// (the K order of StageX).  transpose = 0: X(n, k) = W2[n][k]  (forward Z2 = H1 W2^T: n = unit j, k = input i);
+// transpose = 1: X(n, k) = W2[k][n]  (backward dH1^T = W2^T dZ2^T: n = input i, k = unit j).
+template <int NP>
+__global__ void __launch_bounds__(256) pack_w2_pieces_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img,
+                                                             int transpose) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (n, 8 consecutive k)
+  if (idx >= H * (H / 8)) return;
+  const int n = idx & (H - 1), k8 = idx >> 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = transpose ? w2[(k8 * 8 + e) * H + n] : w2[n * H + k8 * 8 + e];
+  const int g = k8 >> 3, kc = k8 & 7, half = n >> 7, r = n & 127;
+  uint8_t* base = img + (size_t)((kc * 2 + half) * NP) * kXPieceBytes;
+  uint8_t* tiles[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) tiles[p] = base + (size_t)p * kXPieceBytes;
+  store_split_chunk<NP>(tiles, (uint32_t)(r * 16 + g * 2048), v);
+}
+
+int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st) {
+  if (pieces == 3) pack_w2_pieces_kernel<3><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose);
+  else pack_w2_pieces_kernel<2><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose);
+  return check_launch("pack_w2_pieces");
+}
+
+// ---- forward kernel ---------------------------------------------------------------------------------------------------
+// out[rows][P] of one network, fp32-accurate:  H1 = relu([obs] W1^T + b1) is computed on CUDA cores (K = D <= 7, exact
+// fp32 FMAs) by the 16 worker warps straight into split A stages;  Z2 = H1 W2^T is the x3 pair GEMM (6 piece products,
+// B stages bulk-copied from the piece image);  H2 = relu(Z2 + b2) and the P-wide head are the epilogue.
+// A cluster of two CTAs owns 256-row tiles; accumulators are double-buffered in tensor memory (2 x 256 columns), so
+// while the workers run the epilogue of tile j the tensor pipe drains the ring stages they produced for tile j + 1.
+//   worker warps 0..15 : produce(tile j + 1) -> epilogue(tile j)
+//   warp 16            : pair TMEM allocation; in the leader CTA one elected lane issues every tcgen05.mma
+// Barriers (same offsets in both CTAs): full[s] (leader's, 32 worker-warp arrivals: A written and the CTA's B half
+// landed), bfull[s] (local, the bulk copy of the CTA's B half), empty[s] / acc_full[b] (multicast commits),
+// acc_empty[b] (leader's, 32 worker-warp arrivals: accumulator b has been read).
+struct SmemX3F {
+  StageX<3> ring[kXStages];     // 196608
+  float w1s[H][8];              //   8192  [W1 (D <= 7 values, zero padded) | b1 in slot 7]
+  float b2[H];                  //   1024
+  float w3[kMaxPT][H];          //   4096
+  float part[4][TILE][kMaxPT];  //   8192  head partial sums per column quarter
+  uint64_t full[kXStages], bfull[kXStages], empty[kXStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SmemX3F) <= 227 * 1024, "SmemX3F exceeds the 227 KB CTA limit");
+
+template <int P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXThreads, 1)
+tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ out, int tanh_col1) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemX3F& s = *reinterpret_cast<SmemX3F*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kXStages; ++i) {
+      mbar_init(&s.full[i], 32);
+      mbar_init(&s.bfull[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.acc_full[0], 1), mbar_init(&s.acc_full[1], 1);
+    mbar_init(&s.acc_empty[0], 32), mbar_init(&s.acc_empty[1], 32);
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
+  stage_w1s(s.w1s, np);
+  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  const int64_t ntiles = (rows + 255) / 256;
+  const int64_t pr = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
+
+  if (warp < 16) {
+    const int rloc = tid & 127, g = tid >> 7;
+    const int64_t ds = map.dstride();
+    const int D = np.D;
+    uint32_t kcount = 0;
+    auto produce = [&](int64_t tile) {
+      float ob[7];
+      const int64_t row = tile * 256 + rank * 128 + rloc;
+#pragma unroll
+      for (int d = 0; d < 7; ++d) ob[d] = 0.0f;
+      if (row < rows) {
+        const float* base = map.obs + map.offset(row);
+#pragma unroll
+        for (int d = 0; d < 7; ++d)
+          if (d < D) ob[d] = __ldg(base + (int64_t)d * ds);
+      }
+      for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+        const int st = (int)(kcount % kXStages);
+        const uint32_t use = kcount / kXStages;
+        if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+        __syncwarp();
+        if (warp == 0 && elect_one()) {
+          const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * 3) * kXPieceBytes;
+          mbar_expect_tx(&s.bfull[st], 3 * kXPieceBytes);
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+            bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
+        }
+        float v[8];
+        h1_chunk(s.w1s, ob, stage_kgroup(kc, g) * 8, v);
+        uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
+        store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_wait(&s.bfull[st], use & 1);
+          mbar_arrive_cluster(&s.full[st], 0);
+        }
+      }
+    };
+    auto epilogue = [&](int64_t tile, int64_t j) {
+      const int buf = (int)(j & 1);
+      mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
+      fence_after_sync();
+      const int q = warp & 3, cq = warp >> 2, r = q * 32 + lane;
+      const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+      float v0[32], v1[32];
+      tmem_ld32_nowait(acc, v0);
+      tmem_ld32_nowait(acc + 32, v1);
+      tmem_wait_ld();
+      reg_fence32(v0);
+      reg_fence32(v1);
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);  // the accumulator may be overwritten
+      float dot[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) dot[p] = 0.0f;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int col0 = cq * 64 + c2 * 32;
+        const float* v = c2 ? v1 : v0;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
+          const float h0 = fmaxf(v[jj] + b.x, 0.0f), h1 = fmaxf(v[jj + 1] + b.y, 0.0f);
+          const float h2 = fmaxf(v[jj + 2] + b.z, 0.0f), h3 = fmaxf(v[jj + 3] + b.w, 0.0f);
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + jj]);
+            dot[p] = fmaf(h0, w.x, dot[p]);
+            dot[p] = fmaf(h1, w.y, dot[p]);
+            dot[p] = fmaf(h2, w.z, dot[p]);
+            dot[p] = fmaf(h3, w.w, dot[p]);
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) s.part[cq][r][p] = dot[p];
+      worker_bar_sync();
+      if (tid < TILE) {
+        const int64_t row = tile * 256 + rank * 128 + tid;
+        if (row < rows) {
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            float v = ((s.part[0][tid][p] + s.part[1][tid][p]) + (s.part[2][tid][p] + s.part[3][tid][p])) + np.b3[p];
+            if (tanh_col1 && p == 1) v = tanhf(v);
+            out[row * P + p] = v;
+          }
+        }
+      }
+      worker_bar_sync();  // part[] may be rewritten
+    };
+    if (n_my > 0) produce(pr);
+    for (int64_t j = 0; j < n_my; ++j) {
+      if (j + 1 < n_my) produce(pr + (j + 1) * npairs);
+      epilogue(pr + j * npairs, j);
+    }
+  } else if (rank == 0) {
+    // MMA issue: the whole warp follows the barriers, one elected lane issues
+    const uint32_t idesc = instr_desc(256, H, 0, 0);
+    uint32_t kcount = 0;
+    for (int64_t j = 0; j < n_my; ++j) {
+      const int buf = (int)(j & 1);
+      if (j >= 2) mbar_wait_cluster(&s.acc_empty[buf], (uint32_t)(((j >> 1) - 1) & 1));
+      for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+        const int st = (int)(kcount % kXStages);
+        mbar_wait_cluster(&s.full[st], (kcount / kXStages) & 1);
+        fence_after_sync();
+        if (elect_one()) {
+          issue_stage<3>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
+          mma_commit_pair(&s.empty[st]);
+          if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its tensor memory until here
+  if (warp == 16) tmem_dealloc_pair(tmem, 512);
+}
+
+static int launch_forward_x3(const NetParams& np, const RowMap& map, int64_t rows, float* out, int tanh_col1,
+                             cudaStream_t st) {
+  const int64_t ntiles = ceil_div(rows, 256);
+  const int grid = 2 * (int)(ntiles < kNumSMs / 2 ? ntiles : kNumSMs / 2);
+  int rc;
+#define RL8_FWDX(PV)                                                                                   \
+  case PV:                                                                                             \
+    if ((rc = set_smem((const void*)tc3_forward_kernel<PV>, sizeof(SmemX3F)))) return rc;               \
+    tc3_forward_kernel<PV><<<grid, kXThreads, sizeof(SmemX3F), st>>>(np, map, rows, out, tanh_col1);    \
+    break;
+  switch (np.P) {
+    RL8_FWDX(1) RL8_FWDX(2) RL8_FWDX(3) RL8_FWDX(4)
+    default: return RL8_ERR_UNSUPPORTED;
+  }
+#undef RL8_FWDX
+  return check_launch("tc3_forward");
+}
+
+int64_t forward_x3_workspace() { return kXImgBytes; }
+
+int mlp_forward_x3(const rl8_model* m, int which, const RowMap& map, int64_t rows, float* out, int tanh_col1,
+                   void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (m->H != H || m->D > 7 || m->P > kMaxPT) return RL8_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < kXImgBytes) return RL8_ERR_WORKSPACE;
+  uint8_t* img = (uint8_t*)workspace;
+  int rc = launch_pack_w2_pieces(which ? m->vf_w2 : m->pi_w2, img, 0, 3, st);
+  if (rc) return rc;
+  return launch_forward_x3(net_params(m, which, img), map, rows, out, tanh_col1, st);
+}
+
+// collect() in RL8_PREC_FP32_TC: per step the x3 policy forward + the fused sample / env-step / buffer-write kernel
+// of the fp32 path (collect.cu), then one x3 value pass over all T + 1 observation slabs.
+int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st);
+
+int64_t collect_x3_workspace(const rl8_model*, int64_t N, int32_t) { return 2 * (int64_t)kXImgBytes + N * kMaxPT * 4; }
+
+int collect_x3(const rl8_model* model, const rl8_rollout* ro, void* workspace, int64_t workspace_bytes,
+               cudaStream_t st) {
+  if (model->H != H || model->P > kMaxPT || model->D > 7) return RL8_ERR_UNSUPPORTED;
+  const int64_t N = ro->N;
+  if (!workspace || workspace_bytes < collect_x3_workspace(model, N, ro->T)) return RL8_ERR_WORKSPACE;
+  uint8_t* img_pi = (uint8_t*)workspace;
+  uint8_t* img_vf = img_pi + kXImgBytes;
+  float* feat = (float*)(img_vf + kXImgBytes);
+  int rc;
+  if ((rc = launch_pack_w2_pieces(model->pi_w2, img_pi, 0, 3, st))) return rc;
+  if ((rc = launch_pack_w2_pieces(model->vf_w2, img_vf, 0, 3, st))) return rc;
+  const NetParams np_pi = net_params(model, 0, img_pi), np_vf = net_params(model, 1, img_vf);
+  const int continuous = ro->dist_kind != RL8_DIST_CATEGORICAL;
+  RowMap map{};
+  map.mode = 0, map.stride_r = 1, map.stride_d = N, map.D = model->D;
+  for (int t = 0; t < ro->T; ++t) {
+    map.obs = ro->obs + (int64_t)t * model->D * N;
+    if ((rc = launch_forward_x3(np_pi, map, N, feat, continuous, st))) return rc;
+    if ((rc = collect_tail(ro, t, feat, st))) return rc;
+  }
+  RowMap vmap{};
+  vmap.obs = ro->obs, vmap.mode = 2, vmap.D = model->D, vmap.N = N, vmap.T = ro->T;
+  return launch_forward_x3(np_vf, vmap, (int64_t)(ro->T + 1) * N, ro->values, 0, st);
 }
 
 }  // namespace rl8

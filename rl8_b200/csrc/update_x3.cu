@@ -1,0 +1,412 @@
+// PPO update in RL8_PREC_FP32_TC: forward + clipped losses + hand-derived backward of both default networks for one
+// minibatch on split-bf16 pair MMAs (split_tc.cuh), three persistent kernels per row chunk.  No activation ever
+// reaches HBM: every A / B operand that is an activation is RECOMPUTED on CUDA cores straight into split ring
+// stages from 80 bytes per row and network of scratch (dOut [4] fp32 and the two 256-bit ReLU masks).
+//
+//   x3_update_f_kernel  rows x units   Z2 = H1 W2^T            x3 (six piece products: the losses are forward values)
+//       A = H1 = relu([obs] W1^T + b1) computed per stage;  B = W2 piece image (bulk copies)
+//       epilogue: H2 = relu(Z2 + b2), head, per-row PPO loss -> dOut, loss sums, gb3; ReLU masks of H1 / H2 and
+//       dOut -> scratch;  gW3 += H2^T dOut by warp-transposing reductions (the accumulator is read twice)
+//   x3_update_b_kernel  inputs x rows  dH1^T = W2^T dZ2^T      x2 (three piece products: gradients)
+//       A = W2^T piece image;  B = dZ2 = [H2 > 0] .* (dOut W3) computed per stage from the scratch
+//       epilogue (lane = input unit i, columns = rows): dZ1 = [H1 > 0] .* dH1;  gW1[i][:] += dZ1 obs, gb1[i] += dZ1
+//       as plain per-thread FMAs over the rows (no cross-lane work: that is why this GEMM is transposed)
+//   x3_update_w_kernel  units x inputs gW2 = dZ2^T H1          x2, contraction over rows
+//       A = dZ2^T, B = H1, both computed per stage (MN-major tiles); gb2 += column sums of dZ2 in the producer;
+//       the 128 x 256 accumulator of each CTA lives in tensor memory for the whole kernel
+//
+// GEMM work per row and network: 6 + 3 + 3 = 12 bf16-rate 256x256 products (the bf16 path does 3).
+#include <stdlib.h>
+
+#include "ppo_loss_math.cuh"
+#include "split_common.cuh"
+
+namespace rl8 {
+
+using namespace tc;
+
+constexpr int64_t kXChunkRows = 1 << 21;  // rows per kernel triple (scratch: 80 B per row and network)
+
+struct UpdXArgs {
+  const float* obs;      // [T+1][D][N]
+  const void* actions;   // [T+1][N]
+  const float* logp;     // [T+1][N]
+  const float* adv;      // [T+1][N]
+  const float* ret;      // [T+1][N]
+  const int64_t* rows;   // minibatch row indices (n*T + t) or null
+  int64_t row_begin;     // first flattened row when rows == null
+  int64_t M;             // rows of the minibatch
+  int64_t row_off, Mc;   // this chunk: minibatch rows [row_off, row_off + Mc)
+  int64_t N;
+  int64_t slab_env0, slab_nenv;  // nenv > 0: order-free traversal t-major over envs [env0, env0+nenv)
+  int T, dist_kind;
+  int small;             // every row count fits 31 bits: 32-bit index arithmetic
+  int n_pi;              // CTA pairs [0, n_pi) run the policy network, the rest the value network
+  rl8_ppo_hparams hp;
+  float inv_denom;
+  // scratch per network, indexed by the chunk-local row
+  uint32_t* mask1[2];    // [Mc][8]  bit c of the row: H1[c] > 0
+  uint32_t* mask2[2];    // [Mc][8]  bit c of the row: H2[c] > 0
+  float* dout[2];        // [Mc][4]  d(loss) / d(head output)
+  float *gw1[2], *gb1[2], *gw2[2], *gb2[2], *gw3[2], *gb3[2];
+  double* sums;          // [5]
+};
+
+// observations of minibatch row `rw` (zeros past the chunk / minibatch): slots 0..D-1, rest zero
+__device__ __forceinline__ bool load_row_obs(const UpdXArgs& a, int64_t rowl, int D, float* ob, int64_t* idx) {
+#pragma unroll
+  for (int d = 0; d < 7; ++d) ob[d] = 0.0f;
+  int64_t t = 0, n = 0;
+  const bool valid = rowl < a.Mc && minibatch_row_to_tn(a, a.row_off + rowl, t, n);
+  if (valid) {
+    const float* base = a.obs + t * (int64_t)D * a.N + n;
+#pragma unroll
+    for (int d = 0; d < 7; ++d)
+      if (d < D) ob[d] = __ldg(base + (int64_t)d * a.N);
+  }
+  if (idx) *idx = valid ? t * a.N + n : -1;
+  return valid;
+}
+
+// ---- forward + loss kernel ---------------------------------------------------------------------------------------------
+constexpr int kFStages = 4;
+struct SmemXF {
+  StageX<3> ring[kFStages];     // 196608
+  float w1s[H][8];              //   8192
+  float b2[H];                  //   1024
+  float w3[kMaxPT][H];          //   4096
+  float part[4][TILE][kMaxPT];  //   8192  head partial sums per column quarter
+  float dsm[TILE][kMaxPT];      //   2048  dOut of the tile's rows (pass 2)
+  uint64_t full[kFStages], bfull[kFStages], empty[kFStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SmemXF) <= 227 * 1024, "SmemXF exceeds the 227 KB CTA limit");
+
+template <int PN, bool POLICY>
+__device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np, const UpdXArgs& a, int net,
+                                                 int64_t pr, int64_t npairs, uint32_t rank, double* sv) {
+  const uint32_t tmem = s.tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rloc = tid & 127, g = tid >> 7;
+  const int q = warp & 3, cq = warp >> 2, r = q * 32 + lane;
+  const int D = np.D;
+  const int64_t ntiles = (a.Mc + 255) / 256;
+  const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
+  const bool continuous = POLICY && a.dist_kind != RL8_DIST_CATEGORICAL;
+  float b3[PN], gb3_acc[PN], gw3_acc[2][PN];
+#pragma unroll
+  for (int p = 0; p < PN; ++p) b3[p] = np.b3[p], gb3_acc[p] = 0.0f, gw3_acc[0][p] = gw3_acc[1][p] = 0.0f;
+  float s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;
+  uint32_t kcount = 0;
+
+  auto produce = [&](int64_t tile) {
+    float ob[7];
+    const int64_t rowl = tile * 256 + rank * 128 + rloc;
+    const bool valid = load_row_obs(a, rowl, D, ob, nullptr);
+    uint32_t m0 = 0u, m1 = 0u;
+    for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+      const int st = (int)(kcount % kFStages);
+      const uint32_t use = kcount / kFStages;
+      if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+      __syncwarp();
+      if (warp == 0 && elect_one()) {
+        const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * 3) * kXPieceBytes;
+        mbar_expect_tx(&s.bfull[st], 3 * kXPieceBytes);
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
+      }
+      float v[8];
+      const uint32_t bits = h1_chunk(s.w1s, ob, stage_kgroup(kc, g) * 8, v);
+      if (kc < 4) m0 |= bits << (8 * kc);
+      else m1 |= bits << (8 * (kc - 4));
+      uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
+      store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_wait(&s.bfull[st], use & 1);
+        mbar_arrive_cluster(&s.full[st], 0);
+      }
+    }
+    // H1 mask of columns [64 g, 64 g + 64) of this row
+    if (valid) *reinterpret_cast<uint2*>(a.mask1[net] + rowl * 8 + 2 * g) = make_uint2(m0, m1);
+  };
+
+  auto epilogue = [&](int64_t tile, int64_t j) {
+    const int buf = (int)(j & 1);
+    mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
+    fence_after_sync();
+    const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+    const int64_t rowl = tile * 256 + rank * 128 + r;  // chunk-local row of this thread's lane
+    // ---- pass 1: H2, its mask, head partial sums
+    float dot[PN];
+#pragma unroll
+    for (int p = 0; p < PN; ++p) dot[p] = 0.0f;
+    uint32_t mk[2];
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int col0 = cq * 64 + c2 * 32;
+      float v[32];
+      tmem_ld32(acc + (uint32_t)(c2 * 32), v);
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
+        const float z0 = v[jj] + b.x, z1 = v[jj + 1] + b.y, z2 = v[jj + 2] + b.z, z3 = v[jj + 3] + b.w;
+        bits |= (z0 > 0.0f ? 1u : 0u) << jj | (z1 > 0.0f ? 1u : 0u) << (jj + 1) | (z2 > 0.0f ? 1u : 0u) << (jj + 2) |
+                (z3 > 0.0f ? 1u : 0u) << (jj + 3);
+        const float h0 = fmaxf(z0, 0.0f), h1 = fmaxf(z1, 0.0f), h2 = fmaxf(z2, 0.0f), h3 = fmaxf(z3, 0.0f);
+#pragma unroll
+        for (int p = 0; p < PN; ++p) {
+          const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + jj]);
+          dot[p] = fmaf(h0, w.x, dot[p]);
+          dot[p] = fmaf(h1, w.y, dot[p]);
+          dot[p] = fmaf(h2, w.z, dot[p]);
+          dot[p] = fmaf(h3, w.w, dot[p]);
+        }
+      }
+      mk[c2] = bits;
+    }
+    if (rowl < a.Mc) *reinterpret_cast<uint2*>(a.mask2[net] + rowl * 8 + 2 * cq) = make_uint2(mk[0], mk[1]);
+#pragma unroll
+    for (int p = 0; p < PN; ++p) s.part[cq][r][p] = dot[p];
+    worker_bar_sync();
+    // ---- per-row loss -> dOut (threads 0..127 own row tid)
+    if (tid < TILE) {
+      const int64_t rl = tile * 256 + rank * 128 + tid;
+      float d_o[kMaxPT] = {0.0f, 0.0f, 0.0f, 0.0f};
+      int64_t t = 0, n = 0;
+      if (rl < a.Mc && minibatch_row_to_tn(a, a.row_off + rl, t, n)) {
+        const int64_t idx = t * a.N + n;
+        float o[PN];
+#pragma unroll
+        for (int p = 0; p < PN; ++p)
+          o[p] = ((s.part[0][tid][p] + s.part[1][tid][p]) + (s.part[2][tid][p] + s.part[3][tid][p])) + b3[p];
+        RowLoss L;
+        if constexpr (POLICY) {
+          if (continuous) o[1] = tanhf(o[1]);
+          const float act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)((const long long*)a.actions)[idx]
+                                                                : ((const float*)a.actions)[idx];
+          ppo_policy_row<PN>(a.dist_kind, o, act, a.logp[idx], a.adv[idx], a.hp, a.inv_denom, d_o, L);
+          s_ent += L.entropy, s_pol += L.policy, s_kl += L.kl;
+        } else {
+          ppo_value_row(o[0], a.ret[idx], a.hp, a.inv_denom, d_o, L);
+          s_vf += L.vf;
+        }
+#pragma unroll
+        for (int p = 0; p < PN; ++p) gb3_acc[p] += d_o[p];
+        *reinterpret_cast<float4*>(a.dout[net] + rl * 4) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
+      }
+      *reinterpret_cast<float4*>(s.dsm[tid]) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
+    }
+    worker_bar_sync();
+    // ---- pass 2: gW3[p][c] += sum_rows H2[row][c] dOut[row][p]  (lane l ends up with column col0 + l)
+    const float4 dv = *reinterpret_cast<const float4*>(s.dsm[r]);
+    const float dr[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int col0 = cq * 64 + c2 * 32;
+      float v[32];
+      tmem_ld32(acc + (uint32_t)(c2 * 32), v);
+      if (c2 == 1) {  // last read of the accumulator: the tensor pipe may overwrite it
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
+        v[jj] = fmaxf(v[jj] + b.x, 0.0f), v[jj + 1] = fmaxf(v[jj + 1] + b.y, 0.0f);
+        v[jj + 2] = fmaxf(v[jj + 2] + b.z, 0.0f), v[jj + 3] = fmaxf(v[jj + 3] + b.w, 0.0f);
+      }
+#pragma unroll
+      for (int p = 0; p < PN; ++p) {
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = v[i] * dr[p];
+        gw3_acc[c2][p] += transpose_reduce32(x, lane);
+      }
+    }
+  };
+
+  if (n_my > 0) produce(pr);
+  for (int64_t j = 0; j < n_my; ++j) {
+    if (j + 1 < n_my) produce(pr + (j + 1) * npairs);
+    epilogue(pr + j * npairs, j);
+  }
+  // ---- flush
+  if (n_my > 0) {
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+      for (int p = 0; p < PN; ++p) atomicAdd(a.gw3[net] + p * H + cq * 64 + c2 * 32 + lane, gw3_acc[c2][p]);
+    if (tid < TILE) {
+#pragma unroll
+      for (int p = 0; p < PN; ++p) {
+        const float w = warp_sum(gb3_acc[p]);
+        if (lane == 0) atomicAdd(a.gb3[net] + p, w);
+      }
+    }
+  }
+  sv[0] = s_ent, sv[1] = s_pol, sv[2] = s_vf, sv[3] = s_kl;
+}
+
+template <int P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXThreads, 1)
+x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemXF& s = *reinterpret_cast<SmemXF*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t pair = blockIdx.x >> 1, pairs_all = gridDim.x >> 1;
+  const int net = pair < a.n_pi ? 0 : 1;
+  const int64_t pr = net ? pair - a.n_pi : pair, npairs = net ? pairs_all - a.n_pi : a.n_pi;
+  const NetParams np = net ? np_vf : np_pi;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kFStages; ++i) {
+      mbar_init(&s.full[i], 32);
+      mbar_init(&s.bfull[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.acc_full[0], 1), mbar_init(&s.acc_full[1], 1);
+    mbar_init(&s.acc_empty[0], 32), mbar_init(&s.acc_empty[1], 32);
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
+  stage_w1s(s.w1s, np);
+  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  double sv[4] = {0.0, 0.0, 0.0, 0.0};
+  if (warp < 16) {
+    if (net == 0) update_f_workers<P, true>(s, np, a, 0, pr, npairs, rank, sv);
+    else update_f_workers<1, false>(s, np, a, 1, pr, npairs, rank, sv);
+  } else if (rank == 0) {
+    const int64_t ntiles = (a.Mc + 255) / 256;
+    const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
+    const uint32_t idesc = instr_desc(256, H, 0, 0);
+    uint32_t kcount = 0;
+    for (int64_t j = 0; j < n_my; ++j) {
+      const int buf = (int)(j & 1);
+      if (j >= 2) mbar_wait_cluster(&s.acc_empty[buf], (uint32_t)(((j >> 1) - 1) & 1));
+      for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+        const int st = (int)(kcount % kFStages);
+        mbar_wait_cluster(&s.full[st], (kcount / kFStages) & 1);
+        fence_after_sync();
+        if (elect_one()) {
+          issue_stage<3>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
+          mma_commit_pair(&s.empty[st]);
+          if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 16) tmem_dealloc_pair(tmem, 512);
+  __shared__ double red[32];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double t = block_sum(sv[i], red);
+    if (tid == 0 && t != 0.0) atomicAdd(a.sums + i, t);
+  }
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(a.sums + 4, (double)a.Mc);
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+static int x3_stages() {  // development switch: bit 0 forward / loss, bit 1 input-gradient, bit 2 weight-gradient kernel
+  const char* e = getenv("RL8_X3_STAGES");
+  return e ? atoi(e) : 7;
+}
+static int x3_policy_pairs(int pairs) {
+  const char* e = getenv("RL8_X3_POLICY_PAIRS");  // tuning knob: the policy network's epilogue is the heavier one
+  int n = e ? atoi(e) : (pairs * 21 + 18) / 37;   // 42 of 74
+  if (n < 1) n = 1;
+  if (n > pairs - 1) n = pairs - 1;
+  return n;
+}
+
+int64_t ppo_x3_workspace(const rl8_model*, int64_t max_rows) {
+  const int64_t chunk = max_rows < kXChunkRows ? max_rows : kXChunkRows;
+  // forward images (3 pieces) + transposed images (2 pieces) of both networks, scratch of both networks
+  return 2 * (int64_t)kXImgBytes + 2 * (int64_t)(kXImgBytes / 3 * 2) + 2 * chunk * 80 + 256;
+}
+
+int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_batch* batch, const int64_t* rows,
+                     int64_t row_begin, int64_t M, double mean_denominator, const rl8_ppo_hparams* hp,
+                     double* loss_sums, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (model->H != H || model->P > kMaxPT || model->D > 7) return RL8_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < ppo_x3_workspace(model, M)) return RL8_ERR_WORKSPACE;
+  const int64_t chunk = M < kXChunkRows ? M : kXChunkRows;
+  uint8_t* p = (uint8_t*)workspace;
+  uint8_t* img_f[2] = {p, p + kXImgBytes};
+  p += 2 * (int64_t)kXImgBytes;
+  const int64_t img2 = kXImgBytes / 3 * 2;
+  uint8_t* img_b[2] = {p, p + img2};
+  p += 2 * img2;
+  int rc;
+  for (int net = 0; net < 2; ++net) {
+    const float* w2 = net ? model->vf_w2 : model->pi_w2;
+    if ((rc = launch_pack_w2_pieces(w2, img_f[net], 0, 3, st))) return rc;
+    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, 2, st))) return rc;
+  }
+  UpdXArgs a;
+  for (int net = 0; net < 2; ++net) {
+    a.mask1[net] = (uint32_t*)p, p += chunk * 32;
+    a.mask2[net] = (uint32_t*)p, p += chunk * 32;
+    a.dout[net] = (float*)p, p += chunk * 16;
+  }
+  a.obs = batch->obs, a.actions = batch->actions, a.logp = batch->logp;
+  a.adv = batch->advantages, a.ret = batch->returns;
+  a.rows = rows, a.row_begin = row_begin, a.M = M, a.N = batch->N, a.T = batch->T;
+  a.slab_env0 = 0, a.slab_nenv = 0;
+  if (!rows && batch->T > 0 && row_begin % batch->T == 0 && M % batch->T == 0) {
+    a.slab_env0 = row_begin / batch->T;
+    a.slab_nenv = M / batch->T;
+  }
+  a.small = (M < (1ll << 31) && (int64_t)(batch->T + 1) * batch->N < (1ll << 31)) ? 1 : 0;
+  a.dist_kind = batch->dist_kind, a.hp = *hp;
+  a.inv_denom = (float)((double)hp->loss_scale / mean_denominator);
+  a.gw1[0] = (float*)grads->pi_w1, a.gb1[0] = (float*)grads->pi_b1, a.gw2[0] = (float*)grads->pi_w2;
+  a.gb2[0] = (float*)grads->pi_b2, a.gw3[0] = (float*)grads->pi_w3, a.gb3[0] = (float*)grads->pi_b3;
+  a.gw1[1] = (float*)grads->vf_w1, a.gb1[1] = (float*)grads->vf_b1, a.gw2[1] = (float*)grads->vf_w2;
+  a.gb2[1] = (float*)grads->vf_b2, a.gw3[1] = (float*)grads->vf_w3, a.gb3[1] = (float*)grads->vf_b3;
+  a.sums = loss_sums;
+  const NetParams np_pi = net_params(model, 0, img_f[0]), np_vf = net_params(model, 1, img_f[1]);
+  const int stages = x3_stages();
+  for (int64_t off = 0; off < M; off += chunk) {
+    a.row_off = off;
+    a.Mc = M - off < chunk ? M - off : chunk;
+    const int64_t ntiles = ceil_div(a.Mc, 256);
+    int pairs = (int)(2 * ntiles < kNumSMs / 2 ? 2 * ntiles : kNumSMs / 2);
+    if (pairs < 2) pairs = 2;
+    a.n_pi = pairs == kNumSMs / 2 ? x3_policy_pairs(pairs) : pairs / 2;
+    if (stages & 1) {
+#define RL8_UPDF(PV)                                                                                  \
+  case PV:                                                                                            \
+    if ((rc = set_smem((const void*)x3_update_f_kernel<PV>, sizeof(SmemXF)))) return rc;               \
+    x3_update_f_kernel<PV><<<2 * pairs, kXThreads, sizeof(SmemXF), st>>>(np_pi, np_vf, a);             \
+    break;
+      switch (model->P) {
+        RL8_UPDF(2) RL8_UPDF(3) RL8_UPDF(4)
+        default: return RL8_ERR_UNSUPPORTED;
+      }
+#undef RL8_UPDF
+      if ((rc = check_launch("x3_update_f"))) return rc;
+    }
+  }
+  return RL8_OK;
+}
+
+}  // namespace rl8

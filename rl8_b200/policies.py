@@ -64,8 +64,8 @@ class Policy:
         if not (isinstance(self.distribution_cls, type) and issubclass(self.distribution_cls, Distribution)):
             raise NotImplementedError("custom distributions must subclass rl8_b200 distributions")
         self.device = torch.device(device)
-        #: GEMM precision of the kernels (``_lib.PREC_FP32`` | ``_lib.PREC_BF16``).
-        self.precision = _lib.PREC_FP32
+        #: GEMM precision of the kernels (``_lib.PREC_FP32_TC`` | ``_lib.PREC_BF16`` | ``_lib.PREC_FP32``).
+        self.precision = _lib.precision_for(False)
         self._lib = _lib.load()
         self._ws: None | torch.Tensor = None
 

@@ -1,0 +1,130 @@
+"""GPU: the fp32-accurate tensor-core mode (RL8_PREC_FP32_TC: split-bf16 operands, tcgen05 pair MMAs).
+
+The pair selftest pins the cta_group::2 plumbing and bounds each piece-product set against fp64;
+the fused forward kernel is compared with the CPU oracle (the reference's fp32 ``nn.Linear`` chain,
+src/rl8/models/_feedforward.py:263-375) at the north-star tolerance, at row counts on both sides of
+every tile boundary (128-row CTA halves, 256-row pair tiles, more tiles than CTA pairs).
+"""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _lib():
+    from rl8_b200 import _lib as L
+
+    return L, L.load()
+
+
+def _rel(got: torch.Tensor, ref: torch.Tensor) -> float:
+    return float((got.double() - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("K", [32, 256])
+def test_pair_mma_term_sets_against_fp64(K: int) -> None:
+    L, lib = _lib()
+    gen = torch.Generator().manual_seed(K)
+    A = torch.randn(256, K, generator=gen).to(DEV)
+    B = torch.randn(256, K, generator=gen).to(DEV)
+    ref = A.double() @ B.double().T
+    err = {}
+    for terms in (1, 7, 63):
+        D = torch.full((256, 256), float("nan"), device=DEV)
+        assert lib.rl8_tc3_selftest(L.ptr(A), L.ptr(B), L.ptr(D), K, terms, L.stream()) == 0
+        torch.cuda.synchronize()
+        err[terms] = _rel(D, ref)
+    assert 2e-4 < err[1] < 8e-3, err      # one bf16 product: operands really are single pieces
+    assert err[7] < 1.2e-5, err           # x2: two pieces, three products (gradient contractions)
+    assert err[63] < 4e-6, err            # x3: three pieces, six products (forward contraction)
+    # bit-reproducible
+    D2 = torch.empty(256, 256, device=DEV)
+    lib.rl8_tc3_selftest(L.ptr(A), L.ptr(B), L.ptr(D2), K, 63, L.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(D, D2)
+
+
+def test_pair_mma_maps_rows_and_columns_of_both_ctas() -> None:
+    """Exact integer-valued operands: every D[m][n] identifies its row and column (leader rows 0..127,
+    peer rows 128..255; B half of the leader = columns 0..127)."""
+    L, lib = _lib()
+    K = 32
+    A = torch.zeros(256, K)
+    B = torch.zeros(256, K)
+    A[:, 0] = torch.arange(256, dtype=torch.float32)  # row id
+    A[:, 1] = 1.0
+    B[:, 0] = 1.0
+    B[:, 1] = torch.arange(256, dtype=torch.float32) * 256.0  # column id
+    A, B = A.to(DEV), B.to(DEV)
+    D = torch.empty(256, 256, device=DEV)
+    assert lib.rl8_tc3_selftest(L.ptr(A), L.ptr(B), L.ptr(D), K, 63, L.stream()) == 0
+    want = torch.arange(256.0).view(256, 1) + 256.0 * torch.arange(256.0).view(1, 256)
+    assert torch.equal(D.cpu(), want)
+
+
+def _policy(env_name: str, dist: None | str = None):
+    import rl8_b200.env as E
+    from rl8_b200 import distributions as Dm
+    from rl8_b200.policies import Policy
+
+    env = getattr(E, env_name)(8, 8, device=DEV)
+    dcls = {None: None, "normal": Dm.Normal, "squashed_normal": Dm.SquashedNormal}[dist]
+    return Policy(env.observation_spec, env.action_spec, distribution_cls=dcls, device=DEV)
+
+
+@pytest.mark.parametrize("env_name,D", [("CartPole", 5), ("Pendulum", 3), ("DiscreteDummyEnv", 1)])
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 256, 257, 1000, 19_001, 70_000])
+def test_forward_split_matches_oracle(env_name: str, D: int, rows: int) -> None:
+    L, _ = _lib()
+    torch.manual_seed(rows + D)
+    pol = _policy(env_name)
+    pol.precision = L.PREC_FP32_TC
+    params = {k: v.detach().cpu().clone() for k, v in pol.model.state_dict().items()}
+    obs = torch.randn(rows, D) * 2
+    feats, value = O.model_forward(params, obs)
+    head = pol.forward_net(0, obs.to(DEV))
+    vals = pol.forward_net(1, obs.to(DEV))
+    ref_head = torch.cat([t.reshape(rows, -1) for t in feats.values()], dim=1)
+    if "log_std" in feats:  # continuous head: the kernel applies tanh to column 1 like the model does
+        ref_head = torch.cat([feats["mean"].reshape(rows, 1), feats["log_std"].reshape(rows, 1)], dim=1)
+    torch.testing.assert_close(head.cpu(), ref_head, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(vals.cpu(), value.reshape(rows, 1), rtol=RTOL, atol=ATOL)
+    # strided (horizon-major SoA) observations give the same numbers, bit for bit
+    obs_soa = obs.T.contiguous().to(DEV)
+    assert torch.equal(pol.forward_net(1, obs_soa.T), vals)
+
+
+def test_forward_split_trained_scale_weights_against_fp64() -> None:
+    """O(1) head weights and large activations (what a trained policy looks like): the split forward
+    stays within the fp32 path's own distance from fp64."""
+    L, _ = _lib()
+    torch.manual_seed(11)
+    pol = _policy("CartPole")
+    with torch.no_grad():
+        for name, p in pol.model.named_parameters():
+            if name.startswith(("feature_model.2", "vf_model.2")):
+                p.copy_(torch.randn_like(p) * 0.5)
+    rows = 3000
+    obs = (torch.randn(rows, 5) * 3).to(DEV)
+    sd = {k: v.detach().double() for k, v in pol.model.state_dict().items()}
+
+    def mlp64(prefix: str, head: str) -> torch.Tensor:
+        x = obs.double()
+        x = torch.relu(x @ sd[f"{prefix}.0.0.weight"].T + sd[f"{prefix}.0.0.bias"])
+        x = torch.relu(x @ sd[f"{prefix}.0.2.weight"].T + sd[f"{prefix}.0.2.bias"])
+        return x @ sd[f"{head}.weight"].T + sd[f"{head}.bias"]
+
+    ref_pi, ref_vf = mlp64("feature_model", "feature_model.2"), mlp64("vf_model", "vf_model.2")
+    out = {}
+    for prec in (L.PREC_FP32, L.PREC_FP32_TC):
+        pol.precision = prec
+        out[prec] = (_rel(pol.forward_net(0, obs), ref_pi), _rel(pol.forward_net(1, obs), ref_vf))
+    assert max(out[L.PREC_FP32_TC]) < 5e-6, out
+    assert max(out[L.PREC_FP32]) < 5e-6, out
