@@ -96,7 +96,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
   float b3[PN], gb3_acc[PN], gw3_acc[2][PN];
 #pragma unroll
   for (int p = 0; p < PN; ++p) b3[p] = np.b3[p], gb3_acc[p] = 0.0f, gw3_acc[0][p] = gw3_acc[1][p] = 0.0f;
-  float s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;
+  double s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;  // a thread sums hundreds of O(1) terms that cancel
   uint32_t kcount = 0;
 
   auto produce = [&](int64_t tile) {
@@ -324,10 +324,407 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   if (blockIdx.x == 0 && tid == 0) atomicAdd(a.sums + 4, (double)a.Mc);
 }
 
+// dZ2[row][j0 .. j0 + 8) = [H2 > 0] .* (dOut W3) from the scratch values of the row
+template <int PN>
+__device__ __forceinline__ void dz2_chunk(const float (*w3)[H], const float* d, uint32_t mask_byte, int j0, float* v) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int p = 0; p < PN; ++p) {
+      const float4 w = *reinterpret_cast<const float4*>(&w3[p][j0 + 4 * h]);
+      g[0] = fmaf(d[p], w.x, g[0]), g[1] = fmaf(d[p], w.y, g[1]);
+      g[2] = fmaf(d[p], w.z, g[2]), g[3] = fmaf(d[p], w.w, g[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[4 * h + e] = (mask_byte >> (4 * h + e)) & 1u ? g[e] : 0.0f;
+  }
+}
+
+// ---- input-gradient kernel ---------------------------------------------------------------------------------------------
+// dH1^T [input unit i][row] = sum_j W2[j][i] dZ2[row][j]:  M = i (the pair's 256: CTA c owns the half i / 128 = c),
+// N = the 256 rows of a tile (CTA c stages ITS 128 rows as the B half), K = j in 8 stages of 32.
+//   A stage: W2^T piece image (bulk copy, two pieces);  B stage: dZ2 chunks computed by the workers from dOut / mask2
+//   epilogue: lane = input unit i, columns = tile rows: dZ1 = [H1 > 0] .* dH1 (mask1 bit i of the row),
+//             gb1[i] += dZ1, gW1[i][d] += dZ1 obs[row][d] -- per-thread FMAs, the row's obs / mask word are broadcasts
+template <int NPB>
+struct SmemXB {
+  static constexpr int kStages = NPB == 2 ? 6 : 4;
+  StageX<NPB> ring[kStages];  // 196608
+  float w3[kMaxPT][H];       //   4096
+  float os[2][256][8];       //  16384  observations of the tile's rows (zero padded), per accumulator buffer
+  uint32_t m1s[2][256][4];   //   8192  mask1 words of this CTA's input half, per tile row
+  uint64_t full[kStages], bfull[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SmemXB<2>) <= 227 * 1024 && sizeof(SmemXB<3>) <= 227 * 1024, "SmemXB exceeds the 227 KB CTA limit");
+
+template <int PN, int NPB>
+__device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams& np, const UpdXArgs& a, int net,
+                                                 int64_t pr, int64_t npairs, uint32_t rank) {
+  const uint32_t tmem = s.tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rloc = tid & 127, g = tid >> 7;
+  const int q = warp & 3, cq = warp >> 2;
+  const int D = np.D;
+  const int64_t ntiles = (a.Mc + 255) / 256;
+  const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
+  float gw1_acc[7], gb1_acc = 0.0f;
+#pragma unroll
+  for (int d = 0; d < 7; ++d) gw1_acc[d] = 0.0f;
+  uint32_t kcount = 0;
+  constexpr int kStages = SmemXB<NPB>::kStages;
+
+  auto produce = [&](int64_t tile, int64_t j) {
+    const int buf = (int)(j & 1);
+    // epilogue inputs of the tile: obs and this CTA's mask1 words of all 256 rows
+    {
+      const int rt = tid & 255, half = tid >> 8;  // row of the tile; slots 4 half .. 4 half + 3
+      const int64_t rl = tile * 256 + rt;
+      float ob[7];
+      const bool valid = load_row_obs(a, rl, D, ob, nullptr);
+      float4 o4 = half ? make_float4(ob[4], ob[5], ob[6], 0.0f) : make_float4(ob[0], ob[1], ob[2], ob[3]);
+      *reinterpret_cast<float4*>(&s.os[buf][rt][4 * half]) = o4;
+      if (half == 0) {
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) m = *reinterpret_cast<const uint4*>(a.mask1[net] + rl * 8 + 4 * rank);
+        *reinterpret_cast<uint4*>(s.m1s[buf][rt]) = m;
+      }
+    }
+    const int64_t rowl = tile * 256 + rank * 128 + rloc;
+    float d4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t m0 = 0u, m1 = 0u;
+    if (rowl < a.Mc) {
+      const float4 d = *reinterpret_cast<const float4*>(a.dout[net] + rowl * 4);
+      d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
+      const uint2 m = *reinterpret_cast<const uint2*>(a.mask2[net] + rowl * 8 + 2 * g);
+      m0 = m.x, m1 = m.y;
+    }
+    for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+      const int st = (int)(kcount % kStages);
+      const uint32_t use = kcount / kStages;
+      if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+      __syncwarp();
+      if (warp == 0 && elect_one()) {
+        const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * NPB) * kXPieceBytes;
+        mbar_expect_tx(&s.bfull[st], NPB * kXPieceBytes);
+#pragma unroll
+        for (int p = 0; p < NPB; ++p)
+          bulk_g2s(s.ring[st].a[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
+      }
+      float v[8];
+      const uint32_t byte = (kc < 4 ? m0 >> (8 * kc) : m1 >> (8 * (kc - 4))) & 0xffu;
+      dz2_chunk<PN>(s.w3, d4, byte, stage_kgroup(kc, g) * 8, v);
+      uint8_t* tiles[NPB];
+#pragma unroll
+      for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
+      store_split_chunk<NPB>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_wait(&s.bfull[st], use & 1);
+        mbar_arrive_cluster(&s.full[st], 0);
+      }
+    }
+  };
+
+  auto epilogue = [&](int64_t j) {
+    const int buf = (int)(j & 1);
+    worker_bar_sync();  // os / m1s of this tile are complete
+    mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
+    fence_after_sync();
+    const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      float v[32];
+      tmem_ld32(acc + (uint32_t)(c2 * 32), v);
+      if (c2 == 1) {
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int rt = cq * 64 + c2 * 32 + e;
+        const uint32_t word = s.m1s[buf][rt][q];
+        const float dz1 = (word >> lane) & 1u ? v[e] : 0.0f;
+        const float4 oa = *reinterpret_cast<const float4*>(&s.os[buf][rt][0]);
+        const float4 ob = *reinterpret_cast<const float4*>(&s.os[buf][rt][4]);
+        gb1_acc += dz1;
+        gw1_acc[0] = fmaf(dz1, oa.x, gw1_acc[0]), gw1_acc[1] = fmaf(dz1, oa.y, gw1_acc[1]);
+        gw1_acc[2] = fmaf(dz1, oa.z, gw1_acc[2]), gw1_acc[3] = fmaf(dz1, oa.w, gw1_acc[3]);
+        gw1_acc[4] = fmaf(dz1, ob.x, gw1_acc[4]), gw1_acc[5] = fmaf(dz1, ob.y, gw1_acc[5]);
+        gw1_acc[6] = fmaf(dz1, ob.z, gw1_acc[6]);
+      }
+    }
+    worker_bar_sync();  // os / m1s of this buffer may be rewritten
+  };
+
+  if (n_my > 0) produce(pr, 0);
+  for (int64_t j = 0; j < n_my; ++j) {
+    if (j + 1 < n_my) produce(pr + (j + 1) * npairs, j + 1);
+    epilogue(j);
+  }
+  if (n_my > 0) {
+    const int i = 128 * (int)rank + q * 32 + lane;
+#pragma unroll
+    for (int d = 0; d < 7; ++d)
+      if (d < D) atomicAdd(a.gw1[net] + i * D + d, gw1_acc[d]);
+    atomicAdd(a.gb1[net] + i, gb1_acc);
+  }
+}
+
+template <int P, int NPB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXThreads, 1)
+x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemXB<NPB>& s = *reinterpret_cast<SmemXB<NPB>*>(smem_raw);
+  constexpr int kStages = SmemXB<NPB>::kStages;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t pair = blockIdx.x >> 1, pairs_all = gridDim.x >> 1;
+  const int n_pi = (int)(pairs_all / 2);
+  const int net = pair < n_pi ? 0 : 1;
+  const int64_t pr = net ? pair - n_pi : pair, npairs = net ? pairs_all - n_pi : n_pi;
+  const NetParams np = net ? np_vf : np_pi;  // w2_img: the TRANSPOSED NPB-piece image
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&s.full[i], 32);
+      mbar_init(&s.bfull[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.acc_full[0], 1), mbar_init(&s.acc_full[1], 1);
+    mbar_init(&s.acc_empty[0], 32), mbar_init(&s.acc_empty[1], 32);
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  if (warp < 16) {
+    if (net == 0) update_b_workers<P, NPB>(s, np, a, 0, pr, npairs, rank);
+    else update_b_workers<1, NPB>(s, np, a, 1, pr, npairs, rank);
+  } else if (rank == 0) {
+    const int64_t ntiles = (a.Mc + 255) / 256;
+    const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
+    const uint32_t idesc = instr_desc(256, H, 0, 0);
+    uint32_t kcount = 0;
+    for (int64_t j = 0; j < n_my; ++j) {
+      const int buf = (int)(j & 1);
+      if (j >= 2) mbar_wait_cluster(&s.acc_empty[buf], (uint32_t)(((j >> 1) - 1) & 1));
+      for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+        const int st = (int)(kcount % kStages);
+        mbar_wait_cluster(&s.full[st], (kcount / kStages) & 1);
+        fence_after_sync();
+        if (elect_one()) {
+          issue_stage<NPB>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
+          mma_commit_pair(&s.empty[st]);
+          if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 16) tmem_dealloc_pair(tmem, 512);
+}
+
+// ---- weight-gradient kernel ------------------------------------------------------------------------------------------
+// gW2[j][i] += sum_rows dZ2[row][j] H1[row][i].  The contraction runs over rows: a ring stage is 32 rows, both operands
+// are MN-major tiles [32 K rows][128 M / N columns] per piece (off(r, g) = r * 16 + g * 512; LBO 128, SBO 512), CTA c
+// of the pair produces the dZ2 columns j and the H1 columns i of ITS half, so nothing is computed twice.
+//   worker warps 0..7  : dZ2^T chunks  (lane = row of the stage, warp w -> column groups w and w + 8), gb2 on the way
+//   worker warps 8..15 : H1 chunks     (lane = row, warp w - 8 -> column groups w - 8 and w)
+// Pairs [0, n_pi) work on the policy network, the rest on the value network; a pair owns the stages
+// pr, pr + npairs, ... of its network and keeps its 256 x 256 accumulator in tensor memory until the end.
+template <int NPB>
+struct SmemXW {
+  static constexpr int kStages = NPB == 2 ? 6 : 4;
+  StageX<NPB> ring[kStages];  // 196608
+  float w1s[H][8];           //   8192
+  float w3[kMaxPT][H];       //   4096
+  uint64_t full[kStages], empty[kStages], done;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SmemXW<2>) <= 227 * 1024 && sizeof(SmemXW<3>) <= 227 * 1024, "SmemXW exceeds the 227 KB CTA limit");
+
+template <int PN, int NPB>
+__device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams& np, const UpdXArgs& a, int net,
+                                                 int64_t pr, int64_t npairs, uint32_t rank) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = np.D;
+  const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
+  const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
+  constexpr int kWStages = SmemXW<NPB>::kStages;
+  const bool dz_role = warp < 8;
+  const int g0 = dz_role ? warp : warp - 8;  // column groups g0 and g0 + 8 of this CTA's 128-column half
+  float gb2_acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gb2_acc[i][e] = 0.0f;
+  // inputs of this lane's row of a stage: dz role {dOut[4], 16 mask bytes of the CTA's half}; h1 role {obs[7]}
+  float in_f[8];
+  uint4 in_m = make_uint4(0u, 0u, 0u, 0u);
+  auto load_inputs = [&](int64_t k, float* f, uint4& m) {
+    const int64_t rowl = (pr + k * npairs) * kXKc + lane;
+    if (dz_role) {
+      float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      m = make_uint4(0u, 0u, 0u, 0u);
+      if (rowl < a.Mc) {
+        d = *reinterpret_cast<const float4*>(a.dout[net] + rowl * 4);
+        m = *reinterpret_cast<const uint4*>(a.mask2[net] + rowl * 8 + 4 * rank);
+      }
+      f[0] = d.x, f[1] = d.y, f[2] = d.z, f[3] = d.w;
+    } else {
+      load_row_obs(a, rowl, D, f, nullptr);
+    }
+  };
+  if (n_my > 0) load_inputs(0, in_f, in_m);
+  for (int64_t k = 0; k < n_my; ++k) {
+    float cur_f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur_f[i] = in_f[i];
+    const uint4 cur_m = in_m;
+    if (k + 1 < n_my) load_inputs(k + 1, in_f, in_m);
+    const int st = (int)(k % kWStages);
+    const uint32_t use = (uint32_t)(k / kWStages);
+    if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int g = g0 + 8 * i;
+      float v[8];
+      if (dz_role) {
+        const uint32_t word = g < 4 ? cur_m.x : g < 8 ? cur_m.y : g < 12 ? cur_m.z : cur_m.w;
+        dz2_chunk<PN>(s.w3, cur_f, (word >> (8 * (g & 3))) & 0xffu, 128 * (int)rank + 8 * g, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gb2_acc[i][e] += v[e];
+        uint8_t* tiles[NPB];
+#pragma unroll
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].a[p];
+        store_split_chunk<NPB>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+      } else {
+        h1_chunk(s.w1s, cur_f, 128 * (int)rank + 8 * g, v);
+        uint8_t* tiles[NPB];
+#pragma unroll
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
+        store_split_chunk<NPB>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);
+  }
+  if (n_my > 0) {
+    if (dz_role) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float w = warp_sum(gb2_acc[i][e]);
+          if (lane == 0) atomicAdd(a.gb2[net] + 128 * rank + 8 * (g0 + 8 * i) + e, w);
+        }
+    }
+    // flush the accumulator: lane = unit j of this CTA's half, 256 columns i
+    mbar_wait_cluster(&s.done, 0);
+    fence_after_sync();
+    const int q = warp & 3, cq = warp >> 2;
+    const int j = 128 * (int)rank + q * 32 + lane;
+    float* dst = a.gw2[net] + (int64_t)j * H + cq * 64;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      float v[32];
+      tmem_ld32(s.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64 + h * 32), v);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) red_add_v4(dst + h * 32 + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+    }
+  }
+}
+
+template <int P, int NPB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXThreads, 1)
+x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemXW<NPB>& s = *reinterpret_cast<SmemXW<NPB>*>(smem_raw);
+  constexpr int kWStages = SmemXW<NPB>::kStages;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t pair = blockIdx.x >> 1, pairs_all = gridDim.x >> 1;
+  const int n_pi = (int)(pairs_all / 2);
+  const int net = pair < n_pi ? 0 : 1;
+  const int64_t pr = net ? pair - n_pi : pair, npairs = net ? pairs_all - n_pi : n_pi;
+  const NetParams np = net ? np_vf : np_pi;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&s.full[i], 32);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc_pair(&s.tmem_base, 256);
+  stage_w1s(s.w1s, np);
+  for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
+    const int p = i / H, c = i - p * H;
+    s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  fence_after_sync();
+  if (warp < 16) {
+    if (net == 0) update_w_workers<P, NPB>(s, np, a, 0, pr, npairs, rank);
+    else update_w_workers<1, NPB>(s, np, a, 1, pr, npairs, rank);
+  } else if (rank == 0) {
+    const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
+    const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
+    const uint32_t idesc = instr_desc(256, H, 1, 1);
+    using T = Terms<NPB>;
+    for (int64_t k = 0; k < n_my; ++k) {
+      const int st = (int)(k % kWStages);
+      mbar_wait_cluster(&s.full[st], (uint32_t)((k / kWStages) & 1));
+      fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kXKc / 16; ++ks) {
+#pragma unroll
+          for (int i = 0; i < T::n; ++i) {
+            // MN-major tiles: LBO 128 (next 8 K rows), SBO 512 (next 8 M / N columns), 16 K rows = 256 bytes
+            const uint64_t ad = smem_desc(smem_u32(s.ring[st].a[T::a(i)]) + ks * 256, 128, 512);
+            const uint64_t bd = smem_desc(smem_u32(s.ring[st].b[T::b(i)]) + ks * 256, 128, 512);
+            mma_bf16_pair(s.tmem_base, ad, bd, idesc, (k > 0 || ks > 0 || i > 0) ? 1u : 0u);
+          }
+        }
+        mma_commit_pair(&s.empty[st]);
+        if (k == n_my - 1) mma_commit_pair(&s.done);
+      }
+      __syncwarp();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 16) tmem_dealloc_pair(s.tmem_base, 256);
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------------
 static int x3_stages() {  // development switch: bit 0 forward / loss, bit 1 input-gradient, bit 2 weight-gradient kernel
   const char* e = getenv("RL8_X3_STAGES");
   return e ? atoi(e) : 7;
+}
+static int x3_backward_pieces() {  // 3: six piece products in the gradient contractions too; 2: three
+  const char* e = getenv("RL8_X3_BACKWARD_PIECES");
+  return e && atoi(e) == 2 ? 2 : 3;
 }
 static int x3_policy_pairs(int pairs) {
   const char* e = getenv("RL8_X3_POLICY_PAIRS");  // tuning knob: the policy network's epilogue is the heavier one
@@ -340,7 +737,7 @@ static int x3_policy_pairs(int pairs) {
 int64_t ppo_x3_workspace(const rl8_model*, int64_t max_rows) {
   const int64_t chunk = max_rows < kXChunkRows ? max_rows : kXChunkRows;
   // forward images (3 pieces) + transposed images (2 pieces) of both networks, scratch of both networks
-  return 2 * (int64_t)kXImgBytes + 2 * (int64_t)(kXImgBytes / 3 * 2) + 2 * chunk * 80 + 256;
+  return 4 * (int64_t)kXImgBytes + 2 * chunk * 80 + 256;
 }
 
 int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_batch* batch, const int64_t* rows,
@@ -352,14 +749,14 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
   uint8_t* p = (uint8_t*)workspace;
   uint8_t* img_f[2] = {p, p + kXImgBytes};
   p += 2 * (int64_t)kXImgBytes;
-  const int64_t img2 = kXImgBytes / 3 * 2;
-  uint8_t* img_b[2] = {p, p + img2};
-  p += 2 * img2;
+  uint8_t* img_b[2] = {p, p + kXImgBytes};
+  p += 2 * (int64_t)kXImgBytes;
+  const int npb = x3_backward_pieces();
   int rc;
   for (int net = 0; net < 2; ++net) {
     const float* w2 = net ? model->vf_w2 : model->pi_w2;
     if ((rc = launch_pack_w2_pieces(w2, img_f[net], 0, 3, st))) return rc;
-    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, 2, st))) return rc;
+    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, npb, st))) return rc;
   }
   UpdXArgs a;
   for (int net = 0; net < 2; ++net) {
@@ -404,6 +801,46 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
       }
 #undef RL8_UPDF
       if ((rc = check_launch("x3_update_f"))) return rc;
+    }
+    if (stages & 2) {
+      const NetParams nb_pi = net_params(model, 0, img_b[0]), nb_vf = net_params(model, 1, img_b[1]);
+#define RL8_UPDB(PV)                                                                                  \
+  case PV:                                                                                            \
+    if (npb == 2) {                                                                                   \
+      if ((rc = set_smem((const void*)x3_update_b_kernel<PV, 2>, sizeof(SmemXB<2>)))) return rc;       \
+      x3_update_b_kernel<PV, 2><<<2 * pairs, kXThreads, sizeof(SmemXB<2>), st>>>(nb_pi, nb_vf, a);     \
+    } else {                                                                                          \
+      if ((rc = set_smem((const void*)x3_update_b_kernel<PV, 3>, sizeof(SmemXB<3>)))) return rc;       \
+      x3_update_b_kernel<PV, 3><<<2 * pairs, kXThreads, sizeof(SmemXB<3>), st>>>(nb_pi, nb_vf, a);     \
+    }                                                                                                 \
+    break;
+      switch (model->P) {
+        RL8_UPDB(2) RL8_UPDB(3) RL8_UPDB(4)
+        default: return RL8_ERR_UNSUPPORTED;
+      }
+#undef RL8_UPDB
+      if ((rc = check_launch("x3_update_b"))) return rc;
+    }
+    if (stages & 4) {
+      const int64_t nst = ceil_div(a.Mc, kXKc);
+      int wpairs = (int)(nst < kNumSMs / 2 ? nst : kNumSMs / 2);
+      if (wpairs < 2) wpairs = 2;
+#define RL8_UPDW(PV)                                                                                  \
+  case PV:                                                                                            \
+    if (npb == 2) {                                                                                   \
+      if ((rc = set_smem((const void*)x3_update_w_kernel<PV, 2>, sizeof(SmemXW<2>)))) return rc;       \
+      x3_update_w_kernel<PV, 2><<<2 * wpairs, kXThreads, sizeof(SmemXW<2>), st>>>(np_pi, np_vf, a);    \
+    } else {                                                                                          \
+      if ((rc = set_smem((const void*)x3_update_w_kernel<PV, 3>, sizeof(SmemXW<3>)))) return rc;       \
+      x3_update_w_kernel<PV, 3><<<2 * wpairs, kXThreads, sizeof(SmemXW<3>), st>>>(np_pi, np_vf, a);    \
+    }                                                                                                 \
+    break;
+      switch (model->P) {
+        RL8_UPDW(2) RL8_UPDW(3) RL8_UPDW(4)
+        default: return RL8_ERR_UNSUPPORTED;
+      }
+#undef RL8_UPDW
+      if ((rc = check_launch("x3_update_w"))) return rc;
     }
   }
   return RL8_OK;
