@@ -42,6 +42,26 @@ __device__ __forceinline__ void issue_stage(uint32_t acc_tmem, const StageX<NP>&
   }
 }
 
+// The same with the leading products a0 b0 and the correction products in separate accumulators (the tensor pipe
+// truncates the accumulator after every instruction: the leading accumulator then sees 2 truncations per stage
+// instead of 2 * n, and the corrections are 2^-8 of the result).  The consumer adds the two in fp32.
+template <int NP>
+__device__ __forceinline__ void issue_stage_split(uint32_t lead_tmem, uint32_t corr_tmem, const StageX<NP>& stg,
+                                                  uint32_t idesc, bool accumulate_first) {
+  using T = Terms<NP>;
+#pragma unroll
+  for (int ks = 0; ks < kXKc / 16; ++ks) {
+#pragma unroll
+    for (int i = 0; i < T::n; ++i) {
+      const uint64_t ad = smem_desc(smem_u32(stg.a[T::a(i)]) + ks * 4096, 2048, 128);
+      const uint64_t bd = smem_desc(smem_u32(stg.b[T::b(i)]) + ks * 4096, 2048, 128);
+      const bool lead = T::a(i) == 0 && T::b(i) == 0;
+      const bool first = !accumulate_first && ks == 0 && (lead || i == 0);
+      mma_bf16_pair(lead ? lead_tmem : corr_tmem, ad, bd, idesc, first ? 0u : 1u);
+    }
+  }
+}
+
 // [W1 | b1] in fp32: w1s[i][d] = W1[i][d] (d < D <= 7, zero padded), w1s[i][7] = b1[i]
 __device__ __forceinline__ void stage_w1s(float (*w1s)[8], const NetParams& np) {
   for (int e = threadIdx.x; e < H * 8; e += blockDim.x) {

@@ -374,8 +374,12 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   for (int d = 0; d < 7; ++d) gw1_acc[d] = 0.0f;
   uint32_t kcount = 0;
   constexpr int kStages = SmemXB<NPB>::kStages;
+  constexpr int kTileStages = H / kXKc;
+  // inputs of this thread's dZ2 chunks of the tile being produced (its row: dOut, the mask2 words of columns [64 g, +64))
+  float d4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  uint32_t m0 = 0u, m1 = 0u;
 
-  auto produce = [&](int64_t tile, int64_t j) {
+  auto begin_tile = [&](int64_t tile, int64_t j) {
     const int buf = (int)(j & 1);
     // epilogue inputs of the tile: obs and this CTA's mask1 words of all 256 rows
     {
@@ -392,15 +396,17 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       }
     }
     const int64_t rowl = tile * 256 + rank * 128 + rloc;
-    float d4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    uint32_t m0 = 0u, m1 = 0u;
+    d4[0] = d4[1] = d4[2] = d4[3] = 0.0f;
+    m0 = m1 = 0u;
     if (rowl < a.Mc) {
       const float4 d = *reinterpret_cast<const float4*>(a.dout[net] + rowl * 4);
       d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
       const uint2 m = *reinterpret_cast<const uint2*>(a.mask2[net] + rowl * 8 + 2 * g);
       m0 = m.x, m1 = m.y;
     }
-    for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+  };
+  auto produce = [&](int kc0, int kc1) {
+    for (int kc = kc0; kc < kc1; ++kc, ++kcount) {
       const int st = (int)(kcount % kStages);
       const uint32_t use = kcount / kStages;
       if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
@@ -431,23 +437,27 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   auto epilogue = [&](int64_t j) {
     const int buf = (int)(j & 1);
     worker_bar_sync();  // os / m1s of this tile are complete
-    mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
+    mbar_wait_cluster(&s.acc_full[0], (uint32_t)(j & 1));
     fence_after_sync();
-    const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      float v[32];
-      tmem_ld32(acc + (uint32_t)(c2 * 32), v);
-      if (c2 == 1) {
+    const uint32_t acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+#pragma unroll 1
+    for (int c4 = 0; c4 < 4; ++c4) {
+      float v[16], c[16];
+      tmem_ld16_nowait(acc + (uint32_t)(c4 * 16), v);
+      tmem_ld16_nowait(acc + (uint32_t)(H + c4 * 16), c);
+      tmem_wait_ld();
+      reg_fence16f(v);
+      reg_fence16f(c);
+      if (c4 == 3) {  // both accumulators have been read: the tensor pipe may start the next tile
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);
+        if (lane == 0) mbar_arrive_cluster(&s.acc_empty[0], 0);
       }
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int rt = cq * 64 + c2 * 32 + e;
+      for (int e = 0; e < 16; ++e) {
+        const int rt = cq * 64 + c4 * 16 + e;
         const uint32_t word = s.m1s[buf][rt][q];
-        const float dz1 = (word >> lane) & 1u ? v[e] : 0.0f;
+        const float dz1 = (word >> lane) & 1u ? v[e] + c[e] : 0.0f;
         const float4 oa = *reinterpret_cast<const float4*>(&s.os[buf][rt][0]);
         const float4 ob = *reinterpret_cast<const float4*>(&s.os[buf][rt][4]);
         gb1_acc += dz1;
@@ -460,10 +470,22 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
     worker_bar_sync();  // os / m1s of this buffer may be rewritten
   };
 
-  if (n_my > 0) produce(pr, 0);
+  // One accumulator pair (leading + corrections = all 512 columns): the tensor pipe cannot start tile j + 1 before
+  // the epilogue of tile j has read it.  The workers therefore stage as much of tile j + 1 as the ring holds, run the
+  // epilogue (the pipe restarts as soon as the reads are done and finds kStages stages waiting), then the rest.
+  constexpr int kAhead = kStages < kTileStages ? kStages : kTileStages;
+  if (n_my > 0) {
+    begin_tile(pr, 0);
+    produce(0, kTileStages);
+  }
   for (int64_t j = 0; j < n_my; ++j) {
-    if (j + 1 < n_my) produce(pr + (j + 1) * npairs, j + 1);
+    const bool more = j + 1 < n_my;
+    if (more) {
+      begin_tile(pr + (j + 1) * npairs, j + 1);
+      produce(0, kAhead);
+    }
     epilogue(j);
+    if (more) produce(kAhead, kTileStages);
   }
   if (n_my > 0) {
     const int i = 128 * (int)rank + q * 32 + lane;
@@ -517,16 +539,15 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     const uint32_t idesc = instr_desc(256, H, 0, 0);
     uint32_t kcount = 0;
     for (int64_t j = 0; j < n_my; ++j) {
-      const int buf = (int)(j & 1);
-      if (j >= 2) mbar_wait_cluster(&s.acc_empty[buf], (uint32_t)(((j >> 1) - 1) & 1));
+      if (j >= 1) mbar_wait_cluster(&s.acc_empty[0], (uint32_t)((j - 1) & 1));
       for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
         const int st = (int)(kcount % kStages);
         mbar_wait_cluster(&s.full[st], (kcount / kStages) & 1);
         fence_after_sync();
         if (elect_one()) {
-          issue_stage<NPB>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
+          issue_stage_split<NPB>(tmem, tmem + (uint32_t)H, s.ring[st], idesc, kc > 0);
           mma_commit_pair(&s.empty[st]);
-          if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[buf]);
+          if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[0]);
         }
         __syncwarp();
       }
@@ -552,9 +573,16 @@ struct SmemXW {
   StageX<NPB> ring[kStages];  // 196608
   float w1s[H][8];           //   8192
   float w3[kMaxPT][H];       //   4096
-  uint64_t full[kStages], empty[kStages], done;
+  uint64_t full[kStages], empty[kStages], flush_full, flush_empty;
   uint32_t tmem_base;
 };
+// The tensor pipe truncates its fp32 accumulator after every instruction (measured: the error of a long
+// accumulation grows linearly with the number of instructions, tools/check_split_accuracy.py), and this kernel
+// accumulates over ALL rows of a pair.  So (1) the leading products a0 b0 go to one accumulator and the five small
+// correction products to another (256 columns each; the corrections are 2^-8 of the result, their truncation does
+// not matter), and (2) every kFlushStages stages both are added in fp32 (round to nearest) into gW2 and restarted:
+// the leading accumulator sees at most 2 * kFlushStages truncations.
+constexpr int kFlushStages = 128;
 static_assert(sizeof(SmemXW<2>) <= 227 * 1024 && sizeof(SmemXW<3>) <= 227 * 1024, "SmemXW exceeds the 227 KB CTA limit");
 
 template <int PN, int NPB>
@@ -587,6 +615,35 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
       f[0] = d.x, f[1] = d.y, f[2] = d.z, f[3] = d.w;
     } else {
       load_row_obs(a, rowl, D, f, nullptr);
+    }
+  };
+  // accumulator flush f covers the stages [f F, min((f + 1) F, n_my)); the workers run it once they have produced the
+  // kWStages - 1 stages after its last one (what the ring holds without the tensor pipe moving on)
+  const int64_t nflush = (n_my + kFlushStages - 1) / kFlushStages;
+  int64_t next_flush = 0;
+  auto flush = [&](int64_t f) {
+    mbar_wait_cluster(&s.flush_full, (uint32_t)(f & 1));
+    fence_after_sync();
+    const int q = warp & 3, cq = warp >> 2;
+    const int j = 128 * (int)rank + q * 32 + lane;  // lane = unit j of this CTA's half, 256 columns i
+    float* dst = a.gw2[net] + (int64_t)j * H + cq * 64;
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      float v[16], c[16];
+      const uint32_t at = s.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64 + h * 16);
+      tmem_ld16_nowait(at, v);
+      tmem_ld16_nowait(at + H, c);
+      tmem_wait_ld();
+      reg_fence16f(v);
+      reg_fence16f(c);
+      if (h == 3) {
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.flush_empty, 0);
+      }
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        red_add_v4(dst + h * 16 + e, v[e] + c[e], v[e + 1] + c[e + 1], v[e + 2] + c[e + 2], v[e + 3] + c[e + 3]);
     }
   };
   if (n_my > 0) load_inputs(0, in_f, in_m);
@@ -623,30 +680,21 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
     fence_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);
+    while (next_flush < nflush) {
+      const int64_t last = (next_flush + 1) * kFlushStages < n_my ? (next_flush + 1) * kFlushStages - 1 : n_my - 1;
+      const int64_t due = last + kWStages - 1 < n_my - 1 ? last + kWStages - 1 : n_my - 1;
+      if (k < due) break;
+      flush(next_flush++);
+    }
   }
-  if (n_my > 0) {
-    if (dz_role) {
+  if (n_my > 0 && dz_role) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float w = warp_sum(gb2_acc[i][e]);
-          if (lane == 0) atomicAdd(a.gb2[net] + 128 * rank + 8 * (g0 + 8 * i) + e, w);
-        }
-    }
-    // flush the accumulator: lane = unit j of this CTA's half, 256 columns i
-    mbar_wait_cluster(&s.done, 0);
-    fence_after_sync();
-    const int q = warp & 3, cq = warp >> 2;
-    const int j = 128 * (int)rank + q * 32 + lane;
-    float* dst = a.gw2[net] + (int64_t)j * H + cq * 64;
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      float v[32];
-      tmem_ld32(s.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64 + h * 32), v);
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) red_add_v4(dst + h * 32 + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
-    }
+      for (int e = 0; e < 8; ++e) {
+        const float w = warp_sum(gb2_acc[i][e]);
+        if (lane == 0) atomicAdd(a.gb2[net] + 128 * rank + 8 * (g0 + 8 * i) + e, w);
+      }
   }
 }
 
@@ -669,10 +717,11 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
       mbar_init(&s.full[i], 32);
       mbar_init(&s.empty[i], 1);
     }
-    mbar_init(&s.done, 1);
+    mbar_init(&s.flush_full, 1);
+    mbar_init(&s.flush_empty, 32);
     fence_mbar_init();
   }
-  if (warp == 16) tmem_alloc_pair(&s.tmem_base, 256);
+  if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
   stage_w1s(s.w1s, np);
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
@@ -690,8 +739,11 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
     const uint32_t idesc = instr_desc(256, H, 1, 1);
     using T = Terms<NPB>;
+    int64_t nf = 0;  // flushes committed so far
     for (int64_t k = 0; k < n_my; ++k) {
       const int st = (int)(k % kWStages);
+      const bool fresh = k % kFlushStages == 0;  // first stage of a flush interval: both accumulators restart
+      if (fresh && k > 0) mbar_wait_cluster(&s.flush_empty, (uint32_t)((nf - 1) & 1));
       mbar_wait_cluster(&s.full[st], (uint32_t)((k / kWStages) & 1));
       fence_after_sync();
       if (elect_one()) {
@@ -702,19 +754,22 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
             // MN-major tiles: LBO 128 (next 8 K rows), SBO 512 (next 8 M / N columns), 16 K rows = 256 bytes
             const uint64_t ad = smem_desc(smem_u32(s.ring[st].a[T::a(i)]) + ks * 256, 128, 512);
             const uint64_t bd = smem_desc(smem_u32(s.ring[st].b[T::b(i)]) + ks * 256, 128, 512);
-            mma_bf16_pair(s.tmem_base, ad, bd, idesc, (k > 0 || ks > 0 || i > 0) ? 1u : 0u);
+            const bool lead = T::a(i) == 0 && T::b(i) == 0;  // a0 b0 -> leading accumulator, the rest -> corrections
+            const bool first = fresh && ks == 0 && (lead || i == 0);
+            mma_bf16_pair(s.tmem_base + (lead ? 0u : (uint32_t)H), ad, bd, idesc, first ? 0u : 1u);
           }
         }
         mma_commit_pair(&s.empty[st]);
-        if (k == n_my - 1) mma_commit_pair(&s.done);
+        if ((k + 1) % kFlushStages == 0 || k == n_my - 1) mma_commit_pair(&s.flush_full);
       }
       __syncwarp();
+      if ((k + 1) % kFlushStages == 0 || k == n_my - 1) ++nf;
     }
   }
   fence_before_sync();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 16) tmem_dealloc_pair(s.tmem_base, 256);
+  if (warp == 16) tmem_dealloc_pair(s.tmem_base, 512);
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------

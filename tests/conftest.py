@@ -60,6 +60,11 @@ GOLDEN_CASES = [
     "ff_mountain_car",
     "ff_pendulum_squashed",
     "ff_pendulum_normal",
+    # round 2: rows crossing the 128 / 256-row tiles of the tensor-core kernels with ragged minibatches,
+    # normalize_rewards=False, and an early stop (target_kl_div) that triggers inside the reference
+    "ff_cartpole_n320",
+    "ff_pendulum_n300_raw_rewards",
+    "ff_discrete_dummy_early_stop",
 ]
 
 

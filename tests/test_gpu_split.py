@@ -128,3 +128,75 @@ def test_forward_split_trained_scale_weights_against_fp64() -> None:
         out[prec] = (_rel(pol.forward_net(0, obs), ref_pi), _rel(pol.forward_net(1, obs), ref_vf))
     assert max(out[L.PREC_FP32_TC]) < 5e-6, out
     assert max(out[L.PREC_FP32]) < 5e-6, out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# update: the three split kernels against the CUDA-core fp32 update on the SAME buffer and weights
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _twins(env_name: str, dist, n: int, t: int, **kw):  # noqa: ANN001, ANN202
+    import rl8_b200.env as E
+    from rl8_b200 import AlgorithmConfig
+
+    L, _ = _lib()
+    algos = []
+    for prec in (L.PREC_FP32, L.PREC_FP32_TC):
+        torch.manual_seed(7)
+        a = AlgorithmConfig(num_envs=n, horizon=t, distribution_cls=dist, **kw).build(getattr(E, env_name))
+        a.policy.precision = prec
+        algos.append(a)
+    ref, tc = algos
+    tc.policy.model.load_state_dict(ref.policy.model.state_dict())
+    torch.manual_seed(8)
+    tc.collect()  # the buffer comes from the split forward: logp_new == logp_old on the first minibatch
+    ref.buffer._raw.copy_(tc.buffer._raw)
+    ref.state.buffered, ref.state.horizons = True, tc.state.horizons
+    ref.state.reward_scale = tc.state.reward_scale
+    return ref, tc
+
+
+@pytest.mark.parametrize(
+    "env_name,dist,n,t,kw",
+    [("CartPole", None, 1000, 16, {"entropy_coeff": 0.01}),
+     ("CartPole", None, 300, 7, {"sgd_minibatch_size": 700, "shuffle_minibatches": True}),   # ragged tiles, row lists
+     ("MountainCar", None, 1024, 16, {"sgd_minibatch_size": 2048, "accumulate_grads": True}),
+     ("Pendulum", "squashed_normal", 777, 8, {"dual_clip_param": 3.0}),
+     ("ContinuousDummyEnv", "normal", 512, 16, {"entropy_coeff": 0.01}),
+     ("DiscreteDummyEnv", None, 70_000, 4, {})],                                               # more tiles than CTA pairs
+)
+def test_update_split_matches_fp32_cuda_cores(env_name: str, dist, n: int, t: int, kw) -> None:  # noqa: ANN001
+    from rl8_b200 import distributions as Dm
+
+    dcls = {None: None, "normal": Dm.Normal, "squashed_normal": Dm.SquashedNormal}[dist]
+    kw = {"shuffle_minibatches": False, **kw}
+    ref, tc = _twins(env_name, dcls, n, t, num_sgd_iters=1, **kw)
+    grads: list[dict[str, torch.Tensor]] = [{}, {}]
+    for algo, g in zip((ref, tc), grads):
+        algo._on_grads = (lambda named, g=g: g.update({k: v.detach().double().cpu().clone() for k, v in named.items()})
+                          if not g else None)
+    torch.manual_seed(9)
+    s_ref = ref.step()
+    torch.manual_seed(9)  # same minibatch permutation
+    s_tc = tc.step()
+    for k in ("losses/policy", "losses/vf", "losses/total", "losses/entropy", "monitors/kl_div"):
+        assert s_tc[k] == pytest.approx(s_ref[k], rel=2e-5, abs=2e-6), (k, s_tc[k], s_ref[k])
+    assert set(grads[0]) == set(grads[1]) and grads[0]
+    gnorm = float(torch.cat([v.flatten() for v in grads[0].values()]).norm())
+    for k in sorted(grads[0]):
+        a, b = grads[0][k], grads[1][k]
+        err = float((a - b).norm())
+        # 2e-5 of the tensor's own norm, or -- tensors that are sums of cancelling terms -- 2e-6 of the global norm
+        assert err <= max(2e-5 * float(a.norm()), 2e-6 * gnorm), (k, err, float(a.norm()), gnorm)
+    p_ref, p_tc = ref.policy.model.flat_params, tc.policy.model.flat_params
+    # Adam turns a gradient error dg into lr * eps / (|g| + eps)^2 * dg: only elements with |g| ~ eps = 1e-8 move
+    assert float((p_ref - p_tc).abs().max()) < 2e-4
+    assert float(((p_ref - p_tc).abs() > 5e-6).float().mean()) < 2e-3
+
+
+def test_fp32_modes_share_the_golden_case(monkeypatch: pytest.MonkeyPatch) -> None:
+    """RL8_FP32_SIMT=1 selects the CUDA-core GEMMs for enable_amp=False (the cross-check of the split kernels)."""
+    L, _ = _lib()
+    assert L.precision_for(False) == L.PREC_FP32_TC and L.precision_for(True) == L.PREC_BF16
+    monkeypatch.setenv("RL8_FP32_SIMT", "1")
+    assert L.precision_for(False) == L.PREC_FP32
