@@ -138,11 +138,74 @@ def cpu_step_fn(workload: str, N: int, T: int, sgd_iters: int, minibatch: int):
     return step
 
 
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_available(workload: str) -> bool:
+    """The unmodified upstream source staged by tools/stage_ref.py (git-ignored oracle/_ref/)."""
+    return os.path.isdir(os.path.join(REF_DIR, "src", "rl8"))
+
+
+def reference_step_fn(workload: str, N: int, T: int, sgd_iters: int, minibatch: int, device: str = "cpu"):
+    """``collect()`` + ``step()`` of the UNMODIFIED reference (its own AlgorithmConfig / Algorithm classes, eager)
+    behind the arithmetic-free stand-ins of oracle/refshim.
+
+    The reference picks ``"cuda"`` whenever ``torch.cuda.is_available()`` -- whatever ``config.device`` says
+    (src/rl8/algorithms/_feedforward.py:210-216: the conditional binds as ``"cuda" if available else (...)``) -- so
+    for its CPU path CUDA is hidden from it while it builds (``--impl reference`` also hides the GPUs from the whole
+    process before torch is imported)."""
+    os.environ["TORCHDYNAMO_DISABLE"] = "1"  # Inductor's C++ backend does not build in this image (BASELINE.md §2)
+    for p_ in (REF_DIR, os.path.join(REF_DIR, "src"), os.path.join(ROOT, "oracle", "refshim")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    import torch
+    from rl8 import AlgorithmConfig as RefConfig  # noqa: E402  (upstream)
+    from rl8 import RecurrentAlgorithmConfig as RefRecurrentConfig  # noqa: E402
+    from rl8.distributions import SquashedNormal as RefSquashed  # noqa: E402
+    from rl8.env import DiscreteDummyEnv as RefDummy  # noqa: E402
+
+    _, env_name, dist_name, recurrent, _, _, _, _ = WORKLOADS[workload]
+    if env_name == "CartPole":
+        from examples.cartpole.env import CartPole as env_cls  # noqa: E402, N813
+    elif env_name == "Pendulum":
+        from examples.pendulum.env import Pendulum as env_cls  # noqa: E402, N813
+    else:
+        env_cls = RefDummy
+    torch.manual_seed(0)
+    kw = dict(num_envs=N, horizon=T, num_sgd_iters=sgd_iters, sgd_minibatch_size=minibatch or None, device=device)
+    if dist_name == "SquashedNormal":
+        kw["distribution_cls"] = RefSquashed
+    seen = torch.cuda.is_available
+    if device == "cpu":
+        torch.cuda.is_available = lambda: False
+    try:
+        algo = (RefRecurrentConfig if recurrent else RefConfig)(**kw).build(env_cls)
+    finally:
+        torch.cuda.is_available = seen
+    assert str(algo.hparams.device).startswith(device), algo.hparams.device
+
+    def step() -> None:
+        algo.collect()
+        algo.step()
+
+    return step
+
+
+def cpu_leg(workload: str, N: int, T: int, sgd_iters: int, minibatch: int):
+    """(step function, kind): the staged reference when present, else the CPU port of it."""
+    if reference_available(workload):
+        try:
+            return reference_step_fn(workload, N, T, sgd_iters, minibatch), "reference"
+        except Exception as e:  # noqa: BLE001  (a broken staging must not take the bench down)
+            print(f"reference import failed ({type(e).__name__}: {e}); timing the CPU port", file=sys.stderr)
+    return cpu_step_fn(workload, N, T, sgd_iters, minibatch), "port"
+
+
 def cpu_probe(a: argparse.Namespace, budget_s: float, iters: int) -> tuple[int, float]:
     """Pick the largest power-of-two num_envs (<= the workload's) whose `iters` steps fit the
     budget; returns (num_envs, seconds per transition estimate)."""
     N0 = 1024
-    fn = cpu_step_fn(a.workload, N0, a.horizon, a.sgd_iters, 0)
+    fn, _ = cpu_leg(a.workload, N0, a.horizon, a.sgd_iters, 0)
     fn()
     t0 = time.perf_counter()
     fn()
@@ -161,8 +224,10 @@ def run_reference(a: argparse.Namespace) -> None:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    N, _ = cpu_probe(a, 150.0, a.steps + a.warmup)
-    fn = cpu_step_fn(a.workload, N, a.horizon, a.sgd_iters, 0)
+    # the full workload when warm-up + timed steps fit ~10 minutes of host time, else the largest power-of-two
+    # share of its environments that does; the line's config carries the size that actually ran
+    N, _ = cpu_probe(a, 600.0, a.steps + a.warmup)
+    fn, kind = cpu_leg(a.workload, N, a.horizon, a.sgd_iters, 0)
     for _ in range(a.warmup):
         fn()
     t0 = time.perf_counter()
@@ -170,7 +235,13 @@ def run_reference(a: argparse.Namespace) -> None:
         fn()
     dt = time.perf_counter() - t0
     value = N * a.horizon * a.steps / dt
-    sample = f"{WORKLOADS[a.workload][1]} num_envs={N} (of {a.num_envs_per_gpu}), horizon={a.horizon}, {a.steps} collect+step"
+    what = ("the unmodified reference (oracle/_ref, staged by tools/stage_ref.py) behind oracle/refshim, device=cpu, eager"
+            if kind == "reference" else "oracle/ppo_oracle.py (CPU port of the reference, torch fp32 eager)")
+    sample = (f"{WORKLOADS[a.workload][1]} num_envs={N} (of {a.num_envs_per_gpu}), horizon={a.horizon}, "
+              f"{a.warmup} warm-up + {a.steps} timed collect+step of {what}")
+    cfg = workload_config(a, 1)  # same keys as the GPU arm; the environment count is the one that actually ran
+    cfg["num_envs_per_gpu"] = cfg["num_envs_total"] = N
+    cfg["sgd_minibatch_size"] = a.minibatch or N * a.horizon
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -185,13 +256,11 @@ def run_reference(a: argparse.Namespace) -> None:
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(a, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of the reference (oracle/ppo_oracle.py, torch fp32 eager on all host"
-                " cores); the upstream package itself cannot be installed (tensordict/torchrl/mlflow"
-                " absent, no network)",
+        "note": what,
     }
     print(json.dumps(line))
 
@@ -290,8 +359,11 @@ def run_ours(a: argparse.Namespace) -> None:
                 enable_amp=False, distribution_cls=dist_cls,
             ).build(env_cls), "f32"
 
-    torch.manual_seed(rank)
+    # Identical initial weights on every rank (same seed before build(); Algorithm.__init__ also broadcasts rank 0's
+    # parameters), then per-rank streams for the env resets and the sampling noise.
+    torch.manual_seed(0)
     algo, dtype = make()
+    torch.manual_seed(1000 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier() -> None:
@@ -369,7 +441,9 @@ def run_ours(a: argparse.Namespace) -> None:
             enqueue_copy(i ^ 1)
             return dev_noise[i]
 
+    torch.manual_seed(0)
     algo2, _ = make(HostNoise, "bf16" if dtype == "bf16" else "fp32")
+    torch.manual_seed(2000 + rank)
     trainer = trainer_cls(algo2)
 
     def e2e_step() -> int:
@@ -389,6 +463,54 @@ def run_ours(a: argparse.Namespace) -> None:
     peaks = measured_peaks()
     upd = update_roofline(a, algo, _lib, peaks, dtype, flush)
     barrier()
+
+    # ---- the parity mode beside the headline: enable_amp=False = fp32 results on tcgen05 (split-bf16 operands),
+    #      the mode the reference-recorded golden vectors are reproduced in at 1e-5 -------------------------------
+    fp32_mode = None
+    if dtype == "bf16" and not recurrent and a.precision == "auto":
+        torch.manual_seed(0)
+        algo32, _ = make(None, "fp32")
+        torch.manual_seed(3000 + rank)
+
+        def fp32_step() -> int:
+            algo32.collect()
+            algo32.step()
+            return algo32.last_launches["collect"] + algo32.last_launches["step"]
+
+        k32 = max(1, min(a.steps, 5))
+        ms32, launches32 = timed(fp32_step, k32, 3)
+        fp32_mode = {
+            "value": N * T * world * k32 / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32 / k32, "steps": k32,
+            "warmup": 3, "dtype": "f32 (fp32 results on tcgen05: split-bf16 operands, six piece products, fp32 accumulate)",
+            "gpu_launches": launches32, "ms_each_step": list(per_step),
+            "parity": "reference-recorded golden vectors at 1e-5 relative, discrete actions bit-exact (tests/test_gpu_golden.py)",
+            "roofline": update_roofline(a, algo32, _lib, peaks, "f32", flush),
+        }
+        del algo32
+        barrier()
+
+    # ---- BASELINE.json configs[4] exactly: CartPole, 1 048 576 envs in total, horizon 32, one PPO update per collect
+    c5 = None
+    if world > 1 and a.workload == "cartpole" and a.precision == "auto" and (1 << 20) % world == 0:
+        n5 = (1 << 20) // world
+        torch.manual_seed(0)
+        algo5 = config_cls(num_envs=n5, horizon=32, num_sgd_iters=1, enable_amp=True).build(env_cls)
+        torch.manual_seed(4000 + rank)
+
+        def c5_step() -> int:
+            algo5.collect()
+            algo5.step()
+            return algo5.last_launches["collect"] + algo5.last_launches["step"]
+
+        k5 = max(1, min(a.steps, 10))
+        ms5, _ = timed(c5_step, k5, 3)
+        c5 = {"value": (1 << 20) * 32 * k5 / (ms5 / 1e3), "unit": UNIT, "ms_per_step": ms5 / k5, "steps": k5, "warmup": 3,
+              "dtype": "bf16", "config": {"workload": "CartPole env-sharded scaling sweep (BASELINE.json configs[4])",
+                                          "num_envs_total": 1 << 20, "num_envs_per_gpu": n5, "horizon": 32,
+                                          "num_sgd_iters": 1, "sgd_minibatch_size": n5 * 32,
+                                          "parallelism": f"env-sharded dp{world}"}}
+        del algo5
+        barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -416,11 +538,14 @@ def run_ours(a: argparse.Namespace) -> None:
         "gpu_launches": launches,
         "ms_each_step": {"value": core_per_step, "e2e": e2e_per_step},
         "roofline": upd,
+        "fp32_mode": fp32_mode,
+        "c5": c5,
         "stream_rooflines": roofs,
         "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
     }
     if not a.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a)
+        line["reference_on_gpu"] = reference_on_gpu(a)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -431,16 +556,41 @@ def cpu_baseline(a: argparse.Namespace) -> dict:
 
     torch.set_num_threads(os.cpu_count() or 1)
     n, _ = cpu_probe(a, a.cpu_budget_s, 2)
-    fn = cpu_step_fn(a.workload, n, a.horizon, a.sgd_iters, 0)
+    fn, kind = cpu_leg(a.workload, n, a.horizon, a.sgd_iters, 0)
     fn()
     t0 = time.perf_counter()
     fn()
     dt = time.perf_counter() - t0
+    what = ("the unmodified reference (oracle/_ref) behind oracle/refshim, device=cpu, eager" if kind == "reference"
+            else "oracle/ppo_oracle.py (torch fp32 eager)")
     return {
-        "value": n * a.horizon / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "value": n * a.horizon / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
         "sample": f"{WORKLOADS[a.workload][1]} num_envs={n} (of {a.num_envs_per_gpu}), horizon={a.horizon}, 1 warm-up + 1 timed"
-                  " collect+step of oracle/ppo_oracle.py (torch fp32 eager)",
+                  f" collect+step of {what}",
     }
+
+
+def reference_on_gpu(a: argparse.Namespace) -> None | dict:
+    """Context, not the baseline: the unmodified reference on ITS OWN CUDA path (eager PyTorch kernels, cuBLAS) on
+    the same B200, same workload -- what switching the hot path to this library buys a user of the reference."""
+    import torch
+
+    if not reference_available(a.workload):
+        return None
+    try:
+        fn = reference_step_fn(a.workload, a.num_envs_per_gpu, a.horizon, a.sgd_iters, a.minibatch, device="cuda")
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    return {"value": a.num_envs_per_gpu * a.horizon / dt, "unit": UNIT, "ms_per_step": 1e3 * dt,
+            "note": "unmodified reference (oracle/_ref), device=cuda, eager, fp32; 1 warm-up + 3 timed collect+step,"
+                    " wall clock with synchronize"}
 
 
 def _time_kernel(fn, flush, iters: int = 10) -> float:  # noqa: ANN001
@@ -531,7 +681,7 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
     _, _, _, recurrent, _, _, D, P = WORKLOADS[a.workload]
     hp = algo.hparams
     N, T = hp.num_envs, hp.horizon
-    peak = float(peaks["bf16_tflops_sustained"])
+    peak = float(peaks["bf16_tflops_sustained"])  # recurrent: a whole multi-kernel step() is timed
     H = 256
     if recurrent:
         # one full step() = GAE + num_sgd_iters passes over every sequence (fp32 CUDA-core path)
@@ -563,25 +713,38 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
     model = algo.policy.model
     m, g = model.struct_for(model.flat_params), model.struct_for(algo._grads)
     M = hp.sgd_minibatch_size
-    ws = algo._workspace("ppo", int(algo._lib.rl8_ppo_workspace(m, M, algo.policy.precision)))
+    prec = algo.policy.precision
+    ws = algo._workspace("ppo", int(algo._lib.rl8_ppo_workspace(m, M, prec)))
     batch = algo._batch_struct()
     ppo = L.PpoHparams(0.2, 0.0, 0.0, 5.0, 1.0, 1.0)
     sums = torch.zeros(5, dtype=torch.float64, device=algo.device)
 
     def fn() -> None:
-        rc = algo._lib.rl8_ppo_minibatch(m, g, batch, None, 0, M, float(M), ppo, L.ptr(sums),
-                                         algo.policy.precision, L.ptr(ws), ws.numel(), L.stream())
+        rc = algo._lib.rl8_ppo_minibatch(m, g, batch, None, 0, M, float(M), ppo, L.ptr(sums), prec, L.ptr(ws),
+                                         ws.numel(), L.stream())
         assert rc == 0, rc
 
     ms = _time_kernel(fn, flush, iters=5)
     flops = M * 3.0 * 2.0 * (2 * H * H + 2 * D * H + (P + 1) * H)
+    burst = float(peaks["bf16_tflops"])  # the call is timed alone (L2 flushed before it): the burst figure applies
+    if prec == L.PREC_FP32_TC:
+        # every fp32 product of the 256 x 256 contractions is six bf16 piece products on the tensor pipe
+        return {
+            "kernel": "rl8_ppo_minibatch, RL8_PREC_FP32_TC (x3_update_f + x3_update_b + x3_update_w per 2^21-row chunk:"
+                      " split-bf16 pair MMAs, operands recomputed from 80 B/row of scratch)",
+            "bound": "tensor", "achieved": flops / ms / 1e9, "peak": burst / 6.0, "unit": "TFLOP/s",
+            "frac": flops / ms / 1e9 / (burst / 6.0), "traffic": None, "ms": ms, "rows": M, "dtype": "f32",
+            "mma_tflops": 6.0 * flops / ms / 1e9,
+            "peak_source": peaks["source"] + " bf16 burst / 6 (six bf16 piece products per fp32 product; `achieved`"
+                                             " counts fp32-equivalent FLOPs, `mma_tflops` the bf16 work issued)",
+        }
     traffic = NCU_TRAFFIC.get((a.workload, M)) if dtype == "bf16" else None
     return {
         "kernel": "rl8_ppo_minibatch (forward + losses + backward, one minibatch: tc_update_h_kernel +"
                   " tc_update_w_kernel per 2^21-row chunk)",
-        "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
-        "frac": flops / ms / 1e9 / peak, "traffic": traffic, "ms": ms, "rows": M, "dtype": dtype,
-        "peak_source": peaks["source"] + " bf16 sustained",
+        "bound": "tensor", "achieved": flops / ms / 1e9, "peak": burst, "unit": "TFLOP/s",
+        "frac": flops / ms / 1e9 / burst, "traffic": traffic, "ms": ms, "rows": M, "dtype": dtype,
+        "peak_source": peaks["source"] + " bf16 burst (the call is timed alone, L2 flushed before each launch)",
         "traffic_source": "ncu --set full, profiles/r01_update_v8_ncu_summary.md" if traffic else None,
     }
 
@@ -589,6 +752,7 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
 def main() -> None:
     a = parse()
     if a.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference's CPU path (see reference_step_fn); before torch loads
         run_reference(a)
     else:
         run_ours(a)

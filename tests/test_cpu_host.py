@@ -172,7 +172,11 @@ def test_bench_reference_arm_contract() -> None:
     assert d["metric"].startswith("env transitions/sec")
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d, k
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the staged unmodified reference (tools/stage_ref.py -> git-ignored oracle/_ref/) when present, else the CPU port
+    staged = os.path.isdir(os.path.join(root, "oracle", "_ref", "src", "rl8"))
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["num_envs_per_gpu"] == 256 and d["config"]["horizon"] == 8  # the size that actually ran
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("CartPole")
 
