@@ -39,31 +39,16 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
-// arrive on the mbarrier at the same offset in CTA `rank` (release at cluster scope: the smem writes and
-// proxy fences of this thread are ordered before the arrival)
+// Arrive on the mbarrier at the same offset in CTA `rank`.  No cluster-scope release / acquire: nothing written
+// through the generic proxy crosses CTAs behind these barriers -- operand tiles are read by each CTA's tensor core
+// from its own shared memory (made visible by the writer's fence.proxy.async), accumulators are ordered by the
+// tcgen05 fences -- and a cluster-scope acquire compiles to an L1 invalidate (CCTL.IVALL) on every poll.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   const uint32_t addr = map_to_cta(smem_u32(bar), rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-// waits with cluster-scope acquire (arrivals may come from the peer CTA or from a multicast commit)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins) {
-    if (spins > (1u << 24)) __trap();
-  }
-}
+// waits on a barrier whose arrivals may come from the peer CTA or from a multicast commit
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait_sleep(bar, parity); }
 
 // ---- tensor memory, pair form (one warp of EACH CTA of the pair calls these) -------------------------------
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {

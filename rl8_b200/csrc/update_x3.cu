@@ -125,7 +125,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_wait(&s.bfull[st], use & 1);
+        mbar_wait_sleep(&s.bfull[st], use & 1);
         mbar_arrive_cluster(&s.full[st], 0);
       }
     }
@@ -428,7 +428,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_wait(&s.bfull[st], use & 1);
+        mbar_wait_sleep(&s.bfull[st], use & 1);
         mbar_arrive_cluster(&s.full[st], 0);
       }
     }
