@@ -766,7 +766,11 @@ class Algorithm:
             _lib.check(rc, "rl8_ppo_minibatch")
 
         # bf16: 2 x W2 packing + (activation kernel + weight-gradient kernel) per 2^21-row chunk
-        per_call = 2 + 2 * max(1, -(-M // (1 << 21))) if prec == _lib.PREC_BF16 else 34 * max(1, -(-M // 65536))
+        per_call = {
+            _lib.PREC_BF16: 2 + 2 * max(1, -(-M // (1 << 21))),     # 2 x W2 packing + 2 kernels per 2^21-row chunk
+            _lib.PREC_FP32_TC: 4 + 3 * max(1, -(-M // (1 << 21))),  # 4 x W2 piece images + 3 kernels per chunk
+            _lib.PREC_FP32: 34 * max(1, -(-M // 65536)),            # the CUDA-core chain per 65 536-row chunk
+        }[prec]
         return launch, per_call
 
     def _reset_buffer(self) -> None:

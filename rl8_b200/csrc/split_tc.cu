@@ -216,7 +216,7 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_wait_sleep(&s.bfull[st], use & 1);
+          mbar_wait(&s.bfull[st], use & 1);
           mbar_arrive_cluster(&s.full[st], 0);
         }
       }

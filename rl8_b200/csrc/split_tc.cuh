@@ -48,7 +48,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 // waits on a barrier whose arrivals may come from the peer CTA or from a multicast commit
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait_sleep(bar, parity); }
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+// ... sleeping form (suspend-time hint): measured better where all 16 worker warps wait at once and nothing else
+// needs their issue slots (the weight-gradient kernel's ring), worse on the latency-critical waits
+__device__ __forceinline__ void mbar_wait_cluster_sleep(uint64_t* bar, uint32_t parity) { mbar_wait_sleep(bar, parity); }
 
 // ---- tensor memory, pair form (one warp of EACH CTA of the pair calls these) -------------------------------
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {

@@ -125,7 +125,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_wait_sleep(&s.bfull[st], use & 1);
+        mbar_wait(&s.bfull[st], use & 1);
         mbar_arrive_cluster(&s.full[st], 0);
       }
     }
@@ -428,7 +428,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_wait_sleep(&s.bfull[st], use & 1);
+        mbar_wait(&s.bfull[st], use & 1);
         mbar_arrive_cluster(&s.full[st], 0);
       }
     }
@@ -655,7 +655,7 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
     if (k + 1 < n_my) load_inputs(k + 1, in_f, in_m);
     const int st = (int)(k % kWStages);
     const uint32_t use = (uint32_t)(k / kWStages);
-    if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+    if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int g = g0 + 8 * i;
@@ -744,7 +744,7 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
       const int st = (int)(k % kWStages);
       const bool fresh = k % kFlushStages == 0;  // first stage of a flush interval: both accumulators restart
       if (fresh && k > 0) mbar_wait_cluster(&s.flush_empty, (uint32_t)((nf - 1) & 1));
-      mbar_wait_cluster(&s.full[st], (uint32_t)((k / kWStages) & 1));
+      mbar_wait_cluster_sleep(&s.full[st], (uint32_t)((k / kWStages) & 1));
       fence_after_sync();
       if (elect_one()) {
 #pragma unroll
