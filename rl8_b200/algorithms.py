@@ -364,8 +364,9 @@ class Algorithm:
             self.state.reward_scale = float(torch.tensor(mean_std(a[4], a[5], n_r)[1], dtype=torch.float32))
         else:
             self.state.reward_scale = 1.0
-        stats["env/resets"] = hp.num_envs * int(env_was_reset)
-        stats["env/steps"] = hp.num_envs * hp.horizon
+        # global counts (all ranks), like every other statistic of the call
+        stats["env/resets"] = hp.num_envs * world * int(env_was_reset)
+        stats["env/steps"] = hp.num_envs * world * hp.horizon
         stats["profiling/collect_ms"] = (time.perf_counter_ns() - start) / 1e6
         return stats
 
@@ -632,8 +633,9 @@ class Algorithm:
                     means[key].update(run[key])
                     run[key] = 0.0
 
-        self.lr_scheduler.step(hp.num_envs * self.state.horizons)
-        self.entropy_scheduler.step(hp.num_envs * self.state.horizons)
+        # schedules are defined in env transitions of the whole job (src/rl8/schedulers.py:121-232): global env count
+        self.lr_scheduler.step(hp.num_envs * world * self.state.horizons)
+        self.entropy_scheduler.step(hp.num_envs * world * self.state.horizons)
 
         self._reset_buffer()
         self.state.buffered = False
