@@ -165,6 +165,15 @@ int rl8_gae_scan(float* rewards, const float* values, float* advantages, float* 
 int rl8_gae_normalize(float* advantages, int64_t N, int32_t T, int64_t stride_n, int64_t stride_t,
                       const double* moments, rl8_stream_t stream);
 
+/* The device-resident form (no host round trip between collect() and step()): rl8_reward_scale
+ * turns the (all-reduced) accumulator of rl8_collect_stats into out[0] = f32(std(rdr[:, 1:])) -- the reference's
+ * float(torch.std(...)), src/rl8/algorithms/_feedforward.py:428-436; 1 when !normalize_rewards -- and
+ * out[1] = f32(out[0] + 1e-8); rl8_gae_scan_dev is rl8_gae_scan reading that divisor from `reward_scale_dev[1]`. */
+int rl8_reward_scale(const double* acc, double count, int normalize_rewards, float* out, rl8_stream_t stream);
+int rl8_gae_scan_dev(float* rewards, const float* values, float* advantages, float* returns,
+                     int64_t N, int32_t T, int64_t stride_n, int64_t stride_t, double gamma,
+                     double gae_lambda, const float* reward_scale_dev, double* moments, rl8_stream_t stream);
+
 /* ---- collect statistics (src/rl8/algorithms/_feedforward.py:410-436) ----------------- */
 
 /* From horizon-major rewards[T+1][N] and reversed discounted returns rdr[T+1][N] (may be

@@ -142,6 +142,11 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _f64, _f64, _vp, _vp],
     ),
     "rl8_gae_normalize": (_int, [_vp, _i64, _i32, _i64, _i64, _vp, _vp]),
+    "rl8_reward_scale": (_int, [_vp, _f64, _int, _vp, _vp]),
+    "rl8_gae_scan_dev": (
+        _int,
+        [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _f64, _vp, _vp, _vp],
+    ),
     "rl8_collect_stats": (_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "rl8_collect_stats_from": (_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "rl8_lstm_collect_workspace": (_i64, [C.POINTER(LstmModel), _i64, _i32, _int]),

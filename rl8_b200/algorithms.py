@@ -130,6 +130,60 @@ def _index_views(views: Any, idx: Any) -> Any:
     return {k: _index_views(v, idx) for k, v in views.items()}
 
 
+class LazyStats(dict):
+    """``CollectStats`` whose device-computed entries are read back on first access.
+
+    Host-known entries (``env/steps``, ``env/resets``, ``profiling/collect_ms``) are plain items; touching any other
+    key, iterating, printing or unpacking (``{**stats}``) waits -- once -- for the asynchronous device->host copy
+    enqueued by ``collect()`` and fills the rest in."""
+
+    _EAGER = ("env/resets", "env/steps", "profiling/collect_ms")
+
+    def __init__(self, read_back: Any) -> None:
+        super().__init__()
+        self._read_back = read_back
+
+    def set_eager(self, key: str, value: Any) -> None:
+        dict.__setitem__(self, key, value)
+
+    def materialize(self) -> None:
+        if self._read_back is not None:
+            read_back, self._read_back = self._read_back, None
+            for k, v in read_back().items():
+                if not dict.__contains__(self, k):
+                    dict.__setitem__(self, k, v)
+
+    def __getitem__(self, key: str) -> Any:
+        if not dict.__contains__(self, key):
+            self.materialize()
+        return dict.__getitem__(self, key)
+
+    def get(self, key: str, default: Any = None) -> Any:
+        if not dict.__contains__(self, key):
+            self.materialize()
+        return dict.get(self, key, default)
+
+    def __contains__(self, key: object) -> bool:
+        if dict.__contains__(self, key):
+            return True
+        self.materialize()
+        return dict.__contains__(self, key)
+
+    def _full(name: str):  # noqa: ANN202, N805
+        def method(self, *a: Any, **kw: Any) -> Any:
+            self.materialize()
+            return getattr(dict, name)(self, *a, **kw)
+
+        method.__name__ = name
+        return method
+
+    for _n in ("keys", "values", "items", "__iter__", "__len__", "__repr__", "__eq__", "__ne__", "copy", "__or__",
+               "__ror__", "__reduce_ex__", "__reduce__"):
+        locals()[_n] = _full(_n)
+    del _n, _full
+    __hash__ = None  # type: ignore[assignment]
+
+
 class _RunningMean:
     def __init__(self) -> None:
         self.avg, self.n = 0.0, 0
@@ -254,6 +308,8 @@ class Algorithm:
         init[7] = init[9] = -math.inf
         self._stats_init = torch.tensor(init, dtype=torch.float64, device=device)
         self._moments = torch.zeros(3, dtype=torch.float64, device=device)
+        #: [reward scale, f32(scale + 1e-8)] of the last collect(), device-resident for step()
+        self._scale_dev = torch.ones(2, dtype=torch.float32, device=device)
         max_updates = self.hparams.num_sgd_iters * self.hparams.num_minibatches
         self._loss_sums = torch.zeros(max_updates, 5, dtype=torch.float64, device=device)
         #: test / debugging hook: called with the named (unclipped) gradients of every update
@@ -329,7 +385,9 @@ class Algorithm:
         else:
             self._collect_generic(noise, deterministic)
 
-        # statistics + reward scale: one reduction kernel, one readback
+        # statistics + reward scale: one reduction kernel (+ one collective); NOTHING is read back here -- the reward
+        # scale stays on the device for step(), the statistics are copied to pinned memory asynchronously and the
+        # returned mapping waits for them on first access (Trainer.step touches them after step() is enqueued)
         acc = self._stats_acc
         acc.copy_(self._stats_init)
         t0 = self._stats_reward_t0
@@ -338,37 +396,47 @@ class Algorithm:
             _lib.stream(),
         )
         _lib.check(rc, "rl8_collect_stats_from")
-        self.last_launches["collect"] += 1
         world = _world()
         parallel.reduce_collect_acc_(acc)
-        a = acc.tolist()  # the one device->host sync of collect()
         n_r, n_R = float(N * T * world), float(N * world)
-        mean_std = parallel.mean_std
-        r_mean, r_std = mean_std(a[0], a[1], float(N * (T - t0) * world))
-        R_mean, R_std = mean_std(a[2], a[3], n_R)
-        stats: CollectStats = {
-            "returns/min": a[8],
-            "returns/max": a[9],
-            "returns/mean": R_mean,
-            "returns/std": R_std,
-            "rewards/min": a[6],
-            "rewards/max": a[7],
-            "rewards/mean": r_mean,
-            "rewards/std": r_std,
-        }
+        rc = self._lib.rl8_reward_scale(_lib.ptr(acc), n_r, int(hp.normalize_rewards), _lib.ptr(self._scale_dev),
+                                        _lib.stream())
+        _lib.check(rc, "rl8_reward_scale")
+        self.last_launches["collect"] += 2
+        host = torch.empty(18, dtype=torch.float64, pin_memory=True)  # torch's caching host allocator: no cudaHostAlloc
+        host[:16].copy_(acc, non_blocking=True)
+        host[16:18].copy_(self._scale_dev.double(), non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        state = self.state
+        n_reward = float(N * (T - t0) * world)
+
+        def read_back() -> dict[str, float]:
+            ready.synchronize()  # the one device->host wait of collect(), deferred to the first reader
+            a = host.tolist()
+            mean_std = parallel.mean_std
+            r_mean, r_std = mean_std(a[0], a[1], n_reward)
+            R_mean, R_std = mean_std(a[2], a[3], n_R)
+            if state._pending_stats is pending:  # still the latest collect(): its scale is the state's
+                state._reward_scale = a[16]
+                state._pending_stats = None
+            return {
+                "returns/min": a[8], "returns/max": a[9], "returns/mean": R_mean, "returns/std": R_std,
+                "rewards/min": a[6], "rewards/max": a[7], "rewards/mean": r_mean, "rewards/std": r_std,
+            }
+
+        stats = LazyStats(read_back)
+        pending = stats.materialize
+        state._pending_stats = pending
+        state._scale_on_device = True
         self.state.horizons += 1
         self.state.buffered = True
         self._post_collect()
-        if hp.normalize_rewards:
-            # float(torch.std(rdr[:, 1:])) -- an f32 value in the reference
-            self.state.reward_scale = float(torch.tensor(mean_std(a[4], a[5], n_r)[1], dtype=torch.float32))
-        else:
-            self.state.reward_scale = 1.0
         # global counts (all ranks), like every other statistic of the call
-        stats["env/resets"] = hp.num_envs * world * int(env_was_reset)
-        stats["env/steps"] = hp.num_envs * world * hp.horizon
-        stats["profiling/collect_ms"] = (time.perf_counter_ns() - start) / 1e6
-        return stats
+        stats.set_eager("env/resets", hp.num_envs * world * int(env_was_reset))
+        stats.set_eager("env/steps", hp.num_envs * world * hp.horizon)
+        stats.set_eager("profiling/collect_ms", (time.perf_counter_ns() - start) / 1e6)
+        return stats  # type: ignore[return-value]
 
     #: first reward slot of the collect statistics (the recurrent algorithm uses 1)
     _stats_reward_t0 = 0
@@ -509,14 +577,21 @@ class Algorithm:
         st = _lib.stream()
         launches = 0
 
-        # -- GAE ---------------------------------------------------------------------------
+        # -- GAE (the reward scale of the last collect() is read from device memory: no host round trip) ----------
         self._moments.zero_()
-        rc = lib.rl8_gae_scan(
-            _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(buf.hm[DataKeys.VALUES]),
-            _lib.ptr(buf.hm[DataKeys.ADVANTAGES]), _lib.ptr(buf.hm[DataKeys.RETURNS]),
-            N, T, 1, N, hp.gamma, hp.gae_lambda, self.state.reward_scale,
-            _lib.ptr(self._moments), st,
-        )
+        if self.state._scale_on_device:
+            rc = lib.rl8_gae_scan_dev(
+                _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(buf.hm[DataKeys.VALUES]),
+                _lib.ptr(buf.hm[DataKeys.ADVANTAGES]), _lib.ptr(buf.hm[DataKeys.RETURNS]),
+                N, T, 1, N, hp.gamma, hp.gae_lambda, _lib.ptr(self._scale_dev), _lib.ptr(self._moments), st,
+            )
+        else:  # a reward scale assigned by the caller
+            rc = lib.rl8_gae_scan(
+                _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(buf.hm[DataKeys.VALUES]),
+                _lib.ptr(buf.hm[DataKeys.ADVANTAGES]), _lib.ptr(buf.hm[DataKeys.RETURNS]),
+                N, T, 1, N, hp.gamma, hp.gae_lambda, self.state.reward_scale,
+                _lib.ptr(self._moments), st,
+            )
         _lib.check(rc, "rl8_gae_scan")
         launches += 1
         if hp.normalize_advantages:
@@ -660,6 +735,16 @@ class Algorithm:
         world = _world()
         model, dist_cls = self.policy.model, self.policy.distribution_cls
         kind = dist_cls.rl8_kind
+        if model.drop_size > 0:
+            # A "rolling_window" requirement yields N * (T - drop_size) rows while actions, log-probabilities,
+            # advantages and returns keep N * T: the reference assigns such views into its [N * T] buffer and
+            # fails on the batch-size mismatch (src/rl8/algorithms/_feedforward.py:474-482); pairing the shorter
+            # views with row indices over N * T would silently train on misaligned rows.
+            raise RuntimeError(
+                f"view requirements that drop {model.drop_size} leading step(s) per environment (method="
+                "'rolling_window', shift > 0) cannot be batched with the [num_envs * horizon] transition rows;"
+                " use method='padded_rolling_window' (the reference's feedforward algorithm has the same limit)"
+            )
         views = model.apply_view_requirements(
             {k: buf[k][:, :-1] for k in model.view_requirements}, kind="all"
         )

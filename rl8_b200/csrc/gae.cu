@@ -19,7 +19,10 @@ struct GaeConsts {
   float gamma;      // f32(gamma)
   float gl;         // f32(gamma * gae_lambda)  (double product, one rounding)
   float denom;      // f32(reward_scale + 1e-8)
+  const float* denom_dev;  // when set: the same value in device memory (rl8_reward_scale), read by the kernel
 };
+// the reward divisor of this launch: the host value, or the one a previous kernel left on the device
+__device__ __forceinline__ float gae_denom(const GaeConsts& c) { return c.denom_dev ? __ldg(c.denom_dev) : c.denom; }
 
 // ---- horizon-major, VEC envs per thread ----------------------------------------------
 template <int VEC>
@@ -27,6 +30,7 @@ __global__ void __launch_bounds__(256)
 gae_scan_hm_kernel(float* __restrict__ rewards, const float* __restrict__ values,
                    float* __restrict__ adv, float* __restrict__ ret, int64_t N, int T,
                    int64_t st, GaeConsts c, double* __restrict__ moments) {
+  const float denom = gae_denom(c);
   __shared__ double red[32];
   double s1 = 0.0, s2 = 0.0;
   const int64_t groups = N / VEC;
@@ -54,7 +58,7 @@ gae_scan_hm_kernel(float* __restrict__ rewards, const float* __restrict__ values
     // Scaled reward of slot T (the reference divides the whole tensor, :106).
     load(rewards + (int64_t)T * st + n0, tmp);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) tmp[j] = dvd(tmp[j], c.denom);
+    for (int j = 0; j < VEC; ++j) tmp[j] = dvd(tmp[j], denom);
     store(rewards + (int64_t)T * st + n0, tmp);
 
     constexpr int U = 4;  // software pipeline: U time steps of loads in flight
@@ -71,7 +75,7 @@ gae_scan_hm_kernel(float* __restrict__ rewards, const float* __restrict__ values
         float a[VEC], rt[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          r[u][j] = dvd(r[u][j], c.denom);
+          r[u][j] = dvd(r[u][j], denom);
           float delta = add(r[u][j], sub(mul(c.gamma, vnext[j]), v[u][j]));
           a[j] = add(delta, mul(c.gl, prev[j]));
           prev[j] = a[j];
@@ -91,7 +95,7 @@ gae_scan_hm_kernel(float* __restrict__ rewards, const float* __restrict__ values
       load(values + (int64_t)t * st + n0, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        r[j] = dvd(r[j], c.denom);
+        r[j] = dvd(r[j], denom);
         float delta = add(r[j], sub(mul(c.gamma, vnext[j]), v[j]));
         a[j] = add(delta, mul(c.gl, prev[j]));
         prev[j] = a[j];
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__(256)
 gae_scan_strided_kernel(float* __restrict__ rewards, const float* __restrict__ values,
                         float* __restrict__ adv, float* __restrict__ ret, int64_t N, int T,
                         int64_t sn, int64_t st, GaeConsts c, double* __restrict__ moments) {
+  const float denom = gae_denom(c);
   __shared__ double red[32];
   double s1 = 0.0, s2 = 0.0;
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
@@ -129,10 +134,10 @@ gae_scan_strided_kernel(float* __restrict__ rewards, const float* __restrict__ v
     float vnext = values[base + (int64_t)T * st], prev = 0.0f;
     adv[base + (int64_t)T * st] = 0.0f;
     if (ret) ret[base + (int64_t)T * st] = vnext;
-    rewards[base + (int64_t)T * st] = dvd(rewards[base + (int64_t)T * st], c.denom);
+    rewards[base + (int64_t)T * st] = dvd(rewards[base + (int64_t)T * st], denom);
     for (int t = T - 1; t >= 0; --t) {
       const int64_t i = base + (int64_t)t * st;
-      float r = dvd(rewards[i], c.denom), v = values[i];
+      float r = dvd(rewards[i], denom), v = values[i];
       float delta = add(r, sub(mul(c.gamma, vnext), v));
       float a = add(delta, mul(c.gl, prev));
       rewards[i] = r;
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(256)
 gae_scan_em_kernel(float* __restrict__ rewards, const float* __restrict__ values,
                    float* __restrict__ adv, float* __restrict__ ret, int64_t N, int T,
                    int64_t sn, GaeConsts c, double* __restrict__ moments) {
+  const float denom = gae_denom(c);
   __shared__ double red[32];
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -183,14 +189,14 @@ gae_scan_em_kernel(float* __restrict__ rewards, const float* __restrict__ values
       float vT = values[base + T];
       adv[base + T] = 0.0f;
       if (ret) ret[base + T] = vT;
-      rewards[base + T] = dvd(rewards[base + T], c.denom);
+      rewards[base + T] = dvd(rewards[base + T], denom);
     }
     for (int t0 = ((T - 1) / 32) * 32; t0 >= 0; t0 -= 32) {
       const int t = t0 + lane;
       const bool live = t < T;
       float r = 0.0f, v = 0.0f, vn = 0.0f;
       if (live) {
-        r = dvd(rewards[base + t], c.denom);
+        r = dvd(rewards[base + t], denom);
         v = values[base + t];
         vn = values[base + t + 1];
       }
@@ -323,13 +329,12 @@ collect_stats_kernel(const float* __restrict__ rewards, const float* __restrict_
 
 using namespace rl8;
 
-extern "C" int rl8_gae_scan(float* rewards, const float* values, float* advantages, float* returns,
-                            int64_t N, int32_t T, int64_t stride_n, int64_t stride_t, double gamma,
-                            double gae_lambda, double reward_scale, double* moments,
-                            rl8_stream_t stream) {
+static int gae_scan_impl(float* rewards, const float* values, float* advantages, float* returns, int64_t N,
+                         int32_t T, int64_t stride_n, int64_t stride_t, double gamma, double gae_lambda,
+                         double reward_scale, const float* denom_dev, double* moments, rl8_stream_t stream) {
   if (!rewards || !values || !advantages || N <= 0 || T <= 0) return RL8_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  GaeConsts c{(float)gamma, (float)(gamma * gae_lambda), (float)(reward_scale + 1e-8)};
+  GaeConsts c{(float)gamma, (float)(gamma * gae_lambda), (float)(reward_scale + 1e-8), denom_dev};
   auto al = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
   if (stride_n == 1) {
     bool vec = (N % 4 == 0) && (stride_t % 4 == 0) && al(rewards) && al(values) &&
@@ -349,6 +354,45 @@ extern "C" int rl8_gae_scan(float* rewards, const float* values, float* advantag
         rewards, values, advantages, returns, N, T, stride_n, stride_t, c, moments);
   }
   return check_launch("rl8_gae_scan");
+}
+
+extern "C" int rl8_gae_scan(float* rewards, const float* values, float* advantages, float* returns,
+                            int64_t N, int32_t T, int64_t stride_n, int64_t stride_t, double gamma,
+                            double gae_lambda, double reward_scale, double* moments,
+                            rl8_stream_t stream) {
+  return gae_scan_impl(rewards, values, advantages, returns, N, T, stride_n, stride_t, gamma, gae_lambda,
+                       reward_scale, nullptr, moments, stream);
+}
+
+extern "C" int rl8_gae_scan_dev(float* rewards, const float* values, float* advantages, float* returns,
+                                int64_t N, int32_t T, int64_t stride_n, int64_t stride_t, double gamma,
+                                double gae_lambda, const float* reward_scale_dev, double* moments,
+                                rl8_stream_t stream) {
+  if (!reward_scale_dev) return RL8_ERR_ARG;
+  return gae_scan_impl(rewards, values, advantages, returns, N, T, stride_n, stride_t, gamma, gae_lambda, 1.0,
+                       reward_scale_dev + 1, moments, stream);
+}
+
+// out[0] = f32(unbiased std of the reversed discounted returns) from the (all-reduced) accumulator of
+// rl8_collect_stats (acc[4] = sum, acc[5] = sum of squares over `count` elements), 1 when !normalize_rewards;
+// out[1] = f32(out[0] + 1e-8), the divisor rl8_gae_scan_dev uses.
+__global__ void reward_scale_kernel(const double* __restrict__ acc, double count, int normalize_rewards,
+                                    float* __restrict__ out) {
+  float scale = 1.0f;
+  if (normalize_rewards) {
+    const double mean = acc[4] / count;
+    const double var = count > 1.0 ? (acc[5] - acc[4] * mean) / (count - 1.0) : nan("");
+    scale = (float)sqrt(var > 0.0 ? var : (var == var ? 0.0 : var));
+  }
+  out[0] = scale;
+  out[1] = (float)((double)scale + 1e-8);
+}
+
+extern "C" int rl8_reward_scale(const double* acc, double count, int normalize_rewards, float* out,
+                                rl8_stream_t stream) {
+  if (!acc || !out || count <= 0) return RL8_ERR_ARG;
+  reward_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, count, normalize_rewards, out);
+  return check_launch("rl8_reward_scale");
 }
 
 extern "C" int rl8_gae_normalize(float* advantages, int64_t N, int32_t T, int64_t stride_n,

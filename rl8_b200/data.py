@@ -7,8 +7,8 @@ are the drop-in surface ``AlgorithmConfig(...).build(...)`` exposes.
 
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Literal, TypedDict
+from dataclasses import dataclass, field
+from typing import Any, Literal, TypedDict
 
 import torch
 
@@ -119,14 +119,33 @@ class AlgorithmHparams:
 
 @dataclass(kw_only=True)
 class AlgorithmState:
-    """Mutable counters of a feedforward PPO run."""
+    """Mutable counters of a feedforward PPO run.
+
+    ``reward_scale`` (the unbiased std of the reversed discounted returns of the last ``collect``, a Python
+    float in the reference, src/rl8/algorithms/_feedforward.py:428-436) is computed on the device and stays
+    there for ``step()``; reading the attribute waits for the read-back of the last ``collect()``'s statistics,
+    assigning it makes the assigned float the value ``step()`` uses."""
 
     #: ``collect`` ran since the last ``step`` (guards ``step`` against dummy data).
     buffered: bool = False
     #: Number of ``collect`` calls so far (drives the env reset cadence).
     horizons: int = 0
-    #: Unbiased std of the reversed discounted returns of the last ``collect``.
-    reward_scale: float = 1.0
+    _reward_scale: float = field(default=1.0, repr=False)
+    #: read-back of the last collect()'s statistics, run on first use (None: nothing pending)
+    _pending_stats: Any = field(default=None, repr=False, compare=False)
+    #: the device holds the reward scale of the last collect() (False: a float assigned by the caller is used)
+    _scale_on_device: bool = field(default=False, repr=False, compare=False)
+
+    @property
+    def reward_scale(self) -> float:
+        if self._pending_stats is not None:
+            self._pending_stats()
+        return self._reward_scale
+
+    @reward_scale.setter
+    def reward_scale(self, value: float) -> None:
+        self._reward_scale = float(value)
+        self._scale_on_device = False
 
 
 @dataclass(frozen=True, kw_only=True)

@@ -78,13 +78,17 @@ def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
 
 
 def reduce_collect_acc_(acc: torch.Tensor) -> torch.Tensor:
-    """All-reduce the 16-double accumulator of ``rl8_collect_stats`` in place: slots 0..5 are
-    sums, 6/8 minima, 7/9 maxima (include/rl8_b200.h)."""
-    if world_size() > 1:
-        dist.all_reduce(acc[:6])
-        mins = torch.stack((acc[6], -acc[7], acc[8], -acc[9]))
-        dist.all_reduce(mins, op=dist.ReduceOp.MIN)
-        acc[6], acc[7], acc[8], acc[9] = mins[0], -mins[1], mins[2], -mins[3]
+    """Reduce the 16-double accumulator of ``rl8_collect_stats`` over all ranks, in place: slots 0..5 are sums,
+    6 / 8 minima, 7 / 9 maxima (include/rl8_b200.h).  ONE collective (an all-gather of the 16 doubles, combined
+    locally in rank order, so every rank gets bit-identical results) instead of a SUM and a MIN all-reduce."""
+    world = world_size()
+    if world > 1:
+        gathered = [torch.empty_like(acc) for _ in range(world)]
+        dist.all_gather(gathered, acc)
+        parts = torch.stack(gathered)
+        acc[:6] = parts[:, :6].sum(0)
+        acc[6], acc[8] = parts[:, 6].min(), parts[:, 8].min()
+        acc[7], acc[9] = parts[:, 7].max(), parts[:, 9].max()
     return acc
 
 

@@ -422,6 +422,7 @@ class RecurrentAlgorithm(Algorithm):
         self._exp_avg = torch.zeros_like(flat)
         self._exp_avg_sq = torch.zeros_like(flat)
         parallel.sync_replicas(self.policy.model)  # replicas start from rank 0's parameters
+        self._scale_dev = torch.ones(2, dtype=torch.float32, device=device)  # reward scale of the last collect()
         self._grad_norm = torch.zeros(1, device=device)
         self._opt_steps = 0
         self.lr_scheduler = LRScheduler(

@@ -360,3 +360,36 @@ def test_user_defined_model_with_shifted_views_and_rmsprop_learns() -> None:
         last = s["returns/mean"]
         assert all(v == v for v in s.values() if isinstance(v, float))
     assert last > first + 1.0, (first, last)
+
+
+def test_user_defined_model_with_dropping_views_is_rejected() -> None:
+    """method="rolling_window" with shift > 0 drops leading steps: N * (T - shift) view rows cannot be paired with
+    the N * T transition rows (the reference fails on the batch-size mismatch, _feedforward.py:474-482); the update
+    must refuse instead of training on misaligned rows."""
+    import torch.nn as nn
+
+    import rl8_b200.env as E
+    from rl8_b200 import AlgorithmConfig
+    from rl8_b200.models import GenericModel
+    from rl8_b200.views import ViewRequirement
+
+    class Dropping(GenericModel):
+        def __init__(self, observation_spec, action_spec, /) -> None:  # noqa: ANN001
+            super().__init__(observation_spec, action_spec)
+            self.view_requirements["obs"] = ViewRequirement(shift=2, method="rolling_window")
+            self.body = nn.Linear(observation_spec.shape[0] * 3, 16)
+            self.pi, self.vf = nn.Linear(16, action_spec.space.n), nn.Linear(16, 1)
+
+        def forward(self, batch):  # noqa: ANN001, ANN201
+            self._z = torch.tanh(self.body(batch["obs"].flatten(1)))
+            return {"logits": self.pi(self._z).unsqueeze(1)}
+
+        def value_function(self):  # noqa: ANN201
+            return self.vf(self._z)
+
+    torch.manual_seed(0)
+    algo = AlgorithmConfig(num_envs=64, horizon=8, model_cls=Dropping, shuffle_minibatches=False).build(E.DiscreteDummyEnv)
+    assert algo.policy.model.drop_size == 2
+    algo.state.buffered = True  # the update's guard is what is under test, not the rollout
+    with pytest.raises(RuntimeError, match="padded_rolling_window"):
+        algo.step()
