@@ -62,31 +62,49 @@ __device__ __forceinline__ void issue_stage_split(uint32_t lead_tmem, uint32_t c
   }
 }
 
-// [W1 | b1] in fp32: w1s[i][d] = W1[i][d] (d < D <= 7, zero padded), w1s[i][7] = b1[i]
-__device__ __forceinline__ void stage_w1s(float (*w1s)[8], const NetParams& np) {
+// [W1 | b1] in fp32, input-major: w1t[d][i] = W1[i][d] (d < D <= 7; rows D..6 unused), w1t[7][i] = b1[i]
+__device__ __forceinline__ void stage_w1t(float (*w1t)[H], const NetParams& np) {
   for (int e = threadIdx.x; e < H * 8; e += blockDim.x) {
-    const int i = e >> 3, d = e & 7;
-    w1s[i][d] = d < np.D ? np.w1[i * np.D + d] : (d == 7 ? np.b1[i] : 0.0f);
+    const int i = e & (H - 1), d = e >> 8;
+    w1t[d][i] = d < np.D ? np.w1[i * np.D + d] : (d == 7 ? np.b1[i] : 0.0f);
   }
 }
-// Z1[row][c] = b1[c] + sum_d obs[d] W1[c][d] in fp32 (bias first, then d ascending; padded slots add 0)
-__device__ __forceinline__ float z1_value(const float* w1row, const float* ob) {
-  const float4 wa = *reinterpret_cast<const float4*>(w1row);
-  const float4 wb = *reinterpret_cast<const float4*>(w1row + 4);
-  float acc = wb.w;
-  acc = fmaf(ob[0], wa.x, acc), acc = fmaf(ob[1], wa.y, acc), acc = fmaf(ob[2], wa.z, acc);
-  acc = fmaf(ob[3], wa.w, acc), acc = fmaf(ob[4], wb.x, acc), acc = fmaf(ob[5], wb.y, acc);
-  acc = fmaf(ob[6], wb.z, acc);
-  return acc;
+// the row's observations duplicated into register pairs (operands of the packed FMAs)
+struct ObsPairs {
+  float2 v[7];
+};
+__device__ __forceinline__ ObsPairs obs_pairs(const float* ob) {
+  ObsPairs o;
+#pragma unroll
+  for (int d = 0; d < 7; ++d) o.v[d] = make_float2(ob[d], ob[d]);
+  return o;
 }
-// H1[row][c0 .. c0 + 8) = relu(Z1); returns the 8 ReLU-mask bits (bit e: column c0 + e is positive)
-__device__ __forceinline__ uint32_t h1_chunk(const float (*w1s)[8], const float* ob, int c0, float* v) {
+// Z1[row][c0 .. c0 + 8) = b1[c] + sum_d obs[d] W1[c][d] in fp32: bias first, then d ascending -- one FMA per term
+// (two columns per FFMA2); H1 = relu(Z1) -> v; returns the 8 ReLU-mask bits (bit e: column c0 + e is positive)
+__device__ __forceinline__ uint32_t h1_chunk(const float (*w1t)[H], const ObsPairs& ob, int D, int c0, float* v) {
+  float2 z[4];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(&w1t[7][c0]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&w1t[7][c0 + 4]);
+    z[0] = make_float2(b0.x, b0.y), z[1] = make_float2(b0.z, b0.w);
+    z[2] = make_float2(b1.x, b1.y), z[3] = make_float2(b1.z, b1.w);
+  }
+#pragma unroll
+  for (int d = 0; d < 7; ++d) {
+    if (d < D) {  // uniform
+      const float4 w0 = *reinterpret_cast<const float4*>(&w1t[d][c0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&w1t[d][c0 + 4]);
+      z[0] = ffma2(ob.v[d], make_float2(w0.x, w0.y), z[0]);
+      z[1] = ffma2(ob.v[d], make_float2(w0.z, w0.w), z[1]);
+      z[2] = ffma2(ob.v[d], make_float2(w1.x, w1.y), z[2]);
+      z[3] = ffma2(ob.v[d], make_float2(w1.z, w1.w), z[3]);
+    }
+  }
   uint32_t bits = 0u;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float z = z1_value(w1s[c0 + j], ob);
-    bits |= (z > 0.0f ? 1u : 0u) << j;
-    v[j] = fmaxf(z, 0.0f);
+  for (int j = 0; j < 4; ++j) {
+    bits |= (z[j].x > 0.0f ? 1u : 0u) << (2 * j) | (z[j].y > 0.0f ? 1u : 0u) << (2 * j + 1);
+    v[2 * j] = fmaxf(z[j].x, 0.0f), v[2 * j + 1] = fmaxf(z[j].y, 0.0f);
   }
   return bits;
 }

@@ -138,7 +138,7 @@ int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int piec
 // acc_empty[b] (leader's, 32 worker-warp arrivals: accumulator b has been read).
 struct SmemX3F {
   StageX<3> ring[kXStages];     // 196608
-  float w1s[H][8];              //   8192  [W1 (D <= 7 values, zero padded) | b1 in slot 7]
+  float w1t[8][H];              //   8192  [W1^T (D <= 7 rows) | b1 in row 7]
   float b2[H];                  //   1024
   float w3[kMaxPT][H];          //   4096
   float part[4][TILE][kMaxPT];  //   8192  head partial sums per column quarter
@@ -166,7 +166,7 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
-  stage_w1s(s.w1s, np);
+  stage_w1t(s.w1t, np);
   for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
@@ -187,16 +187,17 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
     const int D = np.D;
     uint32_t kcount = 0;
     auto produce = [&](int64_t tile) {
-      float ob[7];
+      float obf[7];
       const int64_t row = tile * 256 + rank * 128 + rloc;
 #pragma unroll
-      for (int d = 0; d < 7; ++d) ob[d] = 0.0f;
+      for (int d = 0; d < 7; ++d) obf[d] = 0.0f;
       if (row < rows) {
         const float* base = map.obs + map.offset(row);
 #pragma unroll
         for (int d = 0; d < 7; ++d)
-          if (d < D) ob[d] = __ldg(base + (int64_t)d * ds);
+          if (d < D) obf[d] = __ldg(base + (int64_t)d * ds);
       }
+      const ObsPairs ob = obs_pairs(obf);
       for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
         const int st = (int)(kcount % kXStages);
         const uint32_t use = kcount / kXStages;
@@ -210,7 +211,7 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
             bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
         }
         float v[8];
-        h1_chunk(s.w1s, ob, stage_kgroup(kc, g) * 8, v);
+        h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
         uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
         store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
         fence_async_smem();

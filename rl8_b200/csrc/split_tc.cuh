@@ -95,17 +95,36 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_f32(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16hi_f32(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
 
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100: two independent round-to-nearest operations per instruction)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // two fp32 values -> NP packed bf16 pairs (piece k of both values in q[k]; x0 in the low half)
 template <int NP>
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t* q) {
-  q[0] = cvt_bf16x2(x0, x1);
+  float2 x = make_float2(x0, x1);
+  q[0] = cvt_bf16x2(x.x, x.y);
   if constexpr (NP > 1) {
-    x0 -= bf16lo_f32(q[0]), x1 -= bf16hi_f32(q[0]);
-    q[1] = cvt_bf16x2(x0, x1);
+    x = fsub2(x, make_float2(bf16lo_f32(q[0]), bf16hi_f32(q[0])));  // exact: the residual of a rounding
+    q[1] = cvt_bf16x2(x.x, x.y);
   }
   if constexpr (NP > 2) {
-    x0 -= bf16lo_f32(q[1]), x1 -= bf16hi_f32(q[1]);
-    q[2] = cvt_bf16x2(x0, x1);
+    x = fsub2(x, make_float2(bf16lo_f32(q[1]), bf16hi_f32(q[1])));
+    q[2] = cvt_bf16x2(x.x, x.y);
   }
 }
 // eight consecutive K (or MN) elements -> one 16-byte chunk per piece at tile_k + off

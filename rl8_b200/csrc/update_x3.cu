@@ -72,7 +72,7 @@ __device__ __forceinline__ bool load_row_obs(const UpdXArgs& a, int64_t rowl, in
 constexpr int kFStages = 4;
 struct SmemXF {
   StageX<3> ring[kFStages];     // 196608
-  float w1s[H][8];              //   8192
+  float w1t[8][H];              //   8192
   float b2[H];                  //   1024
   float w3[kMaxPT][H];          //   4096
   float part[4][TILE][kMaxPT];  //   8192  head partial sums per column quarter
@@ -100,9 +100,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
   uint32_t kcount = 0;
 
   auto produce = [&](int64_t tile) {
-    float ob[7];
+    float obf[7];
     const int64_t rowl = tile * 256 + rank * 128 + rloc;
-    const bool valid = load_row_obs(a, rowl, D, ob, nullptr);
+    const bool valid = load_row_obs(a, rowl, D, obf, nullptr);
+    const ObsPairs ob = obs_pairs(obf);
     uint32_t m0 = 0u, m1 = 0u;
     for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
       const int st = (int)(kcount % kFStages);
@@ -117,7 +118,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
           bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
       }
       float v[8];
-      const uint32_t bits = h1_chunk(s.w1s, ob, stage_kgroup(kc, g) * 8, v);
+      const uint32_t bits = h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
       if (kc < 4) m0 |= bits << (8 * kc);
       else m1 |= bits << (8 * (kc - 4));
       uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
@@ -275,7 +276,7 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
-  stage_w1s(s.w1s, np);
+  stage_w1t(s.w1t, np);
   for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
@@ -327,17 +328,24 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
 // dZ2[row][j0 .. j0 + 8) = [H2 > 0] .* (dOut W3) from the scratch values of the row
 template <int PN>
 __device__ __forceinline__ void dz2_chunk(const float (*w3)[H], const float* d, uint32_t mask_byte, int j0, float* v) {
+  float2 g[4];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    float g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int p = 0; p < PN; ++p) {
-      const float4 w = *reinterpret_cast<const float4*>(&w3[p][j0 + 4 * h]);
-      g[0] = fmaf(d[p], w.x, g[0]), g[1] = fmaf(d[p], w.y, g[1]);
-      g[2] = fmaf(d[p], w.z, g[2]), g[3] = fmaf(d[p], w.w, g[3]);
+  for (int p = 0; p < PN; ++p) {
+    const float4 w0 = *reinterpret_cast<const float4*>(&w3[p][j0]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&w3[p][j0 + 4]);
+    const float2 dp = make_float2(d[p], d[p]);
+    if (p == 0) {  // fma(d, w, 0) == d * w
+      g[0] = fmul2(dp, make_float2(w0.x, w0.y)), g[1] = fmul2(dp, make_float2(w0.z, w0.w));
+      g[2] = fmul2(dp, make_float2(w1.x, w1.y)), g[3] = fmul2(dp, make_float2(w1.z, w1.w));
+    } else {
+      g[0] = ffma2(dp, make_float2(w0.x, w0.y), g[0]), g[1] = ffma2(dp, make_float2(w0.z, w0.w), g[1]);
+      g[2] = ffma2(dp, make_float2(w1.x, w1.y), g[2]), g[3] = ffma2(dp, make_float2(w1.z, w1.w), g[3]);
     }
+  }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[4 * h + e] = (mask_byte >> (4 * h + e)) & 1u ? g[e] : 0.0f;
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = (mask_byte >> (2 * e)) & 1u ? g[e].x : 0.0f;
+    v[2 * e + 1] = (mask_byte >> (2 * e + 1)) & 1u ? g[e].y : 0.0f;
   }
 }
 
@@ -571,7 +579,7 @@ template <int NPB>
 struct SmemXW {
   static constexpr int kStages = NPB == 2 ? 6 : 4;
   StageX<NPB> ring[kStages];  // 196608
-  float w1s[H][8];           //   8192
+  float w1t[8][H];           //   8192
   float w3[kMaxPT][H];       //   4096
   uint64_t full[kStages], empty[kStages], flush_full, flush_empty;
   uint32_t tmem_base;
@@ -670,7 +678,7 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].a[p];
         store_split_chunk<NPB>(tiles, (uint32_t)(lane * 16 + g * 512), v);
       } else {
-        h1_chunk(s.w1s, cur_f, 128 * (int)rank + 8 * g, v);
+        h1_chunk(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);
         uint8_t* tiles[NPB];
 #pragma unroll
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
@@ -722,7 +730,7 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
-  stage_w1s(s.w1s, np);
+  stage_w1t(s.w1t, np);
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
