@@ -629,8 +629,18 @@ def stream_rooflines(lib, L, dev, peaks: dict) -> list[dict]:  # noqa: ANN001
     ms = _time_kernel(lambda: lib.rl8_gae_scan(L.ptr(r), L.ptr(v), L.ptr(adv), L.ptr(ret), N, T, 1, N,
                                                0.95, 0.95, 1.0, L.ptr(mom), st), flush)
     alg = 20.0 * N * T + 20.0 * N
-    out.append({"kernel": "gae_scan_hm_kernel", "bound": "hbm", "bytes": alg, "ms": ms,
+    out.append({"kernel": "gae_scan_hm_kernel (functional form: scaled rewards written back, 20 B per transition)",
+                "bound": "hbm", "bytes": alg, "ms": ms,
                 "achieved": alg / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / hbm,
+                "shape": f"N={N} T={T}"})
+    # the form Algorithm.step() launches: divisor read from device memory, no scaled-reward write-back (the buffer is
+    # dropped right after): SURVEY.md §8d's 16 B per transition + 8 B per env (+ 8 B per env for the slot-T rewards read)
+    scale_dev = torch.ones(2, device=dev)
+    ms = _time_kernel(lambda: lib.rl8_gae_scan_dev(L.ptr(r), L.ptr(v), L.ptr(adv), L.ptr(ret), N, T, 1, N, 0.95, 0.95,
+                                                   L.ptr(scale_dev), 0, L.ptr(mom), st), flush)
+    alg = 16.0 * N * T + 16.0 * N
+    out.append({"kernel": "gae_scan_hm_kernel (Algorithm.step form: no reward write-back)", "bound": "hbm", "bytes": alg,
+                "ms": ms, "achieved": alg / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / hbm,
                 "shape": f"N={N} T={T}"})
     ms = _time_kernel(lambda: lib.rl8_gae_normalize(L.ptr(adv), N, T, 1, N, L.ptr(mom), st), flush)
     alg = 8.0 * N * T

@@ -168,11 +168,15 @@ int rl8_gae_normalize(float* advantages, int64_t N, int32_t T, int64_t stride_n,
 /* The device-resident form (no host round trip between collect() and step()): rl8_reward_scale
  * turns the (all-reduced) accumulator of rl8_collect_stats into out[0] = f32(std(rdr[:, 1:])) -- the reference's
  * float(torch.std(...)), src/rl8/algorithms/_feedforward.py:428-436; 1 when !normalize_rewards -- and
- * out[1] = f32(out[0] + 1e-8); rl8_gae_scan_dev is rl8_gae_scan reading that divisor from `reward_scale_dev[1]`. */
+ * out[1] = f32(out[0] + 1e-8); rl8_gae_scan_dev is rl8_gae_scan reading that divisor from `reward_scale_dev[1]`.
+ * write_scaled_rewards = 0 (horizon-major layout only) leaves `rewards` untouched: Algorithm.step() discards the
+ * rewards right after GAE (src/rl8/algorithms/_feedforward.py:476-478), so the side effect of functional.py:106 is
+ * unobservable there and the scan moves SURVEY.md §8d's 16 B per transition instead of 20. */
 int rl8_reward_scale(const double* acc, double count, int normalize_rewards, float* out, rl8_stream_t stream);
 int rl8_gae_scan_dev(float* rewards, const float* values, float* advantages, float* returns,
                      int64_t N, int32_t T, int64_t stride_n, int64_t stride_t, double gamma,
-                     double gae_lambda, const float* reward_scale_dev, double* moments, rl8_stream_t stream);
+                     double gae_lambda, const float* reward_scale_dev, int write_scaled_rewards, double* moments,
+                     rl8_stream_t stream);
 
 /* ---- collect statistics (src/rl8/algorithms/_feedforward.py:410-436) ----------------- */
 
@@ -348,6 +352,12 @@ int rl8_lstm_ppo_minibatch(const rl8_lstm_model* model, const rl8_lstm_model* gr
 int rl8_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
                   double max_norm, double lr, double beta1, double beta2, double eps,
                   int64_t step, float* norm_out, rl8_stream_t stream);
+
+/* The clip alone -- torch.nn.utils.clip_grad_norm_(parameters, max_norm) of _feedforward.py:587-589 on the flat
+ * gradient buffer: norm_out[0] = ||g||_2, g *= min(1, max_norm / (norm + 1e-6)).  For `optimizer_cls` other than
+ * the fused Adam (_feedforward.py:257-260): the caller's torch optimizer then steps on parameters whose .grad are
+ * views of `grads`. */
+int rl8_clip_grads(float* grads, int64_t count, double max_norm, float* norm_out, rl8_stream_t stream);
 
 /* ---- view requirements (src/rl8/views.py) ------------------------------------------------ */
 

@@ -686,8 +686,13 @@ def step(
     eps: float = 1e-8,
     perms: None | list[torch.Tensor] = None,
     grad_hook: None | Callable[[Params], None] = None,
+    optimizer_cls: Any = torch.optim.Adam,
+    optimizer_config: None | dict[str, Any] = None,
 ) -> dict[str, float]:
     """GAE + PPO epochs + clip + Adam, in place on ``p`` (leaf tensors) and ``buf``.
+
+    ``optimizer_cls(params, **optimizer_config)`` replaces the default Adam the way
+    ``AlgorithmConfig.optimizer_cls / optimizer_config`` do (_feedforward.py:257-260).
 
     ``opt_state`` holds a persistent ``torch.optim.Adam`` across calls (created on first
     use) — the reference uses the same library optimizer
@@ -720,10 +725,14 @@ def step(
     for v in p.values():
         v.requires_grad_(True)
     if "adam" not in opt_state:
-        opt_state["adam"] = torch.optim.Adam(list(p.values()), lr=lr, betas=betas, eps=eps)
+        if optimizer_config is not None or optimizer_cls is not torch.optim.Adam:
+            opt_state["adam"] = optimizer_cls(list(p.values()), **(optimizer_config or {"lr": lr}))
+            opt_state["own_lr"] = True  # the lr of optimizer_config stands (no schedule injected by the caller)
+        else:
+            opt_state["adam"] = torch.optim.Adam(list(p.values()), lr=lr, betas=betas, eps=eps)
     adam = opt_state["adam"]
     for g in adam.param_groups:
-        g["lr"] = lr
+        g["lr"] = g["lr"] if opt_state.get("own_lr") else lr
 
     keys = ("losses/entropy", "losses/policy", "losses/vf", "losses/total", "monitors/kl_div")
     sums = {k: 0.0 for k in keys}

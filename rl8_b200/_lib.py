@@ -145,7 +145,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rl8_reward_scale": (_int, [_vp, _f64, _int, _vp, _vp]),
     "rl8_gae_scan_dev": (
         _int,
-        [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _f64, _vp, _vp, _vp],
+        [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _f64, _vp, _int, _vp, _vp],
     ),
     "rl8_collect_stats": (_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "rl8_collect_stats_from": (_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
@@ -213,6 +213,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         _int,
         [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _vp, _vp],
     ),
+    "rl8_clip_grads": (_int, [_vp, _i64, _f64, _vp, _vp]),
 }
 
 _lib: None | C.CDLL = None

@@ -101,6 +101,69 @@ class _NoopGradScaler:
         return 1.0
 
 
+class FusedAdam(optim.Adam):
+    """``torch.optim.Adam``'s param groups and ``state_dict`` over the flat moment buffers that ``rl8_clip_adam``
+    updates (src/rl8/algorithms/_feedforward.py:257-260): LR schedules mutate ``param_groups`` as in the reference, and
+    ``state_dict()`` / ``load_state_dict()`` carry the moments and the step count, so a save / resume keeps Adam's
+    moments and bias correction.  ``step()`` is never called: the update is the fused kernel."""
+
+    #: optimizer updates applied so far (the 1-based ``step`` of Adam's bias correction)
+    update_count = 0
+
+    def bind_flat(self, model: Any, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor) -> None:
+        self._flat = (model, exp_avg, exp_avg_sq)
+        self._publish()
+
+    def _publish(self) -> None:
+        model, m, v = self._flat
+        vm, vv = model.named_flat_views(m), model.named_flat_views(v)
+        for n, p in model.named_parameters():
+            self.state[p] = {"step": torch.tensor(float(self.update_count)), "exp_avg": vm[n], "exp_avg_sq": vv[n]}
+
+    def state_dict(self) -> dict[str, Any]:
+        for st in self.state.values():
+            st["step"] = torch.tensor(float(self.update_count))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
+        super().load_state_dict(state_dict)  # replaces the per-parameter state with copies
+        model, m, v = self._flat
+        vm, vv = model.named_flat_views(m), model.named_flat_views(v)
+        steps = 0
+        for n, p in model.named_parameters():
+            st = self.state.get(p)
+            if st:
+                vm[n].copy_(st["exp_avg"])
+                vv[n].copy_(st["exp_avg_sq"])
+                steps = int(st["step"])
+            else:
+                vm[n].zero_()
+                vv[n].zero_()
+        self.update_count = steps
+        self._publish()
+
+
+def make_flat_optimizer(model: Any, grads: torch.Tensor, optimizer_cls: Any,
+                        optimizer_config: dict[str, Any]) -> tuple[optim.Optimizer, None | tuple[torch.Tensor, ...]]:
+    """The optimizer of a default (flat-parameter) model.  Plain Adam -- the reference default -- is the fused
+    ``rl8_clip_adam`` behind a :class:`FusedAdam`; returns ``(optimizer, (exp_avg, exp_avg_sq))``.  Any other
+    ``optimizer_cls`` / Adam option (src/rl8/algorithms/_feedforward.py:257-260) is the caller's torch optimizer
+    stepping on the model's parameters with ``.grad`` bound to views of the flat gradient buffer the update kernels
+    fill (``rl8_clip_grads`` does the clipping): returns ``(optimizer, None)``."""
+    plain = {k: v for k, v in optimizer_config.items() if k not in ("lr", "betas", "eps") and v}
+    if optimizer_cls is optim.Adam and not plain:
+        opt = FusedAdam(model.parameters(), **optimizer_config)
+        m, v = torch.zeros_like(grads), torch.zeros_like(grads)
+        opt.bind_flat(model, m, v)
+        return opt, (m, v)
+    opt = optimizer_cls(model.parameters(), **optimizer_config)
+    opt.update_count = 0
+    views = model.named_flat_views(grads)
+    for n, p in model.named_parameters():
+        p.grad = views[n]
+    return opt, None
+
+
 _mem_cache: dict[int, tuple[int, int, int]] = {}  # device -> (allocator bytes reserved, free, total)
 
 
@@ -243,30 +306,20 @@ class Algorithm:
         self._fused_model = self.policy.fused
         optimizer_config = dict(config.optimizer_config or {"lr": 1e-3})
         if self._fused_model:
-            if config.optimizer_cls is not optim.Adam:
-                raise NotImplementedError(
-                    "the fused update of the default models implements Adam (the reference default);"
-                    " other optimizer classes run with user-defined models (rl8_b200.models.GenericModel)"
-                )
-            unsupported = {k: v for k, v in optimizer_config.items()
-                           if k not in ("lr", "betas", "eps") and v}
-            if unsupported:
-                raise NotImplementedError(f"fused Adam does not implement {sorted(unsupported)}")
-            # A real torch optimizer object holds the param groups (lr schedules mutate them);
-            # the update itself runs in rl8_clip_adam on the flat buffers below.
-            self.optimizer = optim.Adam(self.policy.model.parameters(), **optimizer_config)
-            flat = self.policy.model.flat_params
-            self._grads = torch.zeros_like(flat)
-            self._exp_avg = torch.zeros_like(flat)
-            self._exp_avg_sq = torch.zeros_like(flat)
+            # Plain Adam: param groups in a torch optimizer object (lr schedules mutate them), the update itself in
+            # rl8_clip_adam on the flat buffers.  Other optimizer classes / options: torch steps on the flat views.
+            self._grads = torch.zeros_like(self.policy.model.flat_params)
+            self.optimizer, moments = make_flat_optimizer(self.policy.model, self._grads, config.optimizer_cls,
+                                                          optimizer_config)
+            self._exp_avg, self._exp_avg_sq = moments if moments is not None else (None, None)
         else:
             # user-defined torch model: its parameters belong to torch, any optimizer class works
             self.optimizer = config.optimizer_cls(self.policy.model.parameters(), **optimizer_config)
+            self.optimizer.update_count = 0
         # Multi-GPU: replicas start from rank 0's parameters whatever each rank's RNG state was
         # (seed env resets / sampling noise per rank; the model is made identical here).
         parallel.sync_replicas(self.policy.model)
         self._grad_norm = torch.zeros(1, device=device)
-        self._opt_steps = 0
         self.lr_scheduler = LRScheduler(
             self.optimizer, schedule=config.lr_schedule, kind=config.lr_schedule_kind
         )
@@ -318,6 +371,15 @@ class Algorithm:
         self.last_launches = {"collect": 0, "step": 0}
 
     # ------------------------------------------------------------------------------------
+    @property
+    def _opt_steps(self) -> int:
+        """Optimizer updates applied so far (kept on the optimizer object: it travels with its state_dict)."""
+        return self.optimizer.update_count  # type: ignore[attr-defined]
+
+    @_opt_steps.setter
+    def _opt_steps(self, value: int) -> None:
+        self.optimizer.update_count = value  # type: ignore[attr-defined]
+
     @property
     def horizons_per_env_reset(self) -> int:
         return self.hparams.horizons_per_env_reset
@@ -583,7 +645,9 @@ class Algorithm:
             rc = lib.rl8_gae_scan_dev(
                 _lib.ptr(buf.hm[DataKeys.REWARDS]), _lib.ptr(buf.hm[DataKeys.VALUES]),
                 _lib.ptr(buf.hm[DataKeys.ADVANTAGES]), _lib.ptr(buf.hm[DataKeys.RETURNS]),
-                N, T, 1, N, hp.gamma, hp.gae_lambda, _lib.ptr(self._scale_dev), _lib.ptr(self._moments), st,
+                N, T, 1, N, hp.gamma, hp.gae_lambda, _lib.ptr(self._scale_dev),
+                0,  # the buffer (rewards included) is re-zeroed at the end of step(): no scaled-reward write-back
+                _lib.ptr(self._moments), st,
             )
         else:  # a reward scale assigned by the caller
             rc = lib.rl8_gae_scan(
@@ -662,14 +726,20 @@ class Algorithm:
                     if self._on_grads is not None:
                         self._on_grads(model.named_flat_views(self._grads))
                     self._opt_steps += 1
-                    betas = pg.get("betas", (0.9, 0.999))
-                    rc = lib.rl8_clip_adam(
-                        _lib.ptr(model.flat_params), _lib.ptr(self._grads), _lib.ptr(self._exp_avg),
-                        _lib.ptr(self._exp_avg_sq), self._grads.numel(), hp.max_grad_norm,
-                        pg["lr"], betas[0], betas[1], pg.get("eps", 1e-8), self._opt_steps,
-                        _lib.ptr(self._grad_norm), st,
-                    )
-                    _lib.check(rc, "rl8_clip_adam")
+                    if self._exp_avg is not None:
+                        betas = pg.get("betas", (0.9, 0.999))
+                        rc = lib.rl8_clip_adam(
+                            _lib.ptr(model.flat_params), _lib.ptr(self._grads), _lib.ptr(self._exp_avg),
+                            _lib.ptr(self._exp_avg_sq), self._grads.numel(), hp.max_grad_norm,
+                            pg["lr"], betas[0], betas[1], pg.get("eps", 1e-8), self._opt_steps,
+                            _lib.ptr(self._grad_norm), st,
+                        )
+                        _lib.check(rc, "rl8_clip_adam")
+                    else:  # optimizer_cls of the caller: clip here, torch steps on the flat views (.grad = self._grads)
+                        rc = lib.rl8_clip_grads(_lib.ptr(self._grads), self._grads.numel(), hp.max_grad_norm,
+                                                _lib.ptr(self._grad_norm), st)
+                        _lib.check(rc, "rl8_clip_grads")
+                        self.optimizer.step()
                     launches += 2
                     self._grads.zero_()
             if stop_early:

@@ -60,9 +60,26 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   }
 }
 
+__global__ void __launch_bounds__(256)
+clip_scale_kernel(float* __restrict__ g, int64_t count, float max_norm, const float* __restrict__ norm) {
+  const float coef = fminf(dvd(max_norm, add(norm[0], 1e-6f)), 1.0f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    g[i] = mul(g[i], coef);
+}
+
 }  // namespace rl8
 
 using namespace rl8;
+
+extern "C" int rl8_clip_grads(float* grads, int64_t count, double max_norm, float* norm_out, rl8_stream_t stream) {
+  if (!grads || !norm_out || count <= 0) return RL8_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  grad_norm_kernel<<<1, 1024, 0, st>>>(grads, count, norm_out);
+  int rc = check_launch("grad_norm");
+  if (rc) return rc;
+  clip_scale_kernel<<<grid_for(count, 256), 256, 0, st>>>(grads, count, (float)max_norm, norm_out);
+  return check_launch("clip_scale");
+}
 
 extern "C" int rl8_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                              int64_t count, double max_norm, double lr, double beta1,

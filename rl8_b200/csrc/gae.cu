@@ -20,6 +20,7 @@ struct GaeConsts {
   float gl;         // f32(gamma * gae_lambda)  (double product, one rounding)
   float denom;      // f32(reward_scale + 1e-8)
   const float* denom_dev;  // when set: the same value in device memory (rl8_reward_scale), read by the kernel
+  int keep_rewards;        // horizon-major kernel: do not write the scaled rewards back (Algorithm.step drops them)
 };
 // the reward divisor of this launch: the host value, or the one a previous kernel left on the device
 __device__ __forceinline__ float gae_denom(const GaeConsts& c) { return c.denom_dev ? __ldg(c.denom_dev) : c.denom; }
@@ -59,7 +60,7 @@ gae_scan_hm_kernel(float* __restrict__ rewards, const float* __restrict__ values
     load(rewards + (int64_t)T * st + n0, tmp);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) tmp[j] = dvd(tmp[j], denom);
-    store(rewards + (int64_t)T * st + n0, tmp);
+    if (!c.keep_rewards) store(rewards + (int64_t)T * st + n0, tmp);
 
     constexpr int U = 4;  // software pipeline: U time steps of loads in flight
     int t = T - 1;
@@ -84,7 +85,7 @@ gae_scan_hm_kernel(float* __restrict__ rewards, const float* __restrict__ values
           s1 += (double)a[j];
           s2 += (double)a[j] * (double)a[j];
         }
-        store(rewards + (int64_t)(t - u) * st + n0, r[u]);
+        if (!c.keep_rewards) store(rewards + (int64_t)(t - u) * st + n0, r[u]);
         store(adv + (int64_t)(t - u) * st + n0, a);
         if (ret) store(ret + (int64_t)(t - u) * st + n0, rt);
       }
@@ -104,7 +105,7 @@ gae_scan_hm_kernel(float* __restrict__ rewards, const float* __restrict__ values
         s1 += (double)a[j];
         s2 += (double)a[j] * (double)a[j];
       }
-      store(rewards + (int64_t)t * st + n0, r);
+      if (!c.keep_rewards) store(rewards + (int64_t)t * st + n0, r);
       store(adv + (int64_t)t * st + n0, a);
       if (ret) store(ret + (int64_t)t * st + n0, rt);
     }
@@ -331,10 +332,12 @@ using namespace rl8;
 
 static int gae_scan_impl(float* rewards, const float* values, float* advantages, float* returns, int64_t N,
                          int32_t T, int64_t stride_n, int64_t stride_t, double gamma, double gae_lambda,
-                         double reward_scale, const float* denom_dev, double* moments, rl8_stream_t stream) {
+                         double reward_scale, const float* denom_dev, int keep_rewards, double* moments,
+                         rl8_stream_t stream) {
   if (!rewards || !values || !advantages || N <= 0 || T <= 0) return RL8_ERR_ARG;
+  if (keep_rewards && stride_n != 1) return RL8_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  GaeConsts c{(float)gamma, (float)(gamma * gae_lambda), (float)(reward_scale + 1e-8), denom_dev};
+  GaeConsts c{(float)gamma, (float)(gamma * gae_lambda), (float)(reward_scale + 1e-8), denom_dev, keep_rewards};
   auto al = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
   if (stride_n == 1) {
     bool vec = (N % 4 == 0) && (stride_t % 4 == 0) && al(rewards) && al(values) &&
@@ -361,16 +364,16 @@ extern "C" int rl8_gae_scan(float* rewards, const float* values, float* advantag
                             double gae_lambda, double reward_scale, double* moments,
                             rl8_stream_t stream) {
   return gae_scan_impl(rewards, values, advantages, returns, N, T, stride_n, stride_t, gamma, gae_lambda,
-                       reward_scale, nullptr, moments, stream);
+                       reward_scale, nullptr, 0, moments, stream);
 }
 
 extern "C" int rl8_gae_scan_dev(float* rewards, const float* values, float* advantages, float* returns,
                                 int64_t N, int32_t T, int64_t stride_n, int64_t stride_t, double gamma,
-                                double gae_lambda, const float* reward_scale_dev, double* moments,
-                                rl8_stream_t stream) {
+                                double gae_lambda, const float* reward_scale_dev, int write_scaled_rewards,
+                                double* moments, rl8_stream_t stream) {
   if (!reward_scale_dev) return RL8_ERR_ARG;
   return gae_scan_impl(rewards, values, advantages, returns, N, T, stride_n, stride_t, gamma, gae_lambda, 1.0,
-                       reward_scale_dev + 1, moments, stream);
+                       reward_scale_dev + 1, write_scaled_rewards ? 0 : 1, moments, stream);
 }
 
 // out[0] = f32(unbiased std of the reversed discounted returns) from the (all-reduced) accumulator of

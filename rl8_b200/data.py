@@ -85,10 +85,9 @@ class AlgorithmHparams:
             not (self.target_kl_div is not None and self.accumulate_grads),
             "Early-stopping using `target_kl_div` is not compatible with gradient accumulation.",
         )
-        _require(
-            not (self.target_kl_div is not None and self.enable_amp),
-            "Early-stopping using `target_kl_div` is not compatible with AMP.",
-        )
+        # The reference also rejects `target_kl_div` with `enable_amp` (src/rl8/data.py: a skipped minibatch would
+        # leave its GradScaler half-updated).  enable_amp here is bf16 operands with fp32 accumulation: there is no
+        # loss scaling, so the early stop works in that mode too and the combination is accepted.
         _require(
             self.target_kl_div is None or self.target_kl_div > 0, "`target_kl_div` must be > 0."
         )

@@ -27,7 +27,7 @@ import torch.nn as nn
 import torch.optim as optim
 
 from . import _lib, parallel
-from .algorithms import Algorithm, _NoopGradScaler
+from .algorithms import Algorithm, _NoopGradScaler, make_flat_optimizer
 from .buffer import RolloutBuffer
 from .data import DataKeys, Device, RecurrentAlgorithmHparams, RecurrentAlgorithmState
 from .distributions import Distribution
@@ -406,25 +406,14 @@ class RecurrentAlgorithm(Algorithm):
         if config.normalize_rewards:
             self.buffer_spec.set(DataKeys.REVERSED_DISCOUNTED_RETURNS, Unbounded(1, device=device))
         self.buffer = RolloutBuffer(self.buffer_spec, num_envs, horizon, device)
-        if config.optimizer_cls is not optim.Adam:
-            raise NotImplementedError(
-                "the fused update implements Adam (the reference default); other optimizer"
-                " classes are outside the fused hot path"
-            )
         optimizer_config = dict(config.optimizer_config or {"lr": 1e-3})
-        unsupported = {k: v for k, v in optimizer_config.items()
-                       if k not in ("lr", "betas", "eps") and v}
-        if unsupported:
-            raise NotImplementedError(f"fused Adam does not implement {sorted(unsupported)}")
-        self.optimizer = optim.Adam(self.policy.model.parameters(), **optimizer_config)
-        flat = self.policy.model.flat_params
-        self._grads = torch.zeros_like(flat)
-        self._exp_avg = torch.zeros_like(flat)
-        self._exp_avg_sq = torch.zeros_like(flat)
+        self._grads = torch.zeros_like(self.policy.model.flat_params)
+        self.optimizer, moments = make_flat_optimizer(self.policy.model, self._grads, config.optimizer_cls,
+                                                      optimizer_config)
+        self._exp_avg, self._exp_avg_sq = moments if moments is not None else (None, None)
         parallel.sync_replicas(self.policy.model)  # replicas start from rank 0's parameters
         self._scale_dev = torch.ones(2, dtype=torch.float32, device=device)  # reward scale of the last collect()
         self._grad_norm = torch.zeros(1, device=device)
-        self._opt_steps = 0
         self.lr_scheduler = LRScheduler(
             self.optimizer, schedule=config.lr_schedule, kind=config.lr_schedule_kind
         )

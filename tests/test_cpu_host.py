@@ -80,7 +80,7 @@ def _hp(**over):
     [dict(clip_param=0.0), dict(clip_param=1.0), dict(dual_clip_param=1.0), dict(gae_lambda=0.0),
      dict(gamma=1.5), dict(horizon=0), dict(horizons_per_env_reset=0), dict(max_grad_norm=0.0),
      dict(num_sgd_iters=0), dict(sgd_minibatch_size=0), dict(vf_clip_param=0.0), dict(vf_coeff=0.0),
-     dict(target_kl_div=-1.0), dict(target_kl_div=0.1, enable_amp=True),
+     dict(target_kl_div=-1.0),
      dict(target_kl_div=0.1, accumulate_grads=True, sgd_minibatch_size=1024),
      dict(accumulate_grads=True), dict(device="cpu", enable_amp=True)],
 )
@@ -88,6 +88,12 @@ def test_hparam_validation_rules(bad: dict) -> None:
     """src/rl8/data.py:196-252."""
     with pytest.raises(ValueError):
         _hp(**bad)
+
+
+def test_early_stop_is_accepted_with_amp() -> None:
+    """The one validation rule that differs from src/rl8/data.py: the reference rejects target_kl_div with enable_amp
+    because of its GradScaler; enable_amp here is bf16 operands with fp32 accumulation and has no loss scaling."""
+    assert _hp(target_kl_div=0.1, enable_amp=True).target_kl_div == 0.1
 
 
 def test_hparam_properties() -> None:

@@ -377,11 +377,13 @@ def test_user_defined_model_with_dropping_views_is_rejected() -> None:
         def __init__(self, observation_spec, action_spec, /) -> None:  # noqa: ANN001
             super().__init__(observation_spec, action_spec)
             self.view_requirements["obs"] = ViewRequirement(shift=2, method="rolling_window")
-            self.body = nn.Linear(observation_spec.shape[0] * 3, 16)
+            self.body = nn.Linear(observation_spec.shape[0], 16)
             self.pi, self.vf = nn.Linear(16, action_spec.space.n), nn.Linear(16, 1)
 
         def forward(self, batch):  # noqa: ANN001, ANN201
-            self._z = torch.tanh(self.body(batch["obs"].flatten(1)))
+            # un-padded windows are shorter than shift + 1 at the start of a rollout (validate() samples from one
+            # step): pool over whatever window length arrives
+            self._z = torch.tanh(self.body(batch["obs"].mean(1)))
             return {"logits": self.pi(self._z).unsqueeze(1)}
 
         def value_function(self):  # noqa: ANN201
@@ -393,3 +395,140 @@ def test_user_defined_model_with_dropping_views_is_rejected() -> None:
     algo.state.buffered = True  # the update's guard is what is under test, not the rollout
     with pytest.raises(RuntimeError, match="padded_rolling_window"):
         algo.step()
+
+
+# ---------------------------------------------------------------------------------------
+# optimizers of the default models (src/rl8/algorithms/_feedforward.py:257-260, 585-593)
+# ---------------------------------------------------------------------------------------
+
+
+def _teacher_forced_cartpole(N: int, T: int, **cfg):  # noqa: ANN003, ANN202
+    """(algo, oracle twin state): CartPole with the initial state and the sampling noise injected on both sides."""
+    from oracle import ppo_oracle as O
+    from rl8_b200 import AlgorithmConfig
+    from rl8_b200.distributions import Categorical
+
+    E = _envs()
+    gen = torch.Generator().manual_seed(N + T)
+    state0 = torch.randn(4, N, generator=gen) * 0.05
+    noise = torch.empty(T, N, 1, 3).exponential_(1, generator=gen)
+
+    class Env(E.CartPole):
+        def reset(self, *, config=None):  # noqa: ANN001, ANN202
+            super().reset(config=config)
+            return self.set_state(state0.cuda())
+
+    class Dist(Categorical):
+        @classmethod
+        def draw_noise(cls, steps, num, width, device):  # noqa: ANN001, ANN206
+            if steps != T:  # build() -> validate()
+                return super().draw_noise(steps, num, width, device)
+            return noise.reshape(steps, num, width).to(device)
+
+    torch.manual_seed(0)
+    algo = AlgorithmConfig(num_envs=N, horizon=T, distribution_cls=Dist, shuffle_minibatches=False, **cfg).build(Env)
+    params = {k: v.detach().cpu().clone() for k, v in algo.policy.model.state_dict().items()}
+    o_env = O.OracleEnv("cartpole", N)
+    o_buf = O.new_buffer(N, T, 5, "discrete")
+    return algo, O, params, o_env, o_buf, noise, state0
+
+
+@pytest.mark.parametrize(
+    "opt",
+    [("SGD", {"lr": 0.05, "momentum": 0.9, "nesterov": True, "weight_decay": 1e-3}),
+     ("RMSprop", {"lr": 1e-3, "alpha": 0.9, "centered": True}),
+     ("Adam", {"lr": 2e-3, "weight_decay": 1e-2, "amsgrad": True}),   # Adam options the fused kernel does not implement
+     ("AdamW", {"lr": 2e-3})],
+    ids=lambda o: o[0],
+)
+def test_other_optimizers_on_the_default_models_match_the_oracle(opt: tuple[str, dict]) -> None:
+    """`optimizer_cls` / `optimizer_config` other than plain Adam: rl8_clip_grads + the caller's torch optimizer on
+    views of the flat gradient buffer.  Two collect() + step() rounds (momentum / second-moment state carries over)
+    against the oracle running the same torch optimizer class on CPU."""
+    import torch.optim as optim
+
+    name, cfg = opt
+    N, T = 192, 8
+    algo, O, params, o_env, o_buf, noise, state0 = _teacher_forced_cartpole(
+        N, T, optimizer_cls=getattr(optim, name), optimizer_config=cfg, num_sgd_iters=2, sgd_minibatch_size=N * T // 2)
+    assert type(algo.optimizer) is getattr(optim, name)
+    o_state: dict = {}
+    for rnd in range(2):
+        cs = algo.collect()
+        o_cs = O.collect(params, o_env, o_buf, O.Dist("categorical"), noise, reset_state=state0)
+        assert torch.equal(algo.buffer["actions"].cpu(), o_buf["actions"]), rnd
+        ss = algo.step()
+        o_ss = O.step(params, o_buf, O.Dist("categorical"), o_state, reward_scale=o_cs["reward_scale"],
+                      num_sgd_iters=2, sgd_minibatch_size=N * T // 2, optimizer_cls=getattr(optim, name),
+                      optimizer_config=cfg)
+        assert cs["returns/mean"] == pytest.approx(o_cs["returns/mean"], rel=1e-5)
+        for k in ("losses/policy", "losses/vf", "losses/total", "monitors/kl_div"):
+            assert ss[k] == pytest.approx(o_ss[k], rel=5e-5, abs=2e-6), (rnd, k)
+        sd = algo.policy.model.state_dict()
+        for k, v in params.items():
+            torch.testing.assert_close(sd[k].cpu(), v.detach(), rtol=2e-5, atol=5e-6, msg=lambda m: f"{rnd} {k}: {m}")
+    assert algo._opt_steps == 8
+
+
+def test_fused_adam_state_dict_round_trip() -> None:
+    """optimizer.state_dict() of the fused Adam carries the moments and the step count: a resumed run continues
+    bit-identically, and the same state loads into a plain torch.optim.Adam (the reference's optimizer)."""
+    import copy
+
+    import torch.optim as optim
+
+    from rl8_b200 import AlgorithmConfig
+
+    E = _envs()
+
+    def make():  # noqa: ANN202
+        torch.manual_seed(3)
+        return AlgorithmConfig(num_envs=128, horizon=8, num_sgd_iters=2, shuffle_minibatches=False).build(E.CartPole)
+
+    a = make()
+    a.collect()
+    a.step()
+    sd_model = copy.deepcopy(a.policy.model.state_dict())
+    sd_opt = copy.deepcopy(a.optimizer.state_dict())
+    assert len(sd_opt["state"]) == len(list(a.policy.model.parameters()))
+    assert all(float(s["step"]) == 2.0 for s in sd_opt["state"].values())
+    assert any(float(s["exp_avg_sq"].abs().sum()) > 0 for s in sd_opt["state"].values())
+
+    b = make()
+    b.policy.model.load_state_dict(sd_model)
+    b.optimizer.load_state_dict(sd_opt)
+    assert b._opt_steps == 2
+    assert torch.equal(b._exp_avg, a._exp_avg) and torch.equal(b._exp_avg_sq, a._exp_avg_sq)
+    torch.manual_seed(11)
+    a.collect()
+    b.buffer._raw.copy_(a.buffer._raw)
+    b._scale_dev.copy_(a._scale_dev)
+    b.state.buffered, b.state.horizons, b.state._scale_on_device = True, a.state.horizons, True
+    before = a.policy.model.flat_params.clone()
+    a.step()
+    b.step()
+    # gradient sums are accumulated with atomics (run-to-run order differs): equal to rounding, and far from what a
+    # restarted Adam (zero moments, bias correction of step 1) would have produced
+    torch.testing.assert_close(a.policy.model.flat_params, b.policy.model.flat_params, rtol=1e-5, atol=1e-7)
+    assert float((a.policy.model.flat_params - before).abs().max()) > 1e-4
+
+    # the reference's optimizer accepts the state (same keys / shapes per parameter)
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in a.policy.model.parameters()]
+    ref_opt = optim.Adam(ref_params, lr=1e-3)
+    ref_opt.load_state_dict(sd_opt)
+    for p, q in zip(ref_params, a.policy.model.parameters()):
+        assert ref_opt.state[p]["exp_avg"].shape == q.shape
+
+
+def test_early_stop_works_with_amp() -> None:
+    """enable_amp=True (bf16 operands, no GradScaler) accepts target_kl_div: the first minibatch (KL == 0) is applied,
+    the second exceeds the target and stops the update (src/rl8/algorithms/_feedforward.py:576-585)."""
+    from rl8_b200 import AlgorithmConfig
+
+    torch.manual_seed(0)
+    algo = AlgorithmConfig(num_envs=256, horizon=16, num_sgd_iters=8, sgd_minibatch_size=1024, target_kl_div=1e-9,
+                           enable_amp=True).build(_envs().CartPole)
+    algo.collect()
+    stats = algo.step()
+    assert algo._opt_steps == 1
+    assert math.isfinite(stats["monitors/kl_div"])

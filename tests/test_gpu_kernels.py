@@ -242,6 +242,45 @@ def test_gae_matches_oracle(layout: str, shape: tuple[int, int], normalize: bool
         assert torch.equal(out["returns"].cpu(), o_ret)
 
 
+@pytest.mark.parametrize("shape", [(64, 5), (1000, 32), (1003, 33), (4096, 64)])
+def test_gae_scan_device_scale_forms(shape: tuple[int, int]) -> None:
+    """rl8_gae_scan_dev (the form Algorithm.step launches: divisor read from device memory): with the scaled-reward
+    write-back it equals rl8_gae_scan bit for bit; without it (write_scaled_rewards = 0) advantages / returns /
+    moments are the same bits and `rewards` is left untouched (functional.py:106's side effect skipped)."""
+    L, lib = _lib()
+    N, T = shape
+    gen = torch.Generator().manual_seed(N * 7 + T)
+    r0 = torch.randn(T + 1, N, generator=gen).to(DEV)
+    v = torch.randn(T + 1, N, generator=gen).to(DEV)
+    scale = 1.7
+    sdev = torch.tensor([scale, scale + 1e-8], dtype=torch.float32, device=DEV)  # what rl8_reward_scale leaves
+    st = L.stream()
+    res = []
+    for form in ("host", "dev_write", "dev_keep"):
+        r = r0.clone()
+        adv, ret = torch.full_like(r, float("nan")), torch.full_like(r, float("nan"))
+        mom = torch.zeros(3, dtype=torch.float64, device=DEV)
+        if form == "host":
+            rc = lib.rl8_gae_scan(L.ptr(r), L.ptr(v), L.ptr(adv), L.ptr(ret), N, T, 1, N, 0.95, 0.9, scale, L.ptr(mom), st)
+        else:
+            rc = lib.rl8_gae_scan_dev(L.ptr(r), L.ptr(v), L.ptr(adv), L.ptr(ret), N, T, 1, N, 0.95, 0.9, L.ptr(sdev),
+                                      1 if form == "dev_write" else 0, L.ptr(mom), st)
+        assert rc == 0
+        res.append((r, adv[:T], ret[:T], mom))
+    o_r, o_adv, o_ret = O.gae(r0.T.unsqueeze(-1).cpu(), v.T.unsqueeze(-1).cpu(), gamma=0.95, gae_lambda=0.9,
+                              reward_scale=scale, normalize_advantages=False)
+    assert torch.equal(res[0][1].T.cpu(), o_adv.squeeze(-1)[:, :T])
+    for k in (1, 2):
+        assert torch.equal(res[k][1], res[0][1]) and torch.equal(res[k][2], res[0][2])
+        assert torch.equal(res[k][3], res[0][3])
+    assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[0][0].T.cpu(), o_r.squeeze(-1))
+    assert torch.equal(res[2][0], r0)
+    # the env-major layout has no keep-rewards variant
+    rc = lib.rl8_gae_scan_dev(L.ptr(r0), L.ptr(v), L.ptr(adv), L.ptr(ret), N, T, T + 1, 1, 0.95, 0.9, L.ptr(sdev), 0,
+                              L.ptr(mom), st)
+    assert rc != 0
+
+
 def test_gae_golden(kat: Golden) -> None:
     from rl8_b200.nn import generalized_advantage_estimate
 
