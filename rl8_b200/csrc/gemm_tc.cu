@@ -323,7 +323,7 @@ struct SmemLstm {
   uint8_t a[2][kGM * 128 * 2];   //  65536  h tile in two K halves
   float wt[4][kCellD][64];       //   8192  W_ih of this block's units, [gate][d][unit]
   float bi[4][64], bh[4][64];    //   2048
-  uint64_t bar_h[2], bar_acc[2];
+  uint64_t full[2], free_[2], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 struct LstmCellArgs {
@@ -342,7 +342,34 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return __fdividef(e - 1.0f, e + 1.0f);
 }
 
-__global__ void __launch_bounds__(kRThreads, 1) tc_lstm_cell_kernel(LstmCellArgs g) {
+// Warp roles: warps 0..15 run the cell epilogue, warps 16..18 load + convert the h tile (K halves), warp 19 issues
+// the MMAs.  The three run decoupled behind mbarriers: the loaders refill a K half as soon as the MMAs that read it
+// have completed, the issuer starts a tile as soon as its operands and an accumulator buffer are there, and the
+// epilogue of tile k-1 (whose c_prev / observation loads are issued BEFORE it waits for the accumulator) runs under
+// the loads and MMAs of tiles k, k+1 -- the kernel is bound by HBM traffic, so what matters is that loads are in
+// flight all the time, not only between two block-wide barriers.
+constexpr int kLcEpiWarps = 16, kLcLoadWarps = 3;  // + the issuing warp: 20 warps (register allocation is per 4 warps)
+constexpr int kLcThreads = (kLcEpiWarps + kLcLoadWarps + 1) * 32;  // 640
+
+// 256-bit global accesses (sm_100: LDG / STG .256): one full 32-byte sector per lane and HALF the LSU wavefronts of two
+// 128-bit accesses when every lane of the warp addresses a different row
+__device__ __forceinline__ void ldg8(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld8s(const float* p, float* v) {  // eight consecutive floats of shared memory
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+
+template <int D>  // observation width (compile time: the per-unit input FMAs unroll without predicates)
+__global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArgs g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemLstm& s = *reinterpret_cast<SmemLstm*>(smem_raw);
   constexpr int LH = 256;
@@ -351,31 +378,33 @@ __global__ void __launch_bounds__(kRThreads, 1) tc_lstm_cell_kernel(LstmCellArgs
   const int64_t mt0 = blockIdx.x >> 2, mstride = gridDim.x >> 2;
   const int64_t mtiles = (g.rows + kGM - 1) / kGM;
   if (tid == 0) {
-    mbar_init(&s.bar_h[0], 1), mbar_init(&s.bar_h[1], 1);
-    mbar_init(&s.bar_acc[0], 1), mbar_init(&s.bar_acc[1], 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&s.full[h], kLcLoadWarps), mbar_init(&s.free_[h], 1);
+      mbar_init(&s.acc_full[h], 1), mbar_init(&s.acc_empty[h], kLcEpiWarps);
+    }
     fence_mbar_init();
   }
-  if (tid < 32) tmem_alloc(&s.tmem_base, 512);
+  if (warp == kLcEpiWarps + kLcLoadWarps) tmem_alloc(&s.tmem_base, 512);
   // W_hh block: tile row c = gate * 64 + u  <-  W_hh row gate * 256 + 64 nb + u
-  for (int e0 = tid; e0 < kGN * (kRK / 8); e0 += kGBatch * kRThreads) {
-    Chunk8 c[kGBatch];
+  for (int e0 = tid; e0 < kGN * (kRK / 8); e0 += 4 * kLcThreads) {
+    Chunk8 c[4];
 #pragma unroll
-    for (int b = 0; b < kGBatch; ++b) {
-      const int e = e0 + b * kRThreads, row = e >> 5, kc = e & 31;
+    for (int b = 0; b < 4; ++b) {
+      const int e = e0 + b * kLcThreads, row = e >> 5, kc = e & 31;
       const int src = (row >> 6) * LH + nb * 64 + (row & 63);
-      c[b] = load8(g.w_hh + (int64_t)src * LH + kc * 8, true, 8);
+      c[b] = load8(g.w_hh + (int64_t)src * LH + kc * 8, e < kGN * (kRK / 8), 8);
     }
 #pragma unroll
-    for (int b = 0; b < kGBatch; ++b) {
-      const int e = e0 + b * kRThreads, row = e >> 5, kc = e & 31;
-      *reinterpret_cast<uint4*>(s.b + chunk_offset<kGN>(row, kc)) = pack8(c[b]);
+    for (int b = 0; b < 4; ++b) {
+      const int e = e0 + b * kLcThreads, row = e >> 5, kc = e & 31;
+      if (e < kGN * (kRK / 8)) *reinterpret_cast<uint4*>(s.b + chunk_offset<kGN>(row, kc)) = pack8(c[b]);
     }
   }
-  for (int i = tid; i < 4 * kCellD * 64; i += kRThreads) {
+  for (int i = tid; i < 4 * kCellD * 64; i += kLcThreads) {
     const int gate = i / (kCellD * 64), d = (i / 64) % kCellD, u = i % 64;
-    s.wt[gate][d][u] = d < g.D ? g.w_ih[(int64_t)(gate * LH + nb * 64 + u) * g.D + d] : 0.0f;
+    s.wt[gate][d][u] = d < D ? g.w_ih[(int64_t)(gate * LH + nb * 64 + u) * D + d] : 0.0f;
   }
-  for (int i = tid; i < 4 * 64; i += kRThreads) {
+  for (int i = tid; i < 4 * 64; i += kLcThreads) {
     const int gate = i >> 6, u = i & 63;
     s.bi[gate][u] = g.b_ih[gate * LH + nb * 64 + u];
     s.bh[gate][u] = g.b_hh[gate * LH + nb * 64 + u];
@@ -386,121 +415,145 @@ __global__ void __launch_bounds__(kRThreads, 1) tc_lstm_cell_kernel(LstmCellArgs
   fence_after_sync();
   const uint32_t tmem = s.tmem_base;
 
-  auto stage_a = [&](int h, int64_t m0) {
-    Chunk8 c[4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int e = tid + b * kRThreads, row = e >> 4, kc = e & 15;
-      c[b] = load8(g.h_in + (m0 + row) * LH + h * 128 + kc * 8, m0 + row < g.rows, 8);
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int e = tid + b * kRThreads, row = e >> 4, kc = e & 15;
-      *reinterpret_cast<uint4*>(s.a[h] + chunk_offset<kGM>(row, kc)) = pack8(c[b]);
-    }
-  };
-  // the cell of tile mt from accumulator buf: warp (q = warp & 3, part = warp >> 2) -> row 32q + lane, units
-  // [16 part, 16 part + 16) of this block, in two groups of 8 units
-  auto epilogue = [&](int64_t mt, int buf) {
-    const int q = warp & 3, part = warp >> 2;
-    const int64_t r = mt * kGM + q * 32 + lane;
-    const uint32_t base = tmem + (uint32_t)(buf * kGN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16);
-    const bool live = r < g.rows;
-    int64_t xo = 0;
-    const int64_t ds = g.xmap.dstride();
-    float x[kCellD];
-    if (live) xo = g.xmap.offset(r);
-#pragma unroll
-    for (int d = 0; d < kCellD; ++d) x[d] = (live && d < g.D) ? g.xmap.obs[xo + d * ds] : 0.0f;
-    // two groups of 8 units: 32 accumulator values live at a time
+  if (warp >= kLcEpiWarps && warp < kLcEpiWarps + kLcLoadWarps) {
+    // ---- loaders: K half h of the h tile, fp32 -> bf16 chunks; 2048 chunks per half, 16 per thread, 8 in flight ----
+    constexpr int kLoaders = kLcLoadWarps * 32, kChunks = kGM * 16;  // 2048 chunks of 8 values per K half
+    const int lt = tid - kLcEpiWarps * 32;
+    int it = 0;
+    for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
+      const int64_t m0 = mt * kGM;
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int u0 = part * 16 + half * 8;  // first unit of the group inside the block
-      const int j0 = nb * 64 + u0;          // ... and in the layer
-      float pre[4][8];
+      for (int h = 0; h < 2; ++h) {
+        if (it > 0) mbar_wait(&s.free_[h], (uint32_t)((it - 1) & 1));  // the previous tile's MMAs have read it
+#pragma unroll 1
+        for (int e0 = lt; e0 < kChunks; e0 += 8 * kLoaders) {
+          float c[8][8];
 #pragma unroll
-      for (int gate = 0; gate < 4; ++gate) tmem_ld8(base + (uint32_t)(gate * 64 + half * 8), pre[gate]);
-      if (!live) continue;
-      float cp[8];
-      {
-        const float4 c0 = *reinterpret_cast<const float4*>(g.c_prev + r * LH + j0);
-        const float4 c1 = *reinterpret_cast<const float4*>(g.c_prev + r * LH + j0 + 4);
-        cp[0] = c0.x, cp[1] = c0.y, cp[2] = c0.z, cp[3] = c0.w, cp[4] = c1.x, cp[5] = c1.y, cp[6] = c1.z, cp[7] = c1.w;
+          for (int b = 0; b < 8; ++b) {
+            const int e = e0 + b * kLoaders, row = e >> 4, kc = e & 15;
+            if (e < kChunks && m0 + row < g.rows) {
+              ldg8(g.h_in + (m0 + row) * LH + h * 128 + kc * 8, c[b]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) c[b][j] = 0.0f;
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            const int e = e0 + b * kLoaders, row = e >> 4, kc = e & 15;
+            if (e < kChunks) store_chunk(s.a[h], chunk_offset<kGM>(row, kc), c[b]);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(&s.full[h]);
       }
+    }
+  } else if (warp == kLcEpiWarps + kLcLoadWarps) {
+    // ---- issuer ---------------------------------------------------------------------------------------------------
+    int it = 0;
+    for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc = tmem + (uint32_t)(buf * kGN);
+      if (it >= 2) mbar_wait(&s.acc_empty[buf], (uint32_t)(((it >> 1) - 1) & 1));  // epilogue of tile it-2 done
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&s.full[h], (uint32_t)(it & 1));
+        fence_after_sync();
+        if (elect_one()) {
+          issue_gemm(acc, smem_u32(s.a[h]), kGM, false, smem_u32(s.b) + h * 16 * (kGN * 16), kGN, false, kGM, kGN, 128,
+                     h > 0);
+          mma_commit(&s.free_[h]);
+          if (h == 1) mma_commit(&s.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- cell epilogue: warp (q = warp & 3, part = warp >> 2) -> row 32q + lane, units [16 part, 16 part + 16) of this
+    //      block, in two groups of 8 units ----------------------------------------------------------------------------
+    const int q = warp & 3, part = warp >> 2;
+    const int64_t ds = g.xmap.dstride();
+    int it = 0;
+    for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
+      const int buf = it & 1;
+      const int64_t r = mt * kGM + q * 32 + lane;
+      const bool live = r < g.rows;
+      // everything the cell needs from global memory, requested before the wait on the accumulator
+      float x[kCellD], cp[2][8];
+      {
+        int64_t xo = 0;
+        if (live) xo = g.xmap.offset(r);
 #pragma unroll
-      for (int gate = 0; gate < 4; ++gate) {
+        for (int d = 0; d < kCellD; ++d) x[d] = (live && d < D) ? g.xmap.obs[xo + d * ds] : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float a = s.bi[gate][u0 + u];
+        for (int half = 0; half < 2; ++half) {
+          const int j0 = nb * 64 + part * 16 + half * 8;
+          if (live) {
+            ldg8(g.c_prev + r * LH + j0, cp[half]);
+          } else {
 #pragma unroll
-          for (int d = 0; d < kCellD; ++d)
-            if (d < g.D) a = fmaf(x[d], s.wt[gate][d][u0 + u], a);
-          pre[gate][u] = a + (pre[gate][u] + s.bh[gate][u0 + u]);
+            for (int u = 0; u < 8; ++u) cp[half][u] = 0.0f;
+          }
         }
       }
-      float cn[8], hn[8];
+      mbar_wait(&s.acc_full[buf], (uint32_t)((it >> 1) & 1));
+      fence_after_sync();
+      const uint32_t base = tmem + (uint32_t)(buf * kGN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float ig = sigmoid_fast(pre[0][u]), fg = sigmoid_fast(pre[1][u]);
-        const float gg = tanh_fast(pre[2][u]), og = sigmoid_fast(pre[3][u]);
-        pre[0][u] = ig, pre[1][u] = fg, pre[2][u] = gg, pre[3][u] = og;
-        cn[u] = fg * cp[u] + ig * gg;
-        hn[u] = og * tanh_fast(cn[u]);
-      }
-      if (g.act) {
+      for (int half = 0; half < 2; ++half) {
+        const int u0 = part * 16 + half * 8;  // first unit of the group inside the block
+        const int j0 = nb * 64 + u0;          // ... and in the layer
+        float pre[4][8];
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) tmem_ld8(base + (uint32_t)(gate * 64 + half * 8), pre[gate]);
+        if (half == 1) {  // the accumulator buffer is free as soon as it has been read
+          fence_before_sync();
+          __syncwarp();
+          if (elect_one()) mbar_arrive(&s.acc_empty[buf]);
+          __syncwarp();
+        }
+        if (!live) continue;
+        const float* cph = cp[half];
+        // pre = (b_ih + sum_d x_d W_ih[., d]) + (acc + b_hh); the block's weights are read as 128-bit broadcasts (the
+        // scalar form made the kernel LSU-wavefront bound: 7 shared-memory loads per gate value)
 #pragma unroll
         for (int gate = 0; gate < 4; ++gate) {
-          float* dst = g.act + r * 4 * LH + gate * LH + j0;
-          *reinterpret_cast<float4*>(dst) = make_float4(pre[gate][0], pre[gate][1], pre[gate][2], pre[gate][3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(pre[gate][4], pre[gate][5], pre[gate][6], pre[gate][7]);
-        }
-      }
-      *reinterpret_cast<float4*>(g.c_out + r * LH + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-      *reinterpret_cast<float4*>(g.c_out + r * LH + j0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-      *reinterpret_cast<float4*>(g.h_out + r * LH + j0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-      *reinterpret_cast<float4*>(g.h_out + r * LH + j0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-    }
-  };
-
-  int it = 0;
-  int64_t prev = -1;
-  for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
-    const int buf = it & 1;
-    const uint32_t acc = tmem + (uint32_t)(buf * kGN);
+          float a[8];
+          ld8s(&s.bi[gate][u0], a);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (it > 0) {
-        mbar_wait(&s.bar_h[h], (uint32_t)((it - 1) & 1));
-        fence_after_sync();
-      }
-      stage_a(h, mt * kGM);
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (cta_issuer()) {
-        fence_after_sync();
-        issue_gemm(acc, smem_u32(s.a[h]), kGM, false, smem_u32(s.b) + h * 16 * (kGN * 16), kGN, false, kGM, kGN, 128,
-                   h > 0);
-        mma_commit(&s.bar_h[h]);
-        if (h == 1) mma_commit(&s.bar_acc[buf]);
-      }
-      if (h == 0 && prev >= 0) {
-        mbar_wait(&s.bar_acc[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));
-        fence_after_sync();
-        epilogue(prev, buf ^ 1);
-        fence_before_sync();
+          for (int d = 0; d < D; ++d) {
+            float w[8];
+            ld8s(&s.wt[gate][d][u0], w);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = fmaf(x[d], w[u], a[u]);
+          }
+          float bh[8];
+          ld8s(&s.bh[gate][u0], bh);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pre[gate][u] = a[u] + (pre[gate][u] + bh[u]);
+        }
+        float cn[8], hn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ig = sigmoid_fast(pre[0][u]), fg = sigmoid_fast(pre[1][u]);
+          const float gg = tanh_fast(pre[2][u]), og = sigmoid_fast(pre[3][u]);
+          pre[0][u] = ig, pre[1][u] = fg, pre[2][u] = gg, pre[3][u] = og;
+          cn[u] = fg * cph[u] + ig * gg;
+          hn[u] = og * tanh_fast(cn[u]);
+        }
+        if (g.act) {
+#pragma unroll
+          for (int gate = 0; gate < 4; ++gate) stg8(g.act + r * 4 * LH + gate * LH + j0, pre[gate]);
+        }
+        stg8(g.c_out + r * LH + j0, cn);
+        stg8(g.h_out + r * LH + j0, hn);
       }
     }
-    prev = mt;
-  }
-  if (prev >= 0) {
-    mbar_wait(&s.bar_acc[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
-    fence_after_sync();
-    epilogue(prev, (it - 1) & 1);
   }
   fence_before_sync();
   __syncthreads();
-  if (tid < 32) tmem_dealloc(tmem, 512);
+  if (warp == kLcEpiWarps + kLcLoadWarps) tmem_dealloc(tmem, 512);
 }
 
 // h' / c' / gate activations of one LSTM step for `rows` rows (H = 256); h_in must not alias h_out.
@@ -514,12 +567,18 @@ int launch_lstm_cell_tc(const float* h_in, const float* w_hh, const float* w_ih,
   const int64_t mtiles = ceil_div(rows, kGM);
   int64_t per_block = kNumSMs / 4;
   if (per_block > mtiles) per_block = mtiles;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(tc_lstm_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLstm));
-    attr = true;
+  const unsigned grid = (unsigned)(per_block * 4);
+#define RL8_LSTM_CELL(DV)                                                                                         \
+  case DV:                                                                                                         \
+    cudaFuncSetAttribute(tc_lstm_cell_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLstm)); \
+    tc_lstm_cell_kernel<DV><<<grid, kLcThreads, sizeof(SmemLstm), st>>>(g);                                         \
+    break;
+  switch (D) {
+    RL8_LSTM_CELL(1) RL8_LSTM_CELL(2) RL8_LSTM_CELL(3) RL8_LSTM_CELL(4)
+    RL8_LSTM_CELL(5) RL8_LSTM_CELL(6) RL8_LSTM_CELL(7) RL8_LSTM_CELL(8)
+    default: return RL8_ERR_ARG;
   }
-  tc_lstm_cell_kernel<<<(unsigned)(per_block * 4), kRThreads, sizeof(SmemLstm), st>>>(g);
+#undef RL8_LSTM_CELL
   return check_launch("tc_lstm_cell");
 }
 
