@@ -327,7 +327,9 @@ struct SmemLstm {
   uint32_t tmem_base;
 };
 struct LstmCellArgs {
-  const float *h_in, *w_hh, *w_ih, *b_ih, *b_hh, *c_prev;
+  const uint8_t* hb_in;   // h as bf16 in the T128 layout (below): one bulk copy per K half stages the A operand
+  uint8_t* hb_out;        // h' in the same layout for the next step / the weight-gradient GEMM (may be null)
+  const float *w_hh, *w_ih, *b_ih, *b_hh, *c_prev;
   float *act, *c_out, *h_out;  // act may be null (rollout)
   RowMap xmap;
   int64_t rows;
@@ -342,14 +344,23 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return __fdividef(e - 1.0f, e + 1.0f);
 }
 
-// Warp roles: warps 0..15 run the cell epilogue, warps 16..18 load + convert the h tile (K halves), warp 19 issues
-// the MMAs.  The three run decoupled behind mbarriers: the loaders refill a K half as soon as the MMAs that read it
-// have completed, the issuer starts a tile as soon as its operands and an accumulator buffer are there, and the
-// epilogue of tile k-1 (whose c_prev / observation loads are issued BEFORE it waits for the accumulator) runs under
-// the loads and MMAs of tiles k, k+1 -- the kernel is bound by HBM traffic, so what matters is that loads are in
-// flight all the time, not only between two block-wide barriers.
-constexpr int kLcEpiWarps = 16, kLcLoadWarps = 3;  // + the issuing warp: 20 warps (register allocation is per 4 warps)
-constexpr int kLcThreads = (kLcEpiWarps + kLcLoadWarps + 1) * 32;  // 640
+// Warp roles: warps 0..15 run the cell epilogue, warp 16 stages the h tile (one bulk copy per K half from the T128
+// image of h: no registers, no LSU), warp 17 issues the MMAs.  The three run decoupled behind mbarriers: a K half is
+// refilled as soon as the MMAs that read it have completed, the issuer starts a tile as soon as its operands and an
+// accumulator buffer are there, and the epilogue of tile k-1 (whose c_prev / observation loads are issued BEFORE it
+// waits for the accumulator) runs under the loads and MMAs of tiles k, k+1 -- the kernel is bound by HBM traffic, so
+// what matters is that loads are in flight all the time, not only between two block-wide barriers.
+constexpr int kLcEpiWarps = 16, kLcLoadWarps = 1;  // + the issuing warp and two idle ones: 20 warps (register allocation is per 4 warps)
+constexpr int kLcThreads = 640;
+
+// T128 layout of a bf16 matrix X[R][C] in global memory (R padded to a multiple of 128): 16-byte chunks of 8
+// consecutive columns, [row tile of 128][column group][row in tile][8] -- i.e. every 128-row x 8k-column block is stored
+// exactly as the chunked shared-memory operand tile (tc.cuh) it will become, whichever GEMM reads it (rows as M with the
+// columns as K, or rows as K with the columns as M / N), so staging an operand is one bulk copy.
+__host__ __device__ __forceinline__ int64_t t128_offset(int64_t r, int col8, int ncol8) {
+  return (((r >> 7) * ncol8 + col8) << 11) + ((r & 127) << 4);
+}
+int64_t t128_bytes(int64_t rows, int cols) { return ((rows + 127) / 128) * 128 * (int64_t)cols * 2; }
 
 // 256-bit global accesses (sm_100: LDG / STG .256): one full 32-byte sector per lane and HALF the LSU wavefronts of two
 // 128-bit accesses when every lane of the warp addresses a different row
@@ -368,6 +379,31 @@ __device__ __forceinline__ void ld8s(const float* p, float* v) {  // eight conse
   v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
 }
 
+// fp32 X[rows][256] (row-major) -> bf16 T128; rows of the last tile past `rows` are zero
+__global__ void __launch_bounds__(256) pack_t128_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_pad,
+                                                        uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows_pad * 32; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tile = i >> 12;
+    const int c8 = (int)(i >> 7) & 31;
+    const int64_t r = tile * 128 + (i & 127);
+    float v[8];
+    if (r < rows) {
+      ldg8(x + r * 256 + c8 * 8, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    }
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]), q.y = pack_bf16x2(v[2], v[3]), q.z = pack_bf16x2(v[4], v[5]), q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + i * 16) = q;
+  }
+}
+int launch_pack_t128(const float* x, int64_t rows, uint8_t* out, cudaStream_t st) {
+  const int64_t rows_pad = (rows + 127) / 128 * 128;
+  pack_t128_kernel<<<grid_for(rows_pad * 32, 256, 8, 1), 256, 0, st>>>(x, rows, rows_pad, out);
+  return check_launch("pack_t128");
+}
+
 template <int D>  // observation width (compile time: the per-unit input FMAs unroll without predicates)
 __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArgs g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -379,7 +415,7 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
   const int64_t mtiles = (g.rows + kGM - 1) / kGM;
   if (tid == 0) {
     for (int h = 0; h < 2; ++h) {
-      mbar_init(&s.full[h], kLcLoadWarps), mbar_init(&s.free_[h], 1);
+      mbar_init(&s.full[h], 1), mbar_init(&s.free_[h], 1);
       mbar_init(&s.acc_full[h], 1), mbar_init(&s.acc_empty[h], kLcEpiWarps);
     }
     fence_mbar_init();
@@ -415,38 +451,19 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
   fence_after_sync();
   const uint32_t tmem = s.tmem_base;
 
-  if (warp >= kLcEpiWarps && warp < kLcEpiWarps + kLcLoadWarps) {
-    // ---- loaders: K half h of the h tile, fp32 -> bf16 chunks; 2048 chunks per half, 16 per thread, 8 in flight ----
-    constexpr int kLoaders = kLcLoadWarps * 32, kChunks = kGM * 16;  // 2048 chunks of 8 values per K half
-    const int lt = tid - kLcEpiWarps * 32;
+  if (warp == kLcEpiWarps) {
+    // ---- loader: one bulk copy per K half -- the tile's 128 rows x 128 k are 32 KB contiguous in the T128 layout and
+    //      already in the operand format, so nothing passes through registers or the LSU ----------------------------
     int it = 0;
     for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
-      const int64_t m0 = mt * kGM;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         if (it > 0) mbar_wait(&s.free_[h], (uint32_t)((it - 1) & 1));  // the previous tile's MMAs have read it
-#pragma unroll 1
-        for (int e0 = lt; e0 < kChunks; e0 += 8 * kLoaders) {
-          float c[8][8];
-#pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const int e = e0 + b * kLoaders, row = e >> 4, kc = e & 15;
-            if (e < kChunks && m0 + row < g.rows) {
-              ldg8(g.h_in + (m0 + row) * LH + h * 128 + kc * 8, c[b]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) c[b][j] = 0.0f;
-            }
-          }
-#pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const int e = e0 + b * kLoaders, row = e >> 4, kc = e & 15;
-            if (e < kChunks) store_chunk(s.a[h], chunk_offset<kGM>(row, kc), c[b]);
-          }
+        if (elect_one()) {
+          mbar_expect_tx(&s.full[h], kGM * 128 * 2);
+          bulk_g2s(s.a[h], g.hb_in + t128_offset(mt * kGM, h * 16, LH / 8), kGM * 128 * 2, &s.full[h]);
         }
-        fence_async_smem();
         __syncwarp();
-        if (elect_one()) mbar_arrive(&s.full[h]);
       }
     }
   } else if (warp == kLcEpiWarps + kLcLoadWarps) {
@@ -469,7 +486,7 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < kLcEpiWarps) {
     // ---- cell epilogue: warp (q = warp & 3, part = warp >> 2) -> row 32q + lane, units [16 part, 16 part + 16) of this
     //      block, in two groups of 8 units ----------------------------------------------------------------------------
     const int q = warp & 3, part = warp >> 2;
@@ -548,6 +565,12 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
         }
         stg8(g.c_out + r * LH + j0, cn);
         stg8(g.h_out + r * LH + j0, hn);
+        if (g.hb_out) {  // lanes = consecutive rows: 512 contiguous bytes per warp
+          uint4 qh;
+          qh.x = pack_bf16x2(hn[0], hn[1]), qh.y = pack_bf16x2(hn[2], hn[3]);
+          qh.z = pack_bf16x2(hn[4], hn[5]), qh.w = pack_bf16x2(hn[6], hn[7]);
+          *reinterpret_cast<uint4*>(g.hb_out + t128_offset(r, j0 >> 3, LH / 8)) = qh;
+        }
       }
     }
   }
@@ -556,13 +579,14 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
   if (warp == kLcEpiWarps + kLcLoadWarps) tmem_dealloc(tmem, 512);
 }
 
-// h' / c' / gate activations of one LSTM step for `rows` rows (H = 256); h_in must not alias h_out.
-int launch_lstm_cell_tc(const float* h_in, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh,
+// h' / c' / gate activations of one LSTM step for `rows` rows (H = 256).  hb_in: h as bf16 T128 (launch_pack_t128 or
+// a previous call's hb_out); hb_out (may be null): h' in the same form.
+int launch_lstm_cell_tc(const uint8_t* hb_in, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh,
                         const float* c_prev, const RowMap& xmap, int D, int64_t rows, float* act, float* c_out,
-                        float* h_out, cudaStream_t st) {
-  if (D < 1 || D > kCellD || rows <= 0) return RL8_ERR_ARG;
+                        float* h_out, uint8_t* hb_out, cudaStream_t st) {
+  if (D < 1 || D > kCellD || rows <= 0 || !hb_in) return RL8_ERR_ARG;
   LstmCellArgs g;
-  g.h_in = h_in, g.w_hh = w_hh, g.w_ih = w_ih, g.b_ih = b_ih, g.b_hh = b_hh, g.c_prev = c_prev;
+  g.hb_in = hb_in, g.hb_out = hb_out, g.w_hh = w_hh, g.w_ih = w_ih, g.b_ih = b_ih, g.b_hh = b_hh, g.c_prev = c_prev;
   g.act = act, g.c_out = c_out, g.h_out = h_out, g.xmap = xmap, g.rows = rows, g.D = D;
   const int64_t mtiles = ceil_div(rows, kGM);
   int64_t per_block = kNumSMs / 4;

@@ -119,16 +119,25 @@ static int launch_cell_fwd(const rl8_lstm_model* m, const float* G, const RowMap
   return check_launch("lstm_cell_fwd");
 }
 
-// One LSTM step + heads.  G: [rows][4H] scratch.
+// One LSTM step + heads.  G: [rows][4H] scratch.  hb_in / hb_out (tensor-core path): bf16 T128 images of h_in / h_out
+// (hb_in null: h_in is packed into the scratch first; hb_out null: not written).
+static bool lstm_step_on_tc(int prec, int64_t rows, const float* h_in, const float* h_out, const float* c_in,
+                            const float* c_out) {
+  return prec == RL8_PREC_BF16 && rows >= 512 && h_in != h_out && c_in != c_out;
+}
 static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t rows,
                           const float* h_in, const float* c_in, float* h_out, float* c_out,
                           float* act, float* G, float* features, float* values, int tanh_col1,
-                          int prec, cudaStream_t st) {
+                          int prec, cudaStream_t st, const uint8_t* hb_in = nullptr, uint8_t* hb_out = nullptr) {
   int rc;
-  if (prec == RL8_PREC_BF16 && rows >= 512 && h_in != h_out && c_in != c_out) {
+  if (lstm_step_on_tc(prec, rows, h_in, h_out, c_in, c_out)) {
     // tensor-core path: the gate GEMM with the cell in its epilogue (no pre-activation round trip through HBM)
-    if ((rc = launch_lstm_cell_tc(h_in, m->w_hh, m->w_ih, m->b_ih, m->b_hh, c_in, xmap, m->D, rows, act, c_out,
-                                  h_out, st)))
+    if (!hb_in) {  // [rows][4H] floats of scratch hold the [rows_pad][H] bf16 image (rows >= 512)
+      if ((rc = launch_pack_t128(h_in, rows, (uint8_t*)G, st))) return rc;
+      hb_in = (const uint8_t*)G;
+    }
+    if ((rc = launch_lstm_cell_tc(hb_in, m->w_hh, m->w_ih, m->b_ih, m->b_hh, c_in, xmap, m->D, rows, act, c_out,
+                                  h_out, hb_out, st)))
       return rc;
   } else {
     if ((rc = lstm_gemm(prec, true, true, EPI_STORE, h_in, m->w_hh, G, rows, 4 * kLH, kLH, kLH, kLH, 4 * kLH, 1,
@@ -175,23 +184,34 @@ int lstm_collect_fp32(const rl8_lstm_model* m, const rl8_recurrent_rollout* rro,
   RowMap map{};
   map.mode = 0, map.stride_r = 1, map.stride_d = N, map.D = D;
   const int64_t slab = N * kLH;
+  // tensor-core path: h travels between steps as a bf16 T128 image too (two of them, ping-pong, inside the gate scratch
+  // the fused kernel does not need); an image is (re)built from the fp32 slab at t = 0 and after a state reset
+  const bool tc = lstm_step_on_tc(prec, N, nullptr, (const float*)1, nullptr, (const float*)1);
+  uint8_t* hb[2] = {(uint8_t*)G, (uint8_t*)G + t128_bytes(N, kLH)};
+  bool hb_valid = false;
   for (int t = 0; t < T; ++t) {
     float* h_t = rro->hidden + (int64_t)t * slab;
     float* c_t = rro->cell + (int64_t)t * slab;
     if (state_reset_at(rro, t)) {
       cudaMemsetAsync(h_t, 0, slab * 4, st);
       cudaMemsetAsync(c_t, 0, slab * 4, st);
+      hb_valid = false;
     }
+    int rc;
+    if (tc && !hb_valid && (rc = launch_pack_t128(h_t, N, hb[t & 1], st))) return rc;
     map.obs = ro->obs + (int64_t)t * D * N;
-    int rc = lstm_step_fp32(m, map, N, h_t, c_t, h_t + slab, c_t + slab, nullptr, G, feat,
-                            ro->values + (int64_t)t * N, continuous, prec, st);
+    rc = lstm_step_fp32(m, map, N, h_t, c_t, h_t + slab, c_t + slab, nullptr, G, feat,
+                        ro->values + (int64_t)t * N, continuous, prec, st, tc ? hb[t & 1] : nullptr,
+                        tc ? hb[(t + 1) & 1] : nullptr);
+    hb_valid = tc;
     if (rc) return rc;
     if ((rc = collect_tail(ro, t, feat, st))) return rc;
   }
   // bootstrap value from the last observation and the final states (:433-445)
   map.obs = ro->obs + (int64_t)T * D * N;
   return lstm_step_fp32(m, map, N, rro->hidden + (int64_t)T * slab, rro->cell + (int64_t)T * slab,
-                        hs, cs, nullptr, G, nullptr, ro->values + (int64_t)T * N, 0, prec, st);
+                        hs, cs, nullptr, G, nullptr, ro->values + (int64_t)T * N, 0, prec, st,
+                        tc && hb_valid ? hb[T & 1] : nullptr, nullptr);
 }
 
 // ---- update ----------------------------------------------------------------------------------------
@@ -358,8 +378,8 @@ int64_t lstm_ppo_fp32_workspace(int64_t max_seqs, int L) {
   const int64_t C = lstm_chunk_seqs(max_seqs, L);
   // per step: act [C][4H], c [C][H], h [C][H], out_pi/dout_pi [C][kMaxP] x2, out_vf/dout_vf [C] x2
   const int64_t per_step = C * (6 * kLH + 2 * kMaxP + 2);
-  // h0, c0, dh, dc [C][H] each; rows_k [L][C] int64
-  return (L * per_step + 4 * C * kLH) * 4 + L * C * 8 + 64;
+  // h0, c0, dh, dc [C][H] each; rows_k [L][C] int64; bf16 T128 images of h_0 .. h_{L-1} (tensor-core path)
+  return (L * per_step + 4 * C * kLH) * 4 + L * C * 8 + 64 + L * t128_bytes(C, kLH) + 256;
 }
 
 int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
@@ -384,6 +404,8 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
   float* dh = take(C * kLH);
   float* dc = take(C * kLH);
   int64_t* rows_k = (int64_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  uint8_t* hb = (uint8_t*)(((uintptr_t)(rows_k + (int64_t)L * C) + 255) & ~(uintptr_t)255);  // [L] T128 images
+  const int64_t hb_bytes = t128_bytes(C, kLH);
   const bool continuous = b->dist_kind != RL8_DIST_CATEGORICAL;
   const int splits = 64;
 
@@ -396,6 +418,8 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
     if (rc) return rc;
     RowMap map{};
     map.obs = b->obs, map.mode = 1, map.T = b->T, map.D = D, map.N = b->N;
+    const bool tc = lstm_step_on_tc(prec, R, h0, hbuf, c0, cbuf);
+    if (tc && (rc = launch_pack_t128(h0, R, hb, st))) return rc;
 
     // ---- forward through the sequence + per-step losses ------------------------------------
     for (int k = 0; k < L; ++k) {
@@ -407,8 +431,9 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
       const float* c_prev = k ? c_k - C * kLH : c0;
       float* opi = out_pi + (int64_t)k * C * kMaxP;
       float* ovf = out_vf + (int64_t)k * C;
-      if ((rc = lstm_step_fp32(m, map, R, h_prev, c_prev, h_k, c_k, act_k, act_k, opi, ovf,
-                               continuous, prec, st)))
+      if ((rc = lstm_step_fp32(m, map, R, h_prev, c_prev, h_k, c_k, act_k, act_k, opi, ovf, continuous, prec, st,
+                               tc ? hb + (int64_t)k * hb_bytes : nullptr,
+                               tc && k + 1 < L ? hb + (int64_t)(k + 1) * hb_bytes : nullptr)))
         return rc;
       LossArgs la{};
       la.dist_kind = b->dist_kind, la.P = P, la.M = R;
