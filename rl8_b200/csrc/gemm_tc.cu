@@ -353,13 +353,6 @@ __device__ __forceinline__ float tanh_fast(float x) {
 constexpr int kLcEpiWarps = 16, kLcLoadWarps = 1;  // + the issuing warp and two idle ones: 20 warps (register allocation is per 4 warps)
 constexpr int kLcThreads = 640;
 
-// T128 layout of a bf16 matrix X[R][C] in global memory (R padded to a multiple of 128): 16-byte chunks of 8
-// consecutive columns, [row tile of 128][column group][row in tile][8] -- i.e. every 128-row x 8k-column block is stored
-// exactly as the chunked shared-memory operand tile (tc.cuh) it will become, whichever GEMM reads it (rows as M with the
-// columns as K, or rows as K with the columns as M / N), so staging an operand is one bulk copy.
-__host__ __device__ __forceinline__ int64_t t128_offset(int64_t r, int col8, int ncol8) {
-  return (((r >> 7) * ncol8 + col8) << 11) + ((r & 127) << 4);
-}
 int64_t t128_bytes(int64_t rows, int cols) { return ((rows + 127) / 128) * 128 * (int64_t)cols * 2; }
 
 // 256-bit global accesses (sm_100: LDG / STG .256): one full 32-byte sector per lane and HALF the LSU wavefronts of two
@@ -530,7 +523,11 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
           if (elect_one()) mbar_arrive(&s.acc_empty[buf]);
           __syncwarp();
         }
-        if (!live) continue;
+        if (!live) {  // rows of the last tile past the end: a finite (zero) image for the GEMMs that contract over rows
+          if (g.hb_out)
+            *reinterpret_cast<uint4*>(g.hb_out + t128_offset(r, j0 >> 3, LH / 8)) = make_uint4(0u, 0u, 0u, 0u);
+          continue;
+        }
         const float* cph = cp[half];
         // pre = (b_ih + sum_d x_d W_ih[., d]) + (acc + b_hh); the block's weights are read as 128-bit broadcasts (the
         // scalar form made the kernel LSU-wavefront bound: 7 shared-memory loads per gate value)

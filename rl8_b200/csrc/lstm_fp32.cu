@@ -13,6 +13,7 @@
 // Gate packing follows torch.nn.LSTM: [i | f | g | o] blocks of H rows; c' = sig(f) c + sig(i)
 // tanh(g), h' = sig(o) tanh(c') (restated in oracle/recurrent_oracle.py:lstm_cell).
 #include "dist.cuh"
+#include "lstm_tc.cuh"
 #include "mlp_fp32.cuh"
 #include "ppo_loss.cuh"
 
@@ -379,7 +380,9 @@ int64_t lstm_ppo_fp32_workspace(int64_t max_seqs, int L) {
   // per step: act [C][4H], c [C][H], h [C][H], out_pi/dout_pi [C][kMaxP] x2, out_vf/dout_vf [C] x2
   const int64_t per_step = C * (6 * kLH + 2 * kMaxP + 2);
   // h0, c0, dh, dc [C][H] each; rows_k [L][C] int64; bf16 T128 images of h_0 .. h_{L-1} (tensor-core path)
-  return (L * per_step + 4 * C * kLH) * 4 + L * C * 8 + 64 + L * t128_bytes(C, kLH) + 256;
+  // ... and of the gate gradients dG_k [C][4H] and [x | 1] [C][16] of every step
+  return (L * per_step + 4 * C * kLH) * 4 + L * C * 8 + 64 +
+         L * (t128_bytes(C, kLH) + t128_bytes(C, 4 * kLH) + t128_bytes(C, 16)) + 256;
 }
 
 int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
@@ -405,7 +408,9 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
   float* dc = take(C * kLH);
   int64_t* rows_k = (int64_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   uint8_t* hb = (uint8_t*)(((uintptr_t)(rows_k + (int64_t)L * C) + 255) & ~(uintptr_t)255);  // [L] T128 images
-  const int64_t hb_bytes = t128_bytes(C, kLH);
+  const int64_t hb_bytes = t128_bytes(C, kLH), dgb_bytes = t128_bytes(C, 4 * kLH), xb_bytes = t128_bytes(C, 16);
+  uint8_t* dgb = hb + (int64_t)L * hb_bytes;
+  uint8_t* xb = dgb + (int64_t)L * dgb_bytes;
   const bool continuous = b->dist_kind != RL8_DIST_CATEGORICAL;
   const int splits = 64;
 
@@ -458,6 +463,19 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
       const float* dpi = dout_pi + (int64_t)k * C * kMaxP;
       const float* dvf = dout_vf + (int64_t)k * C;
       const int last = k == L - 1;
+      if (tc) {
+        // tensor-core path (lstm_tc.cu): one fused elementwise kernel (heads' term of dL/dh, cell backward, dG and
+        // [x | 1] as bf16 T128 images, head weight gradients), then dh_{k-1} = dG_k W_hh on tcgen05
+        LstmBwdArgs ba{};
+        ba.act = act_k, ba.c = c_k, ba.c_prev = c_prev, ba.h = h_k, ba.dh_rec = last ? nullptr : dh, ba.dc = dc;
+        ba.dpi = dpi, ba.dvf = dvf, ba.pi_w = m->pi_w, ba.vf_w = m->vf_w;
+        ba.dGb = dgb + (int64_t)k * dgb_bytes, ba.xb = xb + (int64_t)k * xb_bytes;
+        ba.gpi_w = (float*)g->pi_w, ba.gvf_w = (float*)g->vf_w;
+        ba.xmap = map, ba.D = D, ba.has_dc_in = !last, ba.rows = R;
+        if ((rc = launch_lstm_cell_bwd_tc(ba, P, st))) return rc;
+        if (k && (rc = launch_lstm_dh_tc(ba.dGb, m->w_hh, dh, R, st))) return rc;
+        continue;
+      }
       // dL/dh_k = heads' contribution (+ the recurrent term left in dh by step k+1)
       if ((rc = launch_dh(P, dpi, dvf, R, m->pi_w, m->vf_w, !last, dh, st))) return rc;
       // head weight gradients
@@ -479,6 +497,15 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
       if (k && (rc = lstm_gemm(prec, true, false, EPI_STORE, act_k, m->w_hh, dh, R, kLH, 4 * kLH, 4 * kLH,
                                kLH, kLH, 1, st)))
         return rc;
+    }
+    if (tc) {  // [gW_hh | gW_ih | gb] += dG^T [h_prev | x | 1] over the L steps of the chunk
+      LstmWgArgs wa{};
+      wa.dGb = dgb, wa.hb = hb, wa.xb = xb;
+      wa.dGb_stride = dgb_bytes, wa.hb_stride = hb_bytes, wa.xb_stride = xb_bytes;
+      wa.L = L, wa.row_tiles = ceil_div(R, (int64_t)128);
+      wa.gw_hh = (float*)g->w_hh, wa.gw_ih = (float*)g->w_ih, wa.gb_ih = (float*)g->b_ih, wa.gb_hh = (float*)g->b_hh;
+      wa.D = D;
+      if ((rc = launch_lstm_wgrad_tc(wa, st))) return rc;
     }
   }
   return RL8_OK;

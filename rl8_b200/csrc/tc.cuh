@@ -393,6 +393,13 @@ template <int ROWS>
 __device__ __forceinline__ uint32_t chunk_offset(int row, int col8 /* col / 8 */) {
   return (uint32_t)row * 16u + (uint32_t)col8 * (uint32_t)(ROWS * 16);
 }
+// T128 layout of a bf16 matrix X[R][C] in GLOBAL memory (R padded to a multiple of 128): 16-byte chunks of 8
+// consecutive columns, [row tile of 128][column group][row in tile][8] -- every 128-row x 8k-column block is stored
+// exactly as the chunked shared-memory operand tile it will become, whichever GEMM reads it (rows as M / N with the
+// columns as K, or rows as K with the columns as M / N), so staging an operand is one bulk copy.
+__host__ __device__ __forceinline__ int64_t t128_offset(int64_t r, int col8, int ncol8) {
+  return (((r >> 7) * ncol8 + col8) << 11) + ((r & 127) << 4);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

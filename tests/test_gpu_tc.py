@@ -342,16 +342,20 @@ def test_tc_gemm_matches_bf16_emulation(a_k: int, b_k: int, M: int, N: int, K: i
     assert err < 2e-4 * float(ref.abs().max()), (err, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("N", [192, 1100])
 @pytest.mark.parametrize("env_name,dist", [("CartPole", None), ("Pendulum", "squashed_normal")])
-def test_recurrent_amp_matches_fp32_path(env_name: str, dist) -> None:
+def test_recurrent_amp_matches_fp32_path(env_name: str, dist, N: int) -> None:
     """RecurrentAlgorithm with ``enable_amp=True`` (LSTM GEMMs in bf16 on tcgen05) against the fp32 path
     from the same weights, env states and noise: rollout values / states to bf16 accuracy, identical
-    discrete actions except where two logits tie within bf16 noise, losses 1e-2, gradient cosine > 0.999."""
+    discrete actions except where two logits tie within bf16 noise, losses 1e-2, gradient cosine > 0.999.
+    N = 192 runs the generic bf16 GEMMs; N = 1100 (>= 512 rows per step, a ragged last tile: 2 200 sequences) the fused
+    kernels -- tc_lstm_cell_kernel forward, lstm_cell_bwd_tc / lstm_dh_tc / lstm_wgrad_tc backward (lstm_tc.cu), with
+    every gradient tensor compared one by one."""
     import rl8_b200.env as E
     from rl8_b200 import RecurrentAlgorithmConfig
     from rl8_b200 import distributions as Dm
 
-    N, T, L = 192, 8, 4
+    T, L = 8, 4
     env_cls = getattr(E, env_name)
     base = {None: None, "squashed_normal": Dm.SquashedNormal}[dist] or Dm.Categorical
     torch.manual_seed(11)
@@ -413,3 +417,6 @@ def test_recurrent_amp_matches_fp32_path(env_name: str, dist) -> None:
         cos = float((full16 * full32).sum() / (full32.norm() * full16.norm()))
         assert cos > 0.999, cos
         assert float((full16 - full32).norm() / full32.norm()) < 3e-2
+        for k in keys:  # every tensor on its own (a wrong small tensor -- biases, W_ih, heads -- hides in the norm above)
+            a, b = grads[0][k].double(), grads[1][k].double()
+            assert float((a - b).norm()) <= 5e-2 * float(a.norm()) + 1e-7, (k, float((a - b).norm()), float(a.norm()))
