@@ -47,7 +47,8 @@ class RolloutBuffer:
                     words[sk] = T1 * N * self.state_dim
             elif k not in words:
                 words[k] = T1 * N
-        self._raw = torch.zeros(sum((w + 3) // 4 * 4 for w in words.values()), device=device)
+        # every field starts on a 256-byte boundary (the kernels use 128- and 256-bit accesses on field bases)
+        self._raw = torch.zeros(sum((w + 63) // 64 * 64 for w in words.values()), device=device)
         self.hm: dict[str, torch.Tensor] = {}
         off = 0
         for k, w in words.items():
@@ -60,7 +61,7 @@ class RolloutBuffer:
                 self.hm[k] = seg.view(T1, N, self.state_dim)
             else:
                 self.hm[k] = seg.view(T1, N)
-            off += (w + 3) // 4 * 4
+            off += (w + 63) // 64 * 64
         self._views: dict[str, Any] = {
             k: self._env_major(k)
             for k in self.hm

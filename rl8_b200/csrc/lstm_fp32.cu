@@ -124,7 +124,10 @@ static int launch_cell_fwd(const rl8_lstm_model* m, const float* G, const RowMap
 // (hb_in null: h_in is packed into the scratch first; hb_out null: not written).
 static bool lstm_step_on_tc(int prec, int64_t rows, const float* h_in, const float* h_out, const float* c_in,
                             const float* c_out) {
-  return prec == RL8_PREC_BF16 && rows >= 512 && h_in != h_out && c_in != c_out;
+  // the fused kernels use 256-bit accesses on the state rows: every row base must be 32-byte aligned
+  auto al32 = [](const void* p) { return ((uintptr_t)p & 31u) == 0; };
+  return prec == RL8_PREC_BF16 && rows >= 512 && h_in != h_out && c_in != c_out && al32(h_out) && al32(c_in) &&
+         al32(c_out);
 }
 static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t rows,
                           const float* h_in, const float* c_in, float* h_out, float* c_out,
@@ -187,7 +190,7 @@ int lstm_collect_fp32(const rl8_lstm_model* m, const rl8_recurrent_rollout* rro,
   const int64_t slab = N * kLH;
   // tensor-core path: h travels between steps as a bf16 T128 image too (two of them, ping-pong, inside the gate scratch
   // the fused kernel does not need); an image is (re)built from the fp32 slab at t = 0 and after a state reset
-  const bool tc = lstm_step_on_tc(prec, N, nullptr, (const float*)1, nullptr, (const float*)1);
+  const bool tc = lstm_step_on_tc(prec, N, nullptr, rro->hidden, nullptr, rro->cell) && (slab * 4) % 32 == 0;
   uint8_t* hb[2] = {(uint8_t*)G, (uint8_t*)G + t128_bytes(N, kLH)};
   bool hb_valid = false;
   for (int t = 0; t < T; ++t) {
@@ -381,7 +384,7 @@ int64_t lstm_ppo_fp32_workspace(int64_t max_seqs, int L) {
   const int64_t per_step = C * (6 * kLH + 2 * kMaxP + 2);
   // h0, c0, dh, dc [C][H] each; rows_k [L][C] int64; bf16 T128 images of h_0 .. h_{L-1} (tensor-core path)
   // ... and of the gate gradients dG_k [C][4H] and [x | 1] [C][16] of every step
-  return (L * per_step + 4 * C * kLH) * 4 + L * C * 8 + 64 +
+  return (L * per_step + 4 * C * kLH) * 4 + L * C * 8 + 64 + 12 * 256 /* array alignment */ +
          L * (t128_bytes(C, kLH) + t128_bytes(C, 4 * kLH) + t128_bytes(C, 16)) + 256;
 }
 
@@ -394,7 +397,7 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
   const int64_t C = lstm_chunk_seqs(M, L);
   if (!workspace || workspace_bytes < lstm_ppo_fp32_workspace(M, L)) return RL8_ERR_WORKSPACE;
   float* p = (float*)workspace;
-  auto take = [&](int64_t n) { float* q = p; p += n; return q; };
+  auto take = [&](int64_t n) { float* q = p; p += (n + 63) / 64 * 64; return q; };  // 256-byte aligned arrays
   float* act = take((int64_t)L * C * 4 * kLH);
   float* cbuf = take((int64_t)L * C * kLH);
   float* hbuf = take((int64_t)L * C * kLH);

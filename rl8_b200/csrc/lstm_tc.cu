@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(kDhThreads, 1) lstm_dh_tc_kernel(LstmDhArgs g)
   // W_hh block: chunk (column group c8, k) = W_hh[k][64 nb + 8 c8 .. + 8)
   for (int e = tid; e < 8 * 1024; e += kDhThreads) {
     const int c8 = e & 7, k = e >> 3;
-    float v[8];
-    ldg8f(g.w_hh + (int64_t)k * kTH + nb * 64 + c8 * 8, v);
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(g.w_hh + (int64_t)k * kTH + nb * 64 + c8 * 8));
+    const float4 hi = __ldg(reinterpret_cast<const float4*>(g.w_hh + (int64_t)k * kTH + nb * 64 + c8 * 8) + 1);
+    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     store_chunk(s.b, (uint32_t)((c8 * 1024 + k) * 16), v);
   }
   fence_async_smem();
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kDhThreads, 1) lstm_dh_tc_kernel(LstmDhArgs g)
 }
 
 int launch_lstm_dh_tc(const uint8_t* dGb, const float* w_hh, float* dh, int64_t rows, cudaStream_t st) {
-  if (!dGb || !w_hh || !dh || rows <= 0) return RL8_ERR_ARG;
+  if (!dGb || !w_hh || !dh || rows <= 0 || ((uintptr_t)dh & 31u) || ((uintptr_t)w_hh & 15u)) return RL8_ERR_ARG;
   LstmDhArgs g{dGb, w_hh, dh, rows};
   const int64_t mtiles = ceil_div(rows, (int64_t)128);
   int64_t per_block = kNumSMs / 4;
