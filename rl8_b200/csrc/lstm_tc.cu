@@ -37,19 +37,23 @@ __device__ __forceinline__ void stg8f(float* p, const float* v) {
 
 // ---- cell backward ----------------------------------------------------------------------------------------------
 
-constexpr int kBwdGroup = 32;  // rows staged per transposition pass
+constexpr int kBwdGroup = 32;  // rows per transposition pass
 
-// thread j <-> hidden unit j; a block walks its rows in groups of 32: the group's dG (4 gates x 256 units, bf16) is
-// transposed through shared memory into T128 chunks and leaves as 512-byte runs
+// lane <-> hidden unit 32 w + lane of warp w; a warp walks its block's rows in groups of 32: the group's dG of the
+// warp's 32 units (4 gates x 4 column groups, bf16) is transposed through the WARP'S OWN 8 KB of shared memory into
+// T128 chunks and leaves as 512-byte runs.  No block-wide barrier anywhere: the 8 warps of a block (and the blocks of
+// an SM) drift apart, so the load bursts of some overlap the arithmetic and the stores of the others.
 template <int P>
 __global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
-  extern __shared__ __align__(16) uint8_t dgs[];  // [128 column groups][32 rows][16 B]
-  const int j = threadIdx.x;
+  extern __shared__ __align__(16) uint8_t dgs_all[];  // per warp: [4 gates x 4 column groups][32 rows][16 B] = 8 KB
+  const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
+  uint8_t* dgs = dgs_all + warp * (16 * kBwdGroup * 16);
   float wpi[P], gpi[P], wvf = a.vf_w[j], gvf = 0.0f;
 #pragma unroll
   for (int p = 0; p < P; ++p) wpi[p] = a.pi_w[p * kTH + j], gpi[p] = 0.0f;
   const int64_t rbeg = (int64_t)blockIdx.x * a.rows_per_block;
   const int64_t rend = rbeg + a.rows_per_block < a.rows_pad ? rbeg + a.rows_per_block : a.rows_pad;
+  const int cg = lane >> 3;  // column group of this lane inside the warp's 32 units
   for (int64_t r0 = rbeg; r0 < rend; r0 += kBwdGroup) {
 #pragma unroll 1
     for (int rr0 = 0; rr0 < kBwdGroup; rr0 += 4) {
@@ -93,25 +97,25 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
         const float dO = dhv * tc_ * og[u] * (1.0f - og[u]);
         if (r < a.rows) a.dc[r * kTH + j] = dcv * fg[u];
         const int rr = rr0 + u;
-        // row slot xor-swizzled by the column group: the 4 column groups a warp writes hit different banks
-        const uint32_t off = (uint32_t)(((j >> 3) * kBwdGroup + (rr ^ (((j >> 3) & 3) << 1))) * 16 + (j & 7) * 2);
-        constexpr uint32_t gate_stride = 32 * kBwdGroup * 16;  // 32 column groups per gate
+        // row slot xor-swizzled by the column group: the 4 column groups of the warp hit different banks
+        const uint32_t off = (uint32_t)((cg * kBwdGroup + (rr ^ (cg << 1))) * 16 + (lane & 7) * 2);
+        constexpr uint32_t gate_stride = 4 * kBwdGroup * 16;  // 4 column groups per gate
         *reinterpret_cast<__nv_bfloat16*>(dgs + off) = __float2bfloat16_rn(di);
         *reinterpret_cast<__nv_bfloat16*>(dgs + gate_stride + off) = __float2bfloat16_rn(df);
         *reinterpret_cast<__nv_bfloat16*>(dgs + 2 * gate_stride + off) = __float2bfloat16_rn(dg);
         *reinterpret_cast<__nv_bfloat16*>(dgs + 3 * gate_stride + off) = __float2bfloat16_rn(dO);
       }
     }
-    __syncthreads();
-    // 128 column groups x 32 rows x 16 B: each run of 32 rows is 512 contiguous bytes of the T128 image
-#pragma unroll 4
-    for (int idx = j; idx < 128 * kBwdGroup; idx += 256) {
-      const int seg = idx >> 5, rr = idx & 31;
-      *reinterpret_cast<uint4*>(a.dGb + t128_offset(r0 + rr, seg, 128)) =
-          *reinterpret_cast<const uint4*>(dgs + (size_t)(seg * kBwdGroup + (rr ^ ((seg & 3) << 1))) * 16);
+    __syncwarp();
+    // 16 (gate, column group) runs of 32 rows x 16 B: lane = row, 512 contiguous bytes of the T128 image per store
+#pragma unroll
+    for (int seg = 0; seg < 16; ++seg) {
+      const int gate = seg >> 2, c = seg & 3;
+      *reinterpret_cast<uint4*>(a.dGb + t128_offset(r0 + lane, gate * 32 + warp * 4 + c, 128)) =
+          *reinterpret_cast<const uint4*>(dgs + (size_t)(seg * kBwdGroup + (lane ^ (c << 1))) * 16);
     }
-    if (j < kBwdGroup) {  // [x | 1] of the group's rows (zeros past the last row)
-      const int64_t r = r0 + j;
+    if (warp == 0) {  // [x | 1] of the group's rows (zeros past the last row)
+      const int64_t r = r0 + lane;
       float x[8];
 #pragma unroll
       for (int d = 0; d < 8; ++d) x[d] = 0.0f;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
       *reinterpret_cast<uint4*>(a.xb + t128_offset(r, 0, 2)) = q0;
       *reinterpret_cast<uint4*>(a.xb + t128_offset(r, 1, 2)) = q1;
     }
-    __syncthreads();
+    __syncwarp();
   }
 #pragma unroll
   for (int p = 0; p < P; ++p) atomicAdd(a.gpi_w + p * kTH + j, gpi[p]);
@@ -140,12 +144,12 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
 int launch_lstm_cell_bwd_tc(const LstmBwdArgs& args, int P, cudaStream_t st) {
   LstmBwdArgs a = args;
   a.rows_pad = (a.rows + 127) / 128 * 128;
-  // ~3 resident blocks per SM (64 KB of shared memory each), every block a whole number of 32-row groups
+  // 3 resident blocks per SM (register-bound), every block a whole number of 32-row groups
   int64_t blocks = (int64_t)kNumSMs * 3;
   int64_t rpb = ceil_div(ceil_div(a.rows_pad, blocks), (int64_t)kBwdGroup) * kBwdGroup;
   blocks = ceil_div(a.rows_pad, rpb);
   a.rows_per_block = rpb;
-  constexpr int smem = 128 * kBwdGroup * 16;
+  constexpr int smem = 8 * 16 * kBwdGroup * 16;
 #define RL8_BWD(PV)                                                                                          \
   case PV:                                                                                                   \
     cudaFuncSetAttribute(lstm_cell_bwd_tc_kernel<PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
