@@ -336,12 +336,25 @@ struct LstmCellArgs {
   int D;
 };
 
-// SFU-based gate non-linearities (2-ulp exp, fast reciprocal): this is the bf16 path, whose gate pre-activations
-// already carry bf16 operand rounding; the fp32 path's cell kernel keeps the exact functions
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// SFU-based gate non-linearities: ex2.approx.ftz / rcp.approx.ftz issued directly (2 ulp each) -- 4 instructions per
+// sigmoid, 5 per tanh.  (__expf / __fdividef wrap every MUFU in denormal and range handling: the epilogue measured
+// ~240 instructions per hidden unit and was issue-bound.)  This is the bf16 path, whose gate pre-activations already
+// carry bf16 operand rounding; the fp32 path's cell kernel keeps the exact functions.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1 / (1 + 2^(-x log2 e)): ex2 -> 0 or +inf at the extremes, rcp(inf) = 0
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+// 2 sigmoid(2 x) - 1 (absolute error ~2e-7; saturates to +-1 without a clamp)
 __device__ __forceinline__ float tanh_fast(float x) {
-  const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
-  return __fdividef(e - 1.0f, e + 1.0f);
+  return fmaf(2.0f, rcp_ftz(1.0f + ex2_ftz(x * -2.8853900817779268f)), -1.0f);
 }
 
 // Warp roles: warps 0..15 run the cell epilogue, warp 16 stages the h tile (one bulk copy per K half from the T128
