@@ -321,41 +321,21 @@ constexpr int kCellD = 8;  // widest observation
 struct SmemLstm {
   uint8_t b[kGN * kRK * 2];      // 131072  W_hh block (4 gates x 64 units), K-major tile of 256 rows
   uint8_t a[2][kGM * 128 * 2];   //  65536  h tile in two K halves
-  float wt[4][kCellD][64];       //   8192  W_ih of this block's units, [gate][d][unit]
-  float bi[4][64], bh[4][64];    //   2048
-  uint64_t full[2], free_[2], acc_full[2], acc_empty[2];
+  uint8_t wx[kGN * 32 * 2];      //  16384  [W_ih | biases] of the block as 32 more k (see the kernel), K-major, 256 rows
+  uint8_t xa[2][kGM * 32 * 2];   //  16384  the matching A columns [x pieces | 1] of two row tiles
+  uint64_t full[2], free_[2], acc_full[2], acc_empty[2], xa_full[2], xa_free[2];
   uint32_t tmem_base;
 };
 struct LstmCellArgs {
   const uint8_t* hb_in;   // h as bf16 in the T128 layout (below): one bulk copy per K half stages the A operand
   uint8_t* hb_out;        // h' in the same layout for the next step / the weight-gradient GEMM (may be null)
   const float *w_hh, *w_ih, *b_ih, *b_hh, *c_prev;
-  float *act, *c_out, *h_out;  // act may be null (rollout)
+  float *c_out, *h_out;
+  uint8_t* zb;            // gate PRE-activations as bf16 T128 [rows_pad][4H] for the backward pass (null in the rollout)
   RowMap xmap;
   int64_t rows;
   int D;
 };
-
-// SFU-based gate non-linearities: ex2.approx.ftz / rcp.approx.ftz issued directly (2 ulp each) -- 4 instructions per
-// sigmoid, 5 per tanh.  (__expf / __fdividef wrap every MUFU in denormal and range handling: the epilogue measured
-// ~240 instructions per hidden unit and was issue-bound.)  This is the bf16 path, whose gate pre-activations already
-// carry bf16 operand rounding; the fp32 path's cell kernel keeps the exact functions.
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_ftz(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 1 / (1 + 2^(-x log2 e)): ex2 -> 0 or +inf at the extremes, rcp(inf) = 0
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
-// 2 sigmoid(2 x) - 1 (absolute error ~2e-7; saturates to +-1 without a clamp)
-__device__ __forceinline__ float tanh_fast(float x) {
-  return fmaf(2.0f, rcp_ftz(1.0f + ex2_ftz(x * -2.8853900817779268f)), -1.0f);
-}
 
 // Warp roles: warps 0..15 run the cell epilogue, warp 16 stages the h tile (one bulk copy per K half from the T128
 // image of h: no registers, no LSU), warp 17 issues the MMAs.  The three run decoupled behind mbarriers: a K half is
@@ -423,6 +403,7 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
     for (int h = 0; h < 2; ++h) {
       mbar_init(&s.full[h], 1), mbar_init(&s.free_[h], 1);
       mbar_init(&s.acc_full[h], 1), mbar_init(&s.acc_empty[h], kLcEpiWarps);
+      mbar_init(&s.xa_full[h], 1), mbar_init(&s.xa_free[h], 1);
     }
     fence_mbar_init();
   }
@@ -442,14 +423,28 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
       if (e < kGN * (kRK / 8)) *reinterpret_cast<uint4*>(s.b + chunk_offset<kGN>(row, kc)) = pack8(c[b]);
     }
   }
-  for (int i = tid; i < 4 * kCellD * 64; i += kLcThreads) {
-    const int gate = i / (kCellD * 64), d = (i / 64) % kCellD, u = i % 64;
-    s.wt[gate][d][u] = d < D ? g.w_ih[(int64_t)(gate * LH + nb * 64 + u) * D + d] : 0.0f;
-  }
-  for (int i = tid; i < 4 * 64; i += kLcThreads) {
-    const int gate = i >> 6, u = i & 63;
-    s.bi[gate][u] = g.b_ih[gate * LH + nb * 64 + u];
-    s.bh[gate][u] = g.b_hh[gate * LH + nb * 64 + u];
+  // The input term and both biases ride on the tensor core as 32 more k, fp32-accurate through hi / lo bf16 pieces
+  // (x = xh + xl, W = Wh + Wl; the dropped xl Wl is 2^-18 of the product):
+  //     A columns  [ xh(8) | xh(8) | xl(8) | 1 1 1 1 0 0 0 0 ]
+  //     B columns  [ Wh(8) | Wl(8) | Wh(8) | b_ih hi, lo, b_hh hi, lo, 0 0 0 0 ]
+  // so the epilogue reads finished pre-activations and carries no per-unit weights at all.
+  for (int row = tid; row < kGN; row += kLcThreads) {
+    const int src = (row >> 6) * LH + nb * 64 + (row & 63);
+    float wh[8], wl[8], bp[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const float w = d < D ? g.w_ih[(int64_t)src * D + d] : 0.0f;
+      wh[d] = __bfloat162float(__float2bfloat16_rn(w));
+      wl[d] = w - wh[d];
+      bp[d] = 0.0f;
+    }
+    const float bi = g.b_ih[src], bh = g.b_hh[src];
+    bp[0] = __bfloat162float(__float2bfloat16_rn(bi)), bp[1] = bi - bp[0];
+    bp[2] = __bfloat162float(__float2bfloat16_rn(bh)), bp[3] = bh - bp[2];
+    store_chunk(s.wx, chunk_offset<kGN>(row, 0), wh);
+    store_chunk(s.wx, chunk_offset<kGN>(row, 1), wl);
+    store_chunk(s.wx, chunk_offset<kGN>(row, 2), wh);
+    store_chunk(s.wx, chunk_offset<kGN>(row, 3), bp);
   }
   fence_async_smem();
   fence_before_sync();
@@ -487,28 +482,67 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
           issue_gemm(acc, smem_u32(s.a[h]), kGM, false, smem_u32(s.b) + h * 16 * (kGN * 16), kGN, false, kGM, kGN, 128,
                      h > 0);
           mma_commit(&s.free_[h]);
-          if (h == 1) mma_commit(&s.acc_full[buf]);
         }
         __syncwarp();
       }
+      mbar_wait(&s.xa_full[buf], (uint32_t)((it >> 1) & 1));
+      fence_after_sync();
+      if (elect_one()) {
+        issue_gemm(acc, smem_u32(s.xa[buf]), kGM, false, smem_u32(s.wx), kGN, false, kGM, kGN, 32, true);
+        mma_commit(&s.xa_free[buf]);
+        mma_commit(&s.acc_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kLcEpiWarps + kLcLoadWarps + 1) {
+    // ---- observation columns: lane l builds rows l, l + 32, l + 64, l + 96 of the tile's [x pieces | 1] operand -----
+    const int64_t ds = g.xmap.dstride();
+    int it = 0;
+    for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
+      const int buf = it & 1;
+      float x[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t r = mt * kGM + i * 32 + lane;
+        const bool live = r < g.rows;
+        int64_t xo = 0;
+        if (live) xo = g.xmap.offset(r);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) x[i][d] = (live && d < D) ? g.xmap.obs[xo + d * ds] : 0.0f;
+      }
+      if (it >= 2) mbar_wait(&s.xa_free[buf], (uint32_t)(((it >> 1) - 1) & 1));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float xh[8], xl[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          xh[d] = __bfloat162float(__float2bfloat16_rn(x[i][d]));
+          xl[d] = x[i][d] - xh[d];
+        }
+        const float ones[8] = {1.0f, 1.0f, 1.0f, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        const int row = i * 32 + lane;
+        store_chunk(s.xa[buf], chunk_offset<kGM>(row, 0), xh);
+        store_chunk(s.xa[buf], chunk_offset<kGM>(row, 1), xh);
+        store_chunk(s.xa[buf], chunk_offset<kGM>(row, 2), xl);
+        store_chunk(s.xa[buf], chunk_offset<kGM>(row, 3), ones);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&s.xa_full[buf]);
+      __syncwarp();
     }
   } else if (warp < kLcEpiWarps) {
     // ---- cell epilogue: warp (q = warp & 3, part = warp >> 2) -> row 32q + lane, units [16 part, 16 part + 16) of this
     //      block, in two groups of 8 units ----------------------------------------------------------------------------
     const int q = warp & 3, part = warp >> 2;
-    const int64_t ds = g.xmap.dstride();
     int it = 0;
     for (int64_t mt = mt0; mt < mtiles; mt += mstride, ++it) {
       const int buf = it & 1;
       const int64_t r = mt * kGM + q * 32 + lane;
       const bool live = r < g.rows;
       // everything the cell needs from global memory, requested before the wait on the accumulator
-      float x[kCellD], cp[2][8];
+      float cp[2][8];
       {
-        int64_t xo = 0;
-        if (live) xo = g.xmap.offset(r);
-#pragma unroll
-        for (int d = 0; d < kCellD; ++d) x[d] = (live && d < D) ? g.xmap.obs[xo + d * ds] : 0.0f;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int j0 = nb * 64 + part * 16 + half * 8;
@@ -542,36 +576,23 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
           continue;
         }
         const float* cph = cp[half];
-        // pre = (b_ih + sum_d x_d W_ih[., d]) + (acc + b_hh); the block's weights are read as 128-bit broadcasts (the
-        // scalar form made the kernel LSU-wavefront bound: 7 shared-memory loads per gate value)
+        // pre[gate][u]: finished pre-activations (h W_hh^T + x W_ih^T + b_ih + b_hh, all accumulated by the tensor core)
+        if (g.zb) {  // kept for the backward pass as bf16: lanes = consecutive rows, 512 contiguous bytes per store
 #pragma unroll
-        for (int gate = 0; gate < 4; ++gate) {
-          float a[8];
-          ld8s(&s.bi[gate][u0], a);
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            float w[8];
-            ld8s(&s.wt[gate][d][u0], w);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = fmaf(x[d], w[u], a[u]);
+          for (int gate = 0; gate < 4; ++gate) {
+            uint4 qz;
+            qz.x = pack_bf16x2(pre[gate][0], pre[gate][1]), qz.y = pack_bf16x2(pre[gate][2], pre[gate][3]);
+            qz.z = pack_bf16x2(pre[gate][4], pre[gate][5]), qz.w = pack_bf16x2(pre[gate][6], pre[gate][7]);
+            *reinterpret_cast<uint4*>(g.zb + t128_offset(r, gate * 32 + (j0 >> 3), 4 * LH / 8)) = qz;
           }
-          float bh[8];
-          ld8s(&s.bh[gate][u0], bh);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) pre[gate][u] = a[u] + (pre[gate][u] + bh[u]);
         }
         float cn[8], hn[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const float ig = sigmoid_fast(pre[0][u]), fg = sigmoid_fast(pre[1][u]);
           const float gg = tanh_fast(pre[2][u]), og = sigmoid_fast(pre[3][u]);
-          pre[0][u] = ig, pre[1][u] = fg, pre[2][u] = gg, pre[3][u] = og;
           cn[u] = fg * cph[u] + ig * gg;
           hn[u] = og * tanh_fast(cn[u]);
-        }
-        if (g.act) {
-#pragma unroll
-          for (int gate = 0; gate < 4; ++gate) stg8(g.act + r * 4 * LH + gate * LH + j0, pre[gate]);
         }
         stg8(g.c_out + r * LH + j0, cn);
         stg8(g.h_out + r * LH + j0, hn);
@@ -592,12 +613,12 @@ __global__ void __launch_bounds__(kLcThreads, 1) tc_lstm_cell_kernel(LstmCellArg
 // h' / c' / gate activations of one LSTM step for `rows` rows (H = 256).  hb_in: h as bf16 T128 (launch_pack_t128 or
 // a previous call's hb_out); hb_out (may be null): h' in the same form.
 int launch_lstm_cell_tc(const uint8_t* hb_in, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh,
-                        const float* c_prev, const RowMap& xmap, int D, int64_t rows, float* act, float* c_out,
+                        const float* c_prev, const RowMap& xmap, int D, int64_t rows, uint8_t* zb, float* c_out,
                         float* h_out, uint8_t* hb_out, cudaStream_t st) {
   if (D < 1 || D > kCellD || rows <= 0 || !hb_in) return RL8_ERR_ARG;
   LstmCellArgs g;
   g.hb_in = hb_in, g.hb_out = hb_out, g.w_hh = w_hh, g.w_ih = w_ih, g.b_ih = b_ih, g.b_hh = b_hh, g.c_prev = c_prev;
-  g.act = act, g.c_out = c_out, g.h_out = h_out, g.xmap = xmap, g.rows = rows, g.D = D;
+  g.zb = zb, g.c_out = c_out, g.h_out = h_out, g.xmap = xmap, g.rows = rows, g.D = D;
   const int64_t mtiles = ceil_div(rows, kGM);
   int64_t per_block = kNumSMs / 4;
   if (per_block > mtiles) per_block = mtiles;

@@ -132,7 +132,8 @@ static bool lstm_step_on_tc(int prec, int64_t rows, const float* h_in, const flo
 static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t rows,
                           const float* h_in, const float* c_in, float* h_out, float* c_out,
                           float* act, float* G, float* features, float* values, int tanh_col1,
-                          int prec, cudaStream_t st, const uint8_t* hb_in = nullptr, uint8_t* hb_out = nullptr) {
+                          int prec, cudaStream_t st, const uint8_t* hb_in = nullptr, uint8_t* hb_out = nullptr,
+                          uint8_t* zb = nullptr) {
   int rc;
   if (lstm_step_on_tc(prec, rows, h_in, h_out, c_in, c_out)) {
     // tensor-core path: the gate GEMM with the cell in its epilogue (no pre-activation round trip through HBM)
@@ -140,7 +141,8 @@ static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t r
       if ((rc = launch_pack_t128(h_in, rows, (uint8_t*)G, st))) return rc;
       hb_in = (const uint8_t*)G;
     }
-    if ((rc = launch_lstm_cell_tc(hb_in, m->w_hh, m->w_ih, m->b_ih, m->b_hh, c_in, xmap, m->D, rows, act, c_out,
+    // (the fused kernel keeps bf16 pre-activations `zb` for the backward pass instead of fp32 activations `act`)
+    if ((rc = launch_lstm_cell_tc(hb_in, m->w_hh, m->w_ih, m->b_ih, m->b_hh, c_in, xmap, m->D, rows, zb, c_out,
                                   h_out, hb_out, st)))
       return rc;
   } else {
@@ -414,6 +416,7 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
   const int64_t hb_bytes = t128_bytes(C, kLH), dgb_bytes = t128_bytes(C, 4 * kLH), xb_bytes = t128_bytes(C, 16);
   uint8_t* dgb = hb + (int64_t)L * hb_bytes;
   uint8_t* xb = dgb + (int64_t)L * dgb_bytes;
+  uint8_t* zb = (uint8_t*)act;  // tensor-core path: bf16 pre-activation images live where the fp32 activations would
   const bool continuous = b->dist_kind != RL8_DIST_CATEGORICAL;
   const int splits = 64;
 
@@ -441,7 +444,8 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
       float* ovf = out_vf + (int64_t)k * C;
       if ((rc = lstm_step_fp32(m, map, R, h_prev, c_prev, h_k, c_k, act_k, act_k, opi, ovf, continuous, prec, st,
                                tc ? hb + (int64_t)k * hb_bytes : nullptr,
-                               tc && k + 1 < L ? hb + (int64_t)(k + 1) * hb_bytes : nullptr)))
+                               tc && k + 1 < L ? hb + (int64_t)(k + 1) * hb_bytes : nullptr,
+                               tc ? zb + (int64_t)k * dgb_bytes : nullptr)))
         return rc;
       LossArgs la{};
       la.dist_kind = b->dist_kind, la.P = P, la.M = R;
@@ -470,7 +474,7 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
         // tensor-core path (lstm_tc.cu): one fused elementwise kernel (heads' term of dL/dh, cell backward, dG and
         // [x | 1] as bf16 T128 images, head weight gradients), then dh_{k-1} = dG_k W_hh on tcgen05
         LstmBwdArgs ba{};
-        ba.act = act_k, ba.c = c_k, ba.c_prev = c_prev, ba.h = h_k, ba.dh_rec = last ? nullptr : dh, ba.dc = dc;
+        ba.zb = zb + (int64_t)k * dgb_bytes, ba.c_prev = c_prev, ba.h = h_k, ba.dh_rec = last ? nullptr : dh, ba.dc = dc;
         ba.dpi = dpi, ba.dvf = dvf, ba.pi_w = m->pi_w, ba.vf_w = m->vf_w;
         ba.dGb = dgb + (int64_t)k * dgb_bytes, ba.xb = xb + (int64_t)k * xb_bytes;
         ba.gpi_w = (float*)g->pi_w, ba.gvf_w = (float*)g->vf_w;

@@ -39,12 +39,14 @@ __device__ __forceinline__ void stg8f(float* p, const float* v) {
 
 constexpr int kBwdGroup = 32;  // rows per transposition pass
 
-// lane <-> hidden unit 32 w + lane of warp w; a warp walks its block's rows in groups of 32: the group's dG of the
-// warp's 32 units (4 gates x 4 column groups, bf16) is transposed through the WARP'S OWN 8 KB of shared memory into
-// T128 chunks and leaves as 512-byte runs.  No block-wide barrier anywhere: the 8 warps of a block (and the blocks of
-// an SM) drift apart, so the load bursts of some overlap the arithmetic and the stores of the others.
+// lane <-> hidden unit 32 w + lane of warp w; a warp walks its block's rows in groups of 32.  The group's gate
+// pre-activations of the warp's 32 units (4 gates x 4 column groups of the bf16 T128 image) arrive as 512-byte runs
+// (lane = row) in the WARP'S OWN 8 KB of shared memory; every thread then reads the values of ITS unit, recomputes the
+// gate activations and c_k from them (cheaper than 6 KB per row of stored fp32 activations), and writes the gate
+// gradient back IN PLACE; the transposed block leaves as 512-byte runs again.  No block-wide barrier anywhere: the 8
+// warps of a block (and the blocks of an SM) drift apart, so the load bursts of some overlap the arithmetic of others.
 template <int P>
-__global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
   extern __shared__ __align__(16) uint8_t dgs_all[];  // per warp: [4 gates x 4 column groups][32 rows][16 B] = 8 KB
   const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
   uint8_t* dgs = dgs_all + warp * (16 * kBwdGroup * 16);
@@ -55,18 +57,32 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
   const int64_t rend = rbeg + a.rows_per_block < a.rows_pad ? rbeg + a.rows_per_block : a.rows_pad;
   const int cg = lane >> 3;  // column group of this lane inside the warp's 32 units
   for (int64_t r0 = rbeg; r0 < rend; r0 += kBwdGroup) {
+    // pre-activations in: 16 (gate, column group) runs, lane = row; row slot xor-swizzled by the column group so that
+    // the per-unit 2-byte accesses below (4 column groups per warp instruction) hit different banks
+#pragma unroll
+    for (int s0 = 0; s0 < 16; s0 += 8) {
+      uint4 zq[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int seg = s0 + e;
+        zq[e] = __ldg(reinterpret_cast<const uint4*>(a.zb + t128_offset(r0 + lane, (seg >> 2) * 32 + warp * 4 + (seg & 3), 128)));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int seg = s0 + e;
+        *reinterpret_cast<uint4*>(dgs + (size_t)(seg * kBwdGroup + (lane ^ ((seg & 3) << 1))) * 16) = zq[e];
+      }
+    }
+    __syncwarp();
 #pragma unroll 1
     for (int rr0 = 0; rr0 < kBwdGroup; rr0 += 4) {
-      float ig[4], fg[4], gg[4], og[4], ck[4], cp[4], dhr[4], dci[4], hk[4], dp[4][P], dv[4];
+      float cp[4], dhr[4], dci[4], hk[4], dp[4][P], dv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t r = r0 + rr0 + u;
         const bool live = r < a.rows;
         const int64_t i = r * kTH + j;
-        const float* ap = a.act + r * 4 * kTH + j;
-        ig[u] = live ? __ldg(ap) : 0.0f, fg[u] = live ? __ldg(ap + kTH) : 0.0f;
-        gg[u] = live ? __ldg(ap + 2 * kTH) : 0.0f, og[u] = live ? __ldg(ap + 3 * kTH) : 0.0f;
-        ck[u] = live ? __ldg(a.c + i) : 0.0f, cp[u] = live ? __ldg(a.c_prev + i) : 0.0f;
+        cp[u] = live ? __ldg(a.c_prev + i) : 0.0f;
         hk[u] = live ? __ldg(a.h + i) : 0.0f;
         dhr[u] = (live && a.dh_rec) ? __ldg(a.dh_rec + i) : 0.0f;
         dci[u] = (live && a.has_dc_in) ? a.dc[i] : 0.0f;
@@ -77,6 +93,18 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t r = r0 + rr0 + u;
+        const int rr = rr0 + u;
+        const bool live = r < a.rows;
+        const uint32_t off = (uint32_t)((cg * kBwdGroup + (rr ^ (cg << 1))) * 16 + (lane & 7) * 2);
+        constexpr uint32_t gate_stride = 4 * kBwdGroup * 16;  // 4 column groups per gate
+        __nv_bfloat16* zi = reinterpret_cast<__nv_bfloat16*>(dgs + off);
+        __nv_bfloat16* zf = reinterpret_cast<__nv_bfloat16*>(dgs + gate_stride + off);
+        __nv_bfloat16* zg = reinterpret_cast<__nv_bfloat16*>(dgs + 2 * gate_stride + off);
+        __nv_bfloat16* zo = reinterpret_cast<__nv_bfloat16*>(dgs + 3 * gate_stride + off);
+        // gates and cell state of the forward step, recomputed (tc_lstm_cell_kernel's functions)
+        const float ig = sigmoid_fast(__bfloat162float(*zi)), fg = sigmoid_fast(__bfloat162float(*zf));
+        const float gg = tanh_fast(__bfloat162float(*zg)), og = sigmoid_fast(__bfloat162float(*zo));
+        const float tc_ = tanh_fast(fg * cp[u] + ig * gg);
         // dL/dh_k = heads' term (+ the recurrent term), in the op order of lstm_dh_kernel
         float dhv = 0.0f;
 #pragma unroll
@@ -88,22 +116,18 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_tc_kernel(LstmBwdArgs a) {
         for (int p = 0; p < P; ++p) gpi[p] = fmaf(dp[u][p], hk[u], gpi[p]);
         gvf = fmaf(dv[u], hk[u], gvf);
         // cell backward (lstm_cell_bwd_kernel)
-        const float tc_ = tanhf(ck[u]);
-        float dcv = dhv * og[u] * (1.0f - tc_ * tc_);
+        float dcv = dhv * og * (1.0f - tc_ * tc_);
         if (a.has_dc_in) dcv += dci[u];
-        const float di = dcv * gg[u] * ig[u] * (1.0f - ig[u]);
-        const float df = dcv * cp[u] * fg[u] * (1.0f - fg[u]);
-        const float dg = dcv * ig[u] * (1.0f - gg[u] * gg[u]);
-        const float dO = dhv * tc_ * og[u] * (1.0f - og[u]);
-        if (r < a.rows) a.dc[r * kTH + j] = dcv * fg[u];
-        const int rr = rr0 + u;
-        // row slot xor-swizzled by the column group: the 4 column groups of the warp hit different banks
-        const uint32_t off = (uint32_t)((cg * kBwdGroup + (rr ^ (cg << 1))) * 16 + (lane & 7) * 2);
-        constexpr uint32_t gate_stride = 4 * kBwdGroup * 16;  // 4 column groups per gate
-        *reinterpret_cast<__nv_bfloat16*>(dgs + off) = __float2bfloat16_rn(di);
-        *reinterpret_cast<__nv_bfloat16*>(dgs + gate_stride + off) = __float2bfloat16_rn(df);
-        *reinterpret_cast<__nv_bfloat16*>(dgs + 2 * gate_stride + off) = __float2bfloat16_rn(dg);
-        *reinterpret_cast<__nv_bfloat16*>(dgs + 3 * gate_stride + off) = __float2bfloat16_rn(dO);
+        const float di = dcv * gg * ig * (1.0f - ig);
+        const float df = dcv * cp[u] * fg * (1.0f - fg);
+        const float dg = dcv * ig * (1.0f - gg * gg);
+        const float dO = dhv * tc_ * og * (1.0f - og);
+        if (live) a.dc[r * kTH + j] = dcv * fg;
+        // rows past the end carry a zero gradient whatever their (unwritten) pre-activations hold
+        *zi = __float2bfloat16_rn(live ? di : 0.0f);
+        *zf = __float2bfloat16_rn(live ? df : 0.0f);
+        *zg = __float2bfloat16_rn(live ? dg : 0.0f);
+        *zo = __float2bfloat16_rn(live ? dO : 0.0f);
       }
     }
     __syncwarp();

@@ -5,8 +5,7 @@
 namespace rl8 {
 
 struct LstmBwdArgs {
-  const float* act;     // [R][4][256] gate activations i, f, g, o of step k
-  const float* c;       // [R][256]    c_k
+  const uint8_t* zb;    // bf16 T128 [R_pad][1024] gate PRE-activations of step k (tc_lstm_cell_kernel)
   const float* c_prev;  // [R][256]
   const float* h;       // [R][256]    h_k (head weight gradients)
   const float* dh_rec;  // [R][256]    dG_{k+1} W_hh, or null at the last step of the sequence

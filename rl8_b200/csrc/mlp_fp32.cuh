@@ -52,12 +52,13 @@ int launch_tc_gemm(bool a_kmajor, bool b_kmajor, int epi, const float* A, const 
                    cudaStream_t st);
 
 // One LSTM step on tensor cores (gemm_tc.cu): gates = h W_hh^T (bf16 operands, fp32 accumulate) with the cell
-// non-linearity in the epilogue; writes act [rows][4H] (may be NULL), c_out, h_out [rows][H].  H = 256.
-// h arrives as bf16 in the T128 layout (hb_in: launch_pack_t128 of the fp32 state, or a previous step's hb_out).
+// non-linearity in the epilogue; writes c_out, h_out [rows][H] and, for the backward pass, the gate PRE-activations as
+// bf16 T128 (zb [rows_pad][4H], may be NULL).  H = 256.  h arrives as bf16 in the T128 layout (hb_in:
+// launch_pack_t128 of the fp32 state, or a previous step's hb_out).
 int64_t t128_bytes(int64_t rows, int cols);
 int launch_pack_t128(const float* x, int64_t rows, uint8_t* out, cudaStream_t st);
 int launch_lstm_cell_tc(const uint8_t* hb_in, const float* w_hh, const float* w_ih, const float* b_ih, const float* b_hh,
-                        const float* c_prev, const RowMap& xmap, int D, int64_t rows, float* act, float* c_out,
+                        const float* c_prev, const RowMap& xmap, int D, int64_t rows, uint8_t* zb, float* c_out,
                         float* h_out, uint8_t* hb_out, cudaStream_t st);
 
 // out[rows][P] = b3 + h2 @ w3^T; column 1 is tanh'ed when tanh_col1 (continuous log_std).

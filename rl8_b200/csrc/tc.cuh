@@ -393,6 +393,27 @@ template <int ROWS>
 __device__ __forceinline__ uint32_t chunk_offset(int row, int col8 /* col / 8 */) {
   return (uint32_t)row * 16u + (uint32_t)col8 * (uint32_t)(ROWS * 16);
 }
+// SFU-based gate non-linearities: ex2.approx.ftz / rcp.approx.ftz issued directly (2 ulp each) -- 4 instructions per
+// sigmoid, 5 per tanh.  (__expf / __fdividef wrap every MUFU in denormal and range handling: the epilogue measured
+// ~240 instructions per hidden unit and was issue-bound.)  This is the bf16 path, whose gate pre-activations already
+// carry bf16 operand rounding; the fp32 path's cell kernel keeps the exact functions.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1 / (1 + 2^(-x log2 e)): ex2 -> 0 or +inf at the extremes, rcp(inf) = 0
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+// 2 sigmoid(2 x) - 1 (absolute error ~2e-7; saturates to +-1 without a clamp)
+__device__ __forceinline__ float tanh_fast(float x) {
+  return fmaf(2.0f, rcp_ftz(1.0f + ex2_ftz(x * -2.8853900817779268f)), -1.0f);
+}
+
 // T128 layout of a bf16 matrix X[R][C] in GLOBAL memory (R padded to a multiple of 128): 16-byte chunks of 8
 // consecutive columns, [row tile of 128][column group][row in tile][8] -- every 128-row x 8k-column block is stored
 // exactly as the chunked shared-memory operand tile it will become, whichever GEMM reads it (rows as M / N with the
