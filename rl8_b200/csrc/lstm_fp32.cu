@@ -151,6 +151,8 @@ static int lstm_step_fp32(const rl8_lstm_model* m, const RowMap& xmap, int64_t r
       return rc;
     if ((rc = launch_cell_fwd(m, G, xmap, rows, c_in, act, c_out, h_out, st))) return rc;
   }
+  if (features && values)  // both heads in one pass over h' (same arithmetic per output)
+    return launch_lstm_heads_fwd(h_out, rows, m->P, m->pi_w, m->pi_b, m->vf_w, m->vf_b, features, values, tanh_col1, st);
   if (features &&
       (rc = launch_head_fwd(h_out, rows, kLH, m->P, m->pi_w, m->pi_b, features, tanh_col1, st)))
     return rc;

@@ -35,6 +35,61 @@ __device__ __forceinline__ void stg8f(float* p, const float* v) {
                : "memory");
 }
 
+// ---- both heads in one pass over h (head_fwd_kernel's arithmetic per output; one warp per row) -----------------------
+template <int P>
+__global__ void __launch_bounds__(256)
+lstm_heads_fwd_kernel(const float* __restrict__ h, int64_t rows, const float* __restrict__ pi_w,
+                      const float* __restrict__ pi_b, const float* __restrict__ vf_w, const float* __restrict__ vf_b,
+                      float* __restrict__ out_pi, float* __restrict__ out_vf, int tanh_col1) {
+  const int lane = threadIdx.x & 31;
+  float w[P + 1][8];
+#pragma unroll
+  for (int p = 0; p <= P; ++p) {
+    const float* src = (p < P ? pi_w + p * kTH : vf_w) + lane * 8;
+    const float4 w0 = *reinterpret_cast<const float4*>(src), w1 = *reinterpret_cast<const float4*>(src + 4);
+    w[p][0] = w0.x, w[p][1] = w0.y, w[p][2] = w0.z, w[p][3] = w0.w;
+    w[p][4] = w1.x, w[p][5] = w1.y, w[p][6] = w1.z, w[p][7] = w1.w;
+  }
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float4 x0 = ld_stream4(h + r * kTH + lane * 8), x1 = ld_stream4(h + r * kTH + lane * 8 + 4);
+    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float acc[P + 1];
+#pragma unroll
+    for (int p = 0; p <= P; ++p) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum = fmaf(x[i], w[p][i], sum);
+      acc[p] = warp_sum(sum);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        float v = acc[p] + pi_b[p];
+        if (tanh_col1 && p == 1) v = tanhf(v);
+        out_pi[r * P + p] = v;
+      }
+      out_vf[r] = acc[P] + vf_b[0];
+    }
+  }
+}
+
+int launch_lstm_heads_fwd(const float* h, int64_t rows, int P, const float* pi_w, const float* pi_b, const float* vf_w,
+                          const float* vf_b, float* out_pi, float* out_vf, int tanh_col1, cudaStream_t st) {
+  const int grid = grid_for(rows * 32, 256, 8, 2);
+#define RL8_HEADS(PV)                                                                                             \
+  case PV:                                                                                                        \
+    lstm_heads_fwd_kernel<PV><<<grid, 256, 0, st>>>(h, rows, pi_w, pi_b, vf_w, vf_b, out_pi, out_vf, tanh_col1);   \
+    break;
+  switch (P) {
+    RL8_HEADS(2) RL8_HEADS(3) RL8_HEADS(4) RL8_HEADS(5) RL8_HEADS(6) RL8_HEADS(7) RL8_HEADS(8)
+    default: return RL8_ERR_UNSUPPORTED;
+  }
+#undef RL8_HEADS
+  return check_launch("lstm_heads_fwd");
+}
+
 // ---- cell backward ----------------------------------------------------------------------------------------------
 
 constexpr int kBwdGroup = 32;  // rows per transposition pass
