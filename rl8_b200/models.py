@@ -174,12 +174,31 @@ class Model(nn.Module):
                 o += p.numel()
         return out
 
-    def load_state_dict(self, state_dict: Any, *a: Any, **kw: Any) -> Any:  # keeps the flat views
+    def load_state_dict(self, state_dict: Any, strict: bool = True, assign: bool = False) -> Any:
+        """``nn.Module.load_state_dict`` that writes THROUGH the parameter views into the flat kernel buffer (the
+        parameters are never re-pointed, so ``assign`` is refused); ``strict`` and the returned
+        ``_IncompatibleKeys`` behave as in torch."""
+        from torch.nn.modules.module import _IncompatibleKeys
+
+        if assign:
+            raise NotImplementedError("assign=True would detach the parameters from the flat kernel buffer")
+        own = dict(self.named_parameters())
+        missing = [k for k in own if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in own]
+        errors = []
+        for k, v in state_dict.items():
+            if k in own and tuple(v.shape) != tuple(own[k].shape):
+                errors.append(f"size mismatch for {k}: copying a param with shape {tuple(v.shape)} from checkpoint, "
+                              f"the shape in current model is {tuple(own[k].shape)}.")
+        if strict and (missing or unexpected):
+            errors.insert(0, f"Missing key(s) in state_dict: {missing}. Unexpected key(s) in state_dict: {unexpected}.")
+        if errors:
+            raise RuntimeError(f"Error(s) in loading state_dict for {type(self).__name__}:\n\t" + "\n\t".join(errors))
         with torch.no_grad():
-            own = dict(self.named_parameters())
             for k, v in state_dict.items():
-                own[k].copy_(v)
-        return None
+                if k in own:
+                    own[k].copy_(v)
+        return _IncompatibleKeys(missing, unexpected)
 
     def value_function(self) -> torch.Tensor:
         assert self._value is not None

@@ -15,7 +15,57 @@ from .specs import TensorSpec
 ViewKind = Literal["last", "all"]
 
 
-class Policy:
+
+class PolicyExport:
+    """``save`` / ``load`` and the pickled form shared by :class:`Policy` and ``RecurrentPolicy``."""
+
+    # -- export (src/rl8/policies/_feedforward.py:178-190) -----------------------------------------
+    def __getstate__(self) -> dict[str, Any]:
+        """Pickled form: everything but the library handle and scratch memory; a default (flat-parameter) model travels
+        as its class, specs, config and a CPU ``state_dict`` -- the reference's parameter names and shapes, so the same
+        tensors load into the reference's ``Policy`` -- and is re-flattened on the loading side."""
+        state = {k: v for k, v in self.__dict__.items() if k not in ("_lib", "_ws", "model")}
+        if getattr(self, "fused", True):
+            m = self.model
+            state["_model_blob"] = (type(m), m.observation_spec, m.action_spec, dict(m.config),
+                                    {k: v.detach().cpu() for k, v in m.state_dict().items()})
+        else:
+            state["model"] = self.model
+        return state
+
+    def __setstate__(self, state: dict[str, Any]) -> None:
+        blob = state.pop("_model_blob", None)
+        self.__dict__.update(state)
+        if not torch.cuda.is_available():
+            raise RuntimeError("rl8_b200 policies run on CUDA only; there is no CPU path.")
+        if blob is not None:
+            cls, obs_spec, act_spec, config, sd = blob
+            self.model = cls(obs_spec, act_spec, **config).flatten_(self.device)
+            self.model.load_state_dict(sd)
+        self._lib = _lib.load()
+        self._ws = None
+
+    def save(self, path: Any, /) -> Any:
+        """Cloud-pickle the policy to ``path`` (the reference's export convention, which it then wraps in an MLflow
+        model -- MLflow is outside this engine's scope); ``Policy.load(path)`` restores it."""
+        import cloudpickle
+
+        with open(path, "wb") as f:
+            cloudpickle.dump(self, f)
+        return self
+
+    @staticmethod
+    def load(path: Any, /) -> Any:
+        import pickle
+
+        with open(path, "rb") as f:
+            policy = pickle.load(f)
+        if not isinstance(policy, PolicyExport):
+            raise TypeError(f"{path!r} does not hold an rl8_b200 policy")
+        return policy
+
+
+class Policy(PolicyExport):
     """Union of a feedforward model and an action distribution.
 
     ``sample`` keeps the reference signature; the forward pass runs through

@@ -33,6 +33,7 @@ from .data import DataKeys, Device, RecurrentAlgorithmHparams, RecurrentAlgorith
 from .distributions import Distribution
 from .env import Env, KernelEnv
 from .models import Model, _small_head
+from .policies import PolicyExport
 from .schedulers import EntropyScheduler, LRScheduler, ScheduleKind
 from .specs import Categorical, Composite, TensorSpec, Unbounded
 from .trainers import Trainer
@@ -168,7 +169,7 @@ class DefaultContinuousRecurrentModel(RecurrentModel):
 # --------------------------------------------------------------------------------------------
 
 
-class RecurrentPolicy:
+class RecurrentPolicy(PolicyExport):
     """Union of a recurrent model and an action distribution
     (src/rl8/policies/_recurrent.py:20-164)."""
 

@@ -532,3 +532,83 @@ def test_early_stop_works_with_amp() -> None:
     stats = algo.step()
     assert algo._opt_steps == 1
     assert math.isfinite(stats["monitors/kl_div"])
+
+
+# ---------------------------------------------------------------------------------------
+# policy export (src/rl8/policies/_feedforward.py:178-190)
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("case", ["discrete_cartpole", "continuous_pendulum_normal", "continuous_pendulum_squashed"])
+@pytest.mark.parametrize("amp", [False, True])
+def test_reference_checkpoint_deploys_here_and_survives_save_load(case: str, amp: bool, tmp_path) -> None:  # noqa: ANN001
+    """tests/golden/policy_export.npz holds a ``state_dict`` of the UNMODIFIED reference ``Policy`` with its
+    deterministic samples on fixed observations (tests/golden/generate_policy_export_golden.py).  Loaded into this
+    engine's ``Policy`` the same observations give the same actions (discrete: bit-exact), log-probabilities and values
+    at 1e-5 (bf16 tolerance with enable_amp); ``Policy.save`` -> ``Policy.load`` reproduces them bit for bit, and the
+    ``state_dict`` that comes back out is the one that went in (so it loads into the reference just the same)."""
+    import numpy as np
+
+    from rl8_b200 import _lib as L
+    from rl8_b200 import distributions as Dm
+    from rl8_b200.policies import Policy
+    from rl8_b200.specs import Categorical, Unbounded
+
+    from .conftest import GOLDEN_DIR
+
+    z = np.load(f"{GOLDEN_DIR}/policy_export.npz")
+    obs = torch.from_numpy(z[f"{case}/obs"]).cuda()
+    d = obs.shape[-1]
+    act_spec = (Categorical(3, shape=torch.Size([1]), device="cuda") if case.startswith("discrete")
+                else Unbounded(shape=torch.Size([1]), device="cuda"))
+    dist_cls = Dm.SquashedNormal if case.endswith("squashed") else None
+    policy = Policy(Unbounded(shape=torch.Size([d]), device="cuda"), act_spec, distribution_cls=dist_cls, device="cuda")
+    policy.precision = L.precision_for(amp)
+    sd = {k[len(case) + 7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{case}/param/")}
+    keys = policy.model.load_state_dict(sd)
+    assert not keys.missing_keys and not keys.unexpected_keys
+    with pytest.raises(RuntimeError):
+        policy.model.load_state_dict({**sd, "nope": torch.zeros(1)})
+
+    def run(p):  # noqa: ANN001, ANN202
+        return p.sample({"obs": obs}, kind="last", deterministic=True, return_actions=True, return_logp=True,
+                        return_values=True)
+
+    got = run(policy)
+    ref_a, ref_v = torch.from_numpy(z[f"{case}/actions"]), torch.from_numpy(z[f"{case}/values"])
+    ref_lp = torch.from_numpy(z[f"{case}/logp"])
+    tol = dict(rtol=3e-2, atol=3e-2) if amp else dict(rtol=1e-5, atol=2e-6)
+    if case.startswith("discrete"):
+        same = (got["actions"].cpu() == ref_a).float().mean()
+        assert float(same) == 1.0 if not amp else float(same) > 0.97
+    else:
+        torch.testing.assert_close(got["actions"].cpu(), ref_a, **tol)
+    torch.testing.assert_close(got["values"].cpu(), ref_v, **tol)
+    if not amp:
+        torch.testing.assert_close(got["logp"].cpu(), ref_lp, rtol=1e-4, atol=1e-5)
+
+    path = tmp_path / "policy.pkl"
+    assert policy.save(path) is policy
+    loaded = Policy.load(path)
+    assert loaded.precision == policy.precision and loaded.distribution_cls is policy.distribution_cls
+    again = run(loaded)
+    for k in ("actions", "logp", "values"):
+        assert torch.equal(again[k], got[k]), k
+    for k, v in loaded.model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+
+
+def test_recurrent_policy_save_load_round_trip(tmp_path) -> None:  # noqa: ANN001
+    from rl8_b200 import RecurrentAlgorithmConfig
+    from rl8_b200.recurrent import RecurrentPolicy
+
+    torch.manual_seed(2)
+    algo = RecurrentAlgorithmConfig(num_envs=16, horizon=4, seq_len=2, seqs_per_state_reset=2).build(_envs().CartPole)
+    path = tmp_path / "rpolicy.pkl"
+    algo.policy.save(path)
+    loaded = RecurrentPolicy.load(path)
+    assert torch.equal(loaded.model.flat_params, algo.policy.model.flat_params)
+    x = torch.randn(16, 5, device="cuda")
+    h, c = torch.randn(16, 256, device="cuda").tanh(), torch.randn(16, 256, device="cuda")
+    for a, b in zip(algo.policy.step_net(x, h, c), loaded.step_net(x, h, c)):
+        assert torch.equal(a, b)
