@@ -679,6 +679,9 @@ def stream_rooflines(lib, L, dev, peaks: dict) -> list[dict]:  # noqa: ANN001
 #: N=65536 T=32 full-batch rl8_ppo_minibatch (tc_update_h + tc_update_w over 2^21 rows), from the
 #: `ncu --set full` captures summarised in profiles/r01_update_v8_ncu_summary.md.
 NCU_TRAFFIC = {("cartpole", 2097152): (84.31e6 + 2089.0e6) + (2190.0e6 + 7.0e6)}
+#: the same call in RL8_PREC_FP32_TC (x3_update_f + x3_update_b + x3_update_w), dram read + write of each kernel from
+#: profiles/r02_x3_update_ncu_summary.md: no dZ2 scratch, 80 B per row and network of masks / dOut instead
+NCU_TRAFFIC_X3 = {("cartpole", 2097152): (86.1e6 + 283.0e6) + (378.4e6 + 5.2e6) + (244.3e6 + 5.1e6)}
 
 
 def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa: ANN001
@@ -712,7 +715,8 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
         flops = hp.num_sgd_iters * N * T * 3.0 * 2.0 * ((D + H) * 4 * H + (P + 1) * H)
         return {
             "kernel": "RecurrentAlgorithm.step (rl8_lstm_ppo_minibatch x num_sgd_iters; LSTM GEMMs: "
-                      + ("tcgen05 bf16, tc_gemm_kernel)" if dtype == "bf16" else "fp32 CUDA cores)"),
+                      + ("tcgen05 bf16: tc_lstm_cell / lstm_cell_bwd_tc / lstm_dh_tc / lstm_wgrad_tc kernels)"
+                         if dtype == "bf16" else "fp32 CUDA cores)"),
             "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
             "frac": flops / ms / 1e9 / peak, "traffic": None, "ms": ms, "rows": N * T, "dtype": dtype,
             "peak_source": peaks["source"] + " bf16 sustained (whole step() incl. its elementwise kernels)",
@@ -741,8 +745,10 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
             "kernel": "rl8_ppo_minibatch, RL8_PREC_FP32_TC (x3_update_f + x3_update_b + x3_update_w per 2^21-row chunk:"
                       " split-bf16 pair MMAs, operands recomputed from 80 B/row of scratch)",
             "bound": "tensor", "achieved": flops / ms / 1e9, "peak": burst / 6.0, "unit": "TFLOP/s",
-            "frac": flops / ms / 1e9 / (burst / 6.0), "traffic": None, "ms": ms, "rows": M, "dtype": "f32",
-            "mma_tflops": 6.0 * flops / ms / 1e9,
+            "frac": flops / ms / 1e9 / (burst / 6.0), "traffic": NCU_TRAFFIC_X3.get((a.workload, M)), "ms": ms,
+            "rows": M, "dtype": "f32", "mma_tflops": 6.0 * flops / ms / 1e9,
+            "traffic_source": ("ncu --set full, profiles/r02_x3_update_ncu_summary.md"
+                               if (a.workload, M) in NCU_TRAFFIC_X3 else None),
             "peak_source": peaks["source"] + " bf16 burst / 6 (six bf16 piece products per fp32 product; `achieved`"
                                              " counts fp32-equivalent FLOPs, `mma_tflops` the bf16 work issued)",
         }
