@@ -405,6 +405,9 @@ int rl8_tc3_selftest(const float* A, const float* B, float* D, int32_t K, int32_
 /* out[128][128] = in[128][128] (32-bit words) through a tensor-memory store / load round trip
  * (tcgen05.st / tcgen05.ld 32x32b.x32), as used to park packed bf16 activations in TMEM. */
 int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream);
+/* Test hook: register layout of tcgen05.ld.16x256b.x4.  in[128][32] goes to tensor memory with the 32x32b store
+ * (thread = lane); out[tid][16 h + j] is register j of warp tid / 32's load of its lanes 16 h .. 16 h + 15. */
+int rl8_tc_selftest_tmem_16x256b(const uint32_t* in, uint32_t* out, rl8_stream_t stream);
 
 /* Microbenchmark: out_cycles[0] = SM cycles for `iters` rounds of tensor-memory reads by `nwarps`
  * warps of one CTA (mode 0: 32x32b.x32 + wait; 1: two loads per wait; 2: x16 loads).  Sizes the
@@ -426,6 +429,17 @@ int rl8_tc_gemm(int a_kmajor, int b_kmajor, int accumulate, const float* A, cons
  * Gives the per-instruction pace by N / operand major and the fixed issue -> commit -> wait latency. */
 int rl8_tc_bench_mma(long long* out_cycles, int32_t N, int32_t k_total, int32_t reps, int a_mn_major,
                      int b_mn_major, rl8_stream_t stream);
+
+/* Development hook: `pairs` clusters of two CTAs each issue reps x 2 x terms tcgen05.mma.cta_group::2 instructions
+ * (M = 256, N = n_cols, K = 16, bf16) back to back; out[2 p] = SM cycles, out[2 p + 1] = nanoseconds of pair p.
+ * Gives the pace of the split kernels' instruction stream with the whole chip busy (power cap included). */
+int rl8_tc3_bench_pace(long long* out, int32_t pairs, int32_t reps, int32_t terms, int32_t n_cols,
+                       rl8_stream_t stream);
+
+/* Development hook (meaningful in `make ABLATE=1` builds): 32 x uint64 on the device (zeroed by the caller) receive, for pair 0 of each network
+ * ([0..15] policy, [16..31] value) of x3_update_f_kernel, the SM cycles its MMA warp waited for ring stage kc
+ * ([0..7]) and for a free accumulator ([8]), its total cycles ([9]) and its tile count ([10]); NULL switches it off. */
+int rl8_x3_debug_buffer(unsigned long long* device_counters);
 
 /* Debug hook: `device_counters` (24 x uint64 on the device, zeroed by the caller) receives the SM
  * cycles CTA 0 of each network spends in the 8 phases of the tensor-core update's activation

@@ -204,11 +204,14 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rl8_tc_selftest": (_int, [_vp, _vp, _vp, _i32, _i32, _int, _int, _vp]),
     "rl8_tc_selftest_tf32": (_int, [_vp, _vp, _vp, _i32, _vp]),
     "rl8_tc_selftest_tmem": (_int, [_vp, _vp, _vp]),
+    "rl8_tc_selftest_tmem_16x256b": (_int, [_vp, _vp, _vp]),
     "rl8_tc3_selftest": (_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "rl8_tc_bench_tmem": (_int, [_vp, _i32, _i32, _i32, _vp]),
     "rl8_tc_phase_buffer": (_int, [_vp]),
     "rl8_tc_gemm": (_int, [_int, _int, _int, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _i64, _i32, _vp]),
     "rl8_tc_bench_mma": (_int, [_vp, _i32, _i32, _i32, _int, _int, _vp]),
+    "rl8_tc3_bench_pace": (_int, [_vp, _i32, _i32, _i32, _i32, _vp]),
+    "rl8_x3_debug_buffer": (_int, [_vp]),
     "rl8_clip_adam": (
         _int,
         [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _vp, _vp],

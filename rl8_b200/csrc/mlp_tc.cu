@@ -464,6 +464,40 @@ tc_selftest_tmem_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ 
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+// Register layout of the 16x256b TMEM load (the shape whose per-thread rows / columns match the warp-level MMA
+// fragments): in[128][32] is stored with 32x32b (thread = row), then every warp reads its 32 lanes x 32 columns as
+// two 16x256b.x4 loads (lanes +0..15 and +16..31); out[tid][0..15] / out[tid][16..31] are the registers of the two
+// loads in order.  tests/test_gpu_tc.py pins the mapping x3_update_f_kernel's gW3 pass relies on.
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_tmem_16x256b_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x;
+  if (tid < 32) tmem_alloc(&tmem_ptr, 32);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_ptr;
+  const int warp = tid >> 5;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  {
+    uint32_t v[32];
+    for (int j = 0; j < 32; ++j) v[j] = in[tid * 32 + j];
+    tmem_st32_raw(tmem + lane_base, v);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  for (int h = 0; h < 2; ++h) {
+    uint32_t v[16];
+    tmem_ld_16x256b_x4(tmem + lane_base + ((uint32_t)(16 * h) << 16), v);
+    tmem_wait_ld();
+    for (int j = 0; j < 16; ++j) out[tid * 32 + 16 * h + j] = v[j];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 32);
+}
+
 // Microbenchmark: cycles for `iters` rounds of tensor-memory reads by `blockDim.x / 32` warps,
 // each warp reading 32 lanes x (32 * width) columns per round.  mode 0: one 32x32b.x32 load +
 // wait per round; mode 1: two loads in flight per wait; mode 2: x16 loads.
@@ -650,6 +684,11 @@ extern "C" int rl8_tc_selftest_tf32(const float* A, const float* B, float* D, in
   if (!A || !B || !D || N < 16 || N > 256 || (N % 16)) return RL8_ERR_ARG;
   tc_selftest_tf32_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(A, B, D, N);
   return check_launch("tc_selftest_tf32");
+}
+extern "C" int rl8_tc_selftest_tmem_16x256b(const uint32_t* in, uint32_t* out, rl8_stream_t stream) {
+  if (!in || !out) return RL8_ERR_ARG;
+  tc_selftest_tmem_16x256b_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(in, out);
+  return check_launch("tc_selftest_tmem_16x256b");
 }
 extern "C" int rl8_tc_selftest_tmem(const uint32_t* in, uint32_t* out, rl8_stream_t stream) {
   if (!in || !out) return RL8_ERR_ARG;

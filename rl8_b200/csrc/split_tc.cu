@@ -95,6 +95,68 @@ tc3_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
 }
 
 
+// ---- pair MMA pace -----------------------------------------------------------------------------------------------
+// Every pair issues `reps` ring stages' worth of piece products (terms per K step, two K steps per stage, operands at
+// the ring's offsets; the data is whatever the shared memory holds) back to back with one commit at the end.
+// out[pair] = {SM cycles, nanoseconds} around the issue + wait of the pair's leader.
+struct SmemPace {
+  StageX<3> ring[4];
+  uint64_t bar;
+  uint32_t tmem_base;
+};
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemPace& s = *reinterpret_cast<SmemPace*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = tid; i < (int)(sizeof(s.ring) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(s.ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    mbar_init(&s.bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair(&s.tmem_base, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t idesc = instr_desc(256, n_cols, 0, 0);
+  long long c0 = 0, t0 = 0;
+  if (rank == 0 && warp == 0) {
+    c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+        const StageX<3>& stg = s.ring[r & 3];
+        for (int ks = 0; ks < 2; ++ks)
+          for (int i = 0; i < terms; ++i) {
+            const uint64_t ad = smem_desc(smem_u32(stg.a[i % 3]) + ks * 4096, 2048, 128);
+            const uint64_t bd = smem_desc(smem_u32(stg.b[(i / 3) % 3]) + ks * 4096, 2048, 128);
+            mma_bf16_pair(tmem, ad, bd, idesc, (r | ks | i) ? 1u : 0u);
+          }
+      }
+      mma_commit_pair(&s.bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait_cluster(&s.bar, 0);
+  fence_after_sync();
+  if (rank == 0 && tid == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    out[2 * (blockIdx.x >> 1)] = clock64() - c0;
+    out[2 * (blockIdx.x >> 1) + 1] = t1 - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tmem, 512);
+}
+
+
 // ---- W2 piece images ------------------------------------------------------------------------------------------------
 // The weight operand of a 256x256 contraction, split once per call into NP bf16 pieces and laid out so that the half
 // a CTA of the pair needs for one ring stage (its 128 rows, the stage's four K groups, every piece) is one contiguous
@@ -384,4 +446,20 @@ extern "C" int rl8_tc3_selftest(const float* A, const float* B, float* D, int32_
   }
   tc3_selftest_kernel<<<2, 256, sizeof(SmemSelf), (cudaStream_t)stream>>>(A, B, D, K, terms);
   return check_launch("tc3_selftest");
+}
+
+// Development hook: pace of back-to-back pair MMAs on `pairs` clusters at once (tools/bench_pair_mma.py).
+extern "C" int rl8_tc3_bench_pace(long long* out, int32_t pairs, int32_t reps, int32_t terms, int32_t n_cols,
+                                  rl8_stream_t stream) {
+  if (!out || pairs < 1 || pairs > kNumSMs / 2 || reps < 1 || terms < 1 || terms > 9 ||
+      (n_cols != 64 && n_cols != 128 && n_cols != 256))
+    return RL8_ERR_ARG;
+  cudaError_t e = cudaFuncSetAttribute(tc3_pace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(SmemPace));
+  if (e != cudaSuccess) {
+    set_last_error("cudaFuncSetAttribute", e);
+    return RL8_ERR_CUDA;
+  }
+  tc3_pace_kernel<<<2 * pairs, 128, sizeof(SmemPace), (cudaStream_t)stream>>>(out, reps, terms, n_cols);
+  return check_launch("tc3_pace");
 }

@@ -256,6 +256,19 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bits per instruction, x4 = 32 columns: thread (g = lane / 4, t = lane % 4) of the warp receives, for
+// column block k = 0..3, rows {g, g + 8} of the 16 addressed lanes and columns {8 k + 2 t, 8 k + 2 t + 1}:
+// v[4 k + 0..1] = row g, v[4 k + 2..3] = row g + 8 (the warp-level MMA accumulator layout; pinned by
+// rl8_tc_selftest_tmem_16x256b).  Issue-only: tmem_wait_ld() before the registers are used.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void reg_fence16f(float* v) {
   asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]),
                     "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]),

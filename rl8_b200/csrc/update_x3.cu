@@ -21,6 +21,17 @@
 #include "ppo_loss_math.cuh"
 #include "split_common.cuh"
 
+// Development build (make ABLATE=1): RL8_X3_ABL switches parts of the worker code off and rl8_x3_debug_buffer
+// collects the MMA warp's wait cycles (tools/ablate_x3.py, profiles/r02_x3_ablation.md).  In the production build
+// both compile to nothing.
+#ifdef RL8_X3_ABLATE
+#define X3_ABL(a) ((a).abl)
+#define X3_CLOCK() clock64()
+#else
+#define X3_ABL(a) 0
+#define X3_CLOCK() 0ll
+#endif
+
 namespace rl8 {
 
 using namespace tc;
@@ -42,6 +53,8 @@ struct UpdXArgs {
   int T, dist_kind;
   int small;             // every row count fits 31 bits: 32-bit index arithmetic
   int n_pi;              // CTA pairs [0, n_pi) run the policy network, the rest the value network
+  int abl;               // development: ablation bits (RL8_X3_ABL), 0 in production
+  unsigned long long* dbg;  // development: wait-cycle counters of pair 0 of each network (rl8_x3_debug_buffer), or null
   rl8_ppo_hparams hp;
   float inv_denom;
   // scratch per network, indexed by the chunk-local row
@@ -112,17 +125,23 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       __syncwarp();
       if (warp == 0 && elect_one()) {
         const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * 3) * kXPieceBytes;
+        if (X3_ABL(a) & 64) {
+          mbar_arrive(&s.bfull[st]);
+        } else {
         mbar_expect_tx(&s.bfull[st], 3 * kXPieceBytes);
 #pragma unroll
         for (int p = 0; p < 3; ++p)
           bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
+        }
       }
+      if (!(X3_ABL(a) & 1)) {
       float v[8];
       const uint32_t bits = h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
       if (kc < 4) m0 |= bits << (8 * kc);
       else m1 |= bits << (8 * (kc - 4));
       uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
       store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -140,6 +159,24 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     fence_after_sync();
     const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
     const int64_t rowl = tile * 256 + rank * 128 + r;  // chunk-local row of this thread's lane
+    // loss inputs of row tid (threads 0..127), requested now so that the loads land under pass 1
+    float in_act = 0.0f, in_logp = 0.0f, in_tgt = 0.0f;  // action, old log-probability, advantage (policy) / return (value)
+    bool in_valid = false;
+    if (tid < TILE) {
+      const int64_t rl = tile * 256 + rank * 128 + tid;
+      int64_t t = 0, n = 0;
+      in_valid = rl < a.Mc && minibatch_row_to_tn(a, a.row_off + rl, t, n);
+      if (in_valid) {
+        const int64_t idx = t * a.N + n;
+        if constexpr (POLICY) {
+          in_act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)((const long long*)a.actions)[idx]
+                                                       : ((const float*)a.actions)[idx];
+          in_logp = a.logp[idx], in_tgt = a.adv[idx];
+        } else {
+          in_tgt = a.ret[idx];
+        }
+      }
+    }
     // ---- pass 1: H2, its mask, head partial sums
     float dot[PN];
 #pragma unroll
@@ -151,6 +188,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       float v[32];
       tmem_ld32(acc + (uint32_t)(c2 * 32), v);
       uint32_t bits = 0u;
+      if (X3_ABL(a) & 2) { dot[0] += v[0] + v[31]; mk[c2] = 0; continue; }
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 4) {
         const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
@@ -174,12 +212,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     for (int p = 0; p < PN; ++p) s.part[cq][r][p] = dot[p];
     worker_bar_sync();
     // ---- per-row loss -> dOut (threads 0..127 own row tid)
-    if (tid < TILE) {
+    if (tid < TILE && !(X3_ABL(a) & 128)) {
       const int64_t rl = tile * 256 + rank * 128 + tid;
       float d_o[kMaxPT] = {0.0f, 0.0f, 0.0f, 0.0f};
-      int64_t t = 0, n = 0;
-      if (rl < a.Mc && minibatch_row_to_tn(a, a.row_off + rl, t, n)) {
-        const int64_t idx = t * a.N + n;
+      if (in_valid) {
         float o[PN];
 #pragma unroll
         for (int p = 0; p < PN; ++p)
@@ -187,12 +223,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         RowLoss L;
         if constexpr (POLICY) {
           if (continuous) o[1] = tanhf(o[1]);
-          const float act = a.dist_kind == RL8_DIST_CATEGORICAL ? (float)((const long long*)a.actions)[idx]
-                                                                : ((const float*)a.actions)[idx];
-          ppo_policy_row<PN>(a.dist_kind, o, act, a.logp[idx], a.adv[idx], a.hp, a.inv_denom, d_o, L);
+          ppo_policy_row<PN>(a.dist_kind, o, in_act, in_logp, in_tgt, a.hp, a.inv_denom, d_o, L);
           s_ent += L.entropy, s_pol += L.policy, s_kl += L.kl;
         } else {
-          ppo_value_row(o[0], a.ret[idx], a.hp, a.inv_denom, d_o, L);
+          ppo_value_row(o[0], in_tgt, a.hp, a.inv_denom, d_o, L);
           s_vf += L.vf;
         }
 #pragma unroll
@@ -202,31 +236,64 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       *reinterpret_cast<float4*>(s.dsm[tid]) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
     }
     worker_bar_sync();
-    // ---- pass 2: gW3[p][c] += sum_rows H2[row][c] dOut[row][p]  (lane l ends up with column col0 + l)
-    const float4 dv = *reinterpret_cast<const float4*>(s.dsm[r]);
-    const float dr[4] = {dv.x, dv.y, dv.z, dv.w};
+    // ---- pass 2: gW3[p][c] += sum_rows H2[row][c] dOut[row][p].  The accumulator is read a second time, now with
+    // the 16x256b shape: thread (g = lane / 4, t = lane % 4) receives rows {g, g + 8, g + 16, g + 24} of the warp's lane
+    // quarter and the 8 columns {8 k + 2 t, 8 k + 2 t + 1}, so four of the 32 rows are summed in registers and only
+    // the 8 lanes that share t are left to reduce: 7 shuffles per 8 columns and head output (the 32x32b shape, one row
+    // per thread, needs 31 per 32).  Lane (g, t) ends up with column col0 + 8 (g / 2) + 2 t + (g & 1).
+    const int g4 = lane >> 2, t4 = lane & 3;
+    float dr[4][PN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 dv = *reinterpret_cast<const float4*>(s.dsm[q * 32 + g4 + 8 * i]);
+      const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int p = 0; p < PN; ++p) dr[i][p] = d4[p];
+    }
 #pragma unroll
     for (int c2 = 0; c2 < 2; ++c2) {
       const int col0 = cq * 64 + c2 * 32;
-      float v[32];
-      tmem_ld32(acc + (uint32_t)(c2 * 32), v);
+      uint32_t zr[2][16];
+      tmem_ld_16x256b_x4(acc + (uint32_t)(c2 * 32), zr[0]);
+      tmem_ld_16x256b_x4(acc + (16u << 16) + (uint32_t)(c2 * 32), zr[1]);
+      tmem_wait_ld();
       if (c2 == 1) {  // last read of the accumulator: the tensor pipe may overwrite it
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);
       }
+      if (X3_ABL(a) & 4) { gw3_acc[c2][0] += __uint_as_float(zr[0][lane & 15]); continue; }
+      // H2 of the thread's 4 rows x 8 columns: hv[i][2 k + e] = row g + 8 i, column col0 + 8 k + 2 t + e
+      float hv[4][8];
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
-        v[jj] = fmaxf(v[jj] + b.x, 0.0f), v[jj + 1] = fmaxf(v[jj + 1] + b.y, 0.0f);
-        v[jj + 2] = fmaxf(v[jj + 2] + b.z, 0.0f), v[jj + 3] = fmaxf(v[jj + 3] + b.w, 0.0f);
+      for (int k = 0; k < 4; ++k) {
+        const float2 b = *reinterpret_cast<const float2*>(&s.b2[col0 + 8 * k + 2 * t4]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          hv[2 * h][2 * k] = fmaxf(__uint_as_float(zr[h][4 * k]) + b.x, 0.0f);
+          hv[2 * h][2 * k + 1] = fmaxf(__uint_as_float(zr[h][4 * k + 1]) + b.y, 0.0f);
+          hv[2 * h + 1][2 * k] = fmaxf(__uint_as_float(zr[h][4 * k + 2]) + b.x, 0.0f);
+          hv[2 * h + 1][2 * k + 1] = fmaxf(__uint_as_float(zr[h][4 * k + 3]) + b.y, 0.0f);
+        }
       }
 #pragma unroll
       for (int p = 0; p < PN; ++p) {
-        float x[32];
+        float x[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = v[i] * dr[p];
-        gw3_acc[c2][p] += transpose_reduce32(x, lane);
+        for (int j = 0; j < 8; ++j)
+          x[j] = fmaf(hv[3][j], dr[3][p], fmaf(hv[2][j], dr[2][p], fmaf(hv[1][j], dr[1][p], hv[0][j] * dr[0][p])));
+        // the 8 lanes that share t (lane bits 2..4) exchange halves: lane (g, t) keeps entry j = g
+#pragma unroll
+        for (int o = 16, n = 4; o >= 4; o >>= 1, n >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const float send = up ? x[i] : x[i + n];
+            const float keep = up ? x[i + n] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        gw3_acc[c2][p] += x[0];
       }
     }
   };
@@ -241,7 +308,9 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
 #pragma unroll
     for (int c2 = 0; c2 < 2; ++c2)
 #pragma unroll
-      for (int p = 0; p < PN; ++p) atomicAdd(a.gw3[net] + p * H + cq * 64 + c2 * 32 + lane, gw3_acc[c2][p]);
+      for (int p = 0; p < PN; ++p)  // lane (g, t) of pass 2 owns column 8 (g / 2) + 2 t + (g & 1) of its 32
+        atomicAdd(a.gw3[net] + p * H + cq * 64 + c2 * 32 + 8 * (lane >> 3) + 2 * (lane & 3) + ((lane >> 2) & 1),
+                  gw3_acc[c2][p]);
     if (tid < TILE) {
 #pragma unroll
       for (int p = 0; p < PN; ++p) {
@@ -296,12 +365,19 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
     const uint32_t idesc = instr_desc(256, H, 0, 0);
     uint32_t kcount = 0;
+    long long w_full[8] = {0, 0, 0, 0, 0, 0, 0, 0}, w_acc = 0;
+    const long long t_begin = X3_CLOCK();
     for (int64_t j = 0; j < n_my; ++j) {
       const int buf = (int)(j & 1);
+      long long c0 = X3_CLOCK();
       if (j >= 2) mbar_wait_cluster(&s.acc_empty[buf], (uint32_t)(((j >> 1) - 1) & 1));
+      w_acc += X3_CLOCK() - c0;
+#pragma unroll
       for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
         const int st = (int)(kcount % kFStages);
+        c0 = X3_CLOCK();
         mbar_wait_cluster(&s.full[st], (kcount / kFStages) & 1);
+        w_full[kc] += X3_CLOCK() - c0;
         fence_after_sync();
         if (elect_one()) {
           issue_stage<3>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
@@ -310,6 +386,13 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
         }
         __syncwarp();
       }
+    }
+    if (X3_ABL(a) >= 0 && X3_CLOCK() != 0 && a.dbg && pr == 0 && (tid & 31) == 0) {
+      unsigned long long* d = a.dbg + 16 * net;
+      for (int i = 0; i < 8; ++i) atomicAdd(d + i, (unsigned long long)w_full[i]);
+      atomicAdd(d + 8, (unsigned long long)w_acc);
+      atomicAdd(d + 9, (unsigned long long)(X3_CLOCK() - t_begin));
+      atomicAdd(d + 10, (unsigned long long)n_my);
     }
   }
   fence_before_sync();
@@ -426,6 +509,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
         for (int p = 0; p < NPB; ++p)
           bulk_g2s(s.ring[st].a[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
       }
+      if (!(X3_ABL(a) & 8)) {
       float v[8];
       const uint32_t byte = (kc < 4 ? m0 >> (8 * kc) : m1 >> (8 * (kc - 4))) & 0xffu;
       dz2_chunk<PN>(s.w3, d4, byte, stage_kgroup(kc, g) * 8, v);
@@ -433,6 +517,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
 #pragma unroll
       for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
       store_split_chunk<NPB>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -461,6 +546,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&s.acc_empty[0], 0);
       }
+      if (X3_ABL(a) & 16) { gb1_acc += v[0] + c[15]; continue; }
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int rt = cq * 64 + c4 * 16 + e;
@@ -666,6 +752,7 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
     if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
+      if (X3_ABL(a) & 32) break;
       const int g = g0 + 8 * i;
       float v[8];
       if (dz_role) {
@@ -781,6 +868,11 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------
+static unsigned long long* g_x3_dbg = nullptr;
+extern "C" int rl8_x3_debug_buffer(unsigned long long* device_counters) {
+  g_x3_dbg = device_counters;
+  return RL8_OK;
+}
 static int x3_stages() {  // development switch: bit 0 forward / loss, bit 1 input-gradient, bit 2 weight-gradient kernel
   const char* e = getenv("RL8_X3_STAGES");
   return e ? atoi(e) : 7;
@@ -843,6 +935,11 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
   a.gw1[1] = (float*)grads->vf_w1, a.gb1[1] = (float*)grads->vf_b1, a.gw2[1] = (float*)grads->vf_w2;
   a.gb2[1] = (float*)grads->vf_b2, a.gw3[1] = (float*)grads->vf_w3, a.gb3[1] = (float*)grads->vf_b3;
   a.sums = loss_sums;
+  {
+    const char* e = getenv("RL8_X3_ABL");
+    a.abl = e ? atoi(e) : 0;  // read by the kernels only in RL8_X3_ABLATE builds
+  }
+  a.dbg = g_x3_dbg;
   const NetParams np_pi = net_params(model, 0, img_f[0]), np_vf = net_params(model, 1, img_f[1]);
   const int stages = x3_stages();
   for (int64_t off = 0; off < M; off += chunk) {

@@ -95,6 +95,28 @@ def test_tmem_store_load_roundtrip() -> None:
     assert torch.equal(x.cpu(), y.cpu())
 
 
+def test_tmem_16x256b_register_layout() -> None:
+    """tcgen05.ld.16x256b.x4: thread (g = lane / 4, t = lane % 4) of a warp receives, from the 16 lanes it addresses,
+    rows {g, g + 8} and the column pairs {8 k + 2 t, 8 k + 2 t + 1} -- the layout x3_update_f_kernel's gW3 pass
+    assumes (rl8_b200/csrc/tc.cuh: tmem_ld_16x256b_x4)."""
+    from rl8_b200 import _lib as L
+
+    lib = L.load()
+    x = (torch.arange(128).view(128, 1) * 256 + torch.arange(32).view(1, 32)).to(torch.int32).to(DEV)
+    y = torch.zeros(128, 32, dtype=torch.int32, device=DEV)
+    assert lib.rl8_tc_selftest_tmem_16x256b(L.ptr(x), L.ptr(y), L.stream()) == 0
+    y = y.cpu()
+    for tid in range(128):
+        warp, lane = divmod(tid, 32)
+        g, t = divmod(lane, 4)
+        for h in range(2):
+            for k in range(4):
+                for e in range(4):
+                    row = 32 * warp + 16 * h + g + 8 * (e // 2)
+                    col = 8 * k + 2 * t + (e % 2)
+                    assert int(y[tid, 16 * h + 4 * k + e]) == row * 256 + col
+
+
 def _algo(env_name: str, dist=None, n: int = 256, t: int = 8, **kw):
     import rl8_b200.env as E
     from rl8_b200 import AlgorithmConfig
