@@ -353,6 +353,15 @@ int rl8_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   double max_norm, double lr, double beta1, double beta2, double eps,
                   int64_t step, float* norm_out, rl8_stream_t stream);
 
+/* rl8_clip_adam with the per-step scalars in device memory, for CUDA-graph replays of the update epochs: the step
+ * counter `step_dev[0]` is advanced by the call itself (bias corrections are formed from the new value, in double,
+ * as rl8_clip_adam forms them on the host) and the learning rate is read from `lr_dev[0]`.  `scratch`: 16 floats
+ * ([0] receives the gradient norm like rl8_clip_adam's norm_out).  Same reference lines as rl8_clip_adam
+ * (src/rl8/algorithms/_feedforward.py:586-593). */
+int rl8_clip_adam_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                      double max_norm, const double* lr_dev, double beta1, double beta2, double eps,
+                      long long* step_dev, float* scratch, rl8_stream_t stream);
+
 /* The clip alone -- torch.nn.utils.clip_grad_norm_(parameters, max_norm) of _feedforward.py:587-589 on the flat
  * gradient buffer: norm_out[0] = ||g||_2, g *= min(1, max_norm / (norm + 1e-6)).  For `optimizer_cls` other than
  * the fused Adam (_feedforward.py:257-260): the caller's torch optimizer then steps on parameters whose .grad are

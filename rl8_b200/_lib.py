@@ -216,6 +216,10 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         _int,
         [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _vp, _vp],
     ),
+    "rl8_clip_adam_dev": (
+        _int,
+        [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _f64, _f64, _f64, _vp, _vp, _vp],
+    ),
     "rl8_clip_grads": (_int, [_vp, _i64, _f64, _vp, _vp]),
 }
 

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import time
 from dataclasses import asdict, dataclass
 from typing import Any, Literal
@@ -369,6 +370,14 @@ class Algorithm:
         self._on_grads: Any = None
         #: number of kernels of this library launched by the last collect() / step()
         self.last_launches = {"collect": 0, "step": 0}
+        # CUDA-graph replay of GAE + the update epochs (see _graph_key): the per-step scalars live on the device
+        self._update_graphs: dict[tuple, tuple[torch.cuda.CUDAGraph, int, list[bool], int]] = {}
+        self._graph_eligible_calls = 0
+        self._lr_dev = torch.zeros(1, dtype=torch.float64, device=device)
+        self._steps_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self._lr_mirror: None | float = None
+        self._steps_mirror: None | int = None
+        self._adam_scratch = torch.zeros(16, dtype=torch.float32, device=device)
 
     # ------------------------------------------------------------------------------------
     @property
@@ -633,13 +642,88 @@ class Algorithm:
                 f"{type(self).__name__} is not buffered. Call `collect` once prior to `step`."
             )
         start = time.perf_counter_ns()
+        hp = self.hparams
+        if not self._fused_model:
+            return self._step_generic_model(start, self._enqueue_gae())
+
+        entropy_coeff = self.entropy_scheduler.coeff
+        if entropy_coeff != 0 and self.policy.distribution_cls.rl8_kind == _lib.DIST_SQUASHED_NORMAL:
+            self.policy.distribution_cls({}, self.policy.model).entropy()  # raises like the reference
+        key = self._graph_key(entropy_coeff)
+        if key is None:
+            launches, k, applied = self._enqueue_update(entropy_coeff, dev_scalars=False)
+        else:
+            launches, k, applied = self._replay_update(key, entropy_coeff)
+        accum = hp.num_minibatches if hp.accumulate_grads else 1
+        return self._finish_step(start, launches, k, applied, accum, entropy_coeff)
+
+    # -- CUDA-graph replay of the update ---------------------------------------------------------------------------
+    #: the feedforward update is a fixed launch sequence; the recurrent one keeps its own host loop
+    _graph_capable = True
+
+    def _graph_key(self, entropy_coeff: float) -> None | tuple:
+        """Key of the CUDA graph that can stand for this call's GAE + update epochs, or None when the sequence
+        depends on the host: early stopping reads a KL per minibatch, shuffled minibatches draw permutations, a
+        caller-assigned reward scale / gradient hook / non-fused optimizer are host values, NCCL calls sit between
+        the kernels when world > 1.  Everything that changes between calls of an eligible configuration lives in
+        device memory: the reward scale, the learning rate and the optimizer step count (rl8_clip_adam_dev)."""
+        hp = self.hparams
+        if (not self._graph_capable or os.environ.get("RL8_CUDA_GRAPH", "1") == "0" or _world() > 1
+                or self._exp_avg is None or hp.target_kl_div is not None or self._on_grads is not None
+                or (hp.shuffle_minibatches and hp.num_minibatches > 1) or not self.state._scale_on_device):
+            return None
+        pg = self.optimizer.param_groups[0]
+        key = (self.policy.precision, float(entropy_coeff), tuple(pg.get("betas", (0.9, 0.999))),
+               float(pg.get("eps", 1e-8)), self.buffer.hm[DataKeys.OBS].data_ptr(),
+               self.policy.model.flat_params.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        if key not in self._update_graphs and len(self._update_graphs) >= 4:
+            return None  # e.g. an entropy schedule that changes every step: not worth a capture per value
+        return key
+
+    def _replay_update(self, key: tuple, entropy_coeff: float) -> tuple[int, int, list[bool]]:
+        pg = self.optimizer.param_groups[0]
+        lr = float(pg["lr"])
+        if self._lr_mirror != lr:
+            self._lr_dev.fill_(lr)
+            self._lr_mirror = lr
+        if self._steps_mirror != self._opt_steps:  # first use, or a loaded optimizer state
+            self._steps_dev.fill_(self._opt_steps)
+            self._steps_mirror = self._opt_steps
+        entry = self._update_graphs.get(key)
+        if entry is None:
+            self._graph_eligible_calls += 1
+            if self._graph_eligible_calls < 2:
+                # the first eligible call runs eagerly: it sizes the workspaces and loads the kernels
+                res = self._enqueue_update(entropy_coeff, dev_scalars=True)
+            else:
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.current_stream().synchronize()
+                with torch.cuda.graph(graph, stream=self._capture_stream()):
+                    res = self._enqueue_update(entropy_coeff, dev_scalars=True)
+                self._update_graphs[key] = (graph, *res)
+                graph.replay()
+        else:
+            entry[0].replay()
+            res = entry[1:]
+        launches, k, applied = res
+        n_opt = sum(applied)
+        self._opt_steps += n_opt
+        self._steps_mirror = self._opt_steps
+        return launches, k, list(applied)
+
+    def _capture_stream(self) -> torch.cuda.Stream:
+        cs = getattr(self, "_capture_stream_obj", None)
+        if cs is None:
+            cs = self._capture_stream_obj = torch.cuda.Stream()
+        return cs
+
+    def _enqueue_gae(self) -> int:
+        """GAE over the buffer (the reward scale of the last collect() is read from device memory: no host round
+        trip).  Returns the number of kernels launched."""
         hp, buf, lib = self.hparams, self.buffer, self._lib
         N, T = hp.num_envs, hp.horizon
-        world = _world()
         st = _lib.stream()
         launches = 0
-
-        # -- GAE (the reward scale of the last collect() is read from device memory: no host round trip) ----------
         self._moments.zero_()
         if self.state._scale_on_device:
             rc = lib.rl8_gae_scan_dev(
@@ -659,29 +743,32 @@ class Algorithm:
         _lib.check(rc, "rl8_gae_scan")
         launches += 1
         if hp.normalize_advantages:
-            if world > 1:
+            if _world() > 1:
                 dist.all_reduce(self._moments)
             rc = lib.rl8_gae_normalize(
                 _lib.ptr(buf.hm[DataKeys.ADVANTAGES]), N, T, 1, N, _lib.ptr(self._moments), st
             )
             _lib.check(rc, "rl8_gae_normalize")
             launches += 1
+        return launches
 
-        if not self._fused_model:
-            return self._step_generic_model(start, launches)
+    def _enqueue_update(self, entropy_coeff: float, dev_scalars: bool) -> tuple[int, int, list[bool]]:
+        """GAE + the PPO epochs on the current stream.  ``dev_scalars``: the learning rate and the optimizer step
+        count are read from (and the count advanced in) device memory, so the launch sequence can be captured in a
+        CUDA graph; the caller then owns the host-side count.  Returns ``(kernel launches, minibatches processed,
+        step-boundary flag per minibatch)``."""
+        hp, lib = self.hparams, self._lib
+        world = _world()
+        st = _lib.stream()
+        launches = self._enqueue_gae()
 
-        # -- PPO epochs ---------------------------------------------------------------------
         model = self.policy.model
-        prec = self.policy.precision
         M = hp.sgd_minibatch_size
         batch = self._batch_struct()
         launch_minibatch, mb_launches = self._minibatch_launcher(batch, M)
         units, rows_per_unit = self._update_units()
 
         accum = hp.num_minibatches if hp.accumulate_grads else 1
-        entropy_coeff = self.entropy_scheduler.coeff
-        if entropy_coeff != 0 and self.policy.distribution_cls.rl8_kind == _lib.DIST_SQUASHED_NORMAL:
-            self.policy.distribution_cls({}, model).entropy()  # raises like the reference
         ppo = _lib.PpoHparams(
             hp.clip_param, hp.dual_clip_param or 0.0, entropy_coeff, hp.vf_clip_param,
             hp.vf_coeff, 1.0 / accum,
@@ -725,9 +812,18 @@ class Algorithm:
                         dist.all_reduce(self._grads)  # grads already carry 1 / (M * world)
                     if self._on_grads is not None:
                         self._on_grads(model.named_flat_views(self._grads))
-                    self._opt_steps += 1
-                    if self._exp_avg is not None:
-                        betas = pg.get("betas", (0.9, 0.999))
+                    betas = pg.get("betas", (0.9, 0.999))
+                    if dev_scalars:
+                        rc = lib.rl8_clip_adam_dev(
+                            _lib.ptr(model.flat_params), _lib.ptr(self._grads), _lib.ptr(self._exp_avg),
+                            _lib.ptr(self._exp_avg_sq), self._grads.numel(), hp.max_grad_norm,
+                            _lib.ptr(self._lr_dev), betas[0], betas[1], pg.get("eps", 1e-8),
+                            _lib.ptr(self._steps_dev), _lib.ptr(self._adam_scratch), st,
+                        )
+                        _lib.check(rc, "rl8_clip_adam_dev")
+                        launches += 1
+                    elif self._exp_avg is not None:
+                        self._opt_steps += 1
                         rc = lib.rl8_clip_adam(
                             _lib.ptr(model.flat_params), _lib.ptr(self._grads), _lib.ptr(self._exp_avg),
                             _lib.ptr(self._exp_avg_sq), self._grads.numel(), hp.max_grad_norm,
@@ -736,6 +832,7 @@ class Algorithm:
                         )
                         _lib.check(rc, "rl8_clip_adam")
                     else:  # optimizer_cls of the caller: clip here, torch steps on the flat views (.grad = self._grads)
+                        self._opt_steps += 1
                         rc = lib.rl8_clip_grads(_lib.ptr(self._grads), self._grads.numel(), hp.max_grad_norm,
                                                 _lib.ptr(self._grad_norm), st)
                         _lib.check(rc, "rl8_clip_grads")
@@ -744,8 +841,7 @@ class Algorithm:
                     self._grads.zero_()
             if stop_early:
                 break
-
-        return self._finish_step(start, launches, k, applied, accum, entropy_coeff)
+        return launches, k, applied
 
     def _finish_step(self, start: int, launches: int, k: int, applied: list[bool], accum: int,
                      entropy_coeff: float) -> StepStats:

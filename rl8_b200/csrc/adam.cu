@@ -60,6 +60,43 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   }
 }
 
+// Device-resident scalars (CUDA-graph replays: nothing of the update may be a launch argument that changes from one
+// optimizer step to the next): one thread advances the step counter and forms the step's constants in double, exactly
+// as rl8_clip_adam forms them on the host.
+__global__ void adam_consts_kernel(long long* __restrict__ step, const double* __restrict__ lr, double max_norm,
+                                   double beta1, double beta2, double eps, AdamConsts* __restrict__ out) {
+  const long long s = step[0] + 1;
+  step[0] = s;
+  const double bc1 = 1.0 - pow(beta1, (double)s);
+  const double bc2 = 1.0 - pow(beta2, (double)s);
+  AdamConsts c;
+  c.max_norm = (float)max_norm;
+  c.w1 = (float)(1.0 - beta1);
+  c.beta2 = (float)beta2;
+  c.w2 = (float)(1.0 - beta2);
+  c.bc2_sqrt = (float)sqrt(bc2);
+  c.eps = (float)eps;
+  c.neg_step_size = (float)(-(lr[0] / bc1));
+  *out = c;
+}
+__global__ void __launch_bounds__(256)
+clip_adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                     int64_t count, const AdamConsts* __restrict__ cp, const float* __restrict__ norm) {
+  const AdamConsts c = *cp;
+  const float coef = fminf(dvd(c.max_norm, add(norm[0], 1e-6f)), 1.0f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = mul(g[i], coef);
+    g[i] = gi;
+    const float mi = add(m[i], mul(c.w1, sub(gi, m[i])));
+    const float vi = add(mul(v[i], c.beta2), mul(mul(c.w2, gi), gi));
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = add(dvd(sqrtf(vi), c.bc2_sqrt), c.eps);
+    p[i] = add(p[i], mul(c.neg_step_size, dvd(mi, denom)));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 clip_scale_kernel(float* __restrict__ g, int64_t count, float max_norm, const float* __restrict__ norm) {
   const float coef = fminf(dvd(max_norm, add(norm[0], 1e-6f)), 1.0f);
@@ -106,4 +143,22 @@ extern "C" int rl8_clip_adam(float* params, float* grads, float* exp_avg, float*
   clip_adam_kernel<<<grid_for(count, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, count,
                                                         c, norm_out);
   return check_launch("clip_adam");
+}
+
+extern "C" int rl8_clip_adam_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                                 double max_norm, const double* lr_dev, double beta1, double beta2, double eps,
+                                 long long* step_dev, float* scratch, rl8_stream_t stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !scratch || count <= 0)
+    return RL8_ERR_ARG;
+  static_assert(sizeof(AdamConsts) <= 8 * sizeof(float), "AdamConsts must fit scratch[8..15]");
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamConsts* consts = reinterpret_cast<AdamConsts*>(scratch + 8);
+  grad_norm_kernel<<<1, 1024, 0, st>>>(grads, count, scratch);
+  int rc = check_launch("grad_norm");
+  if (rc) return rc;
+  adam_consts_kernel<<<1, 1, 0, st>>>(step_dev, lr_dev, max_norm, beta1, beta2, eps, consts);
+  if ((rc = check_launch("adam_consts"))) return rc;
+  clip_adam_dev_kernel<<<grid_for(count, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, count, consts,
+                                                            scratch);
+  return check_launch("clip_adam_dev");
 }

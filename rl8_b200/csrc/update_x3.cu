@@ -112,13 +112,14 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
   double s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;  // a thread sums hundreds of O(1) terms that cancel
   uint32_t kcount = 0;
 
-  auto produce = [&](int64_t tile) {
+  // stages [4 half, 4 half + 4) of a tile: K values [64 g + 32 half, +32) of this thread's row
+  auto produce = [&](int64_t tile, int half) {
     float obf[7];
     const int64_t rowl = tile * 256 + rank * 128 + rloc;
     const bool valid = load_row_obs(a, rowl, D, obf, nullptr);
     const ObsPairs ob = obs_pairs(obf);
-    uint32_t m0 = 0u, m1 = 0u;
-    for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+    uint32_t m0 = 0u;
+    for (int kc = 4 * half; kc < 4 * half + 4; ++kc, ++kcount) {
       const int st = (int)(kcount % kFStages);
       const uint32_t use = kcount / kFStages;
       if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
@@ -137,8 +138,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       if (!(X3_ABL(a) & 1)) {
       float v[8];
       const uint32_t bits = h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
-      if (kc < 4) m0 |= bits << (8 * kc);
-      else m1 |= bits << (8 * (kc - 4));
+      m0 |= bits << (8 * (kc & 3));
       uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
       store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
       }
@@ -149,11 +149,13 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         mbar_arrive_cluster(&s.full[st], 0);
       }
     }
-    // H1 mask of columns [64 g, 64 g + 64) of this row
-    if (valid) *reinterpret_cast<uint2*>(a.mask1[net] + rowl * 8 + 2 * g) = make_uint2(m0, m1);
+    // H1 mask of columns [64 g + 32 half, +32) of this row
+    if (valid) a.mask1[net][rowl * 8 + 2 * g + half] = m0;
   };
 
-  auto epilogue = [&](int64_t tile, int64_t j) {
+  // Epilogue of tile j in two parts (the second half of tile j + 1 is produced between them, so that the ring never
+  // holds less than the tensor pipe consumes during a part): 1 = pass 1 + per-row loss, 2 = the gW3 pass.
+  auto epilogue1 = [&](int64_t tile, int64_t j) {
     const int buf = (int)(j & 1);
     mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
     fence_after_sync();
@@ -236,6 +238,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       *reinterpret_cast<float4*>(s.dsm[tid]) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
     }
     worker_bar_sync();
+  };
+  auto epilogue2 = [&](int64_t j) {
+    const int buf = (int)(j & 1);
+    const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
     // ---- pass 2: gW3[p][c] += sum_rows H2[row][c] dOut[row][p].  The accumulator is read a second time, now with
     // the 16x256b shape: thread (g = lane / 4, t = lane % 4) receives rows {g, g + 8, g + 16, g + 24} of the warp's lane
     // quarter and the 8 columns {8 k + 2 t, 8 k + 2 t + 1}, so four of the 32 rows are summed in registers and only
@@ -298,10 +304,13 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     }
   };
 
-  if (n_my > 0) produce(pr);
+  if (n_my > 0) produce(pr, 0), produce(pr, 1);
   for (int64_t j = 0; j < n_my; ++j) {
-    if (j + 1 < n_my) produce(pr + (j + 1) * npairs);
-    epilogue(pr + j * npairs, j);
+    const bool more = j + 1 < n_my;
+    if (more) produce(pr + (j + 1) * npairs, 0);
+    epilogue1(pr + j * npairs, j);
+    if (more) produce(pr + (j + 1) * npairs, 1);
+    epilogue2(j);
   }
   // ---- flush
   if (n_my > 0) {

@@ -359,6 +359,7 @@ class RecurrentAlgorithm(Algorithm):
     (truncated back-propagation through time) on CUDA kernels."""
 
     _stats_reward_t0 = 1  # statistics over rewards[:, 1:-1] (src/rl8/algorithms/_recurrent.py:449)
+    _graph_capable = False  # the TBPTT host loop allocates per minibatch: not captured
 
     def __init__(self, env_cls: Any, /, config: None | RecurrentAlgorithmConfig = None) -> None:
         config = config or RecurrentAlgorithmConfig()

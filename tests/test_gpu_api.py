@@ -612,3 +612,61 @@ def test_recurrent_policy_save_load_round_trip(tmp_path) -> None:  # noqa: ANN00
     h, c = torch.randn(16, 256, device="cuda").tanh(), torch.randn(16, 256, device="cuda")
     for a, b in zip(algo.policy.step_net(x, h, c), loaded.step_net(x, h, c)):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_update_graph_replay_matches_eager(amp: bool, monkeypatch: pytest.MonkeyPatch) -> None:
+    """GAE + the update epochs replayed from a CUDA graph (learning rate and optimizer step count in device memory,
+    rl8_clip_adam_dev) give what the eager launch sequence gives: same loss statistics and parameters after four
+    Trainer-style iterations with an lr change in between, and the host-side optimizer count stays in step."""
+    import rl8_b200.env as E
+    from rl8_b200 import AlgorithmConfig
+
+    def run(graph: bool):
+        monkeypatch.setenv("RL8_CUDA_GRAPH", "1" if graph else "0")
+        torch.manual_seed(11)
+        algo = AlgorithmConfig(num_envs=512, horizon=8, enable_amp=amp, num_sgd_iters=2, sgd_minibatch_size=1024,
+                               shuffle_minibatches=False).build(E.CartPole)
+        torch.manual_seed(12)
+        stats = []
+        for it in range(4):
+            if it == 2:
+                algo.optimizer.param_groups[0]["lr"] = 3e-4
+            algo.collect()
+            stats.append(algo.step())
+        return algo, stats
+
+    eager, s_e = run(False)
+    graphed, s_g = run(True)
+    assert len(eager._update_graphs) == 0 and len(graphed._update_graphs) == 1
+    assert eager.optimizer.update_count == graphed.optimizer.update_count == 4 * 2 * 4
+    assert int(graphed._steps_dev.item()) == graphed.optimizer.update_count
+    for a, b in zip(s_e, s_g):
+        for k in ("losses/policy", "losses/vf", "losses/total", "monitors/kl_div"):
+            assert b[k] == pytest.approx(a[k], rel=1e-4, abs=1e-7), k
+    pa, pb = eager.policy.model.flat_params, graphed.policy.model.flat_params
+    # fp32 modes: identical kernels, the step constants formed by device pow / sqrt instead of libm's;
+    # bf16 mode: its gradient kernels accumulate with atomics in a run-dependent order
+    torch.testing.assert_close(pb, pa, rtol=1e-3 if amp else 1e-4, atol=2e-5 if amp else 1e-6)
+    sd_e, sd_g = eager.optimizer.state_dict(), graphed.optimizer.state_dict()
+    assert sd_e["param_groups"][0]["lr"] == sd_g["param_groups"][0]["lr"] == 3e-4
+
+
+def test_update_graph_not_used_when_the_host_decides() -> None:
+    """Early stopping, shuffled minibatches and the gradient hook keep the eager path."""
+    import rl8_b200.env as E
+    from rl8_b200 import AlgorithmConfig
+
+    for kw in ({"target_kl_div": 10.0}, {"sgd_minibatch_size": 512, "shuffle_minibatches": True}):
+        algo = AlgorithmConfig(num_envs=128, horizon=8, **kw).build(E.CartPole)
+        for _ in range(3):
+            algo.collect()
+            algo.step()
+        assert len(algo._update_graphs) == 0, kw
+    algo = AlgorithmConfig(num_envs=128, horizon=8).build(E.CartPole)
+    seen = []
+    algo._on_grads = lambda named: seen.append(len(named))
+    for _ in range(3):
+        algo.collect()
+        algo.step()
+    assert len(algo._update_graphs) == 0 and len(seen) == 3 * 4
