@@ -7,7 +7,9 @@
 //     accesses, sequential in t (exactly the reference's op order -> bit-comparable);
 //   env-major (stride_t == 1, the reference layout [N, T+1]): one env row per warp; the
 //     row is loaded coalesced in 32-step chunks and the recurrence
-//     A_t = delta_t + c*A_{t+1} is solved with a 5-step warp shuffle scan;
+//     A_t = delta_t + c*A_{t+1} is solved with a 5-step warp shuffle scan (fmaf and a reassociated sum with
+//     powers c^1..c^16: NOT the reference's rounding sequence -- within 2e-6 / 5e-6 absolute of the oracle on
+//     returns / advantages for N(0,1) inputs up to T = 70, tests/test_gpu_kernels.py; Algorithm.step() never uses it);
 //   anything else: strided sequential.
 // There are no `done` flags in the reference: every env bootstraps from
 // V_T; an optional done mask would only zero `c` and `gamma` per element.

@@ -62,6 +62,23 @@ __device__ __forceinline__ void issue_stage_split(uint32_t lead_tmem, uint32_t c
   }
 }
 
+// One operand is a 0 / 1 mask (a single exact piece, tile b[0]); the other has NP pieces: NP products per K step,
+// a0 b0 into the leading accumulator, the rest into the corrections.
+template <int NP>
+__device__ __forceinline__ void issue_stage_mask_b(uint32_t lead_tmem, uint32_t corr_tmem, const StageX<NP>& stg,
+                                                   uint32_t idesc, bool accumulate_first) {
+#pragma unroll
+  for (int ks = 0; ks < kXKc / 16; ++ks) {
+    const uint64_t bd = smem_desc(smem_u32(stg.b[0]) + ks * 4096, 2048, 128);
+#pragma unroll
+    for (int i = NP - 1; i >= 0; --i) {  // small products first
+      const uint64_t ad = smem_desc(smem_u32(stg.a[i]) + ks * 4096, 2048, 128);
+      const bool first = !accumulate_first && ks == 0 && (i == 0 || i == NP - 1);
+      mma_bf16_pair(i == 0 ? lead_tmem : corr_tmem, ad, bd, idesc, first ? 0u : 1u);
+    }
+  }
+}
+
 // [W1 | b1] in fp32, input-major: w1t[d][i] = W1[i][d] (d < D <= 7; rows D..6 unused), w1t[7][i] = b1[i]
 __device__ __forceinline__ void stage_w1t(float (*w1t)[H], const NetParams& np) {
   for (int e = threadIdx.x; e < H * 8; e += blockDim.x) {
@@ -109,6 +126,15 @@ __device__ __forceinline__ uint32_t h1_chunk(const float (*w1t)[H], const ObsPai
   return bits;
 }
 
+// eight mask bits -> eight bf16 values {0, 1} (one 16-byte operand chunk; a mask is exact in ONE piece)
+__device__ __forceinline__ uint4 mask_byte_to_bf16x8(uint32_t byte) {
+  uint32_t q[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    q[e] = ((byte >> (2 * e)) & 1u) * 0x3f80u | ((byte >> (2 * e + 1)) & 1u) * 0x3f800000u;
+  return make_uint4(q[0], q[1], q[2], q[3]);
+}
+
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // lane l of the warp returns sum over the 32 lanes m of x_m[l]  (x is destroyed): 31 shuffles
@@ -153,6 +179,7 @@ __device__ __forceinline__ bool minibatch_row_to_tn(const A& a, int64_t rw, int6
 }
 
 // split_tc.cu
-int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st);
+int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st,
+                          const float* kscale = nullptr);
 
 }  // namespace rl8

@@ -164,15 +164,21 @@ tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols) {
 //     img[kc][half = n / 128][piece][ (n % 128) * 16 + g * 2048 + (k % 8) * 2 ]     with  k / 8 = 8 g + kc
 // (the K order of StageX).  transpose = 0: X(n, k) = W2[n][k]  (forward Z2 = H1 W2^T: n = unit j, k = input i);
 // transpose = 1: X(n, k) = W2[k][n]  (backward dH1^T = W2^T dZ2^T: n = input i, k = unit j).
+// kscale (transpose = 1 only): X(n, k) = W2[k][n] * kscale[k] in fp32 -- the value network's backward operand with
+// its one-row head folded in (update_x3.cu).
 template <int NP>
 __global__ void __launch_bounds__(256) pack_w2_pieces_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img,
-                                                             int transpose) {
+                                                             int transpose, const float* __restrict__ kscale) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (n, 8 consecutive k)
   if (idx >= H * (H / 8)) return;
   const int n = idx & (H - 1), k8 = idx >> 8;
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = transpose ? w2[(k8 * 8 + e) * H + n] : w2[n * H + k8 * 8 + e];
+  if (kscale) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __fmul_rn(v[e], kscale[k8 * 8 + e]);
+  }
   const int g = k8 >> 3, kc = k8 & 7, half = n >> 7, r = n & 127;
   uint8_t* base = img + (size_t)((kc * 2 + half) * NP) * kXPieceBytes;
   uint8_t* tiles[NP];
@@ -181,9 +187,11 @@ __global__ void __launch_bounds__(256) pack_w2_pieces_kernel(const float* __rest
   store_split_chunk<NP>(tiles, (uint32_t)(r * 16 + g * 2048), v);
 }
 
-int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st) {
-  if (pieces == 3) pack_w2_pieces_kernel<3><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose);
-  else pack_w2_pieces_kernel<2><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose);
+int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st,
+                          const float* kscale) {
+  if (kscale && !transpose) return RL8_ERR_ARG;
+  if (pieces == 3) pack_w2_pieces_kernel<3><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose, kscale);
+  else pack_w2_pieces_kernel<2><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose, kscale);
   return check_launch("pack_w2_pieces");
 }
 

@@ -52,7 +52,8 @@ struct UpdXArgs {
   int64_t slab_env0, slab_nenv;  // nenv > 0: order-free traversal t-major over envs [env0, env0+nenv)
   int T, dist_kind;
   int small;             // every row count fits 31 bits: 32-bit index arithmetic
-  int n_pi;              // CTA pairs [0, n_pi) run the policy network, the rest the value network
+  int n_pi;              // CTA pairs [0, n_pi) run the policy network, the rest the value network (forward kernel)
+  int n_pi_b, n_pi_w;    // the same for the input-gradient / weight-gradient kernels (their value pairs do half the MMAs)
   int abl;               // development: ablation bits (RL8_X3_ABL), 0 in production
   unsigned long long* dbg;  // development: wait-cycle counters of pair 0 of each network (rl8_x3_debug_buffer), or null
   rl8_ppo_hparams hp;
@@ -112,14 +113,13 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
   double s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;  // a thread sums hundreds of O(1) terms that cancel
   uint32_t kcount = 0;
 
-  // stages [4 half, 4 half + 4) of a tile: K values [64 g + 32 half, +32) of this thread's row
-  auto produce = [&](int64_t tile, int half) {
+  auto produce = [&](int64_t tile) {
     float obf[7];
     const int64_t rowl = tile * 256 + rank * 128 + rloc;
     const bool valid = load_row_obs(a, rowl, D, obf, nullptr);
     const ObsPairs ob = obs_pairs(obf);
-    uint32_t m0 = 0u;
-    for (int kc = 4 * half; kc < 4 * half + 4; ++kc, ++kcount) {
+    uint32_t m0 = 0u, m1 = 0u;
+    for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
       const int st = (int)(kcount % kFStages);
       const uint32_t use = kcount / kFStages;
       if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
@@ -138,7 +138,8 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       if (!(X3_ABL(a) & 1)) {
       float v[8];
       const uint32_t bits = h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
-      m0 |= bits << (8 * (kc & 3));
+      if (kc < 4) m0 |= bits << (8 * kc);
+      else m1 |= bits << (8 * (kc - 4));
       uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
       store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
       }
@@ -149,13 +150,11 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         mbar_arrive_cluster(&s.full[st], 0);
       }
     }
-    // H1 mask of columns [64 g + 32 half, +32) of this row
-    if (valid) a.mask1[net][rowl * 8 + 2 * g + half] = m0;
+    // H1 mask of columns [64 g, 64 g + 64) of this row
+    if (valid) *reinterpret_cast<uint2*>(a.mask1[net] + rowl * 8 + 2 * g) = make_uint2(m0, m1);
   };
 
-  // Epilogue of tile j in two parts (the second half of tile j + 1 is produced between them, so that the ring never
-  // holds less than the tensor pipe consumes during a part): 1 = pass 1 + per-row loss, 2 = the gW3 pass.
-  auto epilogue1 = [&](int64_t tile, int64_t j) {
+  auto epilogue = [&](int64_t tile, int64_t j) {
     const int buf = (int)(j & 1);
     mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
     fence_after_sync();
@@ -238,10 +237,6 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       *reinterpret_cast<float4*>(s.dsm[tid]) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
     }
     worker_bar_sync();
-  };
-  auto epilogue2 = [&](int64_t j) {
-    const int buf = (int)(j & 1);
-    const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
     // ---- pass 2: gW3[p][c] += sum_rows H2[row][c] dOut[row][p].  The accumulator is read a second time, now with
     // the 16x256b shape: thread (g = lane / 4, t = lane % 4) receives rows {g, g + 8, g + 16, g + 24} of the warp's lane
     // quarter and the 8 columns {8 k + 2 t, 8 k + 2 t + 1}, so four of the 32 rows are summed in registers and only
@@ -304,13 +299,11 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     }
   };
 
-  if (n_my > 0) produce(pr, 0), produce(pr, 1);
+  // (measured: producing the second half of tile j + 1 between the passes of the epilogue changes nothing)
+  if (n_my > 0) produce(pr);
   for (int64_t j = 0; j < n_my; ++j) {
-    const bool more = j + 1 < n_my;
-    if (more) produce(pr + (j + 1) * npairs, 0);
-    epilogue1(pr + j * npairs, j);
-    if (more) produce(pr + (j + 1) * npairs, 1);
-    epilogue2(j);
+    if (j + 1 < n_my) produce(pr + (j + 1) * npairs);
+    epilogue(pr + j * npairs, j);
   }
   // ---- flush
   if (n_my > 0) {
@@ -459,7 +452,12 @@ struct SmemXB {
 };
 static_assert(sizeof(SmemXB<2>) <= 227 * 1024 && sizeof(SmemXB<3>) <= 227 * 1024, "SmemXB exceeds the 227 KB CTA limit");
 
-template <int PN, int NPB>
+// VNET (the value network, one head output): dZ2[row][j] = dOut[row] * (mask2[row][j] W3[j]), so
+//     dH1[row][i] = dOut[row] * sum_j (W3[j] W2[j][i]) mask2[row][j]
+// -- the A image is W2^T with W3 folded in (pack_w2_pieces_kernel's kscale), the B operand is the MASK itself, exact
+// in one bf16 piece (three piece products instead of six, and nothing to split), and dOut[row] multiplies the
+// accumulator column in the epilogue (it travels in slot 7 of the row's staged observations).
+template <int PN, int NPB, bool VNET>
 __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams& np, const UpdXArgs& a, int net,
                                                  int64_t pr, int64_t npairs, uint32_t rank) {
   const uint32_t tmem = s.tmem_base;
@@ -487,7 +485,9 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       const int64_t rl = tile * 256 + rt;
       float ob[7];
       const bool valid = load_row_obs(a, rl, D, ob, nullptr);
-      float4 o4 = half ? make_float4(ob[4], ob[5], ob[6], 0.0f) : make_float4(ob[0], ob[1], ob[2], ob[3]);
+      float d_row = 0.0f;
+      if (VNET && half && valid) d_row = a.dout[net][rl * 4];
+      float4 o4 = half ? make_float4(ob[4], ob[5], ob[6], d_row) : make_float4(ob[0], ob[1], ob[2], ob[3]);
       *reinterpret_cast<float4*>(&s.os[buf][rt][4 * half]) = o4;
       if (half == 0) {
         uint4 m = make_uint4(0u, 0u, 0u, 0u);
@@ -519,13 +519,17 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
           bulk_g2s(s.ring[st].a[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
       }
       if (!(X3_ABL(a) & 8)) {
-      float v[8];
       const uint32_t byte = (kc < 4 ? m0 >> (8 * kc) : m1 >> (8 * (kc - 4))) & 0xffu;
+      if constexpr (VNET) {
+        *reinterpret_cast<uint4*>(s.ring[st].b[0] + rloc * 16 + g * 2048) = mask_byte_to_bf16x8(byte);
+      } else {
+      float v[8];
       dz2_chunk<PN>(s.w3, d4, byte, stage_kgroup(kc, g) * 8, v);
       uint8_t* tiles[NPB];
 #pragma unroll
       for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
       store_split_chunk<NPB>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+      }
       }
       fence_async_smem();
       __syncwarp();
@@ -560,9 +564,10 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       for (int e = 0; e < 16; ++e) {
         const int rt = cq * 64 + c4 * 16 + e;
         const uint32_t word = s.m1s[buf][rt][q];
-        const float dz1 = (word >> lane) & 1u ? v[e] + c[e] : 0.0f;
         const float4 oa = *reinterpret_cast<const float4*>(&s.os[buf][rt][0]);
         const float4 ob = *reinterpret_cast<const float4*>(&s.os[buf][rt][4]);
+        float dz1 = (word >> lane) & 1u ? v[e] + c[e] : 0.0f;
+        if constexpr (VNET) dz1 *= ob.w;  // dOut of the row
         gb1_acc += dz1;
         gw1_acc[0] = fmaf(dz1, oa.x, gw1_acc[0]), gw1_acc[1] = fmaf(dz1, oa.y, gw1_acc[1]);
         gw1_acc[2] = fmaf(dz1, oa.z, gw1_acc[2]), gw1_acc[3] = fmaf(dz1, oa.w, gw1_acc[3]);
@@ -608,10 +613,10 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank();
   const int64_t pair = blockIdx.x >> 1, pairs_all = gridDim.x >> 1;
-  const int n_pi = (int)(pairs_all / 2);
+  const int n_pi = a.n_pi_b;
   const int net = pair < n_pi ? 0 : 1;
   const int64_t pr = net ? pair - n_pi : pair, npairs = net ? pairs_all - n_pi : n_pi;
-  const NetParams np = net ? np_vf : np_pi;  // w2_img: the TRANSPOSED NPB-piece image
+  const NetParams np = net ? np_vf : np_pi;  // w2_img: the TRANSPOSED NPB-piece image (value network: W3 folded in)
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < kStages; ++i) {
@@ -634,8 +639,8 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   fence_after_sync();
   const uint32_t tmem = s.tmem_base;
   if (warp < 16) {
-    if (net == 0) update_b_workers<P, NPB>(s, np, a, 0, pr, npairs, rank);
-    else update_b_workers<1, NPB>(s, np, a, 1, pr, npairs, rank);
+    if (net == 0) update_b_workers<P, NPB, false>(s, np, a, 0, pr, npairs, rank);
+    else update_b_workers<1, NPB, true>(s, np, a, 1, pr, npairs, rank);
   } else if (rank == 0) {
     const int64_t ntiles = (a.Mc + 255) / 256;
     const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
@@ -648,7 +653,8 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
         mbar_wait_cluster(&s.full[st], (kcount / kStages) & 1);
         fence_after_sync();
         if (elect_one()) {
-          issue_stage_split<NPB>(tmem, tmem + (uint32_t)H, s.ring[st], idesc, kc > 0);
+          if (net == 0) issue_stage_split<NPB>(tmem, tmem + (uint32_t)H, s.ring[st], idesc, kc > 0);
+          else issue_stage_mask_b<NPB>(tmem, tmem + (uint32_t)H, s.ring[st], idesc, kc > 0);
           mma_commit_pair(&s.empty[st]);
           if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[0]);
         }
@@ -802,6 +808,113 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
   }
 }
 
+// The value network (one head output): dZ2[row][j] = dOut[row] mask2[row][j] W3[j], so
+//     gW2[j][i] = W3[j] * sum_rows mask2[row][j] * (dOut[row] H1[row][i]),   gb2[j] = W3[j] * sum_rows dOut[row] mask2[row][j]
+// -- the A operand is the mask itself (exact in one bf16 piece: NPB piece products instead of NPB (NPB + 1) / 2, one
+// 16-byte store per chunk instead of a three-way split), dOut scales the H1 row before it is split, and W3[j] multiplies
+// the accumulator row in the flush.  Every worker warp w produces column group w of BOTH operands for the 32 rows of a
+// stage (lane = row).
+template <int NPB>
+__device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetParams& np, const UpdXArgs& a,
+                                                      int64_t pr, int64_t npairs, uint32_t rank) {
+  constexpr int net = 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = np.D;
+  const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
+  const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
+  constexpr int kWStages = SmemXW<NPB>::kStages;
+  const int g = warp;  // column group of this CTA's 128-column half, both operands
+  float gb2_acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) gb2_acc[e] = 0.0f;
+  // inputs of this lane's row of a stage: obs[0..6], dOut in slot 7, the 4 mask bytes... (one word) of group g / 4
+  float in_f[8];
+  uint32_t in_m = 0u;
+  auto load_inputs = [&](int64_t k, float* f, uint32_t& m) {
+    const int64_t rowl = (pr + k * npairs) * kXKc + lane;
+    load_row_obs(a, rowl, D, f, nullptr);
+    f[7] = 0.0f, m = 0u;
+    if (rowl < a.Mc) {
+      f[7] = a.dout[net][rowl * 4];
+      m = a.mask2[net][rowl * 8 + 4 * rank + (g >> 2)];
+    }
+  };
+  const int64_t nflush = (n_my + kFlushStages - 1) / kFlushStages;
+  int64_t next_flush = 0;
+  auto flush = [&](int64_t f) {
+    mbar_wait_cluster(&s.flush_full, (uint32_t)(f & 1));
+    fence_after_sync();
+    const int q = warp & 3, cq = warp >> 2;
+    const int j = 128 * (int)rank + q * 32 + lane;  // lane = unit j of this CTA's half, 256 columns i
+    const float w3j = s.w3[0][j];
+    float* dst = a.gw2[net] + (int64_t)j * H + cq * 64;
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      float v[16], c[16];
+      const uint32_t at = s.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64 + h * 16);
+      tmem_ld16_nowait(at, v);
+      tmem_ld16_nowait(at + H, c);
+      tmem_wait_ld();
+      reg_fence16f(v);
+      reg_fence16f(c);
+      if (h == 3) {
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.flush_empty, 0);
+      }
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        red_add_v4(dst + h * 16 + e, w3j * (v[e] + c[e]), w3j * (v[e + 1] + c[e + 1]), w3j * (v[e + 2] + c[e + 2]),
+                   w3j * (v[e + 3] + c[e + 3]));
+    }
+  };
+  if (n_my > 0) load_inputs(0, in_f, in_m);
+  for (int64_t k = 0; k < n_my; ++k) {
+    float cur_f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur_f[i] = in_f[i];
+    const uint32_t cur_m = in_m;
+    if (k + 1 < n_my) load_inputs(k + 1, in_f, in_m);
+    const int st = (int)(k % kWStages);
+    const uint32_t use = (uint32_t)(k / kWStages);
+    if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
+    if (!(X3_ABL(a) & 32)) {
+      // A: the mask bits of unit group g  (tile a[0] only)
+      const uint32_t byte = (cur_m >> (8 * (g & 3))) & 0xffu;
+      *reinterpret_cast<uint4*>(s.ring[st].a[0] + lane * 16 + g * 512) = mask_byte_to_bf16x8(byte);
+      const float d = cur_f[7];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gb2_acc[e] += (byte >> e) & 1u ? d : 0.0f;
+      // B: dOut[row] * H1[row][input group g], split
+      float v[8];
+      h1_chunk(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= d;
+      uint8_t* tiles[NPB];
+#pragma unroll
+      for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
+      store_split_chunk<NPB>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);
+    while (next_flush < nflush) {
+      const int64_t last = (next_flush + 1) * kFlushStages < n_my ? (next_flush + 1) * kFlushStages - 1 : n_my - 1;
+      const int64_t due = last + kWStages - 1 < n_my - 1 ? last + kWStages - 1 : n_my - 1;
+      if (k < due) break;
+      flush(next_flush++);
+    }
+  }
+  if (n_my > 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float w = warp_sum(gb2_acc[e]);
+      const int j = 128 * (int)rank + 8 * g + e;
+      if (lane == 0) atomicAdd(a.gb2[net] + j, s.w3[0][j] * w);
+    }
+  }
+}
+
 template <int P, int NPB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXThreads, 1)
 x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
@@ -811,7 +924,7 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank();
   const int64_t pair = blockIdx.x >> 1, pairs_all = gridDim.x >> 1;
-  const int n_pi = (int)(pairs_all / 2);
+  const int n_pi = a.n_pi_w;
   const int net = pair < n_pi ? 0 : 1;
   const int64_t pr = net ? pair - n_pi : pair, npairs = net ? pairs_all - n_pi : n_pi;
   const NetParams np = net ? np_vf : np_pi;
@@ -837,7 +950,7 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   fence_after_sync();
   if (warp < 16) {
     if (net == 0) update_w_workers<P, NPB>(s, np, a, 0, pr, npairs, rank);
-    else update_w_workers<1, NPB>(s, np, a, 1, pr, npairs, rank);
+    else update_w_workers_vnet<NPB>(s, np, a, pr, npairs, rank);
   } else if (rank == 0) {
     const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
     const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
@@ -850,7 +963,23 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
       if (fresh && k > 0) mbar_wait_cluster(&s.flush_empty, (uint32_t)((nf - 1) & 1));
       mbar_wait_cluster_sleep(&s.full[st], (uint32_t)((k / kWStages) & 1));
       fence_after_sync();
-      if (elect_one()) {
+      if (net == 1) {  // (warp-uniform: elect.sync needs the whole warp)
+        if (elect_one()) {
+        // value network: A = the mask (tile a[0]), NPB products a0 b_i per K step, a0 b0 -> leading accumulator
+#pragma unroll
+        for (int ks = 0; ks < kXKc / 16; ++ks) {
+          const uint64_t ad = smem_desc(smem_u32(s.ring[st].a[0]) + ks * 256, 128, 512);
+#pragma unroll
+          for (int i = NPB - 1; i >= 0; --i) {
+            const uint64_t bd = smem_desc(smem_u32(s.ring[st].b[i]) + ks * 256, 128, 512);
+            const bool first = fresh && ks == 0 && (i == 0 || i == NPB - 1);
+            mma_bf16_pair(s.tmem_base + (i == 0 ? 0u : (uint32_t)H), ad, bd, idesc, first ? 0u : 1u);
+          }
+        }
+        mma_commit_pair(&s.empty[st]);
+        if ((k + 1) % kFlushStages == 0 || k == n_my - 1) mma_commit_pair(&s.flush_full);
+        }
+      } else if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < kXKc / 16; ++ks) {
 #pragma unroll
@@ -898,6 +1027,14 @@ static int x3_policy_pairs(int pairs) {
   return n;
 }
 
+static int x3_gradient_policy_pairs(const char* env, int pairs) {
+  const char* e = getenv(env);  // tuning knob
+  int n = e ? atoi(e) : (40 * pairs + 36) / 74;  // measured: 37 -> 2.48 / 2.57 ms (b / w), 40 -> 2.29 / 2.50, 43 -> 2.45 / 2.74
+  if (n < 1) n = 1;
+  if (n > pairs - 1) n = pairs - 1;
+  return n;
+}
+
 int64_t ppo_x3_workspace(const rl8_model*, int64_t max_rows) {
   const int64_t chunk = max_rows < kXChunkRows ? max_rows : kXChunkRows;
   // forward images (3 pieces) + transposed images (2 pieces) of both networks, scratch of both networks
@@ -920,7 +1057,7 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
   for (int net = 0; net < 2; ++net) {
     const float* w2 = net ? model->vf_w2 : model->pi_w2;
     if ((rc = launch_pack_w2_pieces(w2, img_f[net], 0, 3, st))) return rc;
-    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, npb, st))) return rc;
+    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, npb, st, net ? model->vf_w3 : nullptr))) return rc;
   }
   UpdXArgs a;
   for (int net = 0; net < 2; ++net) {
@@ -958,6 +1095,8 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
     int pairs = (int)(2 * ntiles < kNumSMs / 2 ? 2 * ntiles : kNumSMs / 2);
     if (pairs < 2) pairs = 2;
     a.n_pi = pairs == kNumSMs / 2 ? x3_policy_pairs(pairs) : pairs / 2;
+    // value pairs of the gradient kernels issue half the piece products: the policy network gets 40 of 74 pairs
+    a.n_pi_b = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_B", pairs);
     if (stages & 1) {
 #define RL8_UPDF(PV)                                                                                  \
   case PV:                                                                                            \
@@ -994,6 +1133,7 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
       const int64_t nst = ceil_div(a.Mc, kXKc);
       int wpairs = (int)(nst < kNumSMs / 2 ? nst : kNumSMs / 2);
       if (wpairs < 2) wpairs = 2;
+      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs);
 #define RL8_UPDW(PV)                                                                                  \
   case PV:                                                                                            \
     if (npb == 2) {                                                                                   \
