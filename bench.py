@@ -13,9 +13,10 @@ supplied from pinned host memory every step (H2D inside the timed region) and th
 back (D2H).  Working set per step (buffer 112 MB + activations) exceeds nothing by itself,
 so an L2 flush (write of a 256 MB buffer) runs between timed iterations.
 
-``--impl reference`` times the CPU restatement of the reference's own algorithm
-(``oracle/ppo_oracle.py``, bit-exact with the upstream code on the build container, plain
-torch on all host cores) on a bounded sample of the same workload.
+``--impl reference`` times the UNMODIFIED reference (``oracle/_ref``, staged by ``tools/stage_ref.py`` from the
+upstream tree, run behind ``oracle/refshim`` with ``device="cpu"`` on all host cores) on the same workload; only
+when ``oracle/_ref`` is absent does it fall back to the CPU restatement ``oracle/ppo_oracle.py``
+(``cpu_baseline.kind`` says which).
 """
 
 from __future__ import annotations
@@ -746,11 +747,16 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
                       " split-bf16 pair MMAs, operands recomputed from 80 B/row of scratch)",
             "bound": "tensor", "achieved": flops / ms / 1e9, "peak": burst / 6.0, "unit": "TFLOP/s",
             "frac": flops / ms / 1e9 / (burst / 6.0), "traffic": NCU_TRAFFIC_X3.get((a.workload, M)), "ms": ms,
-            "rows": M, "dtype": "f32", "mma_tflops": 6.0 * flops / ms / 1e9,
+            "rows": M, "dtype": "f32",
+            # bf16 piece products actually issued per row: policy network 6 + 6 + 6, value network 6 + 3 + 3 (its
+            # gradient contractions take the ReLU mask as a one-piece operand)
+            "mma_tflops": M * 30.0 * 2.0 * H * H / ms / 1e9, "mma_frac": M * 30.0 * 2.0 * H * H / ms / 1e9 / burst,
             "traffic_source": ("ncu --set full, profiles/r02_x3_update_ncu_summary.md"
                                if (a.workload, M) in NCU_TRAFFIC_X3 else None),
             "peak_source": peaks["source"] + " bf16 burst / 6 (six bf16 piece products per fp32 product; `achieved`"
-                                             " counts fp32-equivalent FLOPs, `mma_tflops` the bf16 work issued)",
+                                             " counts the algorithm's fp32 FLOPs; `mma_tflops` / `mma_frac` count the"
+                                             " bf16 piece products actually issued -- 30 per row, not 36: two of the"
+                                             " value network's contractions need three -- against the plain burst peak)",
         }
     traffic = NCU_TRAFFIC.get((a.workload, M)) if dtype == "bf16" else None
     return {
