@@ -73,7 +73,8 @@ __device__ __forceinline__ void issue_stage_mask_b(uint32_t lead_tmem, uint32_t 
 #pragma unroll
     for (int i = NP - 1; i >= 0; --i) {  // small products first
       const uint64_t ad = smem_desc(smem_u32(stg.a[i]) + ks * 4096, 2048, 128);
-      const bool first = !accumulate_first && ks == 0 && (i == 0 || i == NP - 1);
+      // lead_tmem == corr_tmem: one accumulator, only the first product issued (i = NP - 1) overwrites it
+      const bool first = !accumulate_first && ks == 0 && (i == NP - 1 || (i == 0 && lead_tmem != corr_tmem));
       mma_bf16_pair(i == 0 ? lead_tmem : corr_tmem, ad, bd, idesc, first ? 0u : 1u);
     }
   }

@@ -145,10 +145,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_wait(&s.bfull[st], use & 1);
-        mbar_arrive_cluster(&s.full[st], 0);
-      }
+      if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);  // (the bulk copy reports through warp 16, see the kernel)
     }
     // H1 mask of columns [64 g, 64 g + 64) of this row
     if (valid) *reinterpret_cast<uint2*>(a.mask1[net] + rowl * 8 + 2 * g) = make_uint2(m0, m1);
@@ -338,7 +335,7 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < kFStages; ++i) {
-      mbar_init(&s.full[i], 32);
+      mbar_init(&s.full[i], 33);  // 32 worker warps of the pair + the peer's bulk copy (forwarded by its warp 16)
       mbar_init(&s.bfull[i], 1);
       mbar_init(&s.empty[i], 1);
     }
@@ -379,6 +376,7 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
         const int st = (int)(kcount % kFStages);
         c0 = X3_CLOCK();
         mbar_wait_cluster(&s.full[st], (kcount / kFStages) & 1);
+        mbar_wait(&s.bfull[st], (kcount / kFStages) & 1);  // this CTA's half of the W2 stage has landed
         w_full[kc] += X3_CLOCK() - c0;
         fence_after_sync();
         if (elect_one()) {
@@ -395,6 +393,19 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
       atomicAdd(d + 8, (unsigned long long)w_acc);
       atomicAdd(d + 9, (unsigned long long)(X3_CLOCK() - t_begin));
       atomicAdd(d + 10, (unsigned long long)n_my);
+    }
+  }
+  else {
+    // peer CTA, warp 16: tells the leader's full[] barrier when THIS CTA's half of a W2 stage has landed, so that no
+    // worker warp waits for a bulk copy
+    const int64_t ntiles = (a.Mc + 255) / 256;
+    const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
+    const uint32_t total = (uint32_t)(n_my * (H / kXKc));
+    for (uint32_t kcount = 0; kcount < total; ++kcount) {
+      const int st = (int)(kcount % kFStages);
+      mbar_wait(&s.bfull[st], (kcount / kFStages) & 1);
+      if ((tid & 31) == 0) mbar_arrive_cluster(&s.full[st], 0);
+      __syncwarp();
     }
   }
   fence_before_sync();
@@ -533,40 +544,35 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_wait(&s.bfull[st], use & 1);
-        mbar_arrive_cluster(&s.full[st], 0);
-      }
+      if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);  // (the bulk copy reports through warp 16, see the kernel)
     }
   };
 
   auto epilogue = [&](int64_t j) {
     const int buf = (int)(j & 1);
     worker_bar_sync();  // os / m1s of this tile are complete
-    mbar_wait_cluster(&s.acc_full[0], (uint32_t)(j & 1));
+    mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
     fence_after_sync();
-    const uint32_t acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+    const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
 #pragma unroll 1
     for (int c4 = 0; c4 < 4; ++c4) {
-      float v[16], c[16];
+      float v[16];
       tmem_ld16_nowait(acc + (uint32_t)(c4 * 16), v);
-      tmem_ld16_nowait(acc + (uint32_t)(H + c4 * 16), c);
       tmem_wait_ld();
       reg_fence16f(v);
-      reg_fence16f(c);
-      if (c4 == 3) {  // both accumulators have been read: the tensor pipe may start the next tile
+      if (c4 == 3) {  // the accumulator has been read: the tensor pipe may reuse it for tile j + 2
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&s.acc_empty[0], 0);
+        if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);
       }
-      if (X3_ABL(a) & 16) { gb1_acc += v[0] + c[15]; continue; }
+      if (X3_ABL(a) & 16) { gb1_acc += v[0] + v[15]; continue; }
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int rt = cq * 64 + c4 * 16 + e;
         const uint32_t word = s.m1s[buf][rt][q];
         const float4 oa = *reinterpret_cast<const float4*>(&s.os[buf][rt][0]);
         const float4 ob = *reinterpret_cast<const float4*>(&s.os[buf][rt][4]);
-        float dz1 = (word >> lane) & 1u ? v[e] + c[e] : 0.0f;
+        float dz1 = (word >> lane) & 1u ? v[e] : 0.0f;
         if constexpr (VNET) dz1 *= ob.w;  // dOut of the row
         gb1_acc += dz1;
         gw1_acc[0] = fmaf(dz1, oa.x, gw1_acc[0]), gw1_acc[1] = fmaf(dz1, oa.y, gw1_acc[1]);
@@ -578,22 +584,19 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
     worker_bar_sync();  // os / m1s of this buffer may be rewritten
   };
 
-  // One accumulator pair (leading + corrections = all 512 columns): the tensor pipe cannot start tile j + 1 before
-  // the epilogue of tile j has read it.  The workers therefore stage as much of tile j + 1 as the ring holds, run the
-  // epilogue (the pipe restarts as soon as the reads are done and finds kStages stages waiting), then the rest.
-  constexpr int kAhead = kStages < kTileStages ? kStages : kTileStages;
+  // Two 256-column accumulators (one per tile parity, like the forward kernel: K = 256 is 96 instructions into one
+  // accumulator, whose per-instruction truncation stays below 1e-5 of a gradient): the tensor pipe works on tile
+  // j + 1 while the workers run the epilogue of tile j.
   if (n_my > 0) {
     begin_tile(pr, 0);
     produce(0, kTileStages);
   }
   for (int64_t j = 0; j < n_my; ++j) {
-    const bool more = j + 1 < n_my;
-    if (more) {
+    if (j + 1 < n_my) {
       begin_tile(pr + (j + 1) * npairs, j + 1);
-      produce(0, kAhead);
+      produce(0, kTileStages);
     }
     epilogue(j);
-    if (more) produce(kAhead, kTileStages);
   }
   if (n_my > 0) {
     const int i = 128 * (int)rank + q * 32 + lane;
@@ -620,7 +623,7 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&s.full[i], 32);
+      mbar_init(&s.full[i], 33);  // 32 worker warps of the pair + the peer's bulk copy (forwarded by its warp 16)
       mbar_init(&s.bfull[i], 1);
       mbar_init(&s.empty[i], 1);
     }
@@ -647,19 +650,34 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     const uint32_t idesc = instr_desc(256, H, 0, 0);
     uint32_t kcount = 0;
     for (int64_t j = 0; j < n_my; ++j) {
-      if (j >= 1) mbar_wait_cluster(&s.acc_empty[0], (uint32_t)((j - 1) & 1));
+      const int buf = (int)(j & 1);
+      if (j >= 2) mbar_wait_cluster(&s.acc_empty[buf], (uint32_t)(((j >> 1) - 1) & 1));
       for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
         const int st = (int)(kcount % kStages);
         mbar_wait_cluster(&s.full[st], (kcount / kStages) & 1);
+        mbar_wait(&s.bfull[st], (kcount / kStages) & 1);  // this CTA's half of the W2^T stage has landed
         fence_after_sync();
         if (elect_one()) {
-          if (net == 0) issue_stage_split<NPB>(tmem, tmem + (uint32_t)H, s.ring[st], idesc, kc > 0);
-          else issue_stage_mask_b<NPB>(tmem, tmem + (uint32_t)H, s.ring[st], idesc, kc > 0);
+          const uint32_t acc = tmem + (uint32_t)(buf * H);
+          if (net == 0) issue_stage<NPB>(acc, s.ring[st], idesc, kc > 0);
+          else issue_stage_mask_b<NPB>(acc, acc, s.ring[st], idesc, kc > 0);
           mma_commit_pair(&s.empty[st]);
-          if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[0]);
+          if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[buf]);
         }
         __syncwarp();
       }
+    }
+  }
+  else {
+    // peer CTA, warp 16: forwards the landing of this CTA's W2^T stages to the leader's full[] barriers
+    const int64_t ntiles = (a.Mc + 255) / 256;
+    const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
+    const uint32_t total = (uint32_t)(n_my * (H / kXKc));
+    for (uint32_t kcount = 0; kcount < total; ++kcount) {
+      const int st = (int)(kcount % kStages);
+      mbar_wait(&s.bfull[st], (kcount / kStages) & 1);
+      if ((tid & 31) == 0) mbar_arrive_cluster(&s.full[st], 0);
+      __syncwarp();
     }
   }
   fence_before_sync();
@@ -1021,15 +1039,15 @@ static int x3_backward_pieces() {  // 3: six piece products in the gradient cont
 }
 static int x3_policy_pairs(int pairs) {
   const char* e = getenv("RL8_X3_POLICY_PAIRS");  // tuning knob: the policy network's epilogue is the heavier one
-  int n = e ? atoi(e) : (pairs * 21 + 18) / 37;   // 42 of 74
+  int n = e ? atoi(e) : (pairs * 20 + 18) / 37;   // 40 of 74 (measured: 40 -> 2.23, 42 -> 2.30, 44 -> 2.44 ms)
   if (n < 1) n = 1;
   if (n > pairs - 1) n = pairs - 1;
   return n;
 }
 
-static int x3_gradient_policy_pairs(const char* env, int pairs) {
+static int x3_gradient_policy_pairs(const char* env, int pairs, int of74) {
   const char* e = getenv(env);  // tuning knob
-  int n = e ? atoi(e) : (40 * pairs + 36) / 74;  // measured: 37 -> 2.48 / 2.57 ms (b / w), 40 -> 2.29 / 2.50, 43 -> 2.45 / 2.74
+  int n = e ? atoi(e) : (of74 * pairs + 36) / 74;
   if (n < 1) n = 1;
   if (n > pairs - 1) n = pairs - 1;
   return n;
@@ -1095,8 +1113,9 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
     int pairs = (int)(2 * ntiles < kNumSMs / 2 ? 2 * ntiles : kNumSMs / 2);
     if (pairs < 2) pairs = 2;
     a.n_pi = pairs == kNumSMs / 2 ? x3_policy_pairs(pairs) : pairs / 2;
-    // value pairs of the gradient kernels issue half the piece products: the policy network gets 40 of 74 pairs
-    a.n_pi_b = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_B", pairs);
+    // value pairs of the gradient kernels issue half the piece products: the policy network gets 42 of 74 pairs
+    // (measured, b: 38 -> 2.16, 40 -> 2.05, 42 -> 1.98, 44 -> 2.08 ms)
+    a.n_pi_b = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_B", pairs, 42);
     if (stages & 1) {
 #define RL8_UPDF(PV)                                                                                  \
   case PV:                                                                                            \
@@ -1133,7 +1152,7 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
       const int64_t nst = ceil_div(a.Mc, kXKc);
       int wpairs = (int)(nst < kNumSMs / 2 ? nst : kNumSMs / 2);
       if (wpairs < 2) wpairs = 2;
-      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs);
+      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 39);  // 38 -> 2.45, 40 -> 2.50, 43 -> 2.74 ms
 #define RL8_UPDW(PV)                                                                                  \
   case PV:                                                                                            \
     if (npb == 2) {                                                                                   \
