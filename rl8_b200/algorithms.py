@@ -674,7 +674,9 @@ class Algorithm:
             return None
         pg = self.optimizer.param_groups[0]
         key = (self.policy.precision, float(entropy_coeff), tuple(pg.get("betas", (0.9, 0.999))),
-               float(pg.get("eps", 1e-8)), self.buffer.hm[DataKeys.OBS].data_ptr(),
+               float(pg.get("eps", 1e-8)), hp.clip_param, hp.dual_clip_param, hp.vf_clip_param, hp.vf_coeff,
+               hp.max_grad_norm, hp.gamma, hp.gae_lambda, hp.normalize_advantages, hp.num_sgd_iters,
+               hp.sgd_minibatch_size, hp.accumulate_grads, self.buffer.hm[DataKeys.OBS].data_ptr(),
                self.policy.model.flat_params.data_ptr(), torch.cuda.current_stream().cuda_stream)
         if key not in self._update_graphs and len(self._update_graphs) >= 4:
             return None  # e.g. an entropy schedule that changes every step: not worth a capture per value

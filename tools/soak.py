@@ -1,5 +1,6 @@
-"""Soak run: many Trainer.step() iterations on the bf16 path (feedforward and recurrent), checking that every
-statistic stays finite and that returns improve -- a cheap guard against races that a single step would hide."""
+"""Soak run: many Trainer.step() iterations on the fp32 tensor-core path (the default: split-bf16 kernels, update
+replayed from a CUDA graph) and on the bf16 path (feedforward and recurrent), checking that every statistic stays
+finite and that returns improve -- a cheap guard against races that a single step would hide."""
 import math
 import sys
 import time
@@ -14,6 +15,9 @@ from rl8_b200 import AlgorithmConfig, RecurrentAlgorithmConfig, RecurrentTrainer
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 torch.manual_seed(0)
 for name, trainer, n in (
+    ("CartPole ff fp32-tc N=65536", Trainer(AlgorithmConfig(num_envs=65536, horizon=32).build(E.CartPole)), max(20, steps // 4)),
+    ("Pendulum squashed fp32-tc N=8192, 4 shuffled minibatches",
+     Trainer(AlgorithmConfig(num_envs=8192, horizon=32, sgd_minibatch_size=65536).build(E.Pendulum)), max(20, steps // 4)),
     ("CartPole ff bf16 N=65536", Trainer(AlgorithmConfig(num_envs=65536, horizon=32, enable_amp=True).build(E.CartPole)), steps),
     ("CartPole ff bf16 N=1000 (ragged tiles), shuffled minibatches",
      Trainer(AlgorithmConfig(num_envs=1000, horizon=16, enable_amp=True, sgd_minibatch_size=3200).build(E.CartPole)), steps),
