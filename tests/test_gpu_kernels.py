@@ -439,3 +439,38 @@ def test_clip_adam_matches_torch() -> None:
     # moments mix +-O(1) terms: compare against their own scale, not element-wise ulp
     close(m, st["exp_avg"], rtol=1e-5, atol=1e-7)
     close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+
+
+def test_clip_adam_device_scalars_match_torch() -> None:
+    """rl8_clip_adam_dev (learning rate and step count in device memory: the form a CUDA graph replays) against
+    torch.optim.Adam + clip_grad_norm_, with the learning rate changed between steps."""
+    L, lib = _lib()
+    n = 135_684
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=gen)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    scratch = torch.zeros(16, device=DEV)
+    lr_dev = torch.full((1,), 1e-3, dtype=torch.float64, device=DEV)
+    step_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for step in range(1, 8):
+        if step == 4:
+            opt.param_groups[0]["lr"] = 2.5e-4
+            lr_dev.fill_(2.5e-4)
+        scale = 10.0 if step % 2 else 0.01
+        g = torch.randn(n, generator=gen) * scale
+        p_ref.grad = g.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([p_ref], 5.0)
+        opt.step()
+        gd = g.to(DEV)
+        rc = lib.rl8_clip_adam_dev(L.ptr(p), L.ptr(gd), L.ptr(m), L.ptr(v), n, 5.0, L.ptr(lr_dev), 0.9, 0.999, 1e-8,
+                                   L.ptr(step_dev), L.ptr(scratch), L.stream())
+        assert rc == 0
+        assert int(step_dev.item()) == step
+        close(scratch[:1], ref_norm.reshape(1), rtol=1e-6, atol=0)
+        close(p, p_ref.detach(), rtol=1e-6, atol=1e-7)
+    st = opt.state[p_ref]
+    close(m, st["exp_avg"], rtol=1e-5, atol=1e-7)
+    close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-9)
