@@ -52,32 +52,44 @@ lstm_heads_fwd_kernel(const float* __restrict__ h, int64_t rows, const float* __
   }
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    const float4 x0 = ld_stream4(h + r * kTH + lane * 8), x1 = ld_stream4(h + r * kTH + lane * 8 + 4);
-    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-    float acc[P + 1];
+  // two rows per trip: both rows' loads are in flight before the first dot product (the streaming loads are
+  // volatile asm, the compiler does not hoist them across iterations by itself)
+  for (int64_t r0 = warp; r0 < rows; r0 += 2 * nwarps) {
+    const int64_t r1 = r0 + nwarps;
+    const bool two = r1 < rows;
+    float4 xa[2], xb[2];
+    xa[0] = ld_stream4(h + r0 * kTH + lane * 8), xb[0] = ld_stream4(h + r0 * kTH + lane * 8 + 4);
+    xa[1] = xb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (two) xa[1] = ld_stream4(h + r1 * kTH + lane * 8), xb[1] = ld_stream4(h + r1 * kTH + lane * 8 + 4);
 #pragma unroll
-    for (int p = 0; p <= P; ++p) {
-      float sum = 0.0f;
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const int64_t r = u ? r1 : r0;
+      const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+      float acc[P + 1];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sum = fmaf(x[i], w[p][i], sum);
-      acc[p] = warp_sum(sum);
-    }
-    if (lane == 0) {
+      for (int p = 0; p <= P; ++p) {
+        float sum = 0.0f;
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        float v = acc[p] + pi_b[p];
-        if (tanh_col1 && p == 1) v = tanhf(v);
-        out_pi[r * P + p] = v;
+        for (int i = 0; i < 8; ++i) sum = fmaf(x[i], w[p][i], sum);
+        acc[p] = warp_sum(sum);
       }
-      out_vf[r] = acc[P] + vf_b[0];
+      if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          float v = acc[p] + pi_b[p];
+          if (tanh_col1 && p == 1) v = tanhf(v);
+          out_pi[r * P + p] = v;
+        }
+        out_vf[r] = acc[P] + vf_b[0];
+      }
     }
   }
 }
 
 int launch_lstm_heads_fwd(const float* h, int64_t rows, int P, const float* pi_w, const float* pi_b, const float* vf_w,
                           const float* vf_b, float* out_pi, float* out_vf, int tanh_col1, cudaStream_t st) {
-  const int grid = grid_for(rows * 32, 256, 8, 2);
+  const int grid = grid_for(rows * 32, 256, 8, 1);  // one resident wave: the head weights are loaded once per warp
 #define RL8_HEADS(PV)                                                                                             \
   case PV:                                                                                                        \
     lstm_heads_fwd_kernel<PV><<<grid, 256, 0, st>>>(h, rows, pi_w, pi_b, vf_w, vf_b, out_pi, out_vf, tanh_col1);   \
