@@ -449,15 +449,18 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
                                tc && k + 1 < L ? hb + (int64_t)(k + 1) * hb_bytes : nullptr,
                                tc ? zb + (int64_t)k * dgb_bytes : nullptr)))
         return rc;
+    }
+    {  // the losses of all L steps of the chunk in one launch (nothing in the forward replay depends on them)
       LossArgs la{};
       la.dist_kind = b->dist_kind, la.P = P, la.M = R;
-      la.out_pi = opi, la.out_vf = ovf;
+      la.out_pi = out_pi, la.out_vf = out_vf;
       la.actions = b->actions, la.logp_old = b->logp, la.advantages = b->advantages;
-      la.returns = b->returns, la.rows = map.rows, la.row_begin = 0;
+      la.returns = b->returns, la.rows = rows_k, la.row_begin = 0;
       la.T = b->T, la.N = b->N, la.hp = *hp;
       la.inv_denom = (float)((double)hp->loss_scale / denom);
-      la.dout_pi = dout_pi + (int64_t)k * C * kMaxP, la.dout_vf = dout_vf + (int64_t)k * C;
+      la.dout_pi = dout_pi, la.dout_vf = dout_vf;
       la.gb3_pi = (float*)g->pi_b, la.gb3_vf = (float*)g->vf_b, la.sums = loss_sums;
+      la.steps = L, la.pi_stride = C * kMaxP, la.vf_stride = C, la.rows_stride = R;
       if ((rc = launch_ppo_loss(la, st))) return rc;
     }
 

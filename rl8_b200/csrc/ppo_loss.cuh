@@ -27,6 +27,10 @@ struct LossArgs {
   float* gb3_vf;       // [1]
   double* sums;        // [5] += entropy, policy, vf, kl, count
   int log_std_direct;  // continuous head: dout_pi[:, 1] is d/d(log_std) itself, not d/d(pre-tanh output)
+  // steps > 1: the launch covers `steps` blocks of M rows (the time steps of a TBPTT chunk); block k reads / writes
+  // out_pi + k * pi_stride, out_vf + k * vf_stride (dout_* likewise) and rows + k * rows_stride.  0 means 1.
+  int steps;
+  int64_t pi_stride, vf_stride, rows_stride;
 };
 
 int launch_ppo_loss(const LossArgs& a, cudaStream_t st);
