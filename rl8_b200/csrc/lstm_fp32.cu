@@ -442,12 +442,18 @@ int lstm_ppo_minibatch_fp32(const rl8_lstm_model* m, const rl8_lstm_model* g,
       float* h_k = hbuf + (int64_t)k * C * kLH;
       const float* h_prev = k ? h_k - C * kLH : h0;
       const float* c_prev = k ? c_k - C * kLH : c0;
-      float* opi = out_pi + (int64_t)k * C * kMaxP;
-      float* ovf = out_vf + (int64_t)k * C;
-      if ((rc = lstm_step_fp32(m, map, R, h_prev, c_prev, h_k, c_k, act_k, act_k, opi, ovf, continuous, prec, st,
-                               tc ? hb + (int64_t)k * hb_bytes : nullptr,
+      // (no heads here: nothing in the replay depends on them, they follow for all L steps in one pass over hbuf)
+      if ((rc = lstm_step_fp32(m, map, R, h_prev, c_prev, h_k, c_k, act_k, act_k, nullptr, nullptr, continuous, prec,
+                               st, tc ? hb + (int64_t)k * hb_bytes : nullptr,
                                tc && k + 1 < L ? hb + (int64_t)(k + 1) * hb_bytes : nullptr,
                                tc ? zb + (int64_t)k * dgb_bytes : nullptr)))
+        return rc;
+    }
+    {
+      HeadBlocks blocks;
+      blocks.steps = L, blocks.h_stride = C, blocks.pi_stride = C * kMaxP, blocks.vf_stride = C;
+      if ((rc = launch_lstm_heads_fwd(hbuf, R, m->P, m->pi_w, m->pi_b, m->vf_w, m->vf_b, out_pi, out_vf, continuous, st,
+                                      blocks)))
         return rc;
     }
     {  // the losses of all L steps of the chunk in one launch (nothing in the forward replay depends on them)

@@ -40,7 +40,7 @@ template <int P>
 __global__ void __launch_bounds__(256)
 lstm_heads_fwd_kernel(const float* __restrict__ h, int64_t rows, const float* __restrict__ pi_w,
                       const float* __restrict__ pi_b, const float* __restrict__ vf_w, const float* __restrict__ vf_b,
-                      float* __restrict__ out_pi, float* __restrict__ out_vf, int tanh_col1) {
+                      float* __restrict__ out_pi, float* __restrict__ out_vf, int tanh_col1, HeadBlocks hb) {
   const int lane = threadIdx.x & 31;
   float w[P + 1][8];
 #pragma unroll
@@ -54,17 +54,25 @@ lstm_heads_fwd_kernel(const float* __restrict__ h, int64_t rows, const float* __
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   // two rows per trip: both rows' loads are in flight before the first dot product (the streaming loads are
   // volatile asm, the compiler does not hoist them across iterations by itself)
-  for (int64_t r0 = warp; r0 < rows; r0 += 2 * nwarps) {
+  // row ra of the launch = row r of block ra / rows (the time steps of a TBPTT chunk, or one block)
+  auto locate = [&](int64_t ra, int64_t& hrow, int64_t& pi_at, int64_t& vf_at) {
+    const int64_t blk = hb.steps > 1 ? ra / rows : 0, r = ra - blk * rows;
+    hrow = blk * hb.h_stride + r, pi_at = blk * hb.pi_stride + r * P, vf_at = blk * hb.vf_stride + r;
+  };
+  const int64_t total = rows * (hb.steps > 1 ? hb.steps : 1);
+  for (int64_t r0 = warp; r0 < total; r0 += 2 * nwarps) {
     const int64_t r1 = r0 + nwarps;
-    const bool two = r1 < rows;
+    const bool two = r1 < total;
+    int64_t hr[2] = {0, 0}, pa[2] = {0, 0}, va[2] = {0, 0};
+    locate(r0, hr[0], pa[0], va[0]);
+    if (two) locate(r1, hr[1], pa[1], va[1]);
     float4 xa[2], xb[2];
-    xa[0] = ld_stream4(h + r0 * kTH + lane * 8), xb[0] = ld_stream4(h + r0 * kTH + lane * 8 + 4);
+    xa[0] = ld_stream4(h + hr[0] * kTH + lane * 8), xb[0] = ld_stream4(h + hr[0] * kTH + lane * 8 + 4);
     xa[1] = xb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (two) xa[1] = ld_stream4(h + r1 * kTH + lane * 8), xb[1] = ld_stream4(h + r1 * kTH + lane * 8 + 4);
+    if (two) xa[1] = ld_stream4(h + hr[1] * kTH + lane * 8), xb[1] = ld_stream4(h + hr[1] * kTH + lane * 8 + 4);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !two) break;
-      const int64_t r = u ? r1 : r0;
       const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
       float acc[P + 1];
 #pragma unroll
@@ -79,20 +87,22 @@ lstm_heads_fwd_kernel(const float* __restrict__ h, int64_t rows, const float* __
         for (int p = 0; p < P; ++p) {
           float v = acc[p] + pi_b[p];
           if (tanh_col1 && p == 1) v = tanhf(v);
-          out_pi[r * P + p] = v;
+          out_pi[pa[u] + p] = v;
         }
-        out_vf[r] = acc[P] + vf_b[0];
+        out_vf[va[u]] = acc[P] + vf_b[0];
       }
     }
   }
 }
 
 int launch_lstm_heads_fwd(const float* h, int64_t rows, int P, const float* pi_w, const float* pi_b, const float* vf_w,
-                          const float* vf_b, float* out_pi, float* out_vf, int tanh_col1, cudaStream_t st) {
-  const int grid = grid_for(rows * 32, 256, 8, 1);  // one resident wave: the head weights are loaded once per warp
+                          const float* vf_b, float* out_pi, float* out_vf, int tanh_col1, cudaStream_t st,
+                          HeadBlocks hb) {
+  // one resident wave: the head weights are loaded once per warp
+  const int grid = grid_for(rows * (hb.steps > 1 ? hb.steps : 1) * 32, 256, 8, 1);
 #define RL8_HEADS(PV)                                                                                             \
   case PV:                                                                                                        \
-    lstm_heads_fwd_kernel<PV><<<grid, 256, 0, st>>>(h, rows, pi_w, pi_b, vf_w, vf_b, out_pi, out_vf, tanh_col1);   \
+    lstm_heads_fwd_kernel<PV><<<grid, 256, 0, st>>>(h, rows, pi_w, pi_b, vf_w, vf_b, out_pi, out_vf, tanh_col1, hb); \
     break;
   switch (P) {
     RL8_HEADS(2) RL8_HEADS(3) RL8_HEADS(4) RL8_HEADS(5) RL8_HEADS(6) RL8_HEADS(7) RL8_HEADS(8)

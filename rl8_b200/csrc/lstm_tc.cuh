@@ -22,9 +22,16 @@ struct LstmBwdArgs {
   int D, has_dc_in;
   int64_t rows, rows_pad, rows_per_block;  // rows_per_block: multiple of 32
 };
-// out_pi[rows][P] = pi_b + h pi_w^T (column 1 tanh'ed when tanh_col1), out_vf[rows] = vf_b + h vf_w^T: one pass over h
+// out_pi[rows][P] = pi_b + h pi_w^T (column 1 tanh'ed when tanh_col1), out_vf[rows] = vf_b + h vf_w^T: one pass over h.
+// HeadBlocks: steps > 1 -> the launch covers `steps` blocks of `rows` rows (the time steps of a TBPTT chunk); block k
+// reads h + k * h_stride rows and writes out_pi + k * pi_stride, out_vf + k * vf_stride (strides in elements of each).
+struct HeadBlocks {
+  int steps = 1;
+  int64_t h_stride = 0, pi_stride = 0, vf_stride = 0;
+};
 int launch_lstm_heads_fwd(const float* h, int64_t rows, int P, const float* pi_w, const float* pi_b, const float* vf_w,
-                          const float* vf_b, float* out_pi, float* out_vf, int tanh_col1, cudaStream_t st);
+                          const float* vf_b, float* out_pi, float* out_vf, int tanh_col1, cudaStream_t st,
+                          HeadBlocks hb = HeadBlocks());
 
 // dG_k (bf16 T128), dL/dc for step k-1, [x | 1] (bf16 T128) and the head weight gradients of one BPTT step
 int launch_lstm_cell_bwd_tc(const LstmBwdArgs& args, int P, cudaStream_t st);
