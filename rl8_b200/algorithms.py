@@ -677,6 +677,7 @@ class Algorithm:
                float(pg.get("eps", 1e-8)), hp.clip_param, hp.dual_clip_param, hp.vf_clip_param, hp.vf_coeff,
                hp.max_grad_norm, hp.gamma, hp.gae_lambda, hp.normalize_advantages, hp.num_sgd_iters,
                hp.sgd_minibatch_size, hp.accumulate_grads, self.buffer.hm[DataKeys.OBS].data_ptr(),
+               self._ws["ppo"].data_ptr() if "ppo" in self._ws else 0,  # a re-sized workspace invalidates the capture
                self.policy.model.flat_params.data_ptr(), torch.cuda.current_stream().cuda_stream)
         if key not in self._update_graphs and len(self._update_graphs) >= 4:
             return None  # e.g. an entropy schedule that changes every step: not worth a capture per value
