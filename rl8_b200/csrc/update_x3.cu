@@ -233,23 +233,14 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       }
       *reinterpret_cast<float4*>(s.dsm[tid]) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
     }
-    worker_bar_sync();
     // ---- pass 2: gW3[p][c] += sum_rows H2[row][c] dOut[row][p].  The accumulator is read a second time, now with
     // the 16x256b shape: thread (g = lane / 4, t = lane % 4) receives rows {g, g + 8, g + 16, g + 24} of the warp's lane
     // quarter and the 8 columns {8 k + 2 t, 8 k + 2 t + 1}, so four of the 32 rows are summed in registers and only
     // the 8 lanes that share t are left to reduce: 7 shuffles per 8 columns and head output (the 32x32b shape, one row
     // per thread, needs 31 per 32).  Lane (g, t) ends up with column col0 + 8 (g / 2) + 2 t + (g & 1).
     const int g4 = lane >> 2, t4 = lane & 3;
-    float dr[4][PN];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 dv = *reinterpret_cast<const float4*>(s.dsm[q * 32 + g4 + 8 * i]);
-      const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-      for (int p = 0; p < PN; ++p) dr[i][p] = d4[p];
-    }
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
+    // H2 of the thread's 4 rows x 8 columns of column block c2: hv[i][2 k + e] = row g + 8 i, column col0 + 8 k + 2 t + e
+    auto load_h2 = [&](int c2, float (*hv)[8]) {
       const int col0 = cq * 64 + c2 * 32;
       uint32_t zr[2][16];
       tmem_ld_16x256b_x4(acc + (uint32_t)(c2 * 32), zr[0]);
@@ -260,9 +251,6 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);
       }
-      if (X3_ABL(a) & 4) { gw3_acc[c2][0] += __uint_as_float(zr[0][lane & 15]); continue; }
-      // H2 of the thread's 4 rows x 8 columns: hv[i][2 k + e] = row g + 8 i, column col0 + 8 k + 2 t + e
-      float hv[4][8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 b = *reinterpret_cast<const float2*>(&s.b2[col0 + 8 * k + 2 * t4]);
@@ -274,6 +262,22 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
           hv[2 * h + 1][2 * k + 1] = fmaxf(__uint_as_float(zr[h][4 * k + 3]) + b.y, 0.0f);
         }
       }
+    };
+    float hv[4][8];
+    load_h2(0, hv);      // does not need dOut: the 12 warps without loss rows do it under the loss phase
+    worker_bar_sync();   // dsm (dOut of the tile's rows) is complete
+    float dr[4][PN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 dv = *reinterpret_cast<const float4*>(s.dsm[q * 32 + g4 + 8 * i]);
+      const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int p = 0; p < PN; ++p) dr[i][p] = d4[p];
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      if (c2 == 1) load_h2(1, hv);
+      if (X3_ABL(a) & 4) { gw3_acc[c2][0] += hv[0][lane & 7]; continue; }
 #pragma unroll
       for (int p = 0; p < PN; ++p) {
         float x[8];
