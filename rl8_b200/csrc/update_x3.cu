@@ -492,9 +492,12 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   float d4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   uint32_t m0 = 0u, m1 = 0u;
 
-  auto begin_tile = [&](int64_t tile, int64_t j) {
-    const int buf = (int)(j & 1);
-    // epilogue inputs of the tile: obs and this CTA's mask1 words of all 256 rows
+  // The inputs of a tile are requested one tile ahead (fetch) and handed over when the tile starts (begin_tile):
+  // the global-load latency hides under the production and epilogue of the tile in between.
+  float4 pf_o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), pf_d = pf_o4;
+  uint4 pf_m1 = make_uint4(0u, 0u, 0u, 0u);
+  uint2 pf_m2 = make_uint2(0u, 0u);
+  auto fetch = [&](int64_t tile) {
     {
       const int rt = tid & 255, half = tid >> 8;  // row of the tile; slots 4 half .. 4 half + 3
       const int64_t rl = tile * 256 + rt;
@@ -502,23 +505,25 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       const bool valid = load_row_obs(a, rl, D, ob, nullptr);
       float d_row = 0.0f;
       if (VNET && half && valid) d_row = a.dout[net][rl * 4];
-      float4 o4 = half ? make_float4(ob[4], ob[5], ob[6], d_row) : make_float4(ob[0], ob[1], ob[2], ob[3]);
-      *reinterpret_cast<float4*>(&s.os[buf][rt][4 * half]) = o4;
-      if (half == 0) {
-        uint4 m = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) m = *reinterpret_cast<const uint4*>(a.mask1[net] + rl * 8 + 4 * rank);
-        *reinterpret_cast<uint4*>(s.m1s[buf][rt]) = m;
-      }
+      pf_o4 = half ? make_float4(ob[4], ob[5], ob[6], d_row) : make_float4(ob[0], ob[1], ob[2], ob[3]);
+      pf_m1 = make_uint4(0u, 0u, 0u, 0u);
+      if (half == 0 && valid) pf_m1 = *reinterpret_cast<const uint4*>(a.mask1[net] + rl * 8 + 4 * rank);
     }
     const int64_t rowl = tile * 256 + rank * 128 + rloc;
-    d4[0] = d4[1] = d4[2] = d4[3] = 0.0f;
-    m0 = m1 = 0u;
+    pf_d = make_float4(0.0f, 0.0f, 0.0f, 0.0f), pf_m2 = make_uint2(0u, 0u);
     if (rowl < a.Mc) {
-      const float4 d = *reinterpret_cast<const float4*>(a.dout[net] + rowl * 4);
-      d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
-      const uint2 m = *reinterpret_cast<const uint2*>(a.mask2[net] + rowl * 8 + 2 * g);
-      m0 = m.x, m1 = m.y;
+      if (!VNET) pf_d = *reinterpret_cast<const float4*>(a.dout[net] + rowl * 4);
+      pf_m2 = *reinterpret_cast<const uint2*>(a.mask2[net] + rowl * 8 + 2 * g);
     }
+  };
+  auto begin_tile = [&](int64_t j) {
+    const int buf = (int)(j & 1);
+    // epilogue inputs of the tile: obs and this CTA's mask1 words of all 256 rows
+    const int rt = tid & 255, half = tid >> 8;
+    *reinterpret_cast<float4*>(&s.os[buf][rt][4 * half]) = pf_o4;
+    if (half == 0) *reinterpret_cast<uint4*>(s.m1s[buf][rt]) = pf_m1;
+    d4[0] = pf_d.x, d4[1] = pf_d.y, d4[2] = pf_d.z, d4[3] = pf_d.w;
+    m0 = pf_m2.x, m1 = pf_m2.y;
   };
   auto produce = [&](int kc0, int kc1) {
     for (int kc = kc0; kc < kc1; ++kc, ++kcount) {
@@ -592,12 +597,15 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   // accumulator, whose per-instruction truncation stays below 1e-5 of a gradient): the tensor pipe works on tile
   // j + 1 while the workers run the epilogue of tile j.
   if (n_my > 0) {
-    begin_tile(pr, 0);
+    fetch(pr);
+    begin_tile(0);
+    if (n_my > 1) fetch(pr + npairs);
     produce(0, kTileStages);
   }
   for (int64_t j = 0; j < n_my; ++j) {
     if (j + 1 < n_my) {
-      begin_tile(pr + (j + 1) * npairs, j + 1);
+      begin_tile(j + 1);
+      if (j + 2 < n_my) fetch(pr + (j + 2) * npairs);
       produce(0, kTileStages);
     }
     epilogue(j);
