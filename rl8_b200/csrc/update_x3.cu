@@ -91,6 +91,10 @@ struct SmemXF {
   float w3[kMaxPT][H];          //   4096
   float part[4][TILE][kMaxPT];  //   8192  head partial sums per column quarter
   float dsm[TILE][kMaxPT];      //   2048  dOut of the tile's rows (pass 2)
+  // running sums of the 128 loss threads (thread tid owns slot tid): kept here, not in registers -- every one of the
+  // 512 worker threads would carry them through the whole kernel at 96 registers per thread
+  double lsum[TILE][4];         //   4096  entropy, policy, vf, kl
+  float gb3s[TILE][kMaxPT];     //   2048  sum of dOut (head bias gradient)
   uint64_t full[kFStages], bfull[kFStages], empty[kFStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
@@ -107,10 +111,13 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
   const int64_t ntiles = (a.Mc + 255) / 256;
   const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
   const bool continuous = POLICY && a.dist_kind != RL8_DIST_CATEGORICAL;
-  float b3[PN], gb3_acc[PN], gw3_acc[2][PN];
+  float gw3_acc[2][PN];
 #pragma unroll
-  for (int p = 0; p < PN; ++p) b3[p] = np.b3[p], gb3_acc[p] = 0.0f, gw3_acc[0][p] = gw3_acc[1][p] = 0.0f;
-  double s_ent = 0, s_pol = 0, s_vf = 0, s_kl = 0;  // a thread sums hundreds of O(1) terms that cancel
+  for (int p = 0; p < PN; ++p) gw3_acc[0][p] = gw3_acc[1][p] = 0.0f;
+  if (tid < TILE) {  // (doubles: a thread sums hundreds of O(1) terms that cancel)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s.lsum[tid][i] = 0.0, s.gb3s[tid][i] = 0.0f;
+  }
   uint32_t kcount = 0;
 
   auto produce = [&](int64_t tile) {
@@ -217,18 +224,18 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         float o[PN];
 #pragma unroll
         for (int p = 0; p < PN; ++p)
-          o[p] = ((s.part[0][tid][p] + s.part[1][tid][p]) + (s.part[2][tid][p] + s.part[3][tid][p])) + b3[p];
+          o[p] = ((s.part[0][tid][p] + s.part[1][tid][p]) + (s.part[2][tid][p] + s.part[3][tid][p])) + __ldg(np.b3 + p);
         RowLoss L;
         if constexpr (POLICY) {
           if (continuous) o[1] = tanhf(o[1]);
           ppo_policy_row<PN>(a.dist_kind, o, in_act, in_logp, in_tgt, a.hp, a.inv_denom, d_o, L);
-          s_ent += L.entropy, s_pol += L.policy, s_kl += L.kl;
+          s.lsum[tid][0] += L.entropy, s.lsum[tid][1] += L.policy, s.lsum[tid][3] += L.kl;
         } else {
           ppo_value_row(o[0], in_tgt, a.hp, a.inv_denom, d_o, L);
-          s_vf += L.vf;
+          s.lsum[tid][2] += L.vf;
         }
 #pragma unroll
-        for (int p = 0; p < PN; ++p) gb3_acc[p] += d_o[p];
+        for (int p = 0; p < PN; ++p) s.gb3s[tid][p] += d_o[p];
         *reinterpret_cast<float4*>(a.dout[net] + rl * 4) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
       }
       *reinterpret_cast<float4*>(s.dsm[tid]) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
@@ -317,12 +324,15 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     if (tid < TILE) {
 #pragma unroll
       for (int p = 0; p < PN; ++p) {
-        const float w = warp_sum(gb3_acc[p]);
+        const float w = warp_sum(s.gb3s[tid][p]);
         if (lane == 0) atomicAdd(a.gb3[net] + p, w);
       }
     }
   }
-  sv[0] = s_ent, sv[1] = s_pol, sv[2] = s_vf, sv[3] = s_kl;
+  if (tid < TILE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sv[i] = s.lsum[tid][i];
+  }
 }
 
 template <int P>
