@@ -407,8 +407,9 @@ int rl8_tc_selftest_tf32(const float* A, const float* B, float* D, int32_t N, rl
 /* D[256][256] = A[256][K] * B[256][K]^T through tcgen05.mma.cta_group::2 (one cluster of two CTAs, M = 256,
  * each CTA staging its 128 rows of A and its 128-row half of B) with fp32 operands split into three bf16
  * pieces and the piece products selected by `terms` accumulated in fp32 tensor memory (bit 0 a0b0, 1 a0b1,
- * 2 a1b0, 3 a1b1, 4 a0b2, 5 a2b0; 63 = the fp32-accurate form of RL8_PREC_FP32, 7 = the two-piece form).
- * Pins the pair plumbing and measures each term set's accuracy.  K % 32 == 0. */
+ * 2 a1b0, 3 a1b1, 4 a0b2, 5 a2b0; 63 = the fp32-accurate bf16 form, 7 = the two-piece form).  Bit 6: the
+ * pieces are fp16 (two per operand, term bits 0..3; 64 + 7 = the update kernels' form; the caller keeps the
+ * operands inside fp16's range).  Pins the pair plumbing and measures each term set's accuracy.  K % 32 == 0. */
 int rl8_tc3_selftest(const float* A, const float* B, float* D, int32_t K, int32_t terms, rl8_stream_t stream);
 
 /* out[128][128] = in[128][128] (32-bit words) through a tensor-memory store / load round trip

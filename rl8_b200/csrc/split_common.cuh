@@ -10,7 +10,27 @@ using namespace tc;
 constexpr int kXKc = 32;                              // contraction values per ring stage (two K = 16 instructions)
 constexpr int kXPieceBytes = TILE * (kXKc / 8) * 16;  // 8192: one piece of one operand stage, [128 rows][4 column groups]
 constexpr int kXThreads = 544;                        // 16 worker warps + the TMEM / MMA warp
-constexpr int kXImgBytes = (H / kXKc) * 2 * 3 * kXPieceBytes;  // 393216: W2 piece image (three pieces)
+constexpr int kXImgBytes = (H / kXKc) * 2 * 3 * kXPieceBytes;  // 393216: W2 piece image (room for three pieces)
+
+// Piece format of the update kernels (update_x3.cu): two fp16 pieces + power-of-two operand scales (three piece
+// products per fp32 product), or -- make X3_BF16=1, the first form of this path -- three bf16 pieces (six).
+#ifndef RL8_X3_F16
+#define RL8_X3_F16 1
+#endif
+constexpr bool kUF16 = RL8_X3_F16 != 0;
+constexpr int kUNP = kUF16 ? 2 : 3;  // pieces per operand of the forward contraction
+__host__ __device__ constexpr uint32_t upd_idesc(int a_mn_major, int b_mn_major) {
+  return kUF16 ? instr_desc_f16(256, H, a_mn_major, b_mn_major) : instr_desc(256, H, a_mn_major, b_mn_major);
+}
+
+// Magnitudes behind the operand scales of the fp16 form; device memory, rewritten by every rl8_ppo_minibatch call.
+struct X3Scales {
+  float w2f[2];      // power-of-two scale of the forward W2 piece image, per network (pack_w2_pieces_kernel)
+  float w2b[2];      // ... of the transposed image (value network: with W3 folded in)
+  uint32_t dmax[2];  // bits of max |dOut| over the rows seen so far, per network (forward kernel, atomicMax)
+  uint32_t omax;     // bits of max |obs| over the T slabs of the batch (absmax_bits_kernel)
+  uint32_t pad;
+};
 
 // One ring stage of a K-major operand pair: piece tiles [128 rows][4 column groups of 8 K values],
 // off(r, c) = r * 16 + c * 2048  (LBO 2048 = next K group, SBO 128 = next 8 rows).
@@ -80,12 +100,42 @@ __device__ __forceinline__ void issue_stage_mask_b(uint32_t lead_tmem, uint32_t 
   }
 }
 
-// [W1 | b1] in fp32, input-major: w1t[d][i] = W1[i][d] (d < D <= 7; rows D..6 unused), w1t[7][i] = b1[i]
-__device__ __forceinline__ void stage_w1t(float (*w1t)[H], const NetParams& np) {
+// [W1 | b1] in fp32, input-major: w1t[d][i] = W1[i][d] (d < D <= 7; rows D..6 unused), w1t[7][i] = b1[i];
+// scale: a power of two (exact) -- h1_chunk then yields scale * H1, bit for bit
+__device__ __forceinline__ void stage_w1t(float (*w1t)[H], const NetParams& np, float scale = 1.0f) {
   for (int e = threadIdx.x; e < H * 8; e += blockDim.x) {
     const int i = e & (H - 1), d = e >> 8;
-    w1t[d][i] = d < np.D ? np.w1[i * np.D + d] : (d == 7 ? np.b1[i] : 0.0f);
+    w1t[d][i] = scale * (d < np.D ? np.w1[i * np.D + d] : (d == 7 ? np.b1[i] : 0.0f));
   }
+}
+// max over the block of a non-negative value (all threads call; red: >= 32 floats of shared memory)
+__device__ __forceinline__ float block_max_nonneg(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = 0.0f;
+  for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m = fmaxf(m, red[w]);
+  return m;
+}
+// Bound of H1 = relu(W1 obs + b1) over every row whose |obs| <= omax:  max_i (|b1[i]| + omax sum_d |W1[i][d]|)
+__device__ __forceinline__ float h1_bound(const NetParams& np, float omax, float* red) {
+  float b = 0.0f;
+  if (threadIdx.x < H) {
+    const int i = threadIdx.x;
+    float sum = 0.0f;
+    for (int d = 0; d < np.D; ++d) sum += fabsf(np.w1[i * np.D + d]);
+    b = fabsf(np.b1[i]) + omax * sum;
+  }
+  return block_max_nonneg(b, red);
+}
+// max_j sum_p |W3[p][j]|: dZ2 = [H2 > 0] .* (dOut W3) is bounded by max |dOut| times this
+__device__ __forceinline__ float w3_colsum_bound(const NetParams& np, float* red) {
+  float b = 0.0f;
+  if (threadIdx.x < H)
+    for (int p = 0; p < np.P; ++p) b += fabsf(np.w3[p * H + threadIdx.x]);
+  return block_max_nonneg(b, red);
 }
 // the row's observations duplicated into register pairs (operands of the packed FMAs)
 struct ObsPairs {
@@ -127,12 +177,14 @@ __device__ __forceinline__ uint32_t h1_chunk(const float (*w1t)[H], const ObsPai
   return bits;
 }
 
-// eight mask bits -> eight bf16 values {0, 1} (one 16-byte operand chunk; a mask is exact in ONE piece)
+// eight mask bits -> eight 16-bit values {0, 1} (one 16-byte operand chunk; a mask is exact in ONE piece)
+template <bool F16 = false>
 __device__ __forceinline__ uint4 mask_byte_to_bf16x8(uint32_t byte) {
+  constexpr uint32_t one = F16 ? 0x3c00u : 0x3f80u;
   uint32_t q[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e)
-    q[e] = ((byte >> (2 * e)) & 1u) * 0x3f80u | ((byte >> (2 * e + 1)) & 1u) * 0x3f800000u;
+    q[e] = ((byte >> (2 * e)) & 1u) * one | ((byte >> (2 * e + 1)) & 1u) * (one << 16);
   return make_uint4(q[0], q[1], q[2], q[3]);
 }
 
@@ -180,7 +232,10 @@ __device__ __forceinline__ bool minibatch_row_to_tn(const A& a, int64_t rw, int6
 }
 
 // split_tc.cu
+// pieces = 3 / 2: bf16 pieces;  pieces = -2: two fp16 pieces of W2 * s, the power of two s written to *scale_out
 int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st,
-                          const float* kscale = nullptr);
+                          const float* kscale = nullptr, float* scale_out = nullptr);
+// *out_bits = max(*out_bits, bits of max |x[i]|)  (NaNs are skipped)
+int launch_absmax_bits(const float* x, int64_t n, uint32_t* out_bits, cudaStream_t st);
 
 }  // namespace rl8

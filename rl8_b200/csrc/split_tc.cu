@@ -40,7 +40,8 @@ tc3_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
   const uint32_t tmem = s.tmem_base;
   uint8_t* const a_tiles[3] = {s.a[0], s.a[1], s.a[2]};
   uint8_t* const b_tiles[3] = {s.b[0], s.b[1], s.b[2]};
-  const uint32_t idesc = instr_desc(256, 256, 0, 0);
+  const bool f16 = (terms & 64) != 0;  // two fp16 pieces per operand (the caller scales the operands into range)
+  const uint32_t idesc = f16 ? instr_desc_f16(256, 256, 0, 0) : instr_desc(256, 256, 0, 0);
   uint32_t parity = 0;
   bool first = true;
   for (int k0 = 0; k0 < K; k0 += 32) {
@@ -51,10 +52,12 @@ tc3_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
       float v[8];
       *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(A + g);
       *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(A + g + 4);
-      store_split_chunk<3>(a_tiles, (uint32_t)(row * 16 + cg * 2048), v);
+      if (f16) store_split_chunk<2, true>(a_tiles, (uint32_t)(row * 16 + cg * 2048), v);
+      else store_split_chunk<3>(a_tiles, (uint32_t)(row * 16 + cg * 2048), v);
       *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(B + g);
       *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(B + g + 4);
-      store_split_chunk<3>(b_tiles, (uint32_t)(row * 16 + cg * 2048), v);
+      if (f16) store_split_chunk<2, true>(b_tiles, (uint32_t)(row * 16 + cg * 2048), v);
+      else store_split_chunk<3>(b_tiles, (uint32_t)(row * 16 + cg * 2048), v);
     }
     fence_async_smem();
     fence_before_sync();
@@ -166,9 +169,24 @@ tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols) {
 // transpose = 1: X(n, k) = W2[k][n]  (backward dH1^T = W2^T dZ2^T: n = input i, k = unit j).
 // kscale (transpose = 1 only): X(n, k) = W2[k][n] * kscale[k] in fp32 -- the value network's backward operand with
 // its one-row head folded in (update_x3.cu).
-template <int NP>
+template <int NP, bool F16>
 __global__ void __launch_bounds__(256) pack_w2_pieces_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img,
-                                                             int transpose, const float* __restrict__ kscale) {
+                                                             int transpose, const float* __restrict__ kscale,
+                                                             float* __restrict__ scale_out) {
+  float s = 1.0f;
+  if constexpr (F16) {
+    // fp16 pieces: every block derives the same power-of-two scale from max |X| (64 K values, L2 hits)
+    __shared__ float red[32];
+    float m = 0.0f;
+    for (int i = threadIdx.x; i < H * H / 4; i += blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(w2)[i];
+      const float ks = kscale ? kscale[(i * 4) / H] : 1.0f;  // (kscale: X(n, k) = W2[k][n] kscale[k], k = the row of W2)
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(__fmul_rn(v.x, ks)), fabsf(__fmul_rn(v.y, ks))),
+                         fmaxf(fabsf(__fmul_rn(v.z, ks)), fabsf(__fmul_rn(v.w, ks)))));
+    }
+    s = pow2_scale_for(block_max_nonneg(m, red));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out) *scale_out = s;
+  }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (n, 8 consecutive k)
   if (idx >= H * (H / 8)) return;
   const int n = idx & (H - 1), k8 = idx >> 8;
@@ -179,20 +197,54 @@ __global__ void __launch_bounds__(256) pack_w2_pieces_kernel(const float* __rest
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = __fmul_rn(v[e], kscale[k8 * 8 + e]);
   }
+  if constexpr (F16) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= s;
+  }
   const int g = k8 >> 3, kc = k8 & 7, half = n >> 7, r = n & 127;
   uint8_t* base = img + (size_t)((kc * 2 + half) * NP) * kXPieceBytes;
   uint8_t* tiles[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p) tiles[p] = base + (size_t)p * kXPieceBytes;
-  store_split_chunk<NP>(tiles, (uint32_t)(r * 16 + g * 2048), v);
+  store_split_chunk<NP, F16>(tiles, (uint32_t)(r * 16 + g * 2048), v);
 }
 
 int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st,
-                          const float* kscale) {
+                          const float* kscale, float* scale_out) {
   if (kscale && !transpose) return RL8_ERR_ARG;
-  if (pieces == 3) pack_w2_pieces_kernel<3><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose, kscale);
-  else pack_w2_pieces_kernel<2><<<H * (H / 8) / 256, 256, 0, st>>>(w2, img, transpose, kscale);
+  const int grid = H * (H / 8) / 256;
+  if (pieces == 3) pack_w2_pieces_kernel<3, false><<<grid, 256, 0, st>>>(w2, img, transpose, kscale, nullptr);
+  else if (pieces == 2) pack_w2_pieces_kernel<2, false><<<grid, 256, 0, st>>>(w2, img, transpose, kscale, nullptr);
+  else if (pieces == -2 && scale_out) pack_w2_pieces_kernel<2, true><<<grid, 256, 0, st>>>(w2, img, transpose, kscale, scale_out);
+  else return RL8_ERR_ARG;
   return check_launch("pack_w2_pieces");
+}
+
+// max |x| as float bits (non-negative floats order like their bit patterns), NaNs skipped
+__global__ void __launch_bounds__(256) absmax_bits_kernel(const float* __restrict__ x, int64_t n,
+                                                          uint32_t* __restrict__ out_bits) {
+  float m = 0.0f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = i0; i < n4; i += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (int64_t i = (n4 << 2) + i0; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+  } else {
+    for (int64_t i = i0; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out_bits, __float_as_uint(m));
+}
+int launch_absmax_bits(const float* x, int64_t n, uint32_t* out_bits, cudaStream_t st) {
+  if (n <= 0) return RL8_OK;
+  int64_t blocks = ceil_div(n, (int64_t)256 * 16);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  absmax_bits_kernel<<<(int)blocks, 256, 0, st>>>(x, n, out_bits);
+  return check_launch("absmax_bits");
 }
 
 // ---- forward kernel ---------------------------------------------------------------------------------------------------
@@ -442,10 +494,12 @@ int collect_x3(const rl8_model* model, const rl8_rollout* ro, void* workspace, i
 using namespace rl8;
 
 // Test hook: the pair MMA with split operands (tests/test_gpu_split.py).  terms: bit 0 a0b0, 1 a0b1, 2 a1b0,
-// 3 a1b1, 4 a0b2, 5 a2b0.
+// 3 a1b1, 4 a0b2, 5 a2b0; bit 6: the pieces are fp16 (two per operand, bits 0..3 only).
 extern "C" int rl8_tc3_selftest(const float* A, const float* B, float* D, int32_t K, int32_t terms,
                                 rl8_stream_t stream) {
-  if (!A || !B || !D || K < 32 || (K % 32) || terms < 1 || terms > 63) return RL8_ERR_ARG;
+  if (!A || !B || !D || K < 32 || (K % 32) || terms < 1 || terms > 127 || (terms & 63) == 0 ||
+      ((terms & 64) && (terms & 48)))
+    return RL8_ERR_ARG;
   cudaError_t e = cudaFuncSetAttribute(tc3_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(SmemSelf));
   if (e != cudaSuccess) {

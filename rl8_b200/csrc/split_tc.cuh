@@ -12,12 +12,25 @@
 // src/rl8/models/_feedforward.py:263-289, 336-362); the x2 form is used where the consumer is a gradient
 // (tests bound gradients at 1e-4).
 //
+// FP16 PIECES ("h2", the form the update kernels use).  An fp16 piece carries 11 significant bits against bf16's 8, and
+// kind::f16 multiplies fp16 operands at the same rate, so TWO pieces per operand and THREE piece products
+//
+//     x = h0 + h1 (+ 2^-24 |x|),   h0 = f16(x), h1 = f16(x - h0);      a0b0 + a0b1 + a1b0     dropped a1b1 <= 2^-24 |ab|
+//
+// are as accurate as the six bf16 products at half the tensor-pipe work and two thirds of the splitting work.  The
+// price is fp16's exponent range: every operand tensor is multiplied by a power of two s (exact) chosen from a bound of
+// its magnitude so that |x s| <= 2^14 (pow2_scale_for); elements down to 2^-17 of the bound keep the full 2^-24
+// relative accuracy, smaller ones an absolute error of 2^-39 of the bound (fp16 subnormals).  The consumer multiplies
+// the accumulator by 1 / (s_a s_b), also exact.
+//
 // The MMAs are tcgen05.mma.cta_group::2: a pair of CTAs (one cluster) works on one 256-row tile, each CTA
 // stages ITS 128 rows of A and ITS 128-row half of B (the N index), so per CTA an N = 256 instruction reads
 // 4 KB + 4 KB of shared memory per 128 cycles instead of 4 KB + 8 KB -- with three pieces per operand the
 // single-CTA form would sit at the shared-memory bandwidth limit.  Accumulators: 128 lanes x 256 columns
 // in each CTA's tensor memory (rows of the leader = tile rows 0..127, of the peer = 128..255).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "tc.cuh"
 
 namespace rl8 {
@@ -113,26 +126,53 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-// two fp32 values -> NP packed bf16 pairs (piece k of both values in q[k]; x0 in the low half)
-template <int NP>
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float2 f16x2_f32(uint32_t p) { return __half22float2(*reinterpret_cast<const __half2*>(&p)); }
+
+// The largest power of two s with bound * s <= 2^14 (fp16 pieces: 2^14 leaves a factor 4 below the largest finite
+// fp16 value for the rounding of the bound itself); 1 when the bound is zero or not finite.
+__host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
+  if (!(bound > 0.0f) || !(bound < 1.0e38f)) return 1.0f;
+  int e;
+  frexpf(bound, &e);  // bound = m 2^e, 0.5 <= m < 1
+  int k = 14 - e;
+  k = k < -100 ? -100 : k > 100 ? 100 : k;
+  return ldexpf(1.0f, k);
+}
+
+// two fp32 values -> NP packed 16-bit pairs (piece k of both values in q[k]; x0 in the low half); F16: fp16 pieces
+template <int NP, bool F16 = false>
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t* q) {
-  float2 x = make_float2(x0, x1);
-  q[0] = cvt_bf16x2(x.x, x.y);
-  if constexpr (NP > 1) {
-    x = fsub2(x, make_float2(bf16lo_f32(q[0]), bf16hi_f32(q[0])));  // exact: the residual of a rounding
-    q[1] = cvt_bf16x2(x.x, x.y);
-  }
-  if constexpr (NP > 2) {
-    x = fsub2(x, make_float2(bf16lo_f32(q[1]), bf16hi_f32(q[1])));
-    q[2] = cvt_bf16x2(x.x, x.y);
+  if constexpr (F16) {
+    static_assert(NP <= 2, "fp16 pieces: two carry 22 bits");
+    q[0] = cvt_f16x2(x0, x1);
+    if constexpr (NP > 1) {
+      const float2 r = fsub2(make_float2(x0, x1), f16x2_f32(q[0]));  // exact: the residual of a rounding
+      q[1] = cvt_f16x2(r.x, r.y);
+    }
+  } else {
+    float2 x = make_float2(x0, x1);
+    q[0] = cvt_bf16x2(x.x, x.y);
+    if constexpr (NP > 1) {
+      x = fsub2(x, make_float2(bf16lo_f32(q[0]), bf16hi_f32(q[0])));  // exact: the residual of a rounding
+      q[1] = cvt_bf16x2(x.x, x.y);
+    }
+    if constexpr (NP > 2) {
+      x = fsub2(x, make_float2(bf16lo_f32(q[1]), bf16hi_f32(q[1])));
+      q[2] = cvt_bf16x2(x.x, x.y);
+    }
   }
 }
 // eight consecutive K (or MN) elements -> one 16-byte chunk per piece at tile_k + off
-template <int NP>
+template <int NP, bool F16 = false>
 __device__ __forceinline__ void store_split_chunk(uint8_t* const* piece_tiles, uint32_t off, const float* v) {
   uint32_t q[4][NP];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) split_pair<NP>(v[2 * i], v[2 * i + 1], q[i]);
+  for (int i = 0; i < 4; ++i) split_pair<NP, F16>(v[2 * i], v[2 * i + 1], q[i]);
 #pragma unroll
   for (int k = 0; k < NP; ++k)
     *reinterpret_cast<uint4*>(piece_tiles[k] + off) = make_uint4(q[0][k], q[1][k], q[2][k], q[3][k]);

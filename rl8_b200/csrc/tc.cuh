@@ -343,6 +343,11 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, 
          ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with fp16 operands (format 0)
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return instr_desc(M, N, a_mn_major, b_mn_major) & ~((1u << 7) | (1u << 10));
+}
+
 // kind::tf32: fp32 containers in shared memory (10-bit mantissa used), K = 8 per instruction,
 // both operands K-major.  A 16-byte chunk holds 4 elements; the core matrix is still 8 rows x 16 B.
 __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {

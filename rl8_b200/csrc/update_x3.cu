@@ -64,6 +64,7 @@ struct UpdXArgs {
   float* dout[2];        // [Mc][4]  d(loss) / d(head output)
   float *gw1[2], *gb1[2], *gw2[2], *gb2[2], *gw3[2], *gb3[2];
   double* sums;          // [5]
+  X3Scales* sc;          // operand magnitudes behind the power-of-two scales of the fp16 piece form
 };
 
 // observations of minibatch row `rw` (zeros past the chunk / minibatch): slots 0..D-1, rest zero
@@ -83,9 +84,9 @@ __device__ __forceinline__ bool load_row_obs(const UpdXArgs& a, int64_t rowl, in
 }
 
 // ---- forward + loss kernel ---------------------------------------------------------------------------------------------
-constexpr int kFStages = 4;
+constexpr int kFStages = kUF16 ? 6 : 4;
 struct SmemXF {
-  StageX<3> ring[kFStages];     // 196608
+  StageX<kUNP> ring[kFStages];  // 196608
   float w1t[8][H];              //   8192
   float b2[H];                  //   1024
   float w3[kMaxPT][H];          //   4096
@@ -95,6 +96,8 @@ struct SmemXF {
   // 512 worker threads would carry them through the whole kernel at 96 registers per thread
   double lsum[TILE][4];         //   4096  entropy, policy, vf, kl
   float gb3s[TILE][kMaxPT];     //   2048  sum of dOut (head bias gradient)
+  float dmx[TILE];              //    512  max |dOut| seen by loss thread tid
+  float red[32];
   uint64_t full[kFStages], bfull[kFStages], empty[kFStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
@@ -102,7 +105,8 @@ static_assert(sizeof(SmemXF) <= 227 * 1024, "SmemXF exceeds the 227 KB CTA limit
 
 template <int PN, bool POLICY>
 __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np, const UpdXArgs& a, int net,
-                                                 int64_t pr, int64_t npairs, uint32_t rank, double* sv) {
+                                                 int64_t pr, int64_t npairs, uint32_t rank, float inv_scale,
+                                                 double* sv) {
   const uint32_t tmem = s.tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rloc = tid & 127, g = tid >> 7;
@@ -117,6 +121,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
   if (tid < TILE) {  // (doubles: a thread sums hundreds of O(1) terms that cancel)
 #pragma unroll
     for (int i = 0; i < 4; ++i) s.lsum[tid][i] = 0.0, s.gb3s[tid][i] = 0.0f;
+    s.dmx[tid] = 0.0f;
   }
   uint32_t kcount = 0;
 
@@ -132,13 +137,13 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
       __syncwarp();
       if (warp == 0 && elect_one()) {
-        const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * 3) * kXPieceBytes;
+        const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * kUNP) * kXPieceBytes;
         if (X3_ABL(a) & 64) {
           mbar_arrive(&s.bfull[st]);
         } else {
-        mbar_expect_tx(&s.bfull[st], 3 * kXPieceBytes);
+        mbar_expect_tx(&s.bfull[st], kUNP * kXPieceBytes);
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
+        for (int p = 0; p < kUNP; ++p)
           bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
         }
       }
@@ -147,8 +152,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       const uint32_t bits = h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
       if (kc < 4) m0 |= bits << (8 * kc);
       else m1 |= bits << (8 * (kc - 4));
-      uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
-      store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+      uint8_t* tiles[kUNP];
+#pragma unroll
+      for (int p = 0; p < kUNP; ++p) tiles[p] = s.ring[st].a[p];
+      store_split_chunk<kUNP, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
       }
       fence_async_smem();
       __syncwarp();
@@ -197,7 +204,9 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 4) {
         const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
-        const float z0 = v[jj] + b.x, z1 = v[jj + 1] + b.y, z2 = v[jj + 2] + b.z, z3 = v[jj + 3] + b.w;
+        // (inv_scale is a power of two: fma(v, inv_scale, b) rounds once, like the sum of the un-scaled value and b)
+        const float z0 = fmaf(v[jj], inv_scale, b.x), z1 = fmaf(v[jj + 1], inv_scale, b.y);
+        const float z2 = fmaf(v[jj + 2], inv_scale, b.z), z3 = fmaf(v[jj + 3], inv_scale, b.w);
         bits |= (z0 > 0.0f ? 1u : 0u) << jj | (z1 > 0.0f ? 1u : 0u) << (jj + 1) | (z2 > 0.0f ? 1u : 0u) << (jj + 2) |
                 (z3 > 0.0f ? 1u : 0u) << (jj + 3);
         const float h0 = fmaxf(z0, 0.0f), h1 = fmaxf(z1, 0.0f), h2 = fmaxf(z2, 0.0f), h3 = fmaxf(z3, 0.0f);
@@ -236,6 +245,8 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         }
 #pragma unroll
         for (int p = 0; p < PN; ++p) s.gb3s[tid][p] += d_o[p];
+        if constexpr (kUF16)
+          s.dmx[tid] = fmaxf(s.dmx[tid], fmaxf(fmaxf(fabsf(d_o[0]), fabsf(d_o[1])), fmaxf(fabsf(d_o[2]), fabsf(d_o[3]))));
         *reinterpret_cast<float4*>(a.dout[net] + rl * 4) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
       }
       *reinterpret_cast<float4*>(s.dsm[tid]) = make_float4(d_o[0], d_o[1], d_o[2], d_o[3]);
@@ -263,10 +274,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         const float2 b = *reinterpret_cast<const float2*>(&s.b2[col0 + 8 * k + 2 * t4]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          hv[2 * h][2 * k] = fmaxf(__uint_as_float(zr[h][4 * k]) + b.x, 0.0f);
-          hv[2 * h][2 * k + 1] = fmaxf(__uint_as_float(zr[h][4 * k + 1]) + b.y, 0.0f);
-          hv[2 * h + 1][2 * k] = fmaxf(__uint_as_float(zr[h][4 * k + 2]) + b.x, 0.0f);
-          hv[2 * h + 1][2 * k + 1] = fmaxf(__uint_as_float(zr[h][4 * k + 3]) + b.y, 0.0f);
+          hv[2 * h][2 * k] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k]), inv_scale, b.x), 0.0f);
+          hv[2 * h][2 * k + 1] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k + 1]), inv_scale, b.y), 0.0f);
+          hv[2 * h + 1][2 * k] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k + 2]), inv_scale, b.x), 0.0f);
+          hv[2 * h + 1][2 * k + 1] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k + 3]), inv_scale, b.y), 0.0f);
         }
       }
     };
@@ -327,6 +338,12 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         const float w = warp_sum(s.gb3s[tid][p]);
         if (lane == 0) atomicAdd(a.gb3[net] + p, w);
       }
+      if constexpr (kUF16) {
+        float m = s.dmx[tid];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && m > 0.0f) atomicMax(&a.sc->dmax[net], __float_as_uint(m));
+      }
     }
   }
   if (tid < TILE) {
@@ -358,7 +375,14 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
-  stage_w1t(s.w1t, np);
+  // fp16 pieces: H1 leaves h1_chunk multiplied by s_h (folded into [W1 | b1]), the W2 image carries s_w, and the
+  // epilogue multiplies the accumulator by 1 / (s_h s_w) inside its bias add
+  float s_h = 1.0f, inv_scale = 1.0f;
+  if constexpr (kUF16) {
+    s_h = pow2_scale_for(h1_bound(np, __uint_as_float(a.sc->omax), s.red));
+    inv_scale = (1.0f / s_h) * (1.0f / a.sc->w2f[net]);
+  }
+  stage_w1t(s.w1t, np, s_h);
   for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
@@ -371,12 +395,12 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   const uint32_t tmem = s.tmem_base;
   double sv[4] = {0.0, 0.0, 0.0, 0.0};
   if (warp < 16) {
-    if (net == 0) update_f_workers<P, true>(s, np, a, 0, pr, npairs, rank, sv);
-    else update_f_workers<1, false>(s, np, a, 1, pr, npairs, rank, sv);
+    if (net == 0) update_f_workers<P, true>(s, np, a, 0, pr, npairs, rank, inv_scale, sv);
+    else update_f_workers<1, false>(s, np, a, 1, pr, npairs, rank, inv_scale, sv);
   } else if (rank == 0) {
     const int64_t ntiles = (a.Mc + 255) / 256;
     const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
-    const uint32_t idesc = instr_desc(256, H, 0, 0);
+    const uint32_t idesc = upd_idesc(0, 0);
     uint32_t kcount = 0;
     long long w_full[8] = {0, 0, 0, 0, 0, 0, 0, 0}, w_acc = 0;
     const long long t_begin = X3_CLOCK();
@@ -394,7 +418,7 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
         w_full[kc] += X3_CLOCK() - c0;
         fence_after_sync();
         if (elect_one()) {
-          issue_stage<3>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
+          issue_stage<kUNP>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
           mma_commit_pair(&s.empty[st]);
           if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[buf]);
         }
@@ -472,19 +496,23 @@ struct SmemXB {
   float w3[kMaxPT][H];       //   4096
   float os[2][256][8];       //  16384  observations of the tile's rows (zero padded), per accumulator buffer
   uint32_t m1s[2][256][4];   //   8192  mask1 words of this CTA's input half, per tile row
+  float red[32];
   uint64_t full[kStages], bfull[kStages], empty[kStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(SmemXB<2>) <= 227 * 1024 && sizeof(SmemXB<3>) <= 227 * 1024, "SmemXB exceeds the 227 KB CTA limit");
+constexpr int kNPBMax = kUF16 ? 2 : 3;  // (fp16 pieces come in twos)
 
 // VNET (the value network, one head output): dZ2[row][j] = dOut[row] * (mask2[row][j] W3[j]), so
 //     dH1[row][i] = dOut[row] * sum_j (W3[j] W2[j][i]) mask2[row][j]
 // -- the A image is W2^T with W3 folded in (pack_w2_pieces_kernel's kscale), the B operand is the MASK itself, exact
 // in one bf16 piece (three piece products instead of six, and nothing to split), and dOut[row] multiplies the
 // accumulator column in the epilogue (it travels in slot 7 of the row's staged observations).
+// fp16 pieces: s_d scales dOut (policy network: |dZ2| <= max |dOut| max_j sum_p |W3[p][j]|), the W2^T image carries its
+// own scale, the mask is 0 / 1; the gradient sums stay scaled until inv_scale multiplies them in the final atomics.
 template <int PN, int NPB, bool VNET>
 __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams& np, const UpdXArgs& a, int net,
-                                                 int64_t pr, int64_t npairs, uint32_t rank) {
+                                                 int64_t pr, int64_t npairs, uint32_t rank, float s_d, float inv_scale) {
   const uint32_t tmem = s.tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rloc = tid & 127, g = tid >> 7;
@@ -532,7 +560,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
     const int rt = tid & 255, half = tid >> 8;
     *reinterpret_cast<float4*>(&s.os[buf][rt][4 * half]) = pf_o4;
     if (half == 0) *reinterpret_cast<uint4*>(s.m1s[buf][rt]) = pf_m1;
-    d4[0] = pf_d.x, d4[1] = pf_d.y, d4[2] = pf_d.z, d4[3] = pf_d.w;
+    d4[0] = pf_d.x * s_d, d4[1] = pf_d.y * s_d, d4[2] = pf_d.z * s_d, d4[3] = pf_d.w * s_d;
     m0 = pf_m2.x, m1 = pf_m2.y;
   };
   auto produce = [&](int kc0, int kc1) {
@@ -551,14 +579,14 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       if (!(X3_ABL(a) & 8)) {
       const uint32_t byte = (kc < 4 ? m0 >> (8 * kc) : m1 >> (8 * (kc - 4))) & 0xffu;
       if constexpr (VNET) {
-        *reinterpret_cast<uint4*>(s.ring[st].b[0] + rloc * 16 + g * 2048) = mask_byte_to_bf16x8(byte);
+        *reinterpret_cast<uint4*>(s.ring[st].b[0] + rloc * 16 + g * 2048) = mask_byte_to_bf16x8<kUF16>(byte);
       } else {
       float v[8];
       dz2_chunk<PN>(s.w3, d4, byte, stage_kgroup(kc, g) * 8, v);
       uint8_t* tiles[NPB];
 #pragma unroll
       for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
-      store_split_chunk<NPB>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+      store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
       }
       }
       fence_async_smem();
@@ -624,8 +652,8 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
     const int i = 128 * (int)rank + q * 32 + lane;
 #pragma unroll
     for (int d = 0; d < 7; ++d)
-      if (d < D) atomicAdd(a.gw1[net] + i * D + d, gw1_acc[d]);
-    atomicAdd(a.gb1[net] + i, gb1_acc);
+      if (d < D) atomicAdd(a.gw1[net] + i * D + d, gw1_acc[d] * inv_scale);
+    atomicAdd(a.gb1[net] + i, gb1_acc * inv_scale);
   }
 }
 
@@ -654,6 +682,11 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
+  float s_d = 1.0f, inv_scale = 1.0f;
+  if constexpr (kUF16) {
+    if (net == 0) s_d = pow2_scale_for(__uint_as_float(a.sc->dmax[0]) * w3_colsum_bound(np, s.red));
+    inv_scale = (1.0f / s_d) * (1.0f / a.sc->w2b[net]);
+  }
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
@@ -664,12 +697,12 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   fence_after_sync();
   const uint32_t tmem = s.tmem_base;
   if (warp < 16) {
-    if (net == 0) update_b_workers<P, NPB, false>(s, np, a, 0, pr, npairs, rank);
-    else update_b_workers<1, NPB, true>(s, np, a, 1, pr, npairs, rank);
+    if (net == 0) update_b_workers<P, NPB, false>(s, np, a, 0, pr, npairs, rank, s_d, inv_scale);
+    else update_b_workers<1, NPB, true>(s, np, a, 1, pr, npairs, rank, s_d, inv_scale);
   } else if (rank == 0) {
     const int64_t ntiles = (a.Mc + 255) / 256;
     const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
-    const uint32_t idesc = instr_desc(256, H, 0, 0);
+    const uint32_t idesc = upd_idesc(0, 0);
     uint32_t kcount = 0;
     for (int64_t j = 0; j < n_my; ++j) {
       const int buf = (int)(j & 1);
@@ -722,6 +755,7 @@ struct SmemXW {
   StageX<NPB> ring[kStages];  // 196608
   float w1t[8][H];           //   8192
   float w3[kMaxPT][H];       //   4096
+  float red[32];
   uint64_t full[kStages], empty[kStages], flush_full, flush_empty;
   uint32_t tmem_base;
 };
@@ -734,9 +768,12 @@ struct SmemXW {
 constexpr int kFlushStages = 128;
 static_assert(sizeof(SmemXW<2>) <= 227 * 1024 && sizeof(SmemXW<3>) <= 227 * 1024, "SmemXW exceeds the 227 KB CTA limit");
 
+// fp16 pieces: s_d scales dOut (as in the input-gradient kernel), [W1 | b1] in shared memory carries the H1 scale;
+// inv_scale = 1 / (s_d s_h) multiplies the accumulators in the flush, 1 / s_d the column sums (gb2).
 template <int PN, int NPB>
 __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams& np, const UpdXArgs& a, int net,
-                                                 int64_t pr, int64_t npairs, uint32_t rank) {
+                                                 int64_t pr, int64_t npairs, uint32_t rank, float s_d,
+                                                 float inv_scale) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = np.D;
   const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
@@ -761,7 +798,7 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
         d = *reinterpret_cast<const float4*>(a.dout[net] + rowl * 4);
         m = *reinterpret_cast<const uint4*>(a.mask2[net] + rowl * 8 + 4 * rank);
       }
-      f[0] = d.x, f[1] = d.y, f[2] = d.z, f[3] = d.w;
+      f[0] = d.x * s_d, f[1] = d.y * s_d, f[2] = d.z * s_d, f[3] = d.w * s_d;
     } else {
       load_row_obs(a, rowl, D, f, nullptr);
     }
@@ -792,7 +829,8 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
       }
 #pragma unroll
       for (int e = 0; e < 16; e += 4)
-        red_add_v4(dst + h * 16 + e, v[e] + c[e], v[e + 1] + c[e + 1], v[e + 2] + c[e + 2], v[e + 3] + c[e + 3]);
+        red_add_v4(dst + h * 16 + e, inv_scale * (v[e] + c[e]), inv_scale * (v[e + 1] + c[e + 1]),
+                   inv_scale * (v[e + 2] + c[e + 2]), inv_scale * (v[e + 3] + c[e + 3]));
     }
   };
   if (n_my > 0) load_inputs(0, in_f, in_m);
@@ -818,13 +856,13 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
         uint8_t* tiles[NPB];
 #pragma unroll
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].a[p];
-        store_split_chunk<NPB>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+        store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
       } else {
         h1_chunk(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);
         uint8_t* tiles[NPB];
 #pragma unroll
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
-        store_split_chunk<NPB>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+        store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
       }
     }
     fence_async_smem();
@@ -843,7 +881,7 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float w = warp_sum(gb2_acc[i][e]);
-        if (lane == 0) atomicAdd(a.gb2[net] + 128 * rank + 8 * (g0 + 8 * i) + e, w);
+        if (lane == 0) atomicAdd(a.gb2[net] + 128 * rank + 8 * (g0 + 8 * i) + e, w * (1.0f / s_d));
       }
   }
 }
@@ -854,9 +892,12 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
 // 16-byte store per chunk instead of a three-way split), dOut scales the H1 row before it is split, and W3[j] multiplies
 // the accumulator row in the flush.  Every worker warp w produces column group w of BOTH operands for the 32 rows of a
 // stage (lane = row).
+// fp16 pieces: s_d here scales dOut to at most 1, so that dOut s_d (H1 s_h) stays within the H1 bound; inv_scale =
+// 1 / (s_d s_h); gb2 sums the unscaled dOut.
 template <int NPB>
 __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetParams& np, const UpdXArgs& a,
-                                                      int64_t pr, int64_t npairs, uint32_t rank) {
+                                                      int64_t pr, int64_t npairs, uint32_t rank, float s_d,
+                                                      float inv_scale) {
   constexpr int net = 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = np.D;
@@ -886,7 +927,7 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
     fence_after_sync();
     const int q = warp & 3, cq = warp >> 2;
     const int j = 128 * (int)rank + q * 32 + lane;  // lane = unit j of this CTA's half, 256 columns i
-    const float w3j = s.w3[0][j];
+    const float w3j = s.w3[0][j] * inv_scale;  // (a power of two: exact)
     float* dst = a.gw2[net] + (int64_t)j * H + cq * 64;
 #pragma unroll 1
     for (int h = 0; h < 4; ++h) {
@@ -921,19 +962,20 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
     if (!(X3_ABL(a) & 32)) {
       // A: the mask bits of unit group g  (tile a[0] only)
       const uint32_t byte = (cur_m >> (8 * (g & 3))) & 0xffu;
-      *reinterpret_cast<uint4*>(s.ring[st].a[0] + lane * 16 + g * 512) = mask_byte_to_bf16x8(byte);
+      *reinterpret_cast<uint4*>(s.ring[st].a[0] + lane * 16 + g * 512) = mask_byte_to_bf16x8<kUF16>(byte);
       const float d = cur_f[7];
 #pragma unroll
       for (int e = 0; e < 8; ++e) gb2_acc[e] += (byte >> e) & 1u ? d : 0.0f;
       // B: dOut[row] * H1[row][input group g], split
       float v[8];
       h1_chunk(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);
+      const float ds = d * s_d;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= d;
+      for (int e = 0; e < 8; ++e) v[e] *= ds;
       uint8_t* tiles[NPB];
 #pragma unroll
       for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
-      store_split_chunk<NPB>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+      store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
     }
     fence_async_smem();
     __syncwarp();
@@ -979,7 +1021,15 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
-  stage_w1t(s.w1t, np);
+  float s_h = 1.0f, s_d = 1.0f, inv_scale = 1.0f;
+  if constexpr (kUF16) {
+    s_h = pow2_scale_for(h1_bound(np, __uint_as_float(a.sc->omax), s.red));
+    const float dmax = __uint_as_float(a.sc->dmax[net]);
+    if (net == 0) s_d = pow2_scale_for(dmax * w3_colsum_bound(np, s.red));
+    else s_d = pow2_scale_for(dmax) * (1.0f / 16384.0f);  // max |dOut| s_d <= 1
+    inv_scale = (1.0f / s_d) * (1.0f / s_h);
+  }
+  stage_w1t(s.w1t, np, s_h);
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
@@ -989,12 +1039,12 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   cluster_sync_all();
   fence_after_sync();
   if (warp < 16) {
-    if (net == 0) update_w_workers<P, NPB>(s, np, a, 0, pr, npairs, rank);
-    else update_w_workers_vnet<NPB>(s, np, a, pr, npairs, rank);
+    if (net == 0) update_w_workers<P, NPB>(s, np, a, 0, pr, npairs, rank, s_d, inv_scale);
+    else update_w_workers_vnet<NPB>(s, np, a, pr, npairs, rank, s_d, inv_scale);
   } else if (rank == 0) {
     const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
     const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
-    const uint32_t idesc = instr_desc(256, H, 1, 1);
+    const uint32_t idesc = upd_idesc(1, 1);
     using T = Terms<NPB>;
     int64_t nf = 0;  // flushes committed so far
     for (int64_t k = 0; k < n_my; ++k) {
@@ -1055,7 +1105,8 @@ static int x3_stages() {  // development switch: bit 0 forward / loss, bit 1 inp
   const char* e = getenv("RL8_X3_STAGES");
   return e ? atoi(e) : 7;
 }
-static int x3_backward_pieces() {  // 3: six piece products in the gradient contractions too; 2: three
+static int x3_backward_pieces() {  // bf16 pieces -- 3: six piece products in the gradient contractions too; 2: three
+  if (kUF16) return 2;             // (fp16 pieces come in twos)
   const char* e = getenv("RL8_X3_BACKWARD_PIECES");
   return e && atoi(e) == 2 ? 2 : 3;
 }
@@ -1077,8 +1128,8 @@ static int x3_gradient_policy_pairs(const char* env, int pairs, int of74) {
 
 int64_t ppo_x3_workspace(const rl8_model*, int64_t max_rows) {
   const int64_t chunk = max_rows < kXChunkRows ? max_rows : kXChunkRows;
-  // forward images (3 pieces) + transposed images (2 pieces) of both networks, scratch of both networks
-  return 4 * (int64_t)kXImgBytes + 2 * chunk * 80 + 256;
+  // forward + transposed piece images of both networks, the operand magnitudes, scratch of both networks
+  return 4 * (int64_t)kXImgBytes + 256 + 2 * chunk * 80 + 256;
 }
 
 int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_batch* batch, const int64_t* rows,
@@ -1092,14 +1143,28 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
   p += 2 * (int64_t)kXImgBytes;
   uint8_t* img_b[2] = {p, p + kXImgBytes};
   p += 2 * (int64_t)kXImgBytes;
+  X3Scales* sc = (X3Scales*)p;
+  p += 256;
   const int npb = x3_backward_pieces();
   int rc;
+  if (kUF16) {
+    cudaError_t e = cudaMemsetAsync(sc, 0, sizeof(X3Scales), st);
+    if (e != cudaSuccess) {
+      set_last_error("cudaMemsetAsync", e);
+      return RL8_ERR_CUDA;
+    }
+    // max |obs| over the T slabs the minibatch rows come from: bounds H1 (h1_bound)
+    if ((rc = launch_absmax_bits(batch->obs, (int64_t)batch->T * model->D * batch->N, &sc->omax, st))) return rc;
+  }
   for (int net = 0; net < 2; ++net) {
     const float* w2 = net ? model->vf_w2 : model->pi_w2;
-    if ((rc = launch_pack_w2_pieces(w2, img_f[net], 0, 3, st))) return rc;
-    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, npb, st, net ? model->vf_w3 : nullptr))) return rc;
+    if ((rc = launch_pack_w2_pieces(w2, img_f[net], 0, kUF16 ? -2 : 3, st, nullptr, &sc->w2f[net]))) return rc;
+    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, kUF16 ? -2 : npb, st, net ? model->vf_w3 : nullptr,
+                                    &sc->w2b[net])))
+      return rc;
   }
   UpdXArgs a;
+  a.sc = sc;
   for (int net = 0; net < 2; ++net) {
     a.mask1[net] = (uint32_t*)p, p += chunk * 32;
     a.mask2[net] = (uint32_t*)p, p += chunk * 32;
@@ -1153,15 +1218,15 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
     }
     if (stages & 2) {
       const NetParams nb_pi = net_params(model, 0, img_b[0]), nb_vf = net_params(model, 1, img_b[1]);
-#define RL8_UPDB(PV)                                                                                  \
-  case PV:                                                                                            \
-    if (npb == 2) {                                                                                   \
-      if ((rc = set_smem((const void*)x3_update_b_kernel<PV, 2>, sizeof(SmemXB<2>)))) return rc;       \
-      x3_update_b_kernel<PV, 2><<<2 * pairs, kXThreads, sizeof(SmemXB<2>), st>>>(nb_pi, nb_vf, a);     \
-    } else {                                                                                          \
-      if ((rc = set_smem((const void*)x3_update_b_kernel<PV, 3>, sizeof(SmemXB<3>)))) return rc;       \
-      x3_update_b_kernel<PV, 3><<<2 * pairs, kXThreads, sizeof(SmemXB<3>), st>>>(nb_pi, nb_vf, a);     \
-    }                                                                                                 \
+#define RL8_UPDB(PV)                                                                                            \
+  case PV:                                                                                                      \
+    if (npb == 2) {                                                                                             \
+      if ((rc = set_smem((const void*)x3_update_b_kernel<PV, 2>, sizeof(SmemXB<2>)))) return rc;                 \
+      x3_update_b_kernel<PV, 2><<<2 * pairs, kXThreads, sizeof(SmemXB<2>), st>>>(nb_pi, nb_vf, a);               \
+    } else {                                                                                                    \
+      if ((rc = set_smem((const void*)x3_update_b_kernel<PV, kNPBMax>, sizeof(SmemXB<kNPBMax>)))) return rc;     \
+      x3_update_b_kernel<PV, kNPBMax><<<2 * pairs, kXThreads, sizeof(SmemXB<kNPBMax>), st>>>(nb_pi, nb_vf, a);   \
+    }                                                                                                           \
     break;
       switch (model->P) {
         RL8_UPDB(2) RL8_UPDB(3) RL8_UPDB(4)
@@ -1175,15 +1240,15 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
       int wpairs = (int)(nst < kNumSMs / 2 ? nst : kNumSMs / 2);
       if (wpairs < 2) wpairs = 2;
       a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 39);  // 38 -> 2.45, 40 -> 2.50, 43 -> 2.74 ms
-#define RL8_UPDW(PV)                                                                                  \
-  case PV:                                                                                            \
-    if (npb == 2) {                                                                                   \
-      if ((rc = set_smem((const void*)x3_update_w_kernel<PV, 2>, sizeof(SmemXW<2>)))) return rc;       \
-      x3_update_w_kernel<PV, 2><<<2 * wpairs, kXThreads, sizeof(SmemXW<2>), st>>>(np_pi, np_vf, a);    \
-    } else {                                                                                          \
-      if ((rc = set_smem((const void*)x3_update_w_kernel<PV, 3>, sizeof(SmemXW<3>)))) return rc;       \
-      x3_update_w_kernel<PV, 3><<<2 * wpairs, kXThreads, sizeof(SmemXW<3>), st>>>(np_pi, np_vf, a);    \
-    }                                                                                                 \
+#define RL8_UPDW(PV)                                                                                            \
+  case PV:                                                                                                      \
+    if (npb == 2) {                                                                                             \
+      if ((rc = set_smem((const void*)x3_update_w_kernel<PV, 2>, sizeof(SmemXW<2>)))) return rc;                 \
+      x3_update_w_kernel<PV, 2><<<2 * wpairs, kXThreads, sizeof(SmemXW<2>), st>>>(np_pi, np_vf, a);              \
+    } else {                                                                                                    \
+      if ((rc = set_smem((const void*)x3_update_w_kernel<PV, kNPBMax>, sizeof(SmemXW<kNPBMax>)))) return rc;     \
+      x3_update_w_kernel<PV, kNPBMax><<<2 * wpairs, kXThreads, sizeof(SmemXW<kNPBMax>), st>>>(np_pi, np_vf, a);  \
+    }                                                                                                           \
     break;
       switch (model->P) {
         RL8_UPDW(2) RL8_UPDW(3) RL8_UPDW(4)

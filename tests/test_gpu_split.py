@@ -51,6 +51,36 @@ def test_pair_mma_term_sets_against_fp64(K: int) -> None:
     assert torch.equal(D, D2)
 
 
+@pytest.mark.parametrize("K", [32, 256])
+def test_pair_mma_fp16_pieces_against_fp64(K: int) -> None:
+    """Two fp16 pieces per operand, three piece products (the update kernels' form, split_tc.cuh): as accurate as
+    the six bf16 products once the operands are scaled by a power of two into fp16's range -- also for elements
+    2^-12 of the largest one."""
+    L, lib = _lib()
+    gen = torch.Generator().manual_seed(100 + K)
+    A = torch.randn(256, K, generator=gen)
+    B = torch.randn(256, K, generator=gen)
+    A[:, ::3] *= 2.0**-12  # wide dynamic range inside one operand
+    B[::2] *= 2.0**-9
+    A, B = A.to(DEV), B.to(DEV)
+    ref = A.double() @ B.double().T
+    sa = 2.0 ** (14 - int(torch.ceil(torch.log2(A.abs().max()))))
+    sb = 2.0 ** (14 - int(torch.ceil(torch.log2(B.abs().max()))))
+    err = {}
+    for terms in (64 + 1, 64 + 7, 64 + 15):
+        D = torch.full((256, 256), float("nan"), device=DEV)
+        assert lib.rl8_tc3_selftest(L.ptr(A * sa), L.ptr(B * sb), L.ptr(D), K, terms, L.stream()) == 0
+        torch.cuda.synchronize()
+        err[terms] = _rel(D / (sa * sb), ref)
+    assert 2e-5 < err[65] < 2e-3, err     # one fp16 product: operands really are single pieces
+    assert err[71] < 4e-6, err            # the update kernels' three products
+    assert err[79] < 4e-6, err
+    # per-element: rows of B scaled down by 2^-9 keep their relative accuracy (fp16 subnormals do not bite)
+    small = (D[:, ::2] / (sa * sb)).double()
+    assert float((small - ref[:, ::2]).abs().max() / ref[:, ::2].abs().max()) < 4e-6
+    assert lib.rl8_tc3_selftest(L.ptr(A), L.ptr(B), L.ptr(D), K, 64 + 16, L.stream()) != 0  # no third fp16 piece
+
+
 def test_pair_mma_maps_rows_and_columns_of_both_ctas() -> None:
     """Exact integer-valued operands: every D[m][n] identifies its row and column (leader rows 0..127,
     peer rows 128..255; B half of the leader = columns 0..127)."""
