@@ -101,11 +101,12 @@ __device__ __forceinline__ void issue_stage_mask_b(uint32_t lead_tmem, uint32_t 
 }
 
 // [W1 | b1] in fp32, input-major: w1t[d][i] = W1[i][d] (d < D <= 7; rows D..6 unused), w1t[7][i] = b1[i];
-// scale: a power of two (exact) -- h1_chunk then yields scale * H1, bit for bit
+// scale: a power of two (exact) -- h1_chunk then yields scale * H1, bit for bit.  A NEGATIVE scale stages
+// -|scale| [W1 | b1] for h1_chunk<true> (no entry is -0: a bias of zero must not turn an exact zero sum into -0).
 __device__ __forceinline__ void stage_w1t(float (*w1t)[H], const NetParams& np, float scale = 1.0f) {
   for (int e = threadIdx.x; e < H * 8; e += blockDim.x) {
     const int i = e & (H - 1), d = e >> 8;
-    w1t[d][i] = scale * (d < np.D ? np.w1[i * np.D + d] : (d == 7 ? np.b1[i] : 0.0f));
+    w1t[d][i] = __fadd_rn(scale * (d < np.D ? np.w1[i * np.D + d] : (d == 7 ? np.b1[i] : 0.0f)), 0.0f);
   }
 }
 // max over the block of a non-negative value (all threads call; red: >= 32 floats of shared memory)
@@ -148,7 +149,11 @@ __device__ __forceinline__ ObsPairs obs_pairs(const float* ob) {
   return o;
 }
 // Z1[row][c0 .. c0 + 8) = b1[c] + sum_d obs[d] W1[c][d] in fp32: bias first, then d ascending -- one FMA per term
-// (two columns per FFMA2); H1 = relu(Z1) -> v; returns the 8 ReLU-mask bits (bit e: column c0 + e is positive)
+// (two columns per FFMA2); H1 = relu(Z1) -> v; returns the 8 ReLU-mask bits (bit e: column c0 + e is positive).
+// NEG: w1t holds -s [W1 | b1] (stage_w1t with a negative scale), so the sums are -s Z1: v = min(-s Z1, 0) = -s H1 and
+// the mask bit is the SIGN bit of the sum, gathered with one funnel shift per column instead of compare / select / or
+// (the consumers fold the sign into the factor that removes the operand scales).
+template <bool NEG = false>
 __device__ __forceinline__ uint32_t h1_chunk(const float (*w1t)[H], const ObsPairs& ob, int D, int c0, float* v) {
   float2 z[4];
   {
@@ -169,10 +174,19 @@ __device__ __forceinline__ uint32_t h1_chunk(const float (*w1t)[H], const ObsPai
     }
   }
   uint32_t bits = 0u;
+  if constexpr (NEG) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    bits |= (z[j].x > 0.0f ? 1u : 0u) << (2 * j) | (z[j].y > 0.0f ? 1u : 0u) << (2 * j + 1);
-    v[2 * j] = fmaxf(z[j].x, 0.0f), v[2 * j + 1] = fmaxf(z[j].y, 0.0f);
+    for (int j = 3; j >= 0; --j) {  // bits = (bits << 1) | sign: the last column shifted in lands in bit 0
+      bits = __funnelshift_l(__float_as_uint(z[j].y), bits, 1);
+      bits = __funnelshift_l(__float_as_uint(z[j].x), bits, 1);
+      v[2 * j] = fminf(z[j].x, 0.0f), v[2 * j + 1] = fminf(z[j].y, 0.0f);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bits |= (z[j].x > 0.0f ? 1u : 0u) << (2 * j) | (z[j].y > 0.0f ? 1u : 0u) << (2 * j + 1);
+      v[2 * j] = fmaxf(z[j].x, 0.0f), v[2 * j + 1] = fmaxf(z[j].y, 0.0f);
+    }
   }
   return bits;
 }
@@ -186,6 +200,20 @@ __device__ __forceinline__ uint4 mask_byte_to_bf16x8(uint32_t byte) {
   for (int e = 0; e < 4; ++e)
     q[e] = ((byte >> (2 * e)) & 1u) * one | ((byte >> (2 * e + 1)) & 1u) * (one << 16);
   return make_uint4(q[0], q[1], q[2], q[3]);
+}
+
+// the same through a 16-entry table in shared memory (entry n: the two words of mask bits n & 15): two 8-byte loads
+// per chunk, no bank conflicts (the 16 entries cover the 32 banks once, equal entries broadcast)
+template <bool F16>
+__device__ __forceinline__ void fill_mask_lut(uint2* lut) {
+  if (threadIdx.x < 16) {
+    const uint4 q = mask_byte_to_bf16x8<F16>(threadIdx.x);
+    lut[threadIdx.x] = make_uint2(q.x, q.y);
+  }
+}
+__device__ __forceinline__ uint4 mask_byte_lut(const uint2* lut, uint32_t byte) {
+  const uint2 lo = lut[byte & 15u], hi = lut[(byte >> 4) & 15u];
+  return make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
 
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }

@@ -88,7 +88,7 @@ constexpr int kFStages = kUF16 ? 6 : 4;
 struct SmemXF {
   StageX<kUNP> ring[kFStages];  // 196608
   float w1t[8][H];              //   8192
-  float b2[H];                  //   1024
+  float b2[H];                  //   1024  -b2
   float w3[kMaxPT][H];          //   4096
   float part[4][TILE][kMaxPT];  //   8192  head partial sums per column quarter
   float dsm[TILE][kMaxPT];      //   2048  dOut of the tile's rows (pass 2)
@@ -149,7 +149,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       }
       if (!(X3_ABL(a) & 1)) {
       float v[8];
-      const uint32_t bits = h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
+      const uint32_t bits = h1_chunk<true>(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);  // v = -s_h H1
       if (kc < 4) m0 |= bits << (8 * kc);
       else m1 |= bits << (8 * (kc - 4));
       uint8_t* tiles[kUNP];
@@ -203,23 +203,25 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       if (X3_ABL(a) & 2) { dot[0] += v[0] + v[31]; mk[c2] = 0; continue; }
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 4) {
+        // The accumulator holds -s Z2 (the A operand is -s_h H1) and s.b2 holds -b2, so z = -(Z2 + b2): inv_scale is a
+        // power of two, the fma rounds once like the un-scaled sum; the ReLU-mask bit is the sign bit of z (one funnel
+        // shift per column, first column ends up in bit 31), h = min(z, 0) = -H2 enters the head sums negated.
         const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
-        // (inv_scale is a power of two: fma(v, inv_scale, b) rounds once, like the sum of the un-scaled value and b)
         const float z0 = fmaf(v[jj], inv_scale, b.x), z1 = fmaf(v[jj + 1], inv_scale, b.y);
         const float z2 = fmaf(v[jj + 2], inv_scale, b.z), z3 = fmaf(v[jj + 3], inv_scale, b.w);
-        bits |= (z0 > 0.0f ? 1u : 0u) << jj | (z1 > 0.0f ? 1u : 0u) << (jj + 1) | (z2 > 0.0f ? 1u : 0u) << (jj + 2) |
-                (z3 > 0.0f ? 1u : 0u) << (jj + 3);
-        const float h0 = fmaxf(z0, 0.0f), h1 = fmaxf(z1, 0.0f), h2 = fmaxf(z2, 0.0f), h3 = fmaxf(z3, 0.0f);
+        bits = __funnelshift_l(__float_as_uint(z0), bits, 1), bits = __funnelshift_l(__float_as_uint(z1), bits, 1);
+        bits = __funnelshift_l(__float_as_uint(z2), bits, 1), bits = __funnelshift_l(__float_as_uint(z3), bits, 1);
+        const float h0 = fminf(z0, 0.0f), h1 = fminf(z1, 0.0f), h2 = fminf(z2, 0.0f), h3 = fminf(z3, 0.0f);
 #pragma unroll
         for (int p = 0; p < PN; ++p) {
           const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + jj]);
-          dot[p] = fmaf(h0, w.x, dot[p]);
-          dot[p] = fmaf(h1, w.y, dot[p]);
-          dot[p] = fmaf(h2, w.z, dot[p]);
-          dot[p] = fmaf(h3, w.w, dot[p]);
+          dot[p] = fmaf(-h0, w.x, dot[p]);
+          dot[p] = fmaf(-h1, w.y, dot[p]);
+          dot[p] = fmaf(-h2, w.z, dot[p]);
+          dot[p] = fmaf(-h3, w.w, dot[p]);
         }
       }
-      mk[c2] = bits;
+      mk[c2] = __brev(bits);
     }
     if (rowl < a.Mc) *reinterpret_cast<uint2*>(a.mask2[net] + rowl * 8 + 2 * cq) = make_uint2(mk[0], mk[1]);
 #pragma unroll
@@ -274,10 +276,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         const float2 b = *reinterpret_cast<const float2*>(&s.b2[col0 + 8 * k + 2 * t4]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          hv[2 * h][2 * k] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k]), inv_scale, b.x), 0.0f);
-          hv[2 * h][2 * k + 1] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k + 1]), inv_scale, b.y), 0.0f);
-          hv[2 * h + 1][2 * k] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k + 2]), inv_scale, b.x), 0.0f);
-          hv[2 * h + 1][2 * k + 1] = fmaxf(fmaf(__uint_as_float(zr[h][4 * k + 3]), inv_scale, b.y), 0.0f);
+          hv[2 * h][2 * k] = fminf(fmaf(__uint_as_float(zr[h][4 * k]), inv_scale, b.x), 0.0f);  // -H2
+          hv[2 * h][2 * k + 1] = fminf(fmaf(__uint_as_float(zr[h][4 * k + 1]), inv_scale, b.y), 0.0f);
+          hv[2 * h + 1][2 * k] = fminf(fmaf(__uint_as_float(zr[h][4 * k + 2]), inv_scale, b.x), 0.0f);
+          hv[2 * h + 1][2 * k + 1] = fminf(fmaf(__uint_as_float(zr[h][4 * k + 3]), inv_scale, b.y), 0.0f);
         }
       }
     };
@@ -313,7 +315,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
             x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
-        gw3_acc[c2][p] += x[0];
+        gw3_acc[c2][p] -= x[0];  // (hv holds -H2)
       }
     }
   };
@@ -382,8 +384,8 @@ x3_update_f_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     s_h = pow2_scale_for(h1_bound(np, __uint_as_float(a.sc->omax), s.red));
     inv_scale = (1.0f / s_h) * (1.0f / a.sc->w2f[net]);
   }
-  stage_w1t(s.w1t, np, s_h);
-  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
+  stage_w1t(s.w1t, np, -s_h);                                              // h1_chunk<true>: A = -s_h H1
+  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = 0.0f - np.b2[i];     // -b2, never -0
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
@@ -497,6 +499,7 @@ struct SmemXB {
   float os[2][256][8];       //  16384  observations of the tile's rows (zero padded), per accumulator buffer
   uint32_t m1s[2][256][4];   //   8192  mask1 words of this CTA's input half, per tile row
   float red[32];
+  uint2 lut[16];             //    128  mask nibble -> four 16-bit {0, 1}
   uint64_t full[kStages], bfull[kStages], empty[kStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
@@ -520,9 +523,10 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   const int D = np.D;
   const int64_t ntiles = (a.Mc + 255) / 256;
   const int64_t n_my = pr < ntiles ? (ntiles - pr + npairs - 1) / npairs : 0;
-  float gw1_acc[7], gb1_acc = 0.0f;
+  // gradient sums of input unit i as packed pairs: (gW1[i][0], [1]), ([2], [3]), ([4], [5]), ([6], gb1[i])
+  float2 gacc[4];
 #pragma unroll
-  for (int d = 0; d < 7; ++d) gw1_acc[d] = 0.0f;
+  for (int d = 0; d < 4; ++d) gacc[d] = make_float2(0.0f, 0.0f);
   uint32_t kcount = 0;
   constexpr int kStages = SmemXB<NPB>::kStages;
   constexpr int kTileStages = H / kXKc;
@@ -541,8 +545,14 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       const int64_t rl = tile * 256 + rt;
       float ob[7];
       const bool valid = load_row_obs(a, rl, D, ob, nullptr);
-      float d_row = 0.0f;
-      if (VNET && half && valid) d_row = a.dout[net][rl * 4];
+      // slot 7 multiplies the bias gradient: 1, or -- value network -- dOut of the row, which then scales the
+      // observations too (dZ1 = dOut * [H1 > 0] .* accumulator: the factor moves into the row's [obs | 1])
+      float d_row = 1.0f;
+      if constexpr (VNET) {
+        d_row = valid ? a.dout[net][rl * 4] : 0.0f;
+#pragma unroll
+        for (int d = 0; d < 7; ++d) ob[d] *= d_row;
+      }
       pf_o4 = half ? make_float4(ob[4], ob[5], ob[6], d_row) : make_float4(ob[0], ob[1], ob[2], ob[3]);
       pf_m1 = make_uint4(0u, 0u, 0u, 0u);
       if (half == 0 && valid) pf_m1 = *reinterpret_cast<const uint4*>(a.mask1[net] + rl * 8 + 4 * rank);
@@ -579,7 +589,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
       if (!(X3_ABL(a) & 8)) {
       const uint32_t byte = (kc < 4 ? m0 >> (8 * kc) : m1 >> (8 * (kc - 4))) & 0xffu;
       if constexpr (VNET) {
-        *reinterpret_cast<uint4*>(s.ring[st].b[0] + rloc * 16 + g * 2048) = mask_byte_to_bf16x8<kUF16>(byte);
+        *reinterpret_cast<uint4*>(s.ring[st].b[0] + rloc * 16 + g * 2048) = mask_byte_lut(s.lut, byte);
       } else {
       float v[8];
       dz2_chunk<PN>(s.w3, d4, byte, stage_kgroup(kc, g) * 8, v);
@@ -612,20 +622,17 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&s.acc_empty[buf], 0);
       }
-      if (X3_ABL(a) & 16) { gb1_acc += v[0] + v[15]; continue; }
+      if (X3_ABL(a) & 16) { gacc[3].y += v[0] + v[15]; continue; }
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int rt = cq * 64 + c4 * 16 + e;
         const uint32_t word = s.m1s[buf][rt][q];
         const float4 oa = *reinterpret_cast<const float4*>(&s.os[buf][rt][0]);
-        const float4 ob = *reinterpret_cast<const float4*>(&s.os[buf][rt][4]);
-        float dz1 = (word >> lane) & 1u ? v[e] : 0.0f;
-        if constexpr (VNET) dz1 *= ob.w;  // dOut of the row
-        gb1_acc += dz1;
-        gw1_acc[0] = fmaf(dz1, oa.x, gw1_acc[0]), gw1_acc[1] = fmaf(dz1, oa.y, gw1_acc[1]);
-        gw1_acc[2] = fmaf(dz1, oa.z, gw1_acc[2]), gw1_acc[3] = fmaf(dz1, oa.w, gw1_acc[3]);
-        gw1_acc[4] = fmaf(dz1, ob.x, gw1_acc[4]), gw1_acc[5] = fmaf(dz1, ob.y, gw1_acc[5]);
-        gw1_acc[6] = fmaf(dz1, ob.z, gw1_acc[6]);
+        const float4 ob = *reinterpret_cast<const float4*>(&s.os[buf][rt][4]);  // (obs 4..6, bias factor)
+        const float dz1 = (word >> lane) & 1u ? v[e] : 0.0f;
+        const float2 dz = make_float2(dz1, dz1);
+        gacc[0] = ffma2(dz, make_float2(oa.x, oa.y), gacc[0]), gacc[1] = ffma2(dz, make_float2(oa.z, oa.w), gacc[1]);
+        gacc[2] = ffma2(dz, make_float2(ob.x, ob.y), gacc[2]), gacc[3] = ffma2(dz, make_float2(ob.z, ob.w), gacc[3]);
       }
     }
     worker_bar_sync();  // os / m1s of this buffer may be rewritten
@@ -650,10 +657,11 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   }
   if (n_my > 0) {
     const int i = 128 * (int)rank + q * 32 + lane;
+    const float gw1_acc[8] = {gacc[0].x, gacc[0].y, gacc[1].x, gacc[1].y, gacc[2].x, gacc[2].y, gacc[3].x, gacc[3].y};
 #pragma unroll
     for (int d = 0; d < 7; ++d)
       if (d < D) atomicAdd(a.gw1[net] + i * D + d, gw1_acc[d] * inv_scale);
-    atomicAdd(a.gb1[net] + i, gb1_acc * inv_scale);
+    atomicAdd(a.gb1[net] + i, gw1_acc[7] * inv_scale);
   }
 }
 
@@ -687,6 +695,7 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     if (net == 0) s_d = pow2_scale_for(__uint_as_float(a.sc->dmax[0]) * w3_colsum_bound(np, s.red));
     inv_scale = (1.0f / s_d) * (1.0f / a.sc->w2b[net]);
   }
+  fill_mask_lut<kUF16>(s.lut);
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
@@ -756,6 +765,7 @@ struct SmemXW {
   float w1t[8][H];           //   8192
   float w3[kMaxPT][H];       //   4096
   float red[32];
+  uint2 lut[16];             //    128  mask nibble -> four 16-bit {0, 1}
   uint64_t full[kStages], empty[kStages], flush_full, flush_empty;
   uint32_t tmem_base;
 };
@@ -858,7 +868,7 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].a[p];
         store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
       } else {
-        h1_chunk(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);
+        h1_chunk<true>(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);  // -s_h H1 (inv_scale is negative)
         uint8_t* tiles[NPB];
 #pragma unroll
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
@@ -962,13 +972,13 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
     if (!(X3_ABL(a) & 32)) {
       // A: the mask bits of unit group g  (tile a[0] only)
       const uint32_t byte = (cur_m >> (8 * (g & 3))) & 0xffu;
-      *reinterpret_cast<uint4*>(s.ring[st].a[0] + lane * 16 + g * 512) = mask_byte_to_bf16x8<kUF16>(byte);
+      *reinterpret_cast<uint4*>(s.ring[st].a[0] + lane * 16 + g * 512) = mask_byte_lut(s.lut, byte);
       const float d = cur_f[7];
 #pragma unroll
       for (int e = 0; e < 8; ++e) gb2_acc[e] += (byte >> e) & 1u ? d : 0.0f;
       // B: dOut[row] * H1[row][input group g], split
       float v[8];
-      h1_chunk(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);
+      h1_chunk<true>(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);  // -s_h H1 (inv_scale is negative)
       const float ds = d * s_d;
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] *= ds;
@@ -1029,7 +1039,9 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     else s_d = pow2_scale_for(dmax) * (1.0f / 16384.0f);  // max |dOut| s_d <= 1
     inv_scale = (1.0f / s_d) * (1.0f / s_h);
   }
-  stage_w1t(s.w1t, np, s_h);
+  inv_scale = -inv_scale;  // the H1 operand is staged negated (h1_chunk<true>)
+  stage_w1t(s.w1t, np, -s_h);
+  fill_mask_lut<kUF16>(s.lut);
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;

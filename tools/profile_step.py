@@ -67,3 +67,16 @@ if algo.policy.precision == L.PREC_FP32_TC:
         minibatch()
         print(f"   {name:32s} {min(timed(minibatch) for _ in range(3)):.3f} ms (incl. 4 W2 piece-image launches)")
     os.environ.pop("RL8_X3_STAGES")
+    # optional: sweep of the policy / value split of the 74 CTA pairs per kernel (RL8_X3_SWEEP=1)
+    if os.environ.get("RL8_X3_SWEEP"):
+        for name, bit, var in (("f", 1, "RL8_X3_POLICY_PAIRS"), ("b", 2, "RL8_X3_POLICY_PAIRS_B"),
+                               ("w", 4, "RL8_X3_POLICY_PAIRS_W")):
+            os.environ["RL8_X3_STAGES"] = str(bit)
+            res = []
+            for n_pi in range(30, 52, 2):
+                os.environ[var] = str(n_pi)
+                minibatch()
+                res.append(f"{n_pi}: {min(timed(minibatch) for _ in range(3)):.3f}")
+            os.environ.pop(var)
+            print(f"   sweep {name} (policy pairs of 74: ms)  " + "  ".join(res))
+        os.environ.pop("RL8_X3_STAGES")
