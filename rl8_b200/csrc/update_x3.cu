@@ -758,6 +758,17 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
 //   worker warps 8..15 : H1 chunks     (lane = row, warp w - 8 -> column groups w - 8 and w)
 // Pairs [0, n_pi) work on the policy network, the rest on the value network; a pair owns the stages
 // pr, pr + npairs, ... of its network and keeps its 256 x 256 accumulator in tensor memory until the end.
+// Inputs of the 32 rows of one stage (lane = row), fetched ONCE per CTA by the loader warp (warp 17): the 16 worker
+// warps all need the same rows, and the buffer coordinates of a row (a division) and its D strided observation loads
+// were a quarter of the kernel's instructions when every warp fetched its own copy.
+struct WInSlot {
+  float4 o0[32];  // obs[0..3]
+  float4 o1[32];  // obs[4..6], dOut[0] (value network)
+  float4 dd[32];  // policy network: s_d * dOut[0..3]
+  uint4 mm[32];   // mask2 words of this CTA's 128-unit half
+};
+constexpr int kWIn = 6;
+constexpr int kWThreads = kXThreads + 32;  // + the loader warp
 template <int NPB>
 struct SmemXW {
   static constexpr int kStages = NPB == 2 ? 6 : 4;
@@ -766,7 +777,8 @@ struct SmemXW {
   float w3[kMaxPT][H];       //   4096
   float red[32];
   uint2 lut[16];             //    128  mask nibble -> four 16-bit {0, 1}
-  uint64_t full[kStages], empty[kStages], flush_full, flush_empty;
+  WInSlot in[kWIn];          //  12288  inputs of the next stages' rows, fetched by the loader warp
+  uint64_t full[kStages], empty[kStages], flush_full, flush_empty, in_full[kWIn], in_empty[kWIn];
   uint32_t tmem_base;
 };
 // The tensor pipe truncates its fp32 accumulator after every instruction (measured: the error of a long
@@ -796,22 +808,22 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) gb2_acc[i][e] = 0.0f;
-  // inputs of this lane's row of a stage: dz role {dOut[4], 16 mask bytes of the CTA's half}; h1 role {obs[7]}
-  float in_f[8];
-  uint4 in_m = make_uint4(0u, 0u, 0u, 0u);
-  auto load_inputs = [&](int64_t k, float* f, uint4& m) {
-    const int64_t rowl = (pr + k * npairs) * kXKc + lane;
+  // inputs of this lane's row of a stage (from the loader warp's slot): dz role {s_d dOut[4], 16 mask bytes of the
+  // CTA's half}; h1 role {obs[7]}
+  auto read_inputs = [&](int64_t k, float* f, uint4& m) {
+    const int slot = (int)(k % kWIn);
+    mbar_wait(&s.in_full[slot], (uint32_t)((k / kWIn) & 1));
+    const WInSlot& in = s.in[slot];
     if (dz_role) {
-      float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      m = make_uint4(0u, 0u, 0u, 0u);
-      if (rowl < a.Mc) {
-        d = *reinterpret_cast<const float4*>(a.dout[net] + rowl * 4);
-        m = *reinterpret_cast<const uint4*>(a.mask2[net] + rowl * 8 + 4 * rank);
-      }
-      f[0] = d.x * s_d, f[1] = d.y * s_d, f[2] = d.z * s_d, f[3] = d.w * s_d;
+      const float4 d = in.dd[lane];
+      m = in.mm[lane];
+      f[0] = d.x, f[1] = d.y, f[2] = d.z, f[3] = d.w;
     } else {
-      load_row_obs(a, rowl, D, f, nullptr);
+      const float4 o0 = in.o0[lane], o1 = in.o1[lane];
+      f[0] = o0.x, f[1] = o0.y, f[2] = o0.z, f[3] = o0.w, f[4] = o1.x, f[5] = o1.y, f[6] = o1.z;
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.in_empty[slot]);
   };
   // accumulator flush f covers the stages [f F, min((f + 1) F, n_my)); the workers run it once they have produced the
   // kWStages - 1 stages after its last one (what the ring holds without the tensor pipe moving on)
@@ -843,13 +855,10 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
                    inv_scale * (v[e + 2] + c[e + 2]), inv_scale * (v[e + 3] + c[e + 3]));
     }
   };
-  if (n_my > 0) load_inputs(0, in_f, in_m);
   for (int64_t k = 0; k < n_my; ++k) {
-    float cur_f[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cur_f[i] = in_f[i];
-    const uint4 cur_m = in_m;
-    if (k + 1 < n_my) load_inputs(k + 1, in_f, in_m);
+    float cur_f[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    uint4 cur_m = make_uint4(0u, 0u, 0u, 0u);
+    read_inputs(k, cur_f, cur_m);
     const int st = (int)(k % kWStages);
     const uint32_t use = (uint32_t)(k / kWStages);
     if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
@@ -918,17 +927,17 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
   float gb2_acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) gb2_acc[e] = 0.0f;
-  // inputs of this lane's row of a stage: obs[0..6], dOut in slot 7, the 4 mask bytes... (one word) of group g / 4
-  float in_f[8];
-  uint32_t in_m = 0u;
-  auto load_inputs = [&](int64_t k, float* f, uint32_t& m) {
-    const int64_t rowl = (pr + k * npairs) * kXKc + lane;
-    load_row_obs(a, rowl, D, f, nullptr);
-    f[7] = 0.0f, m = 0u;
-    if (rowl < a.Mc) {
-      f[7] = a.dout[net][rowl * 4];
-      m = a.mask2[net][rowl * 8 + 4 * rank + (g >> 2)];
-    }
+  // inputs of this lane's row of a stage (from the loader warp's slot): obs[0..6], dOut in slot 7, the mask word of
+  // unit group g / 4
+  auto read_inputs = [&](int64_t k, float* f, uint32_t& m) {
+    const int slot = (int)(k % kWIn);
+    mbar_wait(&s.in_full[slot], (uint32_t)((k / kWIn) & 1));
+    const WInSlot& in = s.in[slot];
+    const float4 o0 = in.o0[lane], o1 = in.o1[lane];
+    f[0] = o0.x, f[1] = o0.y, f[2] = o0.z, f[3] = o0.w, f[4] = o1.x, f[5] = o1.y, f[6] = o1.z, f[7] = o1.w;
+    m = reinterpret_cast<const uint32_t*>(&in.mm[lane])[g >> 2];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.in_empty[slot]);
   };
   const int64_t nflush = (n_my + kFlushStages - 1) / kFlushStages;
   int64_t next_flush = 0;
@@ -959,13 +968,10 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
                    w3j * (v[e + 3] + c[e + 3]));
     }
   };
-  if (n_my > 0) load_inputs(0, in_f, in_m);
   for (int64_t k = 0; k < n_my; ++k) {
     float cur_f[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cur_f[i] = in_f[i];
-    const uint32_t cur_m = in_m;
-    if (k + 1 < n_my) load_inputs(k + 1, in_f, in_m);
+    uint32_t cur_m;
+    read_inputs(k, cur_f, cur_m);
     const int st = (int)(k % kWStages);
     const uint32_t use = (uint32_t)(k / kWStages);
     if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
@@ -1008,7 +1014,7 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
 }
 
 template <int P, int NPB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1)
 x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemXW<NPB>& s = *reinterpret_cast<SmemXW<NPB>*>(smem_raw);
@@ -1028,6 +1034,11 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     }
     mbar_init(&s.flush_full, 1);
     mbar_init(&s.flush_empty, 32);
+#pragma unroll
+    for (int i = 0; i < kWIn; ++i) {
+      mbar_init(&s.in_full[i], 1);
+      mbar_init(&s.in_empty[i], 16);
+    }
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
@@ -1053,6 +1064,32 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   if (warp < 16) {
     if (net == 0) update_w_workers<P, NPB>(s, np, a, 0, pr, npairs, rank, s_d, inv_scale);
     else update_w_workers_vnet<NPB>(s, np, a, pr, npairs, rank, s_d, inv_scale);
+  } else if (warp == 17) {
+    // loader warp (both CTAs): the inputs of the rows of stage k, lane = row, up to kWIn stages ahead of the workers
+    const int lane = tid & 31;
+    const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
+    const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
+    for (int64_t k = 0; k < n_my; ++k) {
+      const int slot = (int)(k % kWIn);
+      const int64_t rowl = (pr + k * npairs) * kXKc + lane;
+      float ob[7];
+      const bool valid = load_row_obs(a, rowl, np.D, ob, nullptr);
+      float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      uint4 m = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) {
+        if (net == 0) d = *reinterpret_cast<const float4*>(a.dout[0] + rowl * 4);
+        else d.x = a.dout[1][rowl * 4];
+        m = *reinterpret_cast<const uint4*>(a.mask2[net] + rowl * 8 + 4 * rank);
+      }
+      if (k >= kWIn) mbar_wait_sleep(&s.in_empty[slot], (uint32_t)((k / kWIn - 1) & 1));
+      WInSlot& in = s.in[slot];
+      in.o0[lane] = make_float4(ob[0], ob[1], ob[2], ob[3]);
+      in.o1[lane] = make_float4(ob[4], ob[5], ob[6], d.x);
+      if (net == 0) in.dd[lane] = make_float4(d.x * s_d, d.y * s_d, d.z * s_d, d.w * s_d);
+      in.mm[lane] = m;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.in_full[slot]);
+    }
   } else if (rank == 0) {
     const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
     const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
@@ -1256,10 +1293,10 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
   case PV:                                                                                                      \
     if (npb == 2) {                                                                                             \
       if ((rc = set_smem((const void*)x3_update_w_kernel<PV, 2>, sizeof(SmemXW<2>)))) return rc;                 \
-      x3_update_w_kernel<PV, 2><<<2 * wpairs, kXThreads, sizeof(SmemXW<2>), st>>>(np_pi, np_vf, a);              \
+      x3_update_w_kernel<PV, 2><<<2 * wpairs, kWThreads, sizeof(SmemXW<2>), st>>>(np_pi, np_vf, a);              \
     } else {                                                                                                    \
       if ((rc = set_smem((const void*)x3_update_w_kernel<PV, kNPBMax>, sizeof(SmemXW<kNPBMax>)))) return rc;     \
-      x3_update_w_kernel<PV, kNPBMax><<<2 * wpairs, kXThreads, sizeof(SmemXW<kNPBMax>), st>>>(np_pi, np_vf, a);  \
+      x3_update_w_kernel<PV, kNPBMax><<<2 * wpairs, kWThreads, sizeof(SmemXW<kNPBMax>), st>>>(np_pi, np_vf, a);  \
     }                                                                                                           \
     break;
       switch (model->P) {
