@@ -131,35 +131,50 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     const bool valid = load_row_obs(a, rowl, D, obf, nullptr);
     const ObsPairs ob = obs_pairs(obf);
     uint32_t m0 = 0u, m1 = 0u;
-    for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+    // two ring stages per generic -> async proxy fence (the fence and the warp barrier behind it were an eighth of the
+    // kernel's stall samples with one per stage); kFStages is even, so a pair never wraps around the ring
+    static_assert(kFStages % 2 == 0 && (H / kXKc) % 2 == 0, "stage pairs");
+    for (int kc = 0; kc < H / kXKc; kc += 2, kcount += 2) {
       const int st = (int)(kcount % kFStages);
       const uint32_t use = kcount / kFStages;
-      if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+      if (use > 0) {
+        mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+        mbar_wait_cluster(&s.empty[st + 1], (use - 1) & 1);
+      }
       __syncwarp();
       if (warp == 0 && elect_one()) {
-        const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * kUNP) * kXPieceBytes;
-        if (X3_ABL(a) & 64) {
-          mbar_arrive(&s.bfull[st]);
-        } else {
-        mbar_expect_tx(&s.bfull[st], kUNP * kXPieceBytes);
 #pragma unroll
-        for (int p = 0; p < kUNP; ++p)
-          bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
+        for (int h = 0; h < 2; ++h) {
+          const uint8_t* src = np.w2_img + (size_t)(((kc + h) * 2 + rank) * kUNP) * kXPieceBytes;
+          if (X3_ABL(a) & 64) {
+            mbar_arrive(&s.bfull[st + h]);
+          } else {
+            mbar_expect_tx(&s.bfull[st + h], kUNP * kXPieceBytes);
+#pragma unroll
+            for (int p = 0; p < kUNP; ++p)
+              bulk_g2s(s.ring[st + h].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st + h]);
+          }
         }
       }
       if (!(X3_ABL(a) & 1)) {
-      float v[8];
-      const uint32_t bits = h1_chunk<true>(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);  // v = -s_h H1
-      if (kc < 4) m0 |= bits << (8 * kc);
-      else m1 |= bits << (8 * (kc - 4));
-      uint8_t* tiles[kUNP];
 #pragma unroll
-      for (int p = 0; p < kUNP; ++p) tiles[p] = s.ring[st].a[p];
-      store_split_chunk<kUNP, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+        for (int h = 0; h < 2; ++h) {
+          float v[8];
+          const uint32_t bits = h1_chunk<true>(s.w1t, ob, D, stage_kgroup(kc + h, g) * 8, v);  // v = -s_h H1
+          if (kc < 4) m0 |= bits << (8 * (kc + h));
+          else m1 |= bits << (8 * (kc + h - 4));
+          uint8_t* tiles[kUNP];
+#pragma unroll
+          for (int p = 0; p < kUNP; ++p) tiles[p] = s.ring[st + h].a[p];
+          store_split_chunk<kUNP, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+        }
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);  // (the bulk copy reports through warp 16, see the kernel)
+      if (lane == 0) {  // (the bulk copies report through warp 16, see the kernel)
+        mbar_arrive_cluster(&s.full[st], 0);
+        mbar_arrive_cluster(&s.full[st + 1], 0);
+      }
     }
     // H1 mask of columns [64 g, 64 g + 64) of this row
     if (valid) *reinterpret_cast<uint2*>(a.mask1[net] + rowl * 8 + 2 * g) = make_uint2(m0, m1);
@@ -226,7 +241,9 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     if (rowl < a.Mc) *reinterpret_cast<uint2*>(a.mask2[net] + rowl * 8 + 2 * cq) = make_uint2(mk[0], mk[1]);
 #pragma unroll
     for (int p = 0; p < PN; ++p) s.part[cq][r][p] = dot[p];
-    worker_bar_sync();
+    // Both barriers of the epilogue only connect the four warps of one row quarter q (column quarters cq = 0..3): the
+    // loss thread of row r = 32 q + lane is lane `lane` of warp q, and pass 2 of these warps reads that warp's dOut.
+    quarter_bar_sync(q);
     // ---- per-row loss -> dOut (threads 0..127 own row tid)
     if (tid < TILE && !(X3_ABL(a) & 128)) {
       const int64_t rl = tile * 256 + rank * 128 + tid;
@@ -284,8 +301,8 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
       }
     };
     float hv[4][8];
-    load_h2(0, hv);      // does not need dOut: the 12 warps without loss rows do it under the loss phase
-    worker_bar_sync();   // dsm (dOut of the tile's rows) is complete
+    load_h2(0, hv);        // does not need dOut: the 12 warps without loss rows do it under the loss phase
+    quarter_bar_sync(q);   // dsm (dOut of the quarter's rows) is complete
     float dr[4][PN];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -535,27 +552,29 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   uint32_t m0 = 0u, m1 = 0u;
 
   // The inputs of a tile are requested one tile ahead (fetch) and handed over when the tile starts (begin_tile):
-  // the global-load latency hides under the production and epilogue of the tile in between.
-  float4 pf_o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), pf_d = pf_o4;
+  // the global-load latency hides under the production and epilogue of the tile in between.  fetch() only issues
+  // loads -- nothing in it reads a loaded value.
+  float pf_o[4] = {0.0f, 0.0f, 0.0f, 0.0f}, pf_dr = 0.0f;  // obs slots 4 half .. 4 half + 3 of row rt; its dOut (VNET)
+  float4 pf_d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   uint4 pf_m1 = make_uint4(0u, 0u, 0u, 0u);
   uint2 pf_m2 = make_uint2(0u, 0u);
   auto fetch = [&](int64_t tile) {
     {
       const int rt = tid & 255, half = tid >> 8;  // row of the tile; slots 4 half .. 4 half + 3
       const int64_t rl = tile * 256 + rt;
-      float ob[7];
-      const bool valid = load_row_obs(a, rl, D, ob, nullptr);
-      // slot 7 multiplies the bias gradient: 1, or -- value network -- dOut of the row, which then scales the
-      // observations too (dZ1 = dOut * [H1 > 0] .* accumulator: the factor moves into the row's [obs | 1])
-      float d_row = 1.0f;
-      if constexpr (VNET) {
-        d_row = valid ? a.dout[net][rl * 4] : 0.0f;
+      int64_t t = 0, n = 0;
+      const bool valid = rl < a.Mc && minibatch_row_to_tn(a, a.row_off + rl, t, n);
 #pragma unroll
-        for (int d = 0; d < 7; ++d) ob[d] *= d_row;
+      for (int k = 0; k < 4; ++k) pf_o[k] = 0.0f;
+      pf_dr = 0.0f, pf_m1 = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) {
+        const float* base = a.obs + t * (int64_t)D * a.N + n;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * half + k < D) pf_o[k] = __ldg(base + (int64_t)(4 * half + k) * a.N);
+        if constexpr (VNET) pf_dr = a.dout[net][rl * 4];
+        if (half == 0) pf_m1 = *reinterpret_cast<const uint4*>(a.mask1[net] + rl * 8 + 4 * rank);
       }
-      pf_o4 = half ? make_float4(ob[4], ob[5], ob[6], d_row) : make_float4(ob[0], ob[1], ob[2], ob[3]);
-      pf_m1 = make_uint4(0u, 0u, 0u, 0u);
-      if (half == 0 && valid) pf_m1 = *reinterpret_cast<const uint4*>(a.mask1[net] + rl * 8 + 4 * rank);
     }
     const int64_t rowl = tile * 256 + rank * 128 + rloc;
     pf_d = make_float4(0.0f, 0.0f, 0.0f, 0.0f), pf_m2 = make_uint2(0u, 0u);
@@ -566,42 +585,61 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   };
   auto begin_tile = [&](int64_t j) {
     const int buf = (int)(j & 1);
-    // epilogue inputs of the tile: obs and this CTA's mask1 words of all 256 rows
+    // epilogue inputs of the tile: [obs | bias factor] and this CTA's mask1 words of all 256 rows.  Slot 7 multiplies
+    // the bias gradient: 1, or -- value network -- dOut of the row, which then scales the observations too
+    // (dZ1 = dOut * [H1 > 0] .* accumulator: the factor moves into the row's [obs | 1]).
     const int rt = tid & 255, half = tid >> 8;
-    *reinterpret_cast<float4*>(&s.os[buf][rt][4 * half]) = pf_o4;
+    float4 o4 = make_float4(pf_o[0], pf_o[1], pf_o[2], pf_o[3]);
+    if constexpr (VNET) o4.x *= pf_dr, o4.y *= pf_dr, o4.z *= pf_dr, o4.w *= pf_dr;
+    if (half) o4.w = VNET ? pf_dr : 1.0f;
+    *reinterpret_cast<float4*>(&s.os[buf][rt][4 * half]) = o4;
     if (half == 0) *reinterpret_cast<uint4*>(s.m1s[buf][rt]) = pf_m1;
     d4[0] = pf_d.x * s_d, d4[1] = pf_d.y * s_d, d4[2] = pf_d.z * s_d, d4[3] = pf_d.w * s_d;
     m0 = pf_m2.x, m1 = pf_m2.y;
   };
-  auto produce = [&](int kc0, int kc1) {
-    for (int kc = kc0; kc < kc1; ++kc, ++kcount) {
+  // the 8 ring stages of a tile, two per generic -> async proxy fence (kStages is even: a pair never wraps around)
+  static_assert(kStages % 2 == 0 && kTileStages % 2 == 0, "stage pairs");
+  auto produce = [&]() {
+    for (int kc = 0; kc < kTileStages; kc += 2, kcount += 2) {
       const int st = (int)(kcount % kStages);
       const uint32_t use = kcount / kStages;
-      if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+      if (use > 0) {
+        mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+        mbar_wait_cluster(&s.empty[st + 1], (use - 1) & 1);
+      }
       __syncwarp();
       if (warp == 0 && elect_one()) {
-        const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * NPB) * kXPieceBytes;
-        mbar_expect_tx(&s.bfull[st], NPB * kXPieceBytes);
 #pragma unroll
-        for (int p = 0; p < NPB; ++p)
-          bulk_g2s(s.ring[st].a[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
+        for (int h = 0; h < 2; ++h) {
+          const uint8_t* src = np.w2_img + (size_t)(((kc + h) * 2 + rank) * NPB) * kXPieceBytes;
+          mbar_expect_tx(&s.bfull[st + h], NPB * kXPieceBytes);
+#pragma unroll
+          for (int p = 0; p < NPB; ++p)
+            bulk_g2s(s.ring[st + h].a[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st + h]);
+        }
       }
       if (!(X3_ABL(a) & 8)) {
-      const uint32_t byte = (kc < 4 ? m0 >> (8 * kc) : m1 >> (8 * (kc - 4))) & 0xffu;
-      if constexpr (VNET) {
-        *reinterpret_cast<uint4*>(s.ring[st].b[0] + rloc * 16 + g * 2048) = mask_byte_lut(s.lut, byte);
-      } else {
-      float v[8];
-      dz2_chunk<PN>(s.w3, d4, byte, stage_kgroup(kc, g) * 8, v);
-      uint8_t* tiles[NPB];
 #pragma unroll
-      for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
-      store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
-      }
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t byte = (kc < 4 ? m0 >> (8 * (kc + h)) : m1 >> (8 * (kc + h - 4))) & 0xffu;
+          if constexpr (VNET) {
+            *reinterpret_cast<uint4*>(s.ring[st + h].b[0] + rloc * 16 + g * 2048) = mask_byte_lut(s.lut, byte);
+          } else {
+            float v[8];
+            dz2_chunk<PN>(s.w3, d4, byte, stage_kgroup(kc + h, g) * 8, v);
+            uint8_t* tiles[NPB];
+#pragma unroll
+            for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st + h].b[p];
+            store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+          }
+        }
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);  // (the bulk copy reports through warp 16, see the kernel)
+      if (lane == 0) {  // (the bulk copies report through warp 16, see the kernel)
+        mbar_arrive_cluster(&s.full[st], 0);
+        mbar_arrive_cluster(&s.full[st + 1], 0);
+      }
     }
   };
 
@@ -645,13 +683,13 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
     fetch(pr);
     begin_tile(0);
     if (n_my > 1) fetch(pr + npairs);
-    produce(0, kTileStages);
+    produce();
   }
   for (int64_t j = 0; j < n_my; ++j) {
     if (j + 1 < n_my) {
       begin_tile(j + 1);
       if (j + 2 < n_my) fetch(pr + (j + 2) * npairs);
-      produce(0, kTileStages);
+      produce();
     }
     epilogue(j);
   }
