@@ -1107,26 +1107,43 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
     const int lane = tid & 31;
     const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
     const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
-    for (int64_t k = 0; k < n_my; ++k) {
-      const int slot = (int)(k % kWIn);
-      const int64_t rowl = (pr + k * npairs) * kXKc + lane;
+    // two stages' loads in flight: the loads of stage k + 2 are issued right after stage k has been handed over
+    struct Row {
       float ob[7];
-      const bool valid = load_row_obs(a, rowl, np.D, ob, nullptr);
-      float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      uint4 m = make_uint4(0u, 0u, 0u, 0u);
+      float4 d;
+      uint4 m;
+    };
+    auto issue = [&](int64_t k, Row& r) {
+      const int64_t rowl = (pr + k * npairs) * kXKc + lane;
+      const bool valid = load_row_obs(a, rowl, np.D, r.ob, nullptr);
+      r.d = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r.m = make_uint4(0u, 0u, 0u, 0u);
       if (valid) {
-        if (net == 0) d = *reinterpret_cast<const float4*>(a.dout[0] + rowl * 4);
-        else d.x = a.dout[1][rowl * 4];
-        m = *reinterpret_cast<const uint4*>(a.mask2[net] + rowl * 8 + 4 * rank);
+        if (net == 0) r.d = *reinterpret_cast<const float4*>(a.dout[0] + rowl * 4);
+        else r.d.x = a.dout[1][rowl * 4];
+        r.m = *reinterpret_cast<const uint4*>(a.mask2[net] + rowl * 8 + 4 * rank);
       }
-      if (k >= kWIn) mbar_wait_sleep(&s.in_empty[slot], (uint32_t)((k / kWIn - 1) & 1));
+    };
+    auto hand_over = [&](int64_t k, const Row& r) {
+      const int slot = (int)(k % kWIn);
+      if (k >= kWIn) mbar_wait(&s.in_empty[slot], (uint32_t)((k / kWIn - 1) & 1));
       WInSlot& in = s.in[slot];
-      in.o0[lane] = make_float4(ob[0], ob[1], ob[2], ob[3]);
-      in.o1[lane] = make_float4(ob[4], ob[5], ob[6], d.x);
-      if (net == 0) in.dd[lane] = make_float4(d.x * s_d, d.y * s_d, d.z * s_d, d.w * s_d);
-      in.mm[lane] = m;
+      in.o0[lane] = make_float4(r.ob[0], r.ob[1], r.ob[2], r.ob[3]);
+      in.o1[lane] = make_float4(r.ob[4], r.ob[5], r.ob[6], r.d.x);
+      if (net == 0) in.dd[lane] = make_float4(r.d.x * s_d, r.d.y * s_d, r.d.z * s_d, r.d.w * s_d);
+      in.mm[lane] = r.m;
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.in_full[slot]);
+    };
+    Row ra, rb;
+    if (n_my > 0) issue(0, ra);
+    if (n_my > 1) issue(1, rb);
+    for (int64_t k = 0; k < n_my; k += 2) {
+      hand_over(k, ra);
+      if (k + 2 < n_my) issue(k + 2, ra);
+      if (k + 1 < n_my) {
+        hand_over(k + 1, rb);
+        if (k + 3 < n_my) issue(k + 3, rb);
+      }
     }
   } else if (rank == 0) {
     const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
@@ -1326,7 +1343,7 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
       const int64_t nst = ceil_div(a.Mc, kXKc);
       int wpairs = (int)(nst < kNumSMs / 2 ? nst : kNumSMs / 2);
       if (wpairs < 2) wpairs = 2;
-      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 39);  // 38 -> 2.45, 40 -> 2.50, 43 -> 2.74 ms
+      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 38);  // 36 -> 1.96, 38 -> 1.92, 40 -> 2.04 ms
 #define RL8_UPDW(PV)                                                                                            \
   case PV:                                                                                                      \
     if (npb == 2) {                                                                                             \
