@@ -4,8 +4,8 @@
 
 Workload (BASELINE.json configs[1]): CartPole, ``num_envs=65536`` PER GPU, ``horizon=32``,
 Categorical policy, default ``AlgorithmConfig`` update (4 SGD epochs, full batch, ``enable_amp=False``:
-fp32 results, computed on tcgen05 through split-bf16 operands -- the mode that reproduces the
-reference-recorded golden vectors at 1e-5).  ``amp_mode`` in the same line is ``enable_amp=True`` (plain
+fp32 results, computed on tcgen05 through split operands (two fp16 pieces per fp32 value in the update, three bf16
+pieces in the rollout) -- the mode that reproduces the reference-recorded golden vectors at 1e-5).  ``amp_mode`` in the same line is ``enable_amp=True`` (plain
 bf16 operands); with more than one GPU ``c5`` is BASELINE.json configs[4] exactly.  A "step"
 is one ``collect()`` + one ``step()``.  ``value`` is timed with CUDA events around K steps
 (max over ranks); ``e2e`` repeats it through ``Trainer.step()`` with the sampling noise
@@ -348,7 +348,7 @@ def run_ours(a: argparse.Namespace) -> None:
     lib = _lib.load()
 
     def make(dist_cls=None, precision=a.precision):  # noqa: ANN001, ANN202
-        # auto = the reference's default enable_amp=False: fp32 results (on tcgen05 through split-bf16 operands for
+        # auto = the reference's default enable_amp=False: fp32 results (on tcgen05 through split operands for
         # the feedforward models), the mode the golden vectors are reproduced in; bf16 = enable_amp=True
         amp = precision == "bf16"
         dist_cls = dist_cls or base_dist
@@ -743,22 +743,25 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
     flops = M * 3.0 * 2.0 * (2 * H * H + 2 * D * H + (P + 1) * H)
     burst = float(peaks["bf16_tflops"])  # the call is timed alone (L2 flushed before it): the burst figure applies
     if prec == L.PREC_FP32_TC:
-        # every fp32 product of the 256 x 256 contractions is six bf16 piece products on the tensor pipe
+        # every fp32 product of the 256 x 256 contractions is three fp16 piece products on the tensor pipe (kind::f16
+        # multiplies fp16 operands at the bf16 rate the peak was measured at)
         return {
             "kernel": "rl8_ppo_minibatch, RL8_PREC_FP32_TC (x3_update_f + x3_update_b + x3_update_w per 2^21-row chunk:"
-                      " split-bf16 pair MMAs, operands recomputed from 80 B/row of scratch)",
-            "bound": "tensor", "achieved": flops / ms / 1e9, "peak": burst / 6.0, "unit": "TFLOP/s",
-            "frac": flops / ms / 1e9 / (burst / 6.0), "traffic": NCU_TRAFFIC_X3.get((a.workload, M)), "ms": ms,
+                      " pair MMAs on two fp16 pieces per fp32 operand, operands recomputed from 80 B/row of scratch)",
+            "bound": "tensor", "achieved": flops / ms / 1e9, "peak": burst / 3.0, "unit": "TFLOP/s",
+            "frac": flops / ms / 1e9 / (burst / 3.0), "traffic": NCU_TRAFFIC_X3.get((a.workload, M)), "ms": ms,
             "rows": M, "dtype": "f32",
-            # bf16 piece products actually issued per row: policy network 6 + 6 + 6, value network 6 + 3 + 3 (its
+            # piece products actually issued per row: policy network 3 + 3 + 3, value network 3 + 2 + 2 (its
             # gradient contractions take the ReLU mask as a one-piece operand)
-            "mma_tflops": M * 30.0 * 2.0 * H * H / ms / 1e9, "mma_frac": M * 30.0 * 2.0 * H * H / ms / 1e9 / burst,
+            "mma_tflops": M * 16.0 * 2.0 * H * H / ms / 1e9, "mma_frac": M * 16.0 * 2.0 * H * H / ms / 1e9 / burst,
             "traffic_source": ("ncu --set full, profiles/r02_x3_update_ncu_summary.md"
                                if (a.workload, M) in NCU_TRAFFIC_X3 else None),
-            "peak_source": peaks["source"] + " bf16 burst / 6 (six bf16 piece products per fp32 product; `achieved`"
-                                             " counts the algorithm's fp32 FLOPs; `mma_tflops` / `mma_frac` count the"
-                                             " bf16 piece products actually issued -- 30 per row, not 36: two of the"
-                                             " value network's contractions need three -- against the plain burst peak)",
+            "peak_source": peaks["source"] + " bf16 burst / 3 (three fp16 piece products per fp32 product at the bf16"
+                                             " rate; `achieved` counts the algorithm's fp32 FLOPs; `mma_tflops` /"
+                                             " `mma_frac` count the piece products actually issued -- 16 per row, not"
+                                             " 18: two of the value network's contractions need two -- against the"
+                                             " plain burst peak).  The kernels are bound by the CUDA-core operand"
+                                             " producers and epilogues, not by the tensor pipe (profiles/)",
         }
     traffic = NCU_TRAFFIC.get((a.workload, M)) if dtype == "bf16" else None
     return {
