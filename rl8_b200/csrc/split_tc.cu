@@ -9,7 +9,7 @@ namespace rl8 {
 
 using namespace tc;
 
-constexpr int kXStages = 4;  // ring depth of the forward kernel (48 KB stages)
+constexpr int kXStages = kUF16 ? 6 : 4;  // ring depth of the forward kernel (32 KB / 48 KB stages)
 
 // ---- pair selftest ---------------------------------------------------------------------------------------------
 // One cluster of two CTAs, 256 threads each, synchronous K loop in chunks of 32: stage -> cluster barrier ->
@@ -249,8 +249,11 @@ int launch_absmax_bits(const float* x, int64_t n, uint32_t* out_bits, cudaStream
 
 // ---- forward kernel ---------------------------------------------------------------------------------------------------
 // out[rows][P] of one network, fp32-accurate:  H1 = relu([obs] W1^T + b1) is computed on CUDA cores (K = D <= 7, exact
-// fp32 FMAs) by the 16 worker warps straight into split A stages;  Z2 = H1 W2^T is the x3 pair GEMM (6 piece products,
-// B stages bulk-copied from the piece image);  H2 = relu(Z2 + b2) and the P-wide head are the epilogue.
+// fp32 FMAs) by the 16 worker warps straight into split A stages;  Z2 = H1 W2^T is the split pair GEMM (two fp16
+// pieces per operand and 3 piece products, or -- X3_BF16 build -- three bf16 pieces and 6; B stages bulk-copied from
+// the piece image);  H2 = relu(Z2 + b2) and the P-wide head are the epilogue.  fp16 pieces: the A operand is
+// -s_h H1 with s_h from the bound h1_bound(max |obs| of the rows), the image carries s_w, and the epilogue folds
+// 1 / (s_h s_w) into its bias add (all powers of two: the results are those of the un-scaled sums, bit for bit).
 // A cluster of two CTAs owns 256-row tiles; accumulators are double-buffered in tensor memory (2 x 256 columns), so
 // while the workers run the epilogue of tile j the tensor pipe drains the ring stages they produced for tile j + 1.
 //   worker warps 0..15 : produce(tile j + 1) -> epilogue(tile j)
@@ -259,9 +262,10 @@ int launch_absmax_bits(const float* x, int64_t n, uint32_t* out_bits, cudaStream
 // landed), bfull[s] (local, the bulk copy of the CTA's B half), empty[s] / acc_full[b] (multicast commits),
 // acc_empty[b] (leader's, 32 worker-warp arrivals: accumulator b has been read).
 struct SmemX3F {
-  StageX<3> ring[kXStages];     // 196608
-  float w1t[8][H];              //   8192  [W1^T (D <= 7 rows) | b1 in row 7]
-  float b2[H];                  //   1024
+  StageX<kUNP> ring[kXStages];  // 196608
+  float w1t[8][H];              //   8192  -s_h [W1^T (D <= 7 rows) | b1 in row 7]
+  float b2[H];                  //   1024  -b2
+  float red[32];
   float w3[kMaxPT][H];          //   4096
   float part[4][TILE][kMaxPT];  //   8192  head partial sums per column quarter
   uint64_t full[kXStages], bfull[kXStages], empty[kXStages], acc_full[2], acc_empty[2];
@@ -271,7 +275,8 @@ static_assert(sizeof(SmemX3F) <= 227 * 1024, "SmemX3F exceeds the 227 KB CTA lim
 
 template <int P>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXThreads, 1)
-tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ out, int tanh_col1) {
+tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ out, int tanh_col1,
+                   const float* __restrict__ w2_scale, const uint32_t* __restrict__ omax_bits) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemX3F& s = *reinterpret_cast<SmemX3F*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -288,8 +293,13 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc_pair(&s.tmem_base, 512);
-  stage_w1t(s.w1t, np);
-  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = np.b2[i];
+  float s_h = 1.0f, inv_scale = 1.0f;
+  if constexpr (kUF16) {
+    s_h = pow2_scale_for(h1_bound(np, __uint_as_float(*omax_bits), s.red));
+    inv_scale = (1.0f / s_h) * (1.0f / *w2_scale);
+  }
+  stage_w1t(s.w1t, np, -s_h);                                           // h1_chunk<true>: A = -s_h H1
+  for (int i = tid; i < H; i += blockDim.x) s.b2[i] = 0.0f - np.b2[i];  // -b2, never -0
   for (int i = tid; i < kMaxPT * H; i += blockDim.x) {
     const int p = i / H, c = i - p * H;
     s.w3[p][c] = p < np.P ? np.w3[p * H + c] : 0.0f;
@@ -326,16 +336,18 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
         if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
         __syncwarp();
         if (warp == 0 && elect_one()) {
-          const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * 3) * kXPieceBytes;
-          mbar_expect_tx(&s.bfull[st], 3 * kXPieceBytes);
+          const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * kUNP) * kXPieceBytes;
+          mbar_expect_tx(&s.bfull[st], kUNP * kXPieceBytes);
 #pragma unroll
-          for (int p = 0; p < 3; ++p)
+          for (int p = 0; p < kUNP; ++p)
             bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
         }
         float v[8];
-        h1_chunk(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);
-        uint8_t* const tiles[3] = {s.ring[st].a[0], s.ring[st].a[1], s.ring[st].a[2]};
-        store_split_chunk<3>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+        h1_chunk<true>(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);  // -s_h H1
+        uint8_t* tiles[kUNP];
+#pragma unroll
+        for (int p = 0; p < kUNP; ++p) tiles[p] = s.ring[st].a[p];
+        store_split_chunk<kUNP, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -368,16 +380,18 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
         const float* v = c2 ? v1 : v0;
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4) {
+          // the accumulator holds -s Z2 and s.b2 holds -b2: fma(v, 1 / s, -b2) = -(Z2 + b2), rounded once like the
+          // un-scaled sum; h = min(., 0) = -H2 enters the head sums negated
           const float4 b = *reinterpret_cast<const float4*>(&s.b2[col0 + jj]);
-          const float h0 = fmaxf(v[jj] + b.x, 0.0f), h1 = fmaxf(v[jj + 1] + b.y, 0.0f);
-          const float h2 = fmaxf(v[jj + 2] + b.z, 0.0f), h3 = fmaxf(v[jj + 3] + b.w, 0.0f);
+          const float h0 = fminf(fmaf(v[jj], inv_scale, b.x), 0.0f), h1 = fminf(fmaf(v[jj + 1], inv_scale, b.y), 0.0f);
+          const float h2 = fminf(fmaf(v[jj + 2], inv_scale, b.z), 0.0f), h3 = fminf(fmaf(v[jj + 3], inv_scale, b.w), 0.0f);
 #pragma unroll
           for (int p = 0; p < P; ++p) {
             const float4 w = *reinterpret_cast<const float4*>(&s.w3[p][col0 + jj]);
-            dot[p] = fmaf(h0, w.x, dot[p]);
-            dot[p] = fmaf(h1, w.y, dot[p]);
-            dot[p] = fmaf(h2, w.z, dot[p]);
-            dot[p] = fmaf(h3, w.w, dot[p]);
+            dot[p] = fmaf(-h0, w.x, dot[p]);
+            dot[p] = fmaf(-h1, w.y, dot[p]);
+            dot[p] = fmaf(-h2, w.z, dot[p]);
+            dot[p] = fmaf(-h3, w.w, dot[p]);
           }
         }
       }
@@ -404,7 +418,7 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
     }
   } else if (rank == 0) {
     // MMA issue: the whole warp follows the barriers, one elected lane issues
-    const uint32_t idesc = instr_desc(256, H, 0, 0);
+    const uint32_t idesc = upd_idesc(0, 0);
     uint32_t kcount = 0;
     for (int64_t j = 0; j < n_my; ++j) {
       const int buf = (int)(j & 1);
@@ -414,7 +428,7 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
         mbar_wait_cluster(&s.full[st], (kcount / kXStages) & 1);
         fence_after_sync();
         if (elect_one()) {
-          issue_stage<3>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
+          issue_stage<kUNP>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
           mma_commit_pair(&s.empty[st]);
           if (kc == H / kXKc - 1) mma_commit_pair(&s.acc_full[buf]);
         }
@@ -428,15 +442,37 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
   if (warp == 16) tmem_dealloc_pair(tmem, 512);
 }
 
+// max |obs| over the rows of a map (NaNs skipped) -> *out_bits (atomicMax of the float's bit pattern)
+__global__ void __launch_bounds__(256) absmax_rows_kernel(RowMap map, int64_t rows, int D, uint32_t* __restrict__ out_bits) {
+  float m = 0.0f;
+  const int64_t ds = map.dstride();
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* base = map.obs + map.offset(r);
+    for (int d = 0; d < D; ++d) m = fmaxf(m, fabsf(__ldg(base + (int64_t)d * ds)));
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out_bits, __float_as_uint(m));
+}
+static int launch_absmax_rows(const RowMap& map, int64_t rows, int D, uint32_t* out_bits, cudaStream_t st) {
+  if (rows <= 0) return RL8_OK;
+  int64_t blocks = ceil_div(rows, (int64_t)256 * 4);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  absmax_rows_kernel<<<(int)blocks, 256, 0, st>>>(map, rows, D, out_bits);
+  return check_launch("absmax_rows");
+}
+
+// w2_scale / omax_bits (device): the scale of the W2 piece image and the bits of max |obs| over the rows (fp16 pieces)
 static int launch_forward_x3(const NetParams& np, const RowMap& map, int64_t rows, float* out, int tanh_col1,
-                             cudaStream_t st) {
+                             const float* w2_scale, const uint32_t* omax_bits, cudaStream_t st) {
   const int64_t ntiles = ceil_div(rows, 256);
   const int grid = 2 * (int)(ntiles < kNumSMs / 2 ? ntiles : kNumSMs / 2);
   int rc;
 #define RL8_FWDX(PV)                                                                                   \
   case PV:                                                                                             \
     if ((rc = set_smem((const void*)tc3_forward_kernel<PV>, sizeof(SmemX3F)))) return rc;               \
-    tc3_forward_kernel<PV><<<grid, kXThreads, sizeof(SmemX3F), st>>>(np, map, rows, out, tanh_col1);    \
+    tc3_forward_kernel<PV><<<grid, kXThreads, sizeof(SmemX3F), st>>>(np, map, rows, out, tanh_col1,     \
+                                                                     w2_scale, omax_bits);             \
     break;
   switch (np.P) {
     RL8_FWDX(1) RL8_FWDX(2) RL8_FWDX(3) RL8_FWDX(4)
@@ -446,23 +482,44 @@ static int launch_forward_x3(const NetParams& np, const RowMap& map, int64_t row
   return check_launch("tc3_forward");
 }
 
-int64_t forward_x3_workspace() { return kXImgBytes; }
+// workspace: the piece image, then 256 bytes of operand magnitudes {float w2 scale; uint32 max |obs| bits}
+int64_t forward_x3_workspace() { return kXImgBytes + 256; }
+
+static int zero_words(void* p, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(p, 0, bytes, st);
+  if (e != cudaSuccess) {
+    set_last_error("cudaMemsetAsync", e);
+    return RL8_ERR_CUDA;
+  }
+  return RL8_OK;
+}
 
 int mlp_forward_x3(const rl8_model* m, int which, const RowMap& map, int64_t rows, float* out, int tanh_col1,
                    void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   if (m->H != H || m->D > 7 || m->P > kMaxPT) return RL8_ERR_UNSUPPORTED;
-  if (!workspace || workspace_bytes < kXImgBytes) return RL8_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < forward_x3_workspace()) return RL8_ERR_WORKSPACE;
   uint8_t* img = (uint8_t*)workspace;
-  int rc = launch_pack_w2_pieces(which ? m->vf_w2 : m->pi_w2, img, 0, 3, st);
-  if (rc) return rc;
-  return launch_forward_x3(net_params(m, which, img), map, rows, out, tanh_col1, st);
+  float* w2_scale = (float*)(img + kXImgBytes);
+  uint32_t* omax = (uint32_t*)(w2_scale + 1);
+  int rc;
+  if (kUF16) {
+    if ((rc = zero_words(w2_scale, 8, st))) return rc;
+    if ((rc = launch_absmax_rows(map, rows, m->D, omax, st))) return rc;
+  }
+  if ((rc = launch_pack_w2_pieces(which ? m->vf_w2 : m->pi_w2, img, 0, kUF16 ? -2 : 3, st, nullptr, w2_scale))) return rc;
+  return launch_forward_x3(net_params(m, which, img), map, rows, out, tanh_col1, w2_scale, omax, st);
 }
 
-// collect() in RL8_PREC_FP32_TC: per step the x3 policy forward + the fused sample / env-step / buffer-write kernel
-// of the fp32 path (collect.cu), then one x3 value pass over all T + 1 observation slabs.
+// collect() in RL8_PREC_FP32_TC: per step the split policy forward + the fused sample / env-step / buffer-write kernel
+// of the fp32 path (collect.cu), then one split value pass over all T + 1 observation slabs.
 int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st);
 
-int64_t collect_x3_workspace(const rl8_model*, int64_t N, int32_t) { return 2 * (int64_t)kXImgBytes + N * kMaxPT * 4; }
+// workspace: two piece images, the operand magnitudes {w2 scale pi, w2 scale vf, max |obs| bits of all slabs, of slab
+// 0 .. T}, the head outputs of a step
+static int64_t collect_x3_scale_bytes(int32_t T) { return round_up((int64_t)(T + 4) * 4, 256); }
+int64_t collect_x3_workspace(const rl8_model*, int64_t N, int32_t T) {
+  return 2 * (int64_t)kXImgBytes + collect_x3_scale_bytes(T) + N * kMaxPT * 4;
+}
 
 int collect_x3(const rl8_model* model, const rl8_rollout* ro, void* workspace, int64_t workspace_bytes,
                cudaStream_t st) {
@@ -471,22 +528,29 @@ int collect_x3(const rl8_model* model, const rl8_rollout* ro, void* workspace, i
   if (!workspace || workspace_bytes < collect_x3_workspace(model, N, ro->T)) return RL8_ERR_WORKSPACE;
   uint8_t* img_pi = (uint8_t*)workspace;
   uint8_t* img_vf = img_pi + kXImgBytes;
-  float* feat = (float*)(img_vf + kXImgBytes);
+  float* w2_scale = (float*)(img_vf + kXImgBytes);           // [2]
+  uint32_t* omax_all = (uint32_t*)(w2_scale + 2);            // all T + 1 slabs (value pass)
+  uint32_t* omax_t = omax_all + 1;                           // [T + 1]: slab t (policy forward of step t)
+  float* feat = (float*)((uint8_t*)w2_scale + collect_x3_scale_bytes(ro->T));
   int rc;
-  if ((rc = launch_pack_w2_pieces(model->pi_w2, img_pi, 0, 3, st))) return rc;
-  if ((rc = launch_pack_w2_pieces(model->vf_w2, img_vf, 0, 3, st))) return rc;
+  if (kUF16 && (rc = zero_words(w2_scale, (size_t)collect_x3_scale_bytes(ro->T), st))) return rc;
+  if ((rc = launch_pack_w2_pieces(model->pi_w2, img_pi, 0, kUF16 ? -2 : 3, st, nullptr, w2_scale))) return rc;
+  if ((rc = launch_pack_w2_pieces(model->vf_w2, img_vf, 0, kUF16 ? -2 : 3, st, nullptr, w2_scale + 1))) return rc;
   const NetParams np_pi = net_params(model, 0, img_pi), np_vf = net_params(model, 1, img_vf);
   const int continuous = ro->dist_kind != RL8_DIST_CATEGORICAL;
   RowMap map{};
   map.mode = 0, map.stride_r = 1, map.stride_d = N, map.D = model->D;
   for (int t = 0; t < ro->T; ++t) {
     map.obs = ro->obs + (int64_t)t * model->D * N;
-    if ((rc = launch_forward_x3(np_pi, map, N, feat, continuous, st))) return rc;
+    // (slab t is contiguous: D * N floats written by the reset / the previous step's tail kernel)
+    if (kUF16 && (rc = launch_absmax_bits(map.obs, (int64_t)model->D * N, omax_t + t, st))) return rc;
+    if ((rc = launch_forward_x3(np_pi, map, N, feat, continuous, w2_scale, omax_t + t, st))) return rc;
     if ((rc = collect_tail(ro, t, feat, st))) return rc;
   }
   RowMap vmap{};
   vmap.obs = ro->obs, vmap.mode = 2, vmap.D = model->D, vmap.N = N, vmap.T = ro->T;
-  return launch_forward_x3(np_vf, vmap, (int64_t)(ro->T + 1) * N, ro->values, 0, st);
+  if (kUF16 && (rc = launch_absmax_bits(ro->obs, (int64_t)(ro->T + 1) * model->D * N, omax_all, st))) return rc;
+  return launch_forward_x3(np_vf, vmap, (int64_t)(ro->T + 1) * N, ro->values, 0, w2_scale + 1, omax_all, st);
 }
 
 }  // namespace rl8
