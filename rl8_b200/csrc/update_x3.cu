@@ -792,11 +792,10 @@ x3_update_b_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
 // gW2[j][i] += sum_rows dZ2[row][j] H1[row][i].  The contraction runs over rows: a ring stage is 32 rows, both operands
 // are MN-major tiles [32 K rows][128 M / N columns] per piece (off(r, g) = r * 16 + g * 512; LBO 128, SBO 512), CTA c
 // of the pair produces the dZ2 columns j and the H1 columns i of ITS half, so nothing is computed twice.
-//   worker warps 0..7  : dZ2^T chunks  (lane = row of the stage, warp w -> column groups w and w + 8), gb2 on the way
-//   worker warps 8..15 : H1 chunks     (lane = row, warp w - 8 -> column groups w - 8 and w)
+//   worker warp w (0..15): the dZ2^T chunk and the H1 chunk of column group w (lane = row of the stage), gb2 on the way
 // Pairs [0, n_pi) work on the policy network, the rest on the value network; a pair owns the stages
 // pr, pr + npairs, ... of its network and keeps its 256 x 256 accumulator in tensor memory until the end.
-// Inputs of the 32 rows of one stage (lane = row), fetched ONCE per CTA by the loader warp (warp 17): the 16 worker
+// Inputs of the 32 rows of one stage (lane = row), fetched ONCE per CTA by a loader warp (warps 17, 18): the 16 worker
 // warps all need the same rows, and the buffer coordinates of a row (a division) and its D strided observation loads
 // were a quarter of the kernel's instructions when every warp fetched its own copy.
 struct WInSlot {
@@ -806,7 +805,7 @@ struct WInSlot {
   uint4 mm[32];   // mask2 words of this CTA's 128-unit half
 };
 constexpr int kWIn = 6;
-constexpr int kWThreads = kXThreads + 32;  // + the loader warp
+constexpr int kWThreads = kXThreads + 64;  // + two loader warps
 template <int NPB>
 struct SmemXW {
   static constexpr int kStages = NPB == 2 ? 6 : 4;
@@ -839,27 +838,24 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
   const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
   const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
   constexpr int kWStages = SmemXW<NPB>::kStages;
-  const bool dz_role = warp < 8;
-  const int g0 = dz_role ? warp : warp - 8;  // column groups g0 and g0 + 8 of this CTA's 128-column half
-  float gb2_acc[2][8];
+  // Every worker warp w produces column group w of BOTH operands for the 32 rows of a stage (lane = row): one dZ2^T
+  // chunk and one H1 chunk -- the same work in every warp (with 8 dZ2 warps and 8 H1 warps the lighter role spent a
+  // fifth of its time waiting for ring slots).
+  const int g = warp;
+  float gb2_acc[8];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) gb2_acc[i][e] = 0.0f;
-  // inputs of this lane's row of a stage (from the loader warp's slot): dz role {s_d dOut[4], 16 mask bytes of the
-  // CTA's half}; h1 role {obs[7]}
-  auto read_inputs = [&](int64_t k, float* f, uint4& m) {
+  for (int e = 0; e < 8; ++e) gb2_acc[e] = 0.0f;
+  // inputs of this lane's row of a stage (from the loader warp's slot): s_d dOut[4], the mask word of unit group
+  // g / 4, obs[7]
+  auto read_inputs = [&](int64_t k, float* d4, uint32_t& m, float* ob) {
     const int slot = (int)(k % kWIn);
     mbar_wait(&s.in_full[slot], (uint32_t)((k / kWIn) & 1));
     const WInSlot& in = s.in[slot];
-    if (dz_role) {
-      const float4 d = in.dd[lane];
-      m = in.mm[lane];
-      f[0] = d.x, f[1] = d.y, f[2] = d.z, f[3] = d.w;
-    } else {
-      const float4 o0 = in.o0[lane], o1 = in.o1[lane];
-      f[0] = o0.x, f[1] = o0.y, f[2] = o0.z, f[3] = o0.w, f[4] = o1.x, f[5] = o1.y, f[6] = o1.z;
-    }
+    const float4 d = in.dd[lane];
+    m = reinterpret_cast<const uint32_t*>(&in.mm[lane])[g >> 2];
+    const float4 o0 = in.o0[lane], o1 = in.o1[lane];
+    d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
+    ob[0] = o0.x, ob[1] = o0.y, ob[2] = o0.z, ob[3] = o0.w, ob[4] = o1.x, ob[5] = o1.y, ob[6] = o1.z;
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.in_empty[slot]);
   };
@@ -893,30 +889,34 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
                    inv_scale * (v[e + 2] + c[e + 2]), inv_scale * (v[e + 3] + c[e + 3]));
     }
   };
-  for (int64_t k = 0; k < n_my; ++k) {
-    float cur_f[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    uint4 cur_m = make_uint4(0u, 0u, 0u, 0u);
-    read_inputs(k, cur_f, cur_m);
-    const int st = (int)(k % kWStages);
-    const uint32_t use = (uint32_t)(k / kWStages);
-    if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
+  // Two stages per generic -> async proxy fence: the fence (and the warp barrier behind it) is a serial latency of
+  // every warp and stage -- the stage period of this kernel did not depend on the amount of producer work.  Stage
+  // pairs start at even k (kWStages and kFlushStages are even): a pair never wraps the ring or straddles a flush.
+  static_assert(kWStages % 2 == 0 && kFlushStages % 2 == 0, "stage pairs");
+  for (int64_t k0 = 0; k0 < n_my; k0 += 2) {
+    const int cnt = k0 + 1 < n_my ? 2 : 1;
+    const int st0 = (int)(k0 % kWStages);
+    const uint32_t use = (uint32_t)(k0 / kWStages);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (X3_ABL(a) & 32) break;
-      const int g = g0 + 8 * i;
-      float v[8];
-      if (dz_role) {
-        const uint32_t word = g < 4 ? cur_m.x : g < 8 ? cur_m.y : g < 12 ? cur_m.z : cur_m.w;
-        dz2_chunk<PN>(s.w3, cur_f, (word >> (8 * (g & 3))) & 0xffu, 128 * (int)rank + 8 * g, v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) gb2_acc[i][e] += v[e];
+    for (int h = 0; h < 2; ++h) {
+      if (h >= cnt) break;
+      float cur_d[4], cur_o[7];
+      uint32_t cur_m;
+      read_inputs(k0 + h, cur_d, cur_m, cur_o);
+      const int st = st0 + h;
+      if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
+      if (!(X3_ABL(a) & 32)) {
+        float v[8];
         uint8_t* tiles[NPB];
+        // A: dZ2^T of unit group g
+        dz2_chunk<PN>(s.w3, cur_d, (cur_m >> (8 * (g & 3))) & 0xffu, 128 * (int)rank + 8 * g, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gb2_acc[e] += v[e];
 #pragma unroll
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].a[p];
         store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
-      } else {
-        h1_chunk<true>(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);  // -s_h H1 (inv_scale is negative)
-        uint8_t* tiles[NPB];
+        // B: H1 of input group g
+        h1_chunk<true>(s.w1t, obs_pairs(cur_o), D, 128 * (int)rank + 8 * g, v);  // -s_h H1 (inv_scale is negative)
 #pragma unroll
         for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
         store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
@@ -924,7 +924,11 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
     }
     fence_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);
+    if (lane == 0) {
+      mbar_arrive_cluster(&s.full[st0], 0);
+      if (cnt == 2) mbar_arrive_cluster(&s.full[st0 + 1], 0);
+    }
+    const int64_t k = k0 + cnt - 1;  // the last stage produced
     while (next_flush < nflush) {
       const int64_t last = (next_flush + 1) * kFlushStages < n_my ? (next_flush + 1) * kFlushStages - 1 : n_my - 1;
       const int64_t due = last + kWStages - 1 < n_my - 1 ? last + kWStages - 1 : n_my - 1;
@@ -932,14 +936,12 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
       flush(next_flush++);
     }
   }
-  if (n_my > 0 && dz_role) {
+  if (n_my > 0) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float w = warp_sum(gb2_acc[i][e]);
-        if (lane == 0) atomicAdd(a.gb2[net] + 128 * rank + 8 * (g0 + 8 * i) + e, w * (1.0f / s_d));
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float w = warp_sum(gb2_acc[e]);
+      if (lane == 0) atomicAdd(a.gb2[net] + 128 * rank + 8 * g + e, w * (1.0f / s_d));
+    }
   }
 }
 
@@ -1006,12 +1008,17 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
                    w3j * (v[e + 3] + c[e + 3]));
     }
   };
-  for (int64_t k = 0; k < n_my; ++k) {
+  for (int64_t k0 = 0; k0 < n_my; k0 += 2) {  // (stage pairs, see update_w_workers)
+    const int cnt = k0 + 1 < n_my ? 2 : 1;
+    const int st0 = (int)(k0 % kWStages);
+    const uint32_t use = (uint32_t)(k0 / kWStages);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+    if (h >= cnt) break;
     float cur_f[8];
     uint32_t cur_m;
-    read_inputs(k, cur_f, cur_m);
-    const int st = (int)(k % kWStages);
-    const uint32_t use = (uint32_t)(k / kWStages);
+    read_inputs(k0 + h, cur_f, cur_m);
+    const int st = st0 + h;
     if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
     if (!(X3_ABL(a) & 32)) {
       // A: the mask bits of unit group g  (tile a[0] only)
@@ -1031,9 +1038,14 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
       for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
       store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
     }
+    }
     fence_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(&s.full[st], 0);
+    if (lane == 0) {
+      mbar_arrive_cluster(&s.full[st0], 0);
+      if (cnt == 2) mbar_arrive_cluster(&s.full[st0 + 1], 0);
+    }
+    const int64_t k = k0 + cnt - 1;  // the last stage produced
     while (next_flush < nflush) {
       const int64_t last = (next_flush + 1) * kFlushStages < n_my ? (next_flush + 1) * kFlushStages - 1 : n_my - 1;
       const int64_t due = last + kWStages - 1 < n_my - 1 ? last + kWStages - 1 : n_my - 1;
@@ -1102,12 +1114,15 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
   if (warp < 16) {
     if (net == 0) update_w_workers<P, NPB>(s, np, a, 0, pr, npairs, rank, s_d, inv_scale);
     else update_w_workers_vnet<NPB>(s, np, a, pr, npairs, rank, s_d, inv_scale);
-  } else if (warp == 17) {
-    // loader warp (both CTAs): the inputs of the rows of stage k, lane = row, up to kWIn stages ahead of the workers
+  } else if (warp >= 17) {
+    // loader warps (two in both CTAs): the inputs of the rows of stage k, lane = row, up to kWIn stages ahead of the
+    // workers
     const int lane = tid & 31;
     const int64_t nstages = (a.Mc + kXKc - 1) / kXKc;
     const int64_t n_my = pr < nstages ? (nstages - pr + npairs - 1) / npairs : 0;
-    // two stages' loads in flight: the loads of stage k + 2 are issued right after stage k has been handed over
+    // Each loader warp keeps four stages' loads in flight (the loads of its stage k + 8 are issued right after its stage
+    // k has been handed over): with one warp and one or two stages in flight the whole kernel ran at the pace of the
+    // loader's global-load and index-arithmetic latency, whatever the workers did.
     struct Row {
       float ob[7];
       float4 d;
@@ -1134,15 +1149,27 @@ x3_update_w_kernel(NetParams np_pi, NetParams np_vf, UpdXArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.in_full[slot]);
     };
-    Row ra, rb;
-    if (n_my > 0) issue(0, ra);
-    if (n_my > 1) issue(1, rb);
-    for (int64_t k = 0; k < n_my; k += 2) {
+    // loader warp l (0 / 1) owns the stages k = l (mod 2): k, k + 2, k + 4, k + 6 in flight
+    const int64_t l = warp - 17;
+    Row ra, rb, rc, rd;
+    if (l < n_my) issue(l, ra);
+    if (l + 2 < n_my) issue(l + 2, rb);
+    if (l + 4 < n_my) issue(l + 4, rc);
+    if (l + 6 < n_my) issue(l + 6, rd);
+    for (int64_t k = l; k < n_my; k += 8) {
       hand_over(k, ra);
-      if (k + 2 < n_my) issue(k + 2, ra);
-      if (k + 1 < n_my) {
-        hand_over(k + 1, rb);
-        if (k + 3 < n_my) issue(k + 3, rb);
+      if (k + 8 < n_my) issue(k + 8, ra);
+      if (k + 2 < n_my) {
+        hand_over(k + 2, rb);
+        if (k + 10 < n_my) issue(k + 10, rb);
+      }
+      if (k + 4 < n_my) {
+        hand_over(k + 4, rc);
+        if (k + 12 < n_my) issue(k + 12, rc);
+      }
+      if (k + 6 < n_my) {
+        hand_over(k + 6, rd);
+        if (k + 14 < n_my) issue(k + 14, rd);
       }
     }
   } else if (rank == 0) {
@@ -1343,7 +1370,7 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
       const int64_t nst = ceil_div(a.Mc, kXKc);
       int wpairs = (int)(nst < kNumSMs / 2 ? nst : kNumSMs / 2);
       if (wpairs < 2) wpairs = 2;
-      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 38);  // 36 -> 1.96, 38 -> 1.92, 40 -> 2.04 ms
+      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 40);  // 38 -> 1.66, 40 -> 1.57, 42 -> 1.62 ms
 #define RL8_UPDW(PV)                                                                                            \
   case PV:                                                                                                      \
     if (npb == 2) {                                                                                             \
