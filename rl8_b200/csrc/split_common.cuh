@@ -191,6 +191,44 @@ __device__ __forceinline__ uint32_t h1_chunk(const float (*w1t)[H], const ObsPai
   return bits;
 }
 
+// Two rows at once (the same 8 columns): every [W1 | b1] value is read from shared memory once for both rows -- the
+// producers of the split kernels are bound by the number of shared-memory load instructions, not by their bytes.
+template <bool NEG>
+__device__ __forceinline__ void h1_chunk2(const float (*w1t)[H], const ObsPairs& oa, const ObsPairs& ob, int D, int c0,
+                                          float* va, float* vb, uint32_t& bits_a, uint32_t& bits_b) {
+  float2 za[4], zb[4];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(&w1t[7][c0]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&w1t[7][c0 + 4]);
+    za[0] = zb[0] = make_float2(b0.x, b0.y), za[1] = zb[1] = make_float2(b0.z, b0.w);
+    za[2] = zb[2] = make_float2(b1.x, b1.y), za[3] = zb[3] = make_float2(b1.z, b1.w);
+  }
+#pragma unroll
+  for (int d = 0; d < 7; ++d) {
+    if (d < D) {  // uniform
+      const float4 w0 = *reinterpret_cast<const float4*>(&w1t[d][c0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&w1t[d][c0 + 4]);
+      const float2 p0 = make_float2(w0.x, w0.y), p1 = make_float2(w0.z, w0.w);
+      const float2 p2 = make_float2(w1.x, w1.y), p3 = make_float2(w1.z, w1.w);
+      za[0] = ffma2(oa.v[d], p0, za[0]), zb[0] = ffma2(ob.v[d], p0, zb[0]);
+      za[1] = ffma2(oa.v[d], p1, za[1]), zb[1] = ffma2(ob.v[d], p1, zb[1]);
+      za[2] = ffma2(oa.v[d], p2, za[2]), zb[2] = ffma2(ob.v[d], p2, zb[2]);
+      za[3] = ffma2(oa.v[d], p3, za[3]), zb[3] = ffma2(ob.v[d], p3, zb[3]);
+    }
+  }
+  bits_a = bits_b = 0u;
+  static_assert(NEG, "h1_chunk2: the sign-bit form only");
+#pragma unroll
+  for (int j = 3; j >= 0; --j) {
+    bits_a = __funnelshift_l(__float_as_uint(za[j].y), bits_a, 1);
+    bits_a = __funnelshift_l(__float_as_uint(za[j].x), bits_a, 1);
+    bits_b = __funnelshift_l(__float_as_uint(zb[j].y), bits_b, 1);
+    bits_b = __funnelshift_l(__float_as_uint(zb[j].x), bits_b, 1);
+    va[2 * j] = fminf(za[j].x, 0.0f), va[2 * j + 1] = fminf(za[j].y, 0.0f);
+    vb[2 * j] = fminf(zb[j].x, 0.0f), vb[2 * j + 1] = fminf(zb[j].y, 0.0f);
+  }
+}
+
 // eight mask bits -> eight 16-bit values {0, 1} (one 16-byte operand chunk; a mask is exact in ONE piece)
 template <bool F16 = false>
 __device__ __forceinline__ uint4 mask_byte_to_bf16x8(uint32_t byte) {

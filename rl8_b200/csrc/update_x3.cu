@@ -180,8 +180,10 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     if (valid) *reinterpret_cast<uint2*>(a.mask1[net] + rowl * 8 + 2 * g) = make_uint2(m0, m1);
   };
 
+  long long ph[5] = {0, 0, 0, 0, 0};  // development: cycles in produce / pass 1 / barrier 1 / loss + barrier 2 / pass 2
   auto epilogue = [&](int64_t tile, int64_t j) {
     const int buf = (int)(j & 1);
+    long long pc = X3_CLOCK();
     mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
     fence_after_sync();
     const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
@@ -241,9 +243,11 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     if (rowl < a.Mc) *reinterpret_cast<uint2*>(a.mask2[net] + rowl * 8 + 2 * cq) = make_uint2(mk[0], mk[1]);
 #pragma unroll
     for (int p = 0; p < PN; ++p) s.part[cq][r][p] = dot[p];
+    ph[1] += X3_CLOCK() - pc, pc = X3_CLOCK();
     // Both barriers of the epilogue only connect the four warps of one row quarter q (column quarters cq = 0..3): the
     // loss thread of row r = 32 q + lane is lane `lane` of warp q, and pass 2 of these warps reads that warp's dOut.
     quarter_bar_sync(q);
+    ph[2] += X3_CLOCK() - pc, pc = X3_CLOCK();
     // ---- per-row loss -> dOut (threads 0..127 own row tid)
     if (tid < TILE && !(X3_ABL(a) & 128)) {
       const int64_t rl = tile * 256 + rank * 128 + tid;
@@ -303,6 +307,7 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
     float hv[4][8];
     load_h2(0, hv);        // does not need dOut: the 12 warps without loss rows do it under the loss phase
     quarter_bar_sync(q);   // dsm (dOut of the quarter's rows) is complete
+    ph[3] += X3_CLOCK() - pc, pc = X3_CLOCK();
     float dr[4][PN];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -335,13 +340,21 @@ __device__ __forceinline__ void update_f_workers(SmemXF& s, const NetParams& np,
         gw3_acc[c2][p] -= x[0];  // (hv holds -H2)
       }
     }
+    ph[4] += X3_CLOCK() - pc;
   };
 
   // (measured: producing the second half of tile j + 1 between the passes of the epilogue changes nothing)
   if (n_my > 0) produce(pr);
   for (int64_t j = 0; j < n_my; ++j) {
+    const long long pc = X3_CLOCK();
     if (j + 1 < n_my) produce(pr + (j + 1) * npairs);
+    ph[0] += X3_CLOCK() - pc;
     epilogue(pr + j * npairs, j);
+  }
+  if (X3_CLOCK() != 0 && a.dbg && pr == 0 && rank == 0 && (warp == 5 || warp == 1) && lane == 0) {
+    unsigned long long* d = a.dbg + 16 * net + (warp == 5 ? 11 : 32 + 11);  // warp 5: no loss rows; warp 1: loss rows
+#pragma unroll
+    for (int i = 0; i < 5; ++i) atomicAdd(d + i, (unsigned long long)ph[i]);
   }
   // ---- flush
   if (n_my > 0) {
@@ -897,28 +910,57 @@ __device__ __forceinline__ void update_w_workers(SmemXW<NPB>& s, const NetParams
     const int cnt = k0 + 1 < n_my ? 2 : 1;
     const int st0 = (int)(k0 % kWStages);
     const uint32_t use = (uint32_t)(k0 / kWStages);
+    if (cnt == 2) {
+      // both stages of the pair at once: [W1 | b1] of input group g is read from shared memory once for the two rows
+      float d0[4], d1[4], o0[7], o1[7];
+      uint32_t m0, m1;
+      read_inputs(k0, d0, m0, o0);
+      read_inputs(k0 + 1, d1, m1, o1);
+      if (use > 0) {
+        mbar_wait_cluster_sleep(&s.empty[st0], (use - 1) & 1);
+        mbar_wait_cluster_sleep(&s.empty[st0 + 1], (use - 1) & 1);
+      }
+      if (!(X3_ABL(a) & 32)) {
+        float v[8], w[8];
+        uint8_t* tiles[NPB];
+        // A: dZ2^T of unit group g
+        dz2_chunk<PN>(s.w3, d0, (m0 >> (8 * (g & 3))) & 0xffu, 128 * (int)rank + 8 * g, v);
+        dz2_chunk<PN>(s.w3, d1, (m1 >> (8 * (g & 3))) & 0xffu, 128 * (int)rank + 8 * g, w);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h >= cnt) break;
+        for (int e = 0; e < 8; ++e) gb2_acc[e] += v[e] + w[e];
+#pragma unroll
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st0].a[p];
+        store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+#pragma unroll
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st0 + 1].a[p];
+        store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), w);
+        // B: H1 of input group g  (-s_h H1: inv_scale is negative)
+        uint32_t bits0, bits1;
+        h1_chunk2<true>(s.w1t, obs_pairs(o0), obs_pairs(o1), D, 128 * (int)rank + 8 * g, v, w, bits0, bits1);
+#pragma unroll
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st0].b[p];
+        store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+#pragma unroll
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st0 + 1].b[p];
+        store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), w);
+      }
+    } else {
       float cur_d[4], cur_o[7];
       uint32_t cur_m;
-      read_inputs(k0 + h, cur_d, cur_m, cur_o);
-      const int st = st0 + h;
-      if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
+      read_inputs(k0, cur_d, cur_m, cur_o);
+      if (use > 0) mbar_wait_cluster_sleep(&s.empty[st0], (use - 1) & 1);
       if (!(X3_ABL(a) & 32)) {
         float v[8];
         uint8_t* tiles[NPB];
-        // A: dZ2^T of unit group g
         dz2_chunk<PN>(s.w3, cur_d, (cur_m >> (8 * (g & 3))) & 0xffu, 128 * (int)rank + 8 * g, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) gb2_acc[e] += v[e];
 #pragma unroll
-        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].a[p];
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st0].a[p];
         store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
-        // B: H1 of input group g
-        h1_chunk<true>(s.w1t, obs_pairs(cur_o), D, 128 * (int)rank + 8 * g, v);  // -s_h H1 (inv_scale is negative)
+        h1_chunk<true>(s.w1t, obs_pairs(cur_o), D, 128 * (int)rank + 8 * g, v);
 #pragma unroll
-        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st0].b[p];
         store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
       }
     }
@@ -1012,32 +1054,44 @@ __device__ __forceinline__ void update_w_workers_vnet(SmemXW<NPB>& s, const NetP
     const int cnt = k0 + 1 < n_my ? 2 : 1;
     const int st0 = (int)(k0 % kWStages);
     const uint32_t use = (uint32_t)(k0 / kWStages);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-    if (h >= cnt) break;
-    float cur_f[8];
-    uint32_t cur_m;
-    read_inputs(k0 + h, cur_f, cur_m);
-    const int st = st0 + h;
-    if (use > 0) mbar_wait_cluster_sleep(&s.empty[st], (use - 1) & 1);
-    if (!(X3_ABL(a) & 32)) {
-      // A: the mask bits of unit group g  (tile a[0] only)
-      const uint32_t byte = (cur_m >> (8 * (g & 3))) & 0xffu;
-      *reinterpret_cast<uint4*>(s.ring[st].a[0] + lane * 16 + g * 512) = mask_byte_lut(s.lut, byte);
-      const float d = cur_f[7];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) gb2_acc[e] += (byte >> e) & 1u ? d : 0.0f;
-      // B: dOut[row] * H1[row][input group g], split
-      float v[8];
-      h1_chunk<true>(s.w1t, obs_pairs(cur_f), D, 128 * (int)rank + 8 * g, v);  // -s_h H1 (inv_scale is negative)
-      const float ds = d * s_d;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= ds;
-      uint8_t* tiles[NPB];
-#pragma unroll
-      for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
-      store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+    float f0[8], f1[8];
+    uint32_t m0, m1 = 0u;
+    read_inputs(k0, f0, m0);
+    if (cnt == 2) read_inputs(k0 + 1, f1, m1);
+    if (use > 0) {
+      mbar_wait_cluster_sleep(&s.empty[st0], (use - 1) & 1);
+      if (cnt == 2) mbar_wait_cluster_sleep(&s.empty[st0 + 1], (use - 1) & 1);
     }
+    if (!(X3_ABL(a) & 32)) {
+      // A: the mask bits of unit group g  (tile a[0] only); gb2 on the way
+      auto mask_chunk = [&](int st, uint32_t m, float d) {
+        const uint32_t byte = (m >> (8 * (g & 3))) & 0xffu;
+        *reinterpret_cast<uint4*>(s.ring[st].a[0] + lane * 16 + g * 512) = mask_byte_lut(s.lut, byte);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gb2_acc[e] += (byte >> e) & 1u ? d : 0.0f;
+      };
+      // B: dOut[row] * H1[row][input group g], split  (-s_h H1: inv_scale is negative)
+      auto store_b = [&](int st, float* v, float ds) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= ds;
+        uint8_t* tiles[NPB];
+#pragma unroll
+        for (int p = 0; p < NPB; ++p) tiles[p] = s.ring[st].b[p];
+        store_split_chunk<NPB, kUF16>(tiles, (uint32_t)(lane * 16 + g * 512), v);
+      };
+      float v[8], w[8];
+      mask_chunk(st0, m0, f0[7]);
+      if (cnt == 2) {
+        // both stages of the pair at once: [W1 | b1] of input group g is read once for the two rows
+        mask_chunk(st0 + 1, m1, f1[7]);
+        uint32_t bits0, bits1;
+        h1_chunk2<true>(s.w1t, obs_pairs(f0), obs_pairs(f1), D, 128 * (int)rank + 8 * g, v, w, bits0, bits1);
+        store_b(st0, v, f0[7] * s_d);
+        store_b(st0 + 1, w, f1[7] * s_d);
+      } else {
+        h1_chunk<true>(s.w1t, obs_pairs(f0), D, 128 * (int)rank + 8 * g, v);
+        store_b(st0, v, f0[7] * s_d);
+      }
     }
     fence_async_smem();
     __syncwarp();
@@ -1370,7 +1424,7 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
       const int64_t nst = ceil_div(a.Mc, kXKc);
       int wpairs = (int)(nst < kNumSMs / 2 ? nst : kNumSMs / 2);
       if (wpairs < 2) wpairs = 2;
-      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 40);  // 38 -> 1.66, 40 -> 1.57, 42 -> 1.62 ms
+      a.n_pi_w = x3_gradient_policy_pairs("RL8_X3_POLICY_PAIRS_W", wpairs, 39);  // 36 -> 1.55, 38 -> 1.47, 40 -> 1.52 ms
 #define RL8_UPDW(PV)                                                                                            \
   case PV:                                                                                                      \
     if (npb == 2) {                                                                                             \

@@ -66,7 +66,7 @@ for stages, abl, name in CASES:
 # where the MMA warp of pair 0 waits (x3_update_f_kernel)
 for abl in (0, 7 + 64 + 128):
     os.environ["RL8_X3_STAGES"], os.environ["RL8_X3_ABL"] = "1", str(abl)
-    counters = torch.zeros(32, dtype=torch.int64, device=algo.device)
+    counters = torch.zeros(64, dtype=torch.int64, device=algo.device)
     lib.rl8_x3_debug_buffer(L.ptr(counters))
     minibatch()
     torch.cuda.synchronize()
@@ -77,3 +77,7 @@ for abl in (0, 7 + 64 + 128):
         tiles = max(d[10], 1)
         print(f"abl {abl} {label}: {d[9] / tiles:8.0f} cycles / tile ({tiles} tiles); MMA warp waits per tile: full[kc] "
               + " ".join(f"{x / tiles:6.0f}" for x in d[:8]) + f"  acc_empty {d[8] / tiles:6.0f}")
+        for off, who in ((0, "warp 5 (no loss rows)"), (32, "warp 1 (loss rows)")):
+            w = c[16 * net + off + 11: 16 * net + off + 16]
+            print(f"      {who}: cycles / tile in produce {w[0] / tiles:6.0f}  pass 1 (+ accumulator wait) {w[1] / tiles:6.0f}"
+                  f"  barrier 1 {w[2] / tiles:6.0f}  loss + barrier 2 {w[3] / tiles:6.0f}  pass 2 {w[4] / tiles:6.0f}")
