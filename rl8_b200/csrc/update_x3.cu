@@ -662,12 +662,29 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
     mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
     fence_after_sync();
     const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+    // mask1 bits of THIS thread's input unit for the warp's 64 rows, as two words (bit r: row 64 cq + 32 h + r): lane l
+    // loads the word of row l and the warp transposes the 32 x 32 bit matrix with five shuffles -- instead of one
+    // broadcast shared-memory load per row and thread (the epilogue is bound by its shared-memory instructions)
+    uint32_t mbits[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t x = s.m1s[buf][cq * 64 + 32 * h + lane][q];
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+        const uint32_t keep = sft == 16 ? 0x0000ffffu : sft == 8 ? 0x00ff00ffu : sft == 4 ? 0x0f0f0f0fu
+                              : sft == 2 ? 0x33333333u : 0x55555555u;  // bit positions whose index has bit `sft` clear
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, x, sft);
+        x = (lane & sft) ? (((other >> sft) & keep) | (x & ~keep)) : ((x & keep) | ((other & keep) << sft));
+      }
+      mbits[h] = x;
+    }
 #pragma unroll 1
     for (int c4 = 0; c4 < 4; ++c4) {
       float v[16];
       tmem_ld16_nowait(acc + (uint32_t)(c4 * 16), v);
       tmem_wait_ld();
       reg_fence16f(v);
+      const uint32_t hw = mbits[c4 >> 1] >> (16 * (c4 & 1));  // bit e: row 64 cq + 16 c4 + e
       if (c4 == 3) {  // the accumulator has been read: the tensor pipe may reuse it for tile j + 2
         fence_before_sync();
         __syncwarp();
@@ -677,10 +694,9 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int rt = cq * 64 + c4 * 16 + e;
-        const uint32_t word = s.m1s[buf][rt][q];
         const float4 oa = *reinterpret_cast<const float4*>(&s.os[buf][rt][0]);
         const float4 ob = *reinterpret_cast<const float4*>(&s.os[buf][rt][4]);  // (obs 4..6, bias factor)
-        const float dz1 = (word >> lane) & 1u ? v[e] : 0.0f;
+        const float dz1 = (hw >> e) & 1u ? v[e] : 0.0f;
         const float2 dz = make_float2(dz1, dz1);
         gacc[0] = ffma2(dz, make_float2(oa.x, oa.y), gacc[0]), gacc[1] = ffma2(dz, make_float2(oa.z, oa.w), gacc[1]);
         gacc[2] = ffma2(dz, make_float2(ob.x, ob.y), gacc[2]), gacc[3] = ffma2(dz, make_float2(ob.z, ob.w), gacc[3]);
