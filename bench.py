@@ -683,8 +683,8 @@ def stream_rooflines(lib, L, dev, peaks: dict) -> list[dict]:  # noqa: ANN001
 #: `ncu --set full` captures summarised in profiles/r01_update_v8_ncu_summary.md.
 NCU_TRAFFIC = {("cartpole", 2097152): (84.31e6 + 2089.0e6) + (2190.0e6 + 7.0e6)}
 #: the same call in RL8_PREC_FP32_TC (x3_update_f + x3_update_b + x3_update_w), dram read + write of each kernel from
-#: profiles/r02_x3_update_ncu_summary.md: no dZ2 scratch, 80 B per row and network of masks / dOut instead
-NCU_TRAFFIC_X3 = {("cartpole", 2097152): (86.1e6 + 283.0e6) + (378.4e6 + 5.2e6) + (244.3e6 + 5.1e6)}
+#: profiles/r02_x3_fp16_ncu_summary.md: no dZ2 scratch, 80 B per row and network of masks / dOut instead
+NCU_TRAFFIC_X3 = {("cartpole", 2097152): (84.8e6 + 280.3e6) + (378.2e6 + 5.1e6) + (244.8e6 + 4.7e6)}
 
 
 def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa: ANN001
@@ -754,7 +754,7 @@ def update_roofline(a, algo, L, peaks: dict, dtype: str, flush) -> dict:  # noqa
             # piece products actually issued per row: policy network 3 + 3 + 3, value network 3 + 2 + 2 (its
             # gradient contractions take the ReLU mask as a one-piece operand)
             "mma_tflops": M * 16.0 * 2.0 * H * H / ms / 1e9, "mma_frac": M * 16.0 * 2.0 * H * H / ms / 1e9 / burst,
-            "traffic_source": ("ncu --set full, profiles/r02_x3_update_ncu_summary.md"
+            "traffic_source": ("ncu --set full, profiles/r02_x3_fp16_ncu_summary.md"
                                if (a.workload, M) in NCU_TRAFFIC_X3 else None),
             "peak_source": peaks["source"] + " bf16 burst / 3 (three fp16 piece products per fp32 product at the bf16"
                                              " rate; `achieved` counts the algorithm's fp32 FLOPs; `mma_tflops` /"

@@ -59,10 +59,11 @@ typedef enum {
   RL8_PREC_FP32 = 0,   /* CUDA-core fp32 GEMMs (the cross-check of the mode below) */
   RL8_PREC_BF16 = 1,   /* tcgen05 bf16 GEMMs, fp32 accumulate (reference `enable_amp=True`) */
   RL8_PREC_FP32_TC = 2 /* fp32 results on tcgen05 (reference `enable_amp=False`): every fp32 operand of the
-                        * 256 x 256 contractions is split into bf16 pieces (three for the forward pass: six
-                        * piece products, 2e-6 of fp64 at K = 256; two for the gradient contractions: three
-                        * piece products, 5e-6), fp32 accumulation in tensor memory, pair MMAs
-                        * (cta_group::2); everything else is fp32 on CUDA cores as in RL8_PREC_FP32 */
+                        * 256 x 256 contractions is split into two fp16 pieces after a power-of-two scaling
+                        * derived from a measured bound of the tensor (max |obs|, max |W2|, max |dOut|), three
+                        * piece products per fp32 product (2e-6 of fp64 at K = 256), fp32 accumulation in tensor
+                        * memory, pair MMAs (cta_group::2); everything else is fp32 on CUDA cores as in
+                        * RL8_PREC_FP32.  (`make X3_BF16=1`: three bf16 pieces and six products, no scales.) */
 } rl8_precision;
 
 /* Environment constants, already rounded the way the reference rounds them (Python

@@ -27,7 +27,7 @@ PREC_FP32, PREC_BF16, PREC_FP32_TC = range(3)
 
 def precision_for(enable_amp: bool) -> int:
     """Kernel precision of an ``enable_amp`` setting: ``True`` -> bf16 tcgen05 GEMMs; ``False`` -> fp32
-    results, on tcgen05 through split-bf16 operands (``PREC_FP32_TC``), or -- with ``RL8_FP32_SIMT=1`` in
+    results, on tcgen05 through split operands -- two fp16 pieces per fp32 value (``PREC_FP32_TC``), or -- with ``RL8_FP32_SIMT=1`` in
     the environment -- the CUDA-core fp32 GEMMs the split path is cross-checked against."""
     if enable_amp:
         return PREC_BF16

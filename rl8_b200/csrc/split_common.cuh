@@ -1,4 +1,4 @@
-// Shared pieces of the split-bf16 pair kernels (split_tc.cu: forward / collect; update_x3.cu: PPO update).
+// Shared pieces of the split-operand pair kernels (split_tc.cu: forward / collect; update_x3.cu: PPO update).
 #pragma once
 #include "mlp_tc.cuh"
 #include "split_tc.cuh"

@@ -1,4 +1,5 @@
-// fp32-accurate tensor-core path (RL8_PREC_FP32): split-bf16 operands, tcgen05.mma.cta_group::2 (see split_tc.cuh).
+// fp32-accurate tensor-core path (RL8_PREC_FP32_TC): split operands (two fp16 or three bf16 pieces per fp32 value),
+// tcgen05.mma.cta_group::2 (see split_tc.cuh).
 //
 //   tc3_selftest_kernel   D[256][256] = A[256][K] * B[256][K]^T with a selectable set of piece products: pins the
 //                         pair plumbing (cluster launch, pair TMEM allocation, N-split B operand, multicast commit)
@@ -161,7 +162,8 @@ tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols) {
 
 
 // ---- W2 piece images ------------------------------------------------------------------------------------------------
-// The weight operand of a 256x256 contraction, split once per call into NP bf16 pieces and laid out so that the half
+// The weight operand of a 256x256 contraction, split once per call into NP pieces (bf16, or fp16 pieces of the weights
+// times a power of two derived from max |X|, written to *scale_out) and laid out so that the half
 // a CTA of the pair needs for one ring stage (its 128 rows, the stage's four K groups, every piece) is one contiguous
 // run of NP x 8 KB:
 //     img[kc][half = n / 128][piece][ (n % 128) * 16 + g * 2048 + (k % 8) * 2 ]     with  k / 8 = 8 g + kc

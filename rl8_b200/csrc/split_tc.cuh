@@ -1,4 +1,5 @@
-// fp32-accurate GEMMs on the bf16 tensor pipe: every fp32 operand x is split into bf16 pieces
+// fp32-accurate GEMMs on the half-precision tensor pipe (kind::f16).  BF16 PIECES: every fp32 operand x is split into
+// bf16 pieces
 //
 //     x = p0 + p1 + p2 (+ 2^-27 |x|),   p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1)
 //

@@ -1,21 +1,30 @@
 // PPO update in RL8_PREC_FP32_TC: forward + clipped losses + hand-derived backward of both default networks for one
-// minibatch on split-bf16 pair MMAs (split_tc.cuh), three persistent kernels per row chunk.  No activation ever
+// minibatch on split-operand pair MMAs (split_tc.cuh), three persistent kernels per row chunk.  No activation ever
 // reaches HBM: every A / B operand that is an activation is RECOMPUTED on CUDA cores straight into split ring
 // stages from 80 bytes per row and network of scratch (dOut [4] fp32 and the two 256-bit ReLU masks).
 //
-//   x3_update_f_kernel  rows x units   Z2 = H1 W2^T            x3 (six piece products: the losses are forward values)
+// Pieces: two fp16 pieces per fp32 operand and three piece products per fp32 product (a0b0 + a0b1 + a1b0), every
+// operand tensor scaled by a power of two from a measured bound of its magnitude (X3Scales: max |obs| -> H1, max |W2|,
+// max |dOut| -> dZ2) and the scales divided out of the accumulators -- exact, so the results are those of the
+// un-scaled sums.  `make X3_BF16=1` builds the first form of this path instead: three bf16 pieces, six products.
+// Sign convention: H1 and H2 are produced NEGATED (h1_chunk<true>, -b2 in shared memory) so that a ReLU-mask bit is
+// the sign bit of the sum; the sign travels in the factor that removes the scales.
+//
+//   x3_update_f_kernel  rows x units   Z2 = H1 W2^T            (three piece products)
 //       A = H1 = relu([obs] W1^T + b1) computed per stage;  B = W2 piece image (bulk copies)
 //       epilogue: H2 = relu(Z2 + b2), head, per-row PPO loss -> dOut, loss sums, gb3; ReLU masks of H1 / H2 and
 //       dOut -> scratch;  gW3 += H2^T dOut by warp-transposing reductions (the accumulator is read twice)
-//   x3_update_b_kernel  inputs x rows  dH1^T = W2^T dZ2^T      x2 (three piece products: gradients)
+//   x3_update_b_kernel  inputs x rows  dH1^T = W2^T dZ2^T      (three piece products; value network: two, the B operand
+//                                                               is the ReLU mask itself, exact in one piece)
 //       A = W2^T piece image;  B = dZ2 = [H2 > 0] .* (dOut W3) computed per stage from the scratch
 //       epilogue (lane = input unit i, columns = rows): dZ1 = [H1 > 0] .* dH1;  gW1[i][:] += dZ1 obs, gb1[i] += dZ1
 //       as plain per-thread FMAs over the rows (no cross-lane work: that is why this GEMM is transposed)
-//   x3_update_w_kernel  units x inputs gW2 = dZ2^T H1          x2, contraction over rows
-//       A = dZ2^T, B = H1, both computed per stage (MN-major tiles); gb2 += column sums of dZ2 in the producer;
-//       the 128 x 256 accumulator of each CTA lives in tensor memory for the whole kernel
+//   x3_update_w_kernel  units x inputs gW2 = dZ2^T H1          (three / two piece products), contraction over rows
+//       A = dZ2^T, B = H1, both computed per stage (MN-major tiles) from inputs that two loader warps fetch once per
+//       CTA; gb2 += column sums of dZ2 in the producer; the 128 x 256 accumulator of each CTA lives in tensor memory
 //
-// GEMM work per row and network: 6 + 3 + 3 = 12 bf16-rate 256x256 products (the bf16 path does 3).
+// GEMM work per row: policy network 3 + 3 + 3, value network 3 + 2 + 2 half-precision-rate 256x256 products (the bf16
+// path does 3 per network).
 #include <stdlib.h>
 
 #include "ppo_loss_math.cuh"

@@ -1,4 +1,5 @@
-"""GPU: the fp32-accurate tensor-core mode (RL8_PREC_FP32_TC: split-bf16 operands, tcgen05 pair MMAs).
+"""GPU: the fp32-accurate tensor-core mode (RL8_PREC_FP32_TC: split operands -- two fp16 pieces per fp32 value in the
+kernels, three bf16 pieces in the first form kept as a build option -- on tcgen05 pair MMAs).
 
 The pair selftest pins the cta_group::2 plumbing and bounds each piece-product set against fp64;
 the fused forward kernel is compared with the CPU oracle (the reference's fp32 ``nn.Linear`` chain,

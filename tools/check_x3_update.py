@@ -1,4 +1,4 @@
-"""RL8_PREC_FP32_TC update (split-bf16 pair kernels) beside the CUDA-core fp32 update on the SAME buffer and
+"""RL8_PREC_FP32_TC update (split-operand pair kernels) beside the CUDA-core fp32 update on the SAME buffer and
 weights: loss statistics and every first-step gradient tensor, printed as relative errors.
 
     python tools/check_x3_update.py [N] [T]          (RL8_X3_STAGES=1|3|7 limits the kernels that run)

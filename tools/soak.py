@@ -1,4 +1,4 @@
-"""Soak run: many Trainer.step() iterations on the fp32 tensor-core path (the default: split-bf16 kernels, update
+"""Soak run: many Trainer.step() iterations on the fp32 tensor-core path (the default: split-operand kernels, update
 replayed from a CUDA graph) and on the bf16 path (feedforward and recurrent), checking that every statistic stays
 finite and that returns improve -- a cheap guard against races that a single step would hide."""
 import math
