@@ -132,6 +132,31 @@ def test_forward_split_matches_oracle(env_name: str, D: int, rows: int) -> None:
     assert torch.equal(pol.forward_net(1, obs_soa.T), vals)
 
 
+@pytest.mark.parametrize("obs_scale", [1e-4, 1.0, 3e3, 1e6])
+def test_forward_split_operand_scales_follow_the_observation_range(obs_scale: float) -> None:
+    """fp16 pieces: the power-of-two scale of H1 comes from max |obs| of the rows of the call, so observations of any
+    magnitude -- and rows a thousand times smaller than the largest one in the same call -- keep the fp32 path's accuracy
+    relative to the size of the outputs."""
+    L, _ = _lib()
+    torch.manual_seed(int(obs_scale * 7) % 1000 + 3)
+    pol = _policy("CartPole")
+    pol.precision = L.PREC_FP32_TC
+    params = {k: v.detach().cpu().clone() for k, v in pol.model.state_dict().items()}
+    rows = 1500
+    obs = torch.randn(rows, 5) * obs_scale
+    obs[::7] *= 1e-3
+    feats, value = O.model_forward(params, obs)
+    ref_head = torch.cat([t.reshape(rows, -1) for t in feats.values()], dim=1)
+    head = pol.forward_net(0, obs.to(DEV)).cpu()
+    vals = pol.forward_net(1, obs.to(DEV)).cpu()
+    assert torch.isfinite(head).all() and torch.isfinite(vals).all()
+    for got, ref in ((head, ref_head), (vals, value.reshape(rows, 1))):
+        big = float(ref.abs().max())
+        torch.testing.assert_close(got, ref, rtol=RTOL, atol=max(ATOL, 1e-5 * big))
+        small = slice(0, rows, 7)  # the small rows on their own scale
+        torch.testing.assert_close(got[small], ref[small], rtol=RTOL, atol=max(ATOL, 1e-5 * float(ref[small].abs().max())))
+
+
 def test_forward_split_trained_scale_weights_against_fp64() -> None:
     """O(1) head weights and large activations (what a trained policy looks like): the split forward
     stays within the fp32 path's own distance from fp64."""
@@ -194,6 +219,8 @@ def _twins(env_name: str, dist, n: int, t: int, **kw):  # noqa: ANN001, ANN202
      ("MountainCar", None, 1024, 16, {"sgd_minibatch_size": 2048, "accumulate_grads": True}),
      ("Pendulum", "squashed_normal", 777, 8, {"dual_clip_param": 3.0}),
      ("ContinuousDummyEnv", "normal", 512, 16, {"entropy_coeff": 0.01}),
+     # raw rewards / advantages (max |dOut| two orders of magnitude above the normalised case: the dZ2 operand scale)
+     ("Pendulum", "normal", 512, 8, {"normalize_advantages": False, "normalize_rewards": False, "vf_coeff": 5.0}),
      ("DiscreteDummyEnv", None, 70_000, 4, {})],                                               # more tiles than CTA pairs
 )
 def test_update_split_matches_fp32_cuda_cores(env_name: str, dist, n: int, t: int, kw) -> None:  # noqa: ANN001
