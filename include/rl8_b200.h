@@ -443,7 +443,8 @@ int rl8_tc_bench_mma(long long* out_cycles, int32_t N, int32_t k_total, int32_t 
 
 /* Development hook: `pairs` clusters of two CTAs each issue reps x 2 x terms tcgen05.mma.cta_group::2 instructions
  * (M = 256, N = n_cols, K = 16, bf16) back to back; out[2 p] = SM cycles, out[2 p + 1] = nanoseconds of pair p.
- * Gives the pace of the split kernels' instruction stream with the whole chip busy (power cap included). */
+ * Gives the pace of the split kernels' instruction stream with the whole chip busy (power cap included).
+ * terms + 16: both operands MN-major ([K rows][128 columns] tiles, the weight-gradient kernel's form). */
 int rl8_tc3_bench_pace(long long* out, int32_t pairs, int32_t reps, int32_t terms, int32_t n_cols,
                        rl8_stream_t stream);
 

@@ -109,7 +109,7 @@ struct SmemPace {
   uint32_t tmem_base;
 };
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols) {
+tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols, int mn_major) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemPace& s = *reinterpret_cast<SmemPace*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -127,7 +127,10 @@ tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols) {
   cluster_sync_all();
   fence_after_sync();
   const uint32_t tmem = s.tmem_base;
-  const uint32_t idesc = instr_desc(256, n_cols, 0, 0);
+  // mn_major: both operands as [K rows][128 M / N columns] tiles (the weight-gradient kernel's form: LBO 128, SBO 512,
+  // 16 K rows = 256 bytes) instead of K-major [128 rows][K] tiles (LBO 2048, SBO 128, 16 K values = 4096 bytes)
+  const uint32_t idesc = instr_desc(256, n_cols, mn_major, mn_major);
+  const uint32_t lbo = mn_major ? 128u : 2048u, sbo = mn_major ? 512u : 128u, kstep = mn_major ? 256u : 4096u;
   long long c0 = 0, t0 = 0;
   if (rank == 0 && warp == 0) {
     c0 = clock64();
@@ -137,8 +140,8 @@ tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols) {
         const StageX<3>& stg = s.ring[r & 3];
         for (int ks = 0; ks < 2; ++ks)
           for (int i = 0; i < terms; ++i) {
-            const uint64_t ad = smem_desc(smem_u32(stg.a[i % 3]) + ks * 4096, 2048, 128);
-            const uint64_t bd = smem_desc(smem_u32(stg.b[(i / 3) % 3]) + ks * 4096, 2048, 128);
+            const uint64_t ad = smem_desc(smem_u32(stg.a[i % 3]) + ks * kstep, lbo, sbo);
+            const uint64_t bd = smem_desc(smem_u32(stg.b[(i / 3) % 3]) + ks * kstep, lbo, sbo);
             mma_bf16_pair(tmem, ad, bd, idesc, (r | ks | i) ? 1u : 0u);
           }
       }
@@ -577,8 +580,11 @@ extern "C" int rl8_tc3_selftest(const float* A, const float* B, float* D, int32_
 }
 
 // Development hook: pace of back-to-back pair MMAs on `pairs` clusters at once (tools/bench_pair_mma.py).
+// terms + 16: both operands MN-major (the weight-gradient kernel's tiles).
 extern "C" int rl8_tc3_bench_pace(long long* out, int32_t pairs, int32_t reps, int32_t terms, int32_t n_cols,
                                   rl8_stream_t stream) {
+  const int mn_major = terms >= 16 ? 1 : 0;
+  terms -= 16 * mn_major;
   if (!out || pairs < 1 || pairs > kNumSMs / 2 || reps < 1 || terms < 1 || terms > 9 ||
       (n_cols != 64 && n_cols != 128 && n_cols != 256))
     return RL8_ERR_ARG;
@@ -588,6 +594,6 @@ extern "C" int rl8_tc3_bench_pace(long long* out, int32_t pairs, int32_t reps, i
     set_last_error("cudaFuncSetAttribute", e);
     return RL8_ERR_CUDA;
   }
-  tc3_pace_kernel<<<2 * pairs, 128, sizeof(SmemPace), (cudaStream_t)stream>>>(out, reps, terms, n_cols);
+  tc3_pace_kernel<<<2 * pairs, 128, sizeof(SmemPace), (cudaStream_t)stream>>>(out, reps, terms, n_cols, mn_major);
   return check_launch("tc3_pace");
 }
