@@ -555,7 +555,9 @@ class Algorithm:
         self.last_launches["collect"] = {
             _lib.PREC_FP32: 4 * T + 3 * (T + 1),  # layer 1, SGEMM, head, tail per step; 3 per value slab
             _lib.PREC_BF16: 4,                    # 2 x W2 packing, rollout kernel, value pass
-            _lib.PREC_FP32_TC: 2 + 2 * T + 1,     # 2 x W2 piece images, (split forward + tail) per step, value pass
+            # W2 piece images (one launch), (max |obs| of the slab + split forward + tail) per step, max |obs| of all
+            # slabs + value pass
+            _lib.PREC_FP32_TC: 1 + 3 * T + 2,
         }[self.policy.precision]
 
     def _head_width(self) -> int:
@@ -1024,7 +1026,8 @@ class Algorithm:
         # bf16: 2 x W2 packing + (activation kernel + weight-gradient kernel) per 2^21-row chunk
         per_call = {
             _lib.PREC_BF16: 2 + 2 * max(1, -(-M // (1 << 21))),     # 2 x W2 packing + 2 kernels per 2^21-row chunk
-            _lib.PREC_FP32_TC: 4 + 3 * max(1, -(-M // (1 << 21))),  # 4 x W2 piece images + 3 kernels per chunk
+            # max |obs| + the four W2 piece images (one launch) + 3 kernels per chunk
+            _lib.PREC_FP32_TC: 2 + 3 * max(1, -(-M // (1 << 21))),
             _lib.PREC_FP32: 34 * max(1, -(-M // 65536)),            # the CUDA-core chain per 65 536-row chunk
         }[prec]
         return launch, per_call

@@ -300,7 +300,19 @@ __device__ __forceinline__ bool minibatch_row_to_tn(const A& a, int64_t rw, int6
 }
 
 // split_tc.cu
+// one piece image: X(n, k) = W2[n][k] (transpose = 0) or W2[k][n] * kscale[k] (transpose = 1, kscale may be null)
+struct PackJob {
+  const float* w2;
+  uint8_t* img;
+  const float* kscale;
+  float* scale_out;
+  int transpose;
+};
+struct PackJobs {
+  PackJob j[4];
+};
 // pieces = 3 / 2: bf16 pieces;  pieces = -2: two fp16 pieces of W2 * s, the power of two s written to *scale_out
+int launch_pack_w2_jobs(const PackJobs& jobs, int njobs, int pieces, cudaStream_t st);  // one launch, njobs <= 4
 int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st,
                           const float* kscale = nullptr, float* scale_out = nullptr);
 // *out_bits = max(*out_bits, bits of max |x[i]|)  (NaNs are skipped)

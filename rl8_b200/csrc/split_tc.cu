@@ -174,10 +174,16 @@ tc3_pace_kernel(long long* __restrict__ out, int reps, int terms, int n_cols, in
 // transpose = 1: X(n, k) = W2[k][n]  (backward dH1^T = W2^T dZ2^T: n = input i, k = unit j).
 // kscale (transpose = 1 only): X(n, k) = W2[k][n] * kscale[k] in fp32 -- the value network's backward operand with
 // its one-row head folded in (update_x3.cu).
+// jobs.j[blockIdx.y] is the image this block works on (up to four per launch: the update packs both networks' forward
+// and transposed images at once)
 template <int NP, bool F16>
-__global__ void __launch_bounds__(256) pack_w2_pieces_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img,
-                                                             int transpose, const float* __restrict__ kscale,
-                                                             float* __restrict__ scale_out) {
+__global__ void __launch_bounds__(256) pack_w2_pieces_kernel(PackJobs jobs) {
+  const PackJob& job = jobs.j[blockIdx.y];
+  const float* __restrict__ w2 = job.w2;
+  uint8_t* __restrict__ img = job.img;
+  const int transpose = job.transpose;
+  const float* __restrict__ kscale = job.kscale;
+  float* __restrict__ scale_out = job.scale_out;
   float s = 1.0f;
   if constexpr (F16) {
     // fp16 pieces: every block derives the same power-of-two scale from max |X| (64 K values, L2 hits)
@@ -214,15 +220,24 @@ __global__ void __launch_bounds__(256) pack_w2_pieces_kernel(const float* __rest
   store_split_chunk<NP, F16>(tiles, (uint32_t)(r * 16 + g * 2048), v);
 }
 
-int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st,
-                          const float* kscale, float* scale_out) {
-  if (kscale && !transpose) return RL8_ERR_ARG;
-  const int grid = H * (H / 8) / 256;
-  if (pieces == 3) pack_w2_pieces_kernel<3, false><<<grid, 256, 0, st>>>(w2, img, transpose, kscale, nullptr);
-  else if (pieces == 2) pack_w2_pieces_kernel<2, false><<<grid, 256, 0, st>>>(w2, img, transpose, kscale, nullptr);
-  else if (pieces == -2 && scale_out) pack_w2_pieces_kernel<2, true><<<grid, 256, 0, st>>>(w2, img, transpose, kscale, scale_out);
+int launch_pack_w2_jobs(const PackJobs& jobs, int njobs, int pieces, cudaStream_t st) {
+  if (njobs < 1 || njobs > 4) return RL8_ERR_ARG;
+  for (int i = 0; i < njobs; ++i) {
+    if (jobs.j[i].kscale && !jobs.j[i].transpose) return RL8_ERR_ARG;
+    if (pieces == -2 && !jobs.j[i].scale_out) return RL8_ERR_ARG;
+  }
+  const dim3 grid(H * (H / 8) / 256, njobs);
+  if (pieces == 3) pack_w2_pieces_kernel<3, false><<<grid, 256, 0, st>>>(jobs);
+  else if (pieces == 2) pack_w2_pieces_kernel<2, false><<<grid, 256, 0, st>>>(jobs);
+  else if (pieces == -2) pack_w2_pieces_kernel<2, true><<<grid, 256, 0, st>>>(jobs);
   else return RL8_ERR_ARG;
   return check_launch("pack_w2_pieces");
+}
+int launch_pack_w2_pieces(const float* w2, uint8_t* img, int transpose, int pieces, cudaStream_t st,
+                          const float* kscale, float* scale_out) {
+  PackJobs jobs{};
+  jobs.j[0] = PackJob{w2, img, kscale, scale_out, transpose};
+  return launch_pack_w2_jobs(jobs, 1, pieces, st);
 }
 
 // max |x| as float bits (non-negative floats order like their bit patterns), NaNs skipped
@@ -539,8 +554,12 @@ int collect_x3(const rl8_model* model, const rl8_rollout* ro, void* workspace, i
   float* feat = (float*)((uint8_t*)w2_scale + collect_x3_scale_bytes(ro->T));
   int rc;
   if (kUF16 && (rc = zero_words(w2_scale, (size_t)collect_x3_scale_bytes(ro->T), st))) return rc;
-  if ((rc = launch_pack_w2_pieces(model->pi_w2, img_pi, 0, kUF16 ? -2 : 3, st, nullptr, w2_scale))) return rc;
-  if ((rc = launch_pack_w2_pieces(model->vf_w2, img_vf, 0, kUF16 ? -2 : 3, st, nullptr, w2_scale + 1))) return rc;
+  {
+    PackJobs jobs{};
+    jobs.j[0] = PackJob{model->pi_w2, img_pi, nullptr, w2_scale, 0};
+    jobs.j[1] = PackJob{model->vf_w2, img_vf, nullptr, w2_scale + 1, 0};
+    if ((rc = launch_pack_w2_jobs(jobs, 2, kUF16 ? -2 : 3, st))) return rc;
+  }
   const NetParams np_pi = net_params(model, 0, img_pi), np_vf = net_params(model, 1, img_vf);
   const int continuous = ro->dist_kind != RL8_DIST_CATEGORICAL;
   RowMap map{};

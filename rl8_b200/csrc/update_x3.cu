@@ -1366,12 +1366,23 @@ int ppo_minibatch_x3(const rl8_model* model, const rl8_model* grads, const rl8_b
     // max |obs| over the T slabs the minibatch rows come from: bounds H1 (h1_bound)
     if ((rc = launch_absmax_bits(batch->obs, (int64_t)batch->T * model->D * batch->N, &sc->omax, st))) return rc;
   }
-  for (int net = 0; net < 2; ++net) {
-    const float* w2 = net ? model->vf_w2 : model->pi_w2;
-    if ((rc = launch_pack_w2_pieces(w2, img_f[net], 0, kUF16 ? -2 : 3, st, nullptr, &sc->w2f[net]))) return rc;
-    if ((rc = launch_pack_w2_pieces(w2, img_b[net], 1, kUF16 ? -2 : npb, st, net ? model->vf_w3 : nullptr,
-                                    &sc->w2b[net])))
-      return rc;
+  {
+    // the four piece images of the call in one launch; with bf16 pieces the forward image has three pieces and the
+    // transposed ones may have two (RL8_X3_BACKWARD_PIECES): then two launches
+    PackJobs fwd{}, bwd{};
+    for (int net = 0; net < 2; ++net) {
+      const float* w2 = net ? model->vf_w2 : model->pi_w2;
+      fwd.j[net] = PackJob{w2, img_f[net], nullptr, &sc->w2f[net], 0};
+      bwd.j[net] = PackJob{w2, img_b[net], net ? model->vf_w3 : nullptr, &sc->w2b[net], 1};
+    }
+    if (kUF16 || npb == 3) {
+      PackJobs all = fwd;
+      all.j[2] = bwd.j[0], all.j[3] = bwd.j[1];
+      if ((rc = launch_pack_w2_jobs(all, 4, kUF16 ? -2 : 3, st))) return rc;
+    } else {
+      if ((rc = launch_pack_w2_jobs(fwd, 2, 3, st))) return rc;
+      if ((rc = launch_pack_w2_jobs(bwd, 2, npb, st))) return rc;
+    }
   }
   UpdXArgs a;
   a.sc = sc;
