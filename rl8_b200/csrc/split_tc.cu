@@ -278,8 +278,8 @@ int launch_absmax_bits(const float* x, int64_t n, uint32_t* out_bits, cudaStream
 // while the workers run the epilogue of tile j the tensor pipe drains the ring stages they produced for tile j + 1.
 //   worker warps 0..15 : produce(tile j + 1) -> epilogue(tile j)
 //   warp 16            : pair TMEM allocation; in the leader CTA one elected lane issues every tcgen05.mma
-// Barriers (same offsets in both CTAs): full[s] (leader's, 32 worker-warp arrivals: A written and the CTA's B half
-// landed), bfull[s] (local, the bulk copy of the CTA's B half), empty[s] / acc_full[b] (multicast commits),
+// Barriers (same offsets in both CTAs): full[s] (leader's, 32 worker-warp arrivals: A written, + 1 from the peer's warp
+// 16: the peer's B half landed), bfull[s] (local, the bulk copy of the CTA's B half), empty[s] / acc_full[b] (multicast commits),
 // acc_empty[b] (leader's, 32 worker-warp arrivals: accumulator b has been read).
 struct SmemX3F {
   StageX<kUNP> ring[kXStages];  // 196608
@@ -304,7 +304,7 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < kXStages; ++i) {
-      mbar_init(&s.full[i], 32);
+      mbar_init(&s.full[i], 33);  // 32 worker warps of the pair + the peer's bulk copy (forwarded by its warp 16)
       mbar_init(&s.bfull[i], 1);
       mbar_init(&s.empty[i], 1);
     }
@@ -350,29 +350,41 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
           if (d < D) obf[d] = __ldg(base + (int64_t)d * ds);
       }
       const ObsPairs ob = obs_pairs(obf);
-      for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
+      // two ring stages per generic -> async proxy fence; no worker warp waits for a bulk copy (the leader's MMA warp
+      // waits for its own half of a W2 stage, the peer's warp 16 forwards the peer's) -- as in x3_update_f_kernel
+      static_assert(kXStages % 2 == 0 && (H / kXKc) % 2 == 0, "stage pairs");
+      for (int kc = 0; kc < H / kXKc; kc += 2, kcount += 2) {
         const int st = (int)(kcount % kXStages);
         const uint32_t use = kcount / kXStages;
-        if (use > 0) mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+        if (use > 0) {
+          mbar_wait_cluster(&s.empty[st], (use - 1) & 1);
+          mbar_wait_cluster(&s.empty[st + 1], (use - 1) & 1);
+        }
         __syncwarp();
         if (warp == 0 && elect_one()) {
-          const uint8_t* src = np.w2_img + (size_t)((kc * 2 + rank) * kUNP) * kXPieceBytes;
-          mbar_expect_tx(&s.bfull[st], kUNP * kXPieceBytes);
 #pragma unroll
-          for (int p = 0; p < kUNP; ++p)
-            bulk_g2s(s.ring[st].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st]);
+          for (int h = 0; h < 2; ++h) {
+            const uint8_t* src = np.w2_img + (size_t)(((kc + h) * 2 + rank) * kUNP) * kXPieceBytes;
+            mbar_expect_tx(&s.bfull[st + h], kUNP * kXPieceBytes);
+#pragma unroll
+            for (int p = 0; p < kUNP; ++p)
+              bulk_g2s(s.ring[st + h].b[p], src + (size_t)p * kXPieceBytes, kXPieceBytes, &s.bfull[st + h]);
+          }
         }
-        float v[8];
-        h1_chunk<true>(s.w1t, ob, D, stage_kgroup(kc, g) * 8, v);  // -s_h H1
-        uint8_t* tiles[kUNP];
 #pragma unroll
-        for (int p = 0; p < kUNP; ++p) tiles[p] = s.ring[st].a[p];
-        store_split_chunk<kUNP, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+        for (int h = 0; h < 2; ++h) {
+          float v[8];
+          h1_chunk<true>(s.w1t, ob, D, stage_kgroup(kc + h, g) * 8, v);  // -s_h H1
+          uint8_t* tiles[kUNP];
+#pragma unroll
+          for (int p = 0; p < kUNP; ++p) tiles[p] = s.ring[st + h].a[p];
+          store_split_chunk<kUNP, kUF16>(tiles, (uint32_t)(rloc * 16 + g * 2048), v);
+        }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_wait(&s.bfull[st], use & 1);
           mbar_arrive_cluster(&s.full[st], 0);
+          mbar_arrive_cluster(&s.full[st + 1], 0);
         }
       }
     };
@@ -446,6 +458,7 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
       for (int kc = 0; kc < H / kXKc; ++kc, ++kcount) {
         const int st = (int)(kcount % kXStages);
         mbar_wait_cluster(&s.full[st], (kcount / kXStages) & 1);
+        mbar_wait(&s.bfull[st], (kcount / kXStages) & 1);  // this CTA's half of the W2 stage has landed
         fence_after_sync();
         if (elect_one()) {
           issue_stage<kUNP>(tmem + (uint32_t)(buf * H), s.ring[st], idesc, kc > 0);
@@ -454,6 +467,15 @@ tc3_forward_kernel(NetParams np, RowMap map, int64_t rows, float* __restrict__ o
         }
         __syncwarp();
       }
+    }
+  } else {
+    // peer CTA, warp 16: tells the leader's full[] barrier when THIS CTA's half of a W2 stage has landed
+    const uint32_t total = (uint32_t)(n_my * (H / kXKc));
+    for (uint32_t kcount = 0; kcount < total; ++kcount) {
+      const int st = (int)(kcount % kXStages);
+      mbar_wait(&s.bfull[st], (kcount / kXStages) & 1);
+      if ((tid & 31) == 0) mbar_arrive_cluster(&s.full[st], 0);
+      __syncwarp();
     }
   }
   fence_before_sync();
