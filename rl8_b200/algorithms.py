@@ -555,9 +555,8 @@ class Algorithm:
         self.last_launches["collect"] = {
             _lib.PREC_FP32: 4 * T + 3 * (T + 1),  # layer 1, SGEMM, head, tail per step; 3 per value slab
             _lib.PREC_BF16: 4,                    # 2 x W2 packing, rollout kernel, value pass
-            # W2 piece images (one launch), (max |obs| of the slab + split forward + tail) per step, max |obs| of all
-            # slabs + value pass
-            _lib.PREC_FP32_TC: 1 + 3 * T + 2,
+            # W2 piece images (one launch), max |obs| of slab 0 (two launches), (split forward + tail) per step, value pass
+            _lib.PREC_FP32_TC: 1 + 2 + 2 * T + 1,
         }[self.policy.precision]
 
     def _head_width(self) -> int:

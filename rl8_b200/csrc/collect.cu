@@ -18,8 +18,10 @@ sample_step_store_kernel(rl8_env_cfg cfg, int dist_kind, int deterministic,
                          float* __restrict__ state, float* __restrict__ obs_next,
                          void* __restrict__ action_out, float* __restrict__ logp_out,
                          float* __restrict__ reward_out, const float* __restrict__ rdr_prev,
-                         float* __restrict__ rdr_next, float gamma, int64_t N) {
+                         float* __restrict__ rdr_next, float gamma, int64_t N,
+                         uint32_t* __restrict__ omax_next, uint32_t* __restrict__ omax_all) {
   using Tr = EnvTraits<KIND>;
+  float omax = 0.0f;  // max |obs| this thread writes (the fp16-piece forward derives its H1 scale from it)
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
        n += (int64_t)gridDim.x * blockDim.x) {
     float o[P];
@@ -63,15 +65,24 @@ sample_step_store_kernel(rl8_env_cfg cfg, int dist_kind, int deterministic,
 #pragma unroll
     for (int i = 0; i < Tr::S; ++i) state[(int64_t)i * N + n] = s[i];
 #pragma unroll
-    for (int i = 0; i < Tr::D; ++i) obs_next[(int64_t)i * N + n] = ob[i];
+    for (int i = 0; i < Tr::D; ++i) obs_next[(int64_t)i * N + n] = ob[i], omax = fmaxf(omax, fabsf(ob[i]));
     reward_out[n] = r;
     // rdr[t+1] = gamma * rdr[t] + reward   (:378-383)
     if (rdr_next) rdr_next[n] = add(mul(gamma, rdr_prev[n]), r);
   }
+  if (omax_next) {  // (uniform) max |obs| of the slab just written, as float bits; NaNs are skipped by fmaxf
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+    if ((threadIdx.x & 31) == 0 && omax > 0.0f) {
+      atomicMax(omax_next, __float_as_uint(omax));
+      atomicMax(omax_all, __float_as_uint(omax));
+    }
+  }
 }
 
 template <int KIND, int P>
-static int launch_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st) {
+static int launch_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st, uint32_t* omax_next,
+                       uint32_t* omax_all) {
   using Tr = EnvTraits<KIND>;
   const int64_t N = ro->N;
   const size_t asz = Tr::discrete ? 8 : 4;
@@ -82,7 +93,7 @@ static int launch_tail(const rl8_rollout* ro, int t, const float* feat, cudaStre
       ro->obs + (int64_t)(t + 1) * Tr::D * N, (char*)ro->actions + (size_t)t * N * asz,
       ro->logp + (int64_t)t * N, ro->rewards + (int64_t)t * N,
       ro->rdr ? ro->rdr + (int64_t)t * N : nullptr,
-      ro->rdr ? ro->rdr + (int64_t)(t + 1) * N : nullptr, ro->gamma, N);
+      ro->rdr ? ro->rdr + (int64_t)(t + 1) * N : nullptr, ro->gamma, N, omax_next, omax_all);
   return check_launch("sample_step_store");
 }
 
@@ -118,13 +129,16 @@ int validate_rollout(const rl8_model* model, const rl8_rollout* ro) {
   return validate_rollout_dims(model->D, model->H, model->P, ro);
 }
 
-int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st) {
+// omax_next / omax_all (both or neither): receive the bits of max |obs| of slab t + 1 (atomicMax)
+int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st, uint32_t* omax_next = nullptr,
+                 uint32_t* omax_all = nullptr) {
+  if ((omax_next == nullptr) != (omax_all == nullptr)) return RL8_ERR_ARG;
   switch (ro->env_kind) {
-    case RL8_ENV_DISCRETE_DUMMY: return launch_tail<RL8_ENV_DISCRETE_DUMMY, 2>(ro, t, feat, st);
-    case RL8_ENV_CONTINUOUS_DUMMY: return launch_tail<RL8_ENV_CONTINUOUS_DUMMY, 2>(ro, t, feat, st);
-    case RL8_ENV_CARTPOLE: return launch_tail<RL8_ENV_CARTPOLE, 3>(ro, t, feat, st);
-    case RL8_ENV_MOUNTAIN_CAR: return launch_tail<RL8_ENV_MOUNTAIN_CAR, 3>(ro, t, feat, st);
-    case RL8_ENV_PENDULUM: return launch_tail<RL8_ENV_PENDULUM, 2>(ro, t, feat, st);
+    case RL8_ENV_DISCRETE_DUMMY: return launch_tail<RL8_ENV_DISCRETE_DUMMY, 2>(ro, t, feat, st, omax_next, omax_all);
+    case RL8_ENV_CONTINUOUS_DUMMY: return launch_tail<RL8_ENV_CONTINUOUS_DUMMY, 2>(ro, t, feat, st, omax_next, omax_all);
+    case RL8_ENV_CARTPOLE: return launch_tail<RL8_ENV_CARTPOLE, 3>(ro, t, feat, st, omax_next, omax_all);
+    case RL8_ENV_MOUNTAIN_CAR: return launch_tail<RL8_ENV_MOUNTAIN_CAR, 3>(ro, t, feat, st, omax_next, omax_all);
+    case RL8_ENV_PENDULUM: return launch_tail<RL8_ENV_PENDULUM, 2>(ro, t, feat, st, omax_next, omax_all);
   }
   return RL8_ERR_ARG;
 }

@@ -21,7 +21,8 @@ namespace rl8 {
 
 // collect.cu
 int validate_rollout_dims(int mD, int mH, int mP, const rl8_rollout* ro);
-int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st);
+int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st, uint32_t* omax_next = nullptr,
+                 uint32_t* omax_all = nullptr);
 
 // The recurrent path's GEMM: CUDA-core fp32 or tcgen05 bf16 by precision.
 static int lstm_gemm(int prec, bool a_kmajor, bool b_kmajor, int epi, const float* A, const float* B, float* C,

@@ -554,7 +554,8 @@ int mlp_forward_x3(const rl8_model* m, int which, const RowMap& map, int64_t row
 
 // collect() in RL8_PREC_FP32_TC: per step the split policy forward + the fused sample / env-step / buffer-write kernel
 // of the fp32 path (collect.cu), then one split value pass over all T + 1 observation slabs.
-int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st);
+int collect_tail(const rl8_rollout* ro, int t, const float* feat, cudaStream_t st, uint32_t* omax_next = nullptr,
+                 uint32_t* omax_all = nullptr);
 
 // workspace: two piece images, the operand magnitudes {w2 scale pi, w2 scale vf, max |obs| bits of all slabs, of slab
 // 0 .. T}, the head outputs of a step
@@ -586,16 +587,19 @@ int collect_x3(const rl8_model* model, const rl8_rollout* ro, void* workspace, i
   const int continuous = ro->dist_kind != RL8_DIST_CATEGORICAL;
   RowMap map{};
   map.mode = 0, map.stride_r = 1, map.stride_d = N, map.D = model->D;
+  // max |obs| per slab: slab 0 (written by the reset / the previous rollout) by its own kernel, slab t + 1 by the tail
+  // kernel of step t that writes it; omax_all collects the maximum over all T + 1 slabs for the value pass
+  if (kUF16) {
+    if ((rc = launch_absmax_bits(ro->obs, (int64_t)model->D * N, omax_t, st))) return rc;
+    if ((rc = launch_absmax_bits(ro->obs, (int64_t)model->D * N, omax_all, st))) return rc;
+  }
   for (int t = 0; t < ro->T; ++t) {
     map.obs = ro->obs + (int64_t)t * model->D * N;
-    // (slab t is contiguous: D * N floats written by the reset / the previous step's tail kernel)
-    if (kUF16 && (rc = launch_absmax_bits(map.obs, (int64_t)model->D * N, omax_t + t, st))) return rc;
     if ((rc = launch_forward_x3(np_pi, map, N, feat, continuous, w2_scale, omax_t + t, st))) return rc;
-    if ((rc = collect_tail(ro, t, feat, st))) return rc;
+    if ((rc = collect_tail(ro, t, feat, st, kUF16 ? omax_t + t + 1 : nullptr, kUF16 ? omax_all : nullptr))) return rc;
   }
   RowMap vmap{};
   vmap.obs = ro->obs, vmap.mode = 2, vmap.D = model->D, vmap.N = N, vmap.T = ro->T;
-  if (kUF16 && (rc = launch_absmax_bits(ro->obs, (int64_t)(ro->T + 1) * model->D * N, omax_all, st))) return rc;
   return launch_forward_x3(np_vf, vmap, (int64_t)(ro->T + 1) * N, ro->values, 0, w2_scale + 1, omax_all, st);
 }
 
