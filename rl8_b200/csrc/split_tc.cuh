@@ -135,13 +135,15 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
 __device__ __forceinline__ float2 f16x2_f32(uint32_t p) { return __half22float2(*reinterpret_cast<const __half2*>(&p)); }
 
 // The largest power of two s with bound * s <= 2^14 (fp16 pieces: 2^14 leaves a factor 4 below the largest finite
-// fp16 value for the rounding of the bound itself); 1 when the bound is zero or not finite.
+// fp16 value for the rounding of the bound itself); 1 when the bound is zero or not finite.  Any finite bound gets a
+// normal s (k >= -113); tiny bounds stop at 2^60 (tensors below 2^-46 lose piece precision, not range) so that the
+// product of two inverse scales never underflows.
 __host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
   if (!(bound > 0.0f) || !(bound < 1.0e38f)) return 1.0f;
   int e;
   frexpf(bound, &e);  // bound = m 2^e, 0.5 <= m < 1
   int k = 14 - e;
-  k = k < -100 ? -100 : k > 100 ? 100 : k;
+  k = k > 60 ? 60 : k;
   return ldexpf(1.0f, k);
 }
 
