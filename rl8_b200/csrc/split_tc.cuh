@@ -16,11 +16,13 @@
 // FP16 PIECES ("h2", the form the update kernels use).  An fp16 piece carries 11 significant bits against bf16's 8, and
 // kind::f16 multiplies fp16 operands at the same rate, so TWO pieces per operand and THREE piece products
 //
-//     x = h0 + h1 (+ 2^-24 |x|),   h0 = f16(x), h1 = f16(x - h0);      a0b0 + a0b1 + a1b0     dropped a1b1 <= 2^-24 |ab|
+//     x = h0 + h1 (+ 2^-22 |x|),   h0 = f16(x), h1 = f16(x - h0);      a0b0 + a0b1 + a1b0     dropped a1b1 <= 2^-22 |ab|
 //
-// are as accurate as the six bf16 products at half the tensor-pipe work and two thirds of the splitting work.  The
+// carry 22 bits per operand: 8e-8 of the result at K = 256 (tests/test_cpu_split_arith.py) against 6e-9 for the six bf16
+// products and 5e-7 for an fp32 dot product accumulated in fp32 (the reference's own nn.Linear) -- i.e. still below the
+// rounding the reference itself carries, at half the tensor-pipe work and two thirds of the splitting work.  The
 // price is fp16's exponent range: every operand tensor is multiplied by a power of two s (exact) chosen from a bound of
-// its magnitude so that |x s| <= 2^14 (pow2_scale_for); elements down to 2^-17 of the bound keep the full 2^-24
+// its magnitude so that |x s| <= 2^14 (pow2_scale_for); elements down to 2^-17 of the bound keep the full 2^-22
 // relative accuracy, smaller ones an absolute error of 2^-39 of the bound (fp16 subnormals).  The consumer multiplies
 // the accumulator by 1 / (s_a s_b), also exact.
 //

@@ -54,9 +54,9 @@ def test_pair_mma_term_sets_against_fp64(K: int) -> None:
 
 @pytest.mark.parametrize("K", [32, 256])
 def test_pair_mma_fp16_pieces_against_fp64(K: int) -> None:
-    """Two fp16 pieces per operand, three piece products (the update kernels' form, split_tc.cuh): as accurate as
-    the six bf16 products once the operands are scaled by a power of two into fp16's range -- also for elements
-    2^-12 of the largest one."""
+    """Two fp16 pieces per operand, three piece products (the kernels' form, split_tc.cuh): 22 bits per operand once
+    the operands are scaled by a power of two into fp16's range -- also for elements 2^-12 of the largest one; the
+    bound is the one of the six bf16 products (the fp32 accumulation in tensor memory dominates both)."""
     L, lib = _lib()
     gen = torch.Generator().manual_seed(100 + K)
     A = torch.randn(256, K, generator=gen)
