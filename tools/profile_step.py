@@ -65,7 +65,7 @@ if algo.policy.precision == L.PREC_FP32_TC:
                       ("x3_update_w (weight gradient)", 4)):
         os.environ["RL8_X3_STAGES"] = str(bit)
         minibatch()
-        print(f"   {name:32s} {min(timed(minibatch) for _ in range(3)):.3f} ms (incl. 4 W2 piece-image launches)")
+        print(f"   {name:32s} {min(timed(minibatch) for _ in range(3)):.3f} ms (incl. the max |obs| and W2 piece-image launches)")
     os.environ.pop("RL8_X3_STAGES")
     # optional: sweep of the policy / value split of the 74 CTA pairs per kernel (RL8_X3_SWEEP=1)
     if os.environ.get("RL8_X3_SWEEP"):
