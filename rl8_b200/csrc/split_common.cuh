@@ -257,6 +257,8 @@ __device__ __forceinline__ uint4 mask_byte_lut(const uint2* lut, uint32_t byte) 
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 // the four worker warps {q, q + 4, q + 8, q + 12} that share the accumulator lanes 32 q .. 32 q + 31 (named barriers 2..5)
 __device__ __forceinline__ void quarter_bar_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 2) : "memory"); }
+// the four worker warps {4 cq .. 4 cq + 3} that share the accumulator columns 64 cq .. 64 cq + 63 (named barriers 6..9)
+__device__ __forceinline__ void colq_bar_sync(int cq) { asm volatile("bar.sync %0, 128;" ::"r"(cq + 6) : "memory"); }
 
 // lane l of the warp returns sum over the 32 lanes m of x_m[l]  (x is destroyed): 31 shuffles
 __device__ __forceinline__ float transpose_reduce32(float* x, int lane) {

@@ -582,7 +582,9 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
   uint2 pf_m2 = make_uint2(0u, 0u);
   auto fetch = [&](int64_t tile) {
     {
-      const int rt = tid & 255, half = tid >> 8;  // row of the tile; slots 4 half .. 4 half + 3
+      // row of the tile and slots 4 half .. 4 half + 3: the four warps that share cq stage exactly the 64 rows their
+      // epilogues read, so the hand-over needs a barrier of those four warps only
+      const int rt = cq * 64 + q * 16 + (lane & 15), half = lane >> 4;
       const int64_t rl = tile * 256 + rt;
       int64_t t = 0, n = 0;
       const bool valid = rl < a.Mc && minibatch_row_to_tn(a, a.row_off + rl, t, n);
@@ -610,7 +612,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
     // epilogue inputs of the tile: [obs | bias factor] and this CTA's mask1 words of all 256 rows.  Slot 7 multiplies
     // the bias gradient: 1, or -- value network -- dOut of the row, which then scales the observations too
     // (dZ1 = dOut * [H1 > 0] .* accumulator: the factor moves into the row's [obs | 1]).
-    const int rt = tid & 255, half = tid >> 8;
+    const int rt = cq * 64 + q * 16 + (lane & 15), half = lane >> 4;
     float4 o4 = make_float4(pf_o[0], pf_o[1], pf_o[2], pf_o[3]);
     if constexpr (VNET) o4.x *= pf_dr, o4.y *= pf_dr, o4.z *= pf_dr, o4.w *= pf_dr;
     if (half) o4.w = VNET ? pf_dr : 1.0f;
@@ -667,7 +669,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
 
   auto epilogue = [&](int64_t j) {
     const int buf = (int)(j & 1);
-    worker_bar_sync();  // os / m1s of this tile are complete
+    colq_bar_sync(cq);  // os / m1s of the 64 rows of this column quarter are complete
     mbar_wait_cluster(&s.acc_full[buf], (uint32_t)((j >> 1) & 1));
     fence_after_sync();
     const uint32_t acc = tmem + (uint32_t)(buf * H) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
@@ -711,7 +713,7 @@ __device__ __forceinline__ void update_b_workers(SmemXB<NPB>& s, const NetParams
         gacc[2] = ffma2(dz, make_float2(ob.x, ob.y), gacc[2]), gacc[3] = ffma2(dz, make_float2(ob.z, ob.w), gacc[3]);
       }
     }
-    worker_bar_sync();  // os / m1s of this buffer may be rewritten
+    colq_bar_sync(cq);  // os / m1s of this buffer may be rewritten
   };
 
   // Two 256-column accumulators (one per tile parity, like the forward kernel: K = 256 is 96 instructions into one
